@@ -1,0 +1,23 @@
+# Builds the C-ABI library (CUDA, sm_100a), the plain-C oracle restatement and, when /root/reference
+# is present, the reference itself (oracle/_ref).  Used by __graft_entry__.build().
+NVCC      ?= nvcc
+CXX       ?= g++
+CC        ?= gcc
+ARCH      := -gencode arch=compute_100a,code=sm_100a
+NVFLAGS   := -O3 -std=c++17 -lineinfo $(ARCH) -Xcompiler -fPIC
+PKG       := vc2_reference_b200
+CSRC      := $(PKG)/csrc
+LIB       := $(PKG)/libvc2b200.so
+OBJS      := $(CSRC)/dwt.o $(CSRC)/slices.o $(CSRC)/cabi.o
+
+all: $(LIB)
+
+$(CSRC)/%.o: $(CSRC)/%.cu $(CSRC)/*.cuh include/vc2_cabi.h
+	$(NVCC) $(NVFLAGS) -c $< -o $@
+
+$(LIB): $(OBJS)
+	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -lcudart
+
+clean:
+	rm -f $(OBJS) $(LIB)
+.PHONY: all clean

@@ -19,6 +19,9 @@
 #include "VLC.h"
 #include "WaveletTransform.h"
 
+// defined (non-static, undeclared in the header) in the reference's Quantisation.cpp:40-83
+const int quant_factor(int q);
+const int quant_offset(int q);
 // defined in the reference's EncodeStream.cpp (compiled with -Dmain=... below)
 const Array2D quantIndicesCBR(const Picture& coefficients, const Array1D& qMatrix,
                               const Array2D& sliceBytes, const int scalar);
@@ -68,6 +71,10 @@ int ref_padded_size(int size, int depth) { return paddedSize(size, depth); }
 int ref_slice_size_is_valid(int depth, int luma, int chroma, int n) {
   return sliceSizeIsValid(depth, luma, chroma, n);
 }
+
+// Quantisation.cpp:40-66, 78-83
+int ref_quant_factor(int q) { try { return quant_factor(q); } catch (...) { return -1; } }
+int ref_quant_offset(int q) { try { return quant_offset(q); } catch (...) { return -1; } }
 
 // WaveletTransform.cpp:345-423
 int ref_quant_matrix(int kernel, int depth, int* out) {

@@ -1,0 +1,207 @@
+"""GPU parity: every Library-surface C-ABI entry point against the compiled reference, bit exact."""
+import numpy as np
+import pytest
+
+import vc2_reference_b200 as vc2
+
+pytestmark = pytest.mark.gpu
+
+KN = ["DD97", "LeGall", "DD137", "Haar0", "Haar1", "Fidelity", "Daub97"]
+
+
+def rnd(shape, lo, hi, seed):
+    return np.random.default_rng(seed).integers(lo, hi + 1, size=shape, dtype=np.int64).astype(np.int32)
+
+
+def same(got, want, what):
+    got, want = np.asarray(got), np.asarray(want)
+    assert got.shape == want.shape, (what, got.shape, want.shape)
+    if not np.array_equal(got, want):
+        bad = np.argwhere(got != want)
+        first = tuple(bad[0])
+        raise AssertionError("%s: %d of %d differ, first at %s: got %d want %d"
+                             % (what, len(bad), got.size, first, got[first], want[first]))
+
+
+# survey Appendix B.4: depth-1 transform of a[y][x] = (3x^2+17y)%101-50 (4x8), rows 0 and 1
+DWT_KAT = {
+    "DD97": ([-101, -2, -80, -13, 28, 141, -30, 83], [0, 0, 0, 0, 25, 101, 25, 0]),
+    "LeGall": ([-103, -6, -79, -6, 31, 146, -30, 78], [0, 0, 0, 0, 25, 101, 25, 0]),
+    "DD137": ([-102, -2, -85, -13, 29, 143, -26, 83], [0, 0, -3, 0, 28, 101, 28, 0]),
+    "Haar0": ([-39, 3, -21, 15, 21, 27, -14, 39], [17, 0, 17, 0, 17, 0, 17, 0]),
+    "Haar1": ([-80, 6, -44, 30, 40, 54, -30, 78], [34, 0, 34, 0, 34, 0, 34, 0]),
+    "Fidelity": ([-168, 9, -139, -17, 45, 58, -23, 26], [-4, 3, -13, -4, 16, 21, 15, -10]),
+    "Daub97": ([-136, 0, -108, -20, 33, 128, -30, 84], [2, 0, 1, -3, 26, 70, 27, -7]),
+}
+
+
+@pytest.mark.parametrize("kernel", KN)
+def test_dwt_known_answers(ctx, kernel):
+    y, x = np.mgrid[0:4, 0:8]
+    a = ((3 * x * x + 17 * y) % 101 - 50).astype(np.int32)
+    t = ctx.waveletTransform(a, kernel, 1)
+    assert t[0].tolist() == DWT_KAT[kernel][0]
+    assert t[1].tolist() == DWT_KAT[kernel][1]
+    same(ctx.inverseWaveletTransform(t, kernel, 1, (4, 8)), a, "inverse of KAT")
+
+
+SHAPES = [(4, 8), (2, 2), (16, 16), (37, 53), (64, 128), (66, 130), (129, 257), (135, 240), (200, 300), (270, 481)]
+
+
+@pytest.mark.parametrize("kernel", KN)
+@pytest.mark.parametrize("depth", [1, 2, 3, 4])
+def test_dwt_forward_inverse_vs_reference(ctx, ref, kernel, depth):
+    k = vc2.KERNELS[kernel]
+    for i, (h, w) in enumerate(SHAPES):
+        if min(h, w) < (1 << depth) // 2:
+            continue
+        a = rnd((h, w), -512, 511, 1000 * depth + i)
+        want = ref.dwt_forward(a, k, depth)
+        got = ctx.waveletTransform(a, kernel, depth)
+        same(got, want, "forward %s d%d %dx%d" % (kernel, depth, h, w))
+        # inverse on arbitrary (not necessarily reachable) coefficients, with crop
+        c = rnd(want.shape, -3000, 3000, 77 + i)
+        same(ctx.inverseWaveletTransform(c, kernel, depth, (h, w)), ref.dwt_inverse(c, k, depth, (h, w)),
+             "inverse %s d%d %dx%d" % (kernel, depth, h, w))
+        same(ctx.inverseWaveletTransform(got, kernel, depth, (h, w)), a, "round trip")
+
+
+def test_dwt_large_values_fidelity(ctx, ref):
+    # 12-bit content through Fidelity depth 4 reaches +-4.6e5: int32 everywhere
+    a = rnd((144, 272), -2048, 2047, 5)
+    same(ctx.waveletTransform(a, "Fidelity", 4), ref.dwt_forward(a, 5, 4), "fidelity 12 bit")
+
+
+def _slice_cfg(depth, ny, nx, sy, sx):
+    return (ny * sy << depth, nx * sx << depth)
+
+
+@pytest.mark.parametrize("depth,ny,nx,mh,mw", [(1, 3, 5, 2, 1), (2, 4, 3, 1, 2), (3, 5, 6, 1, 2), (4, 2, 3, 1, 1)])
+def test_quantise_dequantise_vs_reference(ctx, ref, depth, ny, nx, mh, mw):
+    ph, pw = _slice_cfg(depth, ny, nx, mh, mw)
+    coef = rnd((ph, pw), -70000, 70000, depth)
+    coef[::3, ::5] = rnd(coef[::3, ::5].shape, -40, 40, 9)
+    for kernel in ("LeGall", "Fidelity", "Haar0"):
+        qm = vc2.quant_matrix(kernel, depth)
+        qidx = rnd((ny, nx), 0, 60, 3 + depth)
+        want = ref.quantise_np(coef, qidx, qm)
+        same(ctx.quantise_transform_np(coef, qidx, qm), want, "quantise")
+        same(ctx.inverse_quantise_transform_np(want, qidx, qm), ref.dequantise_np(want, qidx, qm), "dequantise")
+        small = rnd((ph, pw), -300, 300, 11)
+        same(ctx.inverse_quantise_transform(small, qidx, qm), ref.dequantise_ld(small, qidx, qm), "LD dequantise")
+
+
+def test_quantise_all_indices_exact_division(ctx, ref):
+    # every quantiser index 0..115 (beyond that the reference's int quant_factor is negative): exactness of the
+    # multiply-shift division against the reference's integer division, incl. values around multiples
+    qm = np.zeros(4, np.int32)
+    for q in range(0, 116):
+        qf = ref.quant_factor(q)
+        base = np.arange(0, 64, dtype=np.int64)[:, None] * qf // 4
+        vals = (base + np.arange(-2, 3)[None, :]).ravel()
+        vals = np.concatenate([vals, -vals, rnd((192,), -(1 << 28), 1 << 28, q)]).astype(np.int64)
+        vals = vals[np.abs(vals) < (1 << 29)][:512]
+        coef = np.zeros((16, 32), np.int32)
+        coef.ravel()[:vals.size] = vals
+        qidx = np.full((1, 1), q, np.int32)
+        same(ctx.quantise_transform_np(coef, qidx, qm), ref.quantise_np(coef, qidx, qm), "quant q=%d" % q)
+    with pytest.raises(vc2.Vc2Error) as e:
+        ctx.quantise_transform_np(np.zeros((2, 2), np.int32), np.full((1, 1), 120, np.int32), qm)
+    assert "quantization index exceeds maximum implemented value" in str(e.value)
+
+
+def _quantised_picture(ref, geom, kernel, seed, amp=400, q=None):
+    depth = geom.depth
+    (ph, pw), (ch, cw) = vc2.api.padded_dims(geom)
+    ny, nx = geom.slices_y, geom.slices_x
+    qm = vc2.quant_matrix(kernel, depth)
+    planes = [rnd((ph, pw), -amp, amp, seed), rnd((ch, cw), -amp, amp, seed + 1), rnd((ch, cw), -amp, amp, seed + 2)]
+    # make some slices sparse / all zero and some with long zero tails
+    planes[0][: ph // ny, : pw // nx] = 0
+    planes[1][: ch // ny] //= 64
+    planes[2][:, : cw // 2] //= 16
+    qidx = rnd((ny, nx), 0, 40, seed + 3) if q is None else np.full((ny, nx), q, np.int32)
+    quant = [ref.quantise_np(p, qidx, qm) for p in planes]
+    return planes, quant, qidx, qm
+
+
+PACK_CASES = [
+    # h, w, chroma, kernel, depth, u, a, prefix, scalar
+    (64, 128, "422", "LeGall", 3, 1, 2, 0, 1),
+    (48, 96, "444", "DD97", 2, 2, 3, 1, 2),
+    (70, 46 * 2, "420", "Haar1", 1, 2, 2, 2, 1),
+    (128, 256, "422", "DD137", 4, 1, 2, 0, 4),
+    (96, 96, "444", "Fidelity", 2, 3, 3, 0, 3),
+]
+
+
+@pytest.mark.parametrize("case", PACK_CASES)
+def test_hq_pack_unpack_vbr_vs_reference(ctx, ref, case):
+    h, w, cf, kernel, depth, u, a, prefix, scalar = case
+    g = vc2.make_geom(h, w, cf, kernel, depth, u, a, prefix, scalar)
+    planes, quant, qidx, qm = _quantised_picture(ref, g, kernel, 42)
+    want = ref.pack_slices(quant[0], quant[1], quant[2], depth, qidx, 0, prefix, scalar)
+    got, off = ctx.hq_pack(quant[0], quant[1], quant[2], g, qidx, "HQ_VBR")
+    assert len(got) == len(want)
+    assert got == want, "first differing byte %d" % next(i for i in range(len(want)) if got[i] != want[i])
+    assert off[-1] == len(want)
+    assert off.tolist() == vc2.hq_index_slices(want, g.slices_x * g.slices_y, prefix, scalar).tolist()
+    y, uu, v, q = ctx.hq_unpack(want, g)
+    (ph, pw), (ch, cw) = vc2.api.padded_dims(g)
+    ry, ru, rv, rq = ref.unpack_slices(want, ph, pw, ch, cw, depth, g.slices_y, g.slices_x, 0, prefix, scalar)
+    same(q, rq, "qindex")
+    same(y, ry, "Y")
+    same(uu, ru, "U")
+    same(v, rv, "V")
+    same(y, quant[0], "Y vs source")
+
+
+@pytest.mark.parametrize("case", PACK_CASES)
+def test_cbr_rate_control_and_pack_vs_reference(ctx, ref, case):
+    h, w, cf, kernel, depth, u, a, prefix, scalar = case
+    g = vc2.make_geom(h, w, cf, kernel, depth, u, a, prefix, scalar)
+    planes, _, _, qm = _quantised_picture(ref, g, kernel, 7, amp=900)
+    ncoef = sum(p.size for p in planes)
+    for ratio in (3, 6):
+        total = ncoef * 10 // 8 // ratio
+        sb = vc2.slice_bytes(g.slices_y, g.slices_x, total, scalar)
+        want_q = ref.cbr_qindices(planes[0], planes[1], planes[2], qm, sb, scalar)
+        got_q = ctx.quantIndicesCBR(planes[0], planes[1], planes[2], g, qm, sb)
+        same(got_q, want_q, "CBR qindex ratio %d" % ratio)
+        quant = [ref.quantise_np(p, want_q, qm) for p in planes]
+        want = ref.pack_slices(quant[0], quant[1], quant[2], depth, want_q, 1, prefix, scalar, sb)
+        got, off = ctx.hq_pack(quant[0], quant[1], quant[2], g, want_q, "HQ_CBR", sb)
+        assert got == want
+        y, uu, v, q = ctx.hq_unpack(want, g)
+        same(q, want_q, "qindex")
+        same(y, quant[0], "Y")
+        same(uu, quant[1], "U")
+        same(v, quant[2], "V")
+
+
+def test_slice_scalar_too_small_is_reported(ctx, ref):
+    g = vc2.make_geom(64, 128, "444", "LeGall", 2, 8, 16, 0, 1)   # one 32x64 slice per 32x64 block: > 255 bytes
+    planes, quant, qidx, qm = _quantised_picture(ref, g, "LeGall", 3, amp=30000, q=0)
+    with pytest.raises(Exception) as e_ref:
+        ref.pack_slices(quant[0], quant[1], quant[2], 2, qidx, 0, 0, 1)
+    with pytest.raises(vc2.Vc2Error) as e:
+        ctx.hq_pack(quant[0], quant[1], quant[2], g, qidx, "HQ_VBR")
+    assert "Slice scalar is too small" in str(e.value) and "Slice scalar is too small" in str(e_ref.value)
+
+
+def test_ld_unpack_vs_reference(ctx, ref):
+    depth, kernel = 3, "LeGall"
+    g = vc2.make_geom(64, 128, "422", kernel, depth, 1, 2)
+    (ph, pw), (ch, cw) = vc2.api.padded_dims(g)
+    qm = vc2.quant_matrix(kernel, depth)
+    planes = [rnd((ph, pw), -60, 60, 1), rnd((ch, cw), -60, 60, 2), rnd((ch, cw), -60, 60, 3)]
+    qidx = rnd((g.slices_y, g.slices_x), 8, 30, 4)
+    quant = [ref.quantise_ld(p, qidx, qm) for p in planes]
+    sb = vc2.slice_bytes(g.slices_y, g.slices_x, 120 * g.slices_y * g.slices_x + 13, 1)
+    data = ref.pack_slices(quant[0], quant[1], quant[2], depth, qidx, 2, 0, 1, sb)
+    ry, ru, rv, rq = ref.unpack_slices(data, ph, pw, ch, cw, depth, g.slices_y, g.slices_x, 2, 0, 1, sb)
+    y, u, v, q = ctx.ld_unpack(data, g, sb)
+    same(q, rq, "qindex")
+    same(y, ry, "Y")
+    same(u, ru, "U")
+    same(v, rv, "V")

@@ -1,0 +1,96 @@
+"""CPU-only: host-side helpers of the C-ABI against the reference (live taps) and its known answers."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import vc2_reference_b200 as vc2
+from vc2_reference_b200._cabi import lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+# quantMatrix known answers dumped from the compiled reference
+QM_KAT = {
+    ("DD97", 4): [5, 3, 3, 0, 4, 4, 1, 5, 5, 2, 6, 6, 3],
+    ("LeGall", 4): [4, 2, 2, 0, 4, 4, 2, 5, 5, 3, 7, 7, 5],
+    ("DD137", 4): [5, 3, 3, 0, 4, 4, 1, 5, 5, 2, 6, 6, 3],
+    ("Haar1", 4): [8, 4, 4, 0, 4, 4, 0, 4, 4, 0, 4, 4, 0],
+    ("Haar0", 4): [20, 16, 16, 12, 12, 12, 8, 8, 8, 4, 4, 4, 0],
+    ("Fidelity", 4): [0, 4, 4, 8, 8, 8, 12, 13, 13, 17, 17, 17, 21],
+    ("Daub97", 4): [3, 1, 1, 0, 4, 4, 2, 6, 6, 5, 9, 9, 7],
+}
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "vc2_cabi.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    names = set(re.findall(r"\b(vc2_[a-z0-9_]+)\s*\(", hdr))
+    assert len(names) > 40
+    raw = C.CDLL(vc2.lib_path)
+    missing = [n for n in sorted(names) if not hasattr(raw, n)]
+    assert not missing, missing
+    # and the ctypes binding declares all of them
+    assert set(lib._vc2_symbols) == names
+
+
+def test_quant_matrix_known_answers():
+    for (k, d), want in QM_KAT.items():
+        assert vc2.quant_matrix(k, d).tolist() == want
+    assert vc2.quant_matrix("LeGall", 0).tolist() == [0]
+
+
+def test_quant_matrix_vs_reference(ref):
+    for k in range(7):
+        for d in range(0, 7):
+            assert vc2.quant_matrix(k, d).tolist() == ref.quant_matrix(k, d).tolist(), (k, d)
+
+
+def test_quant_factor_table_vs_reference(ref):
+    for q in range(-3, 116):
+        assert lib.vc2_quant_factor(q) == ref.quant_factor(q), q
+        assert lib.vc2_quant_offset(q) == ref.quant_offset(q), q
+    # reference unit test (tests/Quantisation.cpp:6-12): index 130 is beyond the table
+    assert ref.quant_factor(130) == -1
+
+
+def test_slice_bytes(ref):
+    assert vc2.slice_bytes(3, 4, 1000, 1).ravel().tolist() == [83, 83, 84, 83, 83, 84, 83, 83, 84, 83, 83, 84]
+    assert (vc2.slice_bytes(135, 120, 2073600, 1) == 128).all()
+    for ny, nx, total, scalar in [(3, 4, 1000, 1), (135, 120, 2073600, 1), (7, 5, 9999, 3), (17, 11, 123457, 4), (2, 2, 64, 8)]:
+        assert (vc2.slice_bytes(ny, nx, total, scalar) == ref.slice_bytes(ny, nx, total, scalar)).all()
+
+
+def test_padding_and_slice_validity(ref):
+    for size in (1, 7, 8, 1080, 1081, 2160, 4320):
+        for d in range(1, 6):
+            assert vc2.padded_size(size, d) == ref.padded_size(size, d)
+    for d in range(1, 6):
+        for luma, chroma in ((1080, 1080), (1920, 960), (188, 94), (174, 87), (352, 176), (100, 100)):
+            for n in range(0, 12):
+                assert lib.vc2_slice_size_is_valid(d, luma, chroma, n) == ref.slice_size_is_valid(d, luma, chroma, n)
+
+
+def test_make_geom_rejects_invalid_slicing():
+    g = vc2.make_geom(1080, 1920, "422", "LeGall", 3, 1, 2)
+    assert (g.slices_y, g.slices_x, g.chroma_w) == (135, 120, 960)
+    with pytest.raises(vc2.Vc2Error):
+        vc2.make_geom(120, 200, "422", "LeGall", 3, 1, 2)
+
+
+def test_hq_index_slices():
+    # two slices, prefix 1, scalar 2: [pfx q ly Y.. lu U.. lv V..]
+    s0 = bytes([9, 5, 1]) + b"ab" + bytes([0]) + bytes([2]) + b"cdef"
+    s1 = bytes([9, 6, 0, 0, 0])
+    off = vc2.hq_index_slices(s0 + s1, 2, 1, 2)
+    assert off.tolist() == [0, len(s0), len(s0) + len(s1)]
+    with pytest.raises(vc2.Vc2Error):
+        vc2.hq_index_slices((s0 + s1)[:-1], 2, 1, 2)
+
+
+def test_no_cpu_fallback_without_gpu():
+    if lib.vc2_device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(vc2.Vc2Error):
+        vc2.Context(0)

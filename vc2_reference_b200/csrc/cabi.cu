@@ -1,0 +1,1129 @@
+// C-ABI implementation (include/vc2_cabi.h): context, host-side helpers, Library-surface
+// operations and the batched fused picture codec.  All compute goes through the CUDA kernels in
+// dwt.cu / slices.cu; there is deliberately no CPU path for any of it.
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "dwt.cuh"
+#include "slices.cuh"
+
+namespace vc2 {
+cudaError_t dwt_level_launch(cudaStream_t s, bool inverse, int kernel, int sample_kind, const DwtParams& p, int npictures);
+cudaError_t layout_launch(cudaStream_t s, bool to_planar, const int32_t* src, int32_t* dst, const PlaneGeom& g,
+                          long long src_pic_stride, long long dst_pic_stride, int npictures);
+}  // namespace vc2
+
+using namespace vc2;
+
+// ================================================================================================
+// host-side helpers (pure host code)
+// ================================================================================================
+
+extern "C" int vc2_padded_size(int size, int depth) {
+  const int cell = 1 << depth;   // WaveletTransform.cpp:74-77
+  return cell * ((size + cell - 1) / cell);
+}
+
+extern "C" int vc2_slice_size_is_valid(int depth, int luma, int chroma, int n) {
+  // WaveletTransform.cpp:116-136
+  if (depth <= 0 || depth > 31) return 0;
+  const int cell = 1 << depth;
+  const int max_slices = std::min(luma, chroma) / cell;
+  if (n <= 0 || n > max_slices) return 0;
+  const int transform_size = n * cell;
+  const int pl = vc2_padded_size(luma, depth), pc = vc2_padded_size(chroma, depth);
+  const int ns = (pl + transform_size - 1) / transform_size;
+  if (pl % ns == 0 && (pl / ns) % cell == 0 && pc % ns == 0 && (pc / ns) % cell == 0) return ns;
+  return 0;
+}
+
+extern "C" int vc2_quant_matrix(int kernel, int depth, int32_t* out) {
+  // WaveletTransform.cpp:345-423.  Same float expression order as the reference so that the
+  // rounding of 4*log2(gain/minGain) lands on the same integers.
+  if (depth < 0 || depth > VC2_MAX_DEPTH || !out) return VC2_ERR_ARG;
+  if (depth == 0) { out[0] = 0; return VC2_OK; }
+  float alpha, beta;
+  int shift;
+  switch (kernel) {
+    case VC2_DD97: alpha = 1.280868846f; beta = 0.820572875f; shift = 1; break;
+    case VC2_LEGALL: alpha = 1.224744871f; beta = 0.847791248f; shift = 1; break;
+    case VC2_DD137: alpha = 1.280868846f; beta = 0.809253958f; shift = 1; break;
+    case VC2_HAAR0: alpha = 1.414213562f; beta = 0.707106871f; shift = 0; break;
+    case VC2_HAAR1: alpha = 1.414213562f; beta = 0.707106871f; shift = 1; break;
+    case VC2_FIDELITY: alpha = 0.682408629f; beta = 1.367856979f; shift = 0; break;
+    case VC2_DAUB97: alpha = 1.139917028f; beta = 0.887168005f; shift = 1; break;
+    default: return VC2_ERR_ARG;
+  }
+  const float a2 = alpha * alpha, ab = alpha * beta, b2 = beta * beta;
+  std::vector<float> ll(depth + 1), lh(depth + 1), hh(depth + 1);
+  float min_gain = 3.402823466e+38f;
+  for (int level = depth; level > 0; --level) {
+    const float scale = pow(a2, depth - level) / pow(2.0f, shift * (depth - level + 1));
+    ll[level] = scale * a2;
+    lh[level] = scale * ab;
+    hh[level] = scale * b2;
+    min_gain = std::min(std::min(std::min(ll[level], lh[level]), hh[level]), min_gain);
+  }
+  std::vector<int> llq(depth + 1), lhq(depth + 1), hhq(depth + 1);
+  for (int level = depth; level > 0; --level) {
+    llq[level] = static_cast<int>(floor(4.0f * log(ll[level] / min_gain) / log(2.0f) + 0.5f));
+    lhq[level] = static_cast<int>(floor(4.0f * log(lh[level] / min_gain) / log(2.0f) + 0.5f));
+    hhq[level] = static_cast<int>(floor(4.0f * log(hh[level] / min_gain) / log(2.0f) + 0.5f));
+  }
+  int i = 0;
+  out[i++] = llq[1];
+  for (int level = 1; level <= depth; ++level) {
+    out[i++] = lhq[level];
+    out[i++] = lhq[level];
+    out[i++] = hhq[level];
+  }
+  return VC2_OK;
+}
+
+extern "C" int vc2_quant_factor(int q) {
+  // ST 2042-1 closed form; equals the 120-entry table of Quantisation.cpp:42-59 (checked in tests)
+  if (q < 0) q = 0;
+  const unsigned long long b = 1ull << (q / 4);
+  switch (q & 3) {
+    case 0: return (int)(unsigned)(4 * b);
+    case 1: return (int)(unsigned)((503829ull * b + 52958ull) / 105917ull);
+    case 2: return (int)(unsigned)((665857ull * b + 58854ull) / 117708ull);
+    default: return (int)(unsigned)((440253ull * b + 32722ull) / 65444ull);
+  }
+}
+
+extern "C" int vc2_quant_offset(int q) {
+  // Quantisation.cpp:78-83
+  if (q < 0) q = 0;
+  if (q == 0) return 1;
+  if (q == 1) return 2;
+  return (vc2_quant_factor(q) + 1) / 2;
+}
+
+static int gcd_int(int a, int b) {
+  if (a < 0) a = -a;
+  if (b < 0) b = -b;
+  while (b) { const int t = a % b; a = b; b = t; }
+  return a;
+}
+
+extern "C" int vc2_slice_bytes(int ny, int nx, int total, int scalar, int32_t* out) {
+  // Slices.cpp:28-49
+  if (ny <= 0 || nx <= 0 || scalar <= 0 || !out) return VC2_ERR_ARG;
+  int num = total / scalar - 4 * (ny * nx), den = ny * nx;
+  const int g = gcd_int(num, den);
+  if (g) { num /= g; den /= g; }
+  const int ratio = num / den;
+  const int remainder = num - ratio * den;
+  int residue = 0;
+  for (int i = 0; i < ny * nx; ++i) {
+    residue += remainder;
+    if (residue < den) out[i] = ratio * scalar + 4;
+    else { out[i] = (ratio + 1) * scalar + 4; residue -= den; }
+  }
+  return VC2_OK;
+}
+
+extern "C" int vc2_make_geom(int height, int width, int chroma_format, int kernel, int depth, int v_slice, int h_slice,
+                             int prefix, int scalar, vc2_geom* g) {
+  if (!g || height < 1 || width < 1 || depth < 1 || depth > VC2_MAX_DEPTH || kernel < 0 || kernel > VC2_DAUB97 ||
+      chroma_format < 0 || chroma_format > 2 || prefix < 0 || scalar < 1)
+    return VC2_ERR_ARG;
+  g->luma_h = height; g->luma_w = width;
+  // PictureFormat::construct, Picture.cpp:49-73
+  g->chroma_w = chroma_format == 0 ? width : width / 2;
+  g->chroma_h = chroma_format == 2 ? height / 2 : height;
+  g->kernel = kernel; g->depth = depth;
+  g->slices_y = vc2_slice_size_is_valid(depth, g->luma_h, g->chroma_h, v_slice);
+  g->slices_x = vc2_slice_size_is_valid(depth, g->luma_w, g->chroma_w, h_slice);
+  g->prefix = prefix; g->scalar = scalar;
+  if (g->slices_y == 0 || g->slices_x == 0) return VC2_ERR_ARG;
+  return VC2_OK;
+}
+
+extern "C" int vc2_hq_index_slices(const uint8_t* p, size_t len, int n_slices, int prefix, int scalar, uint32_t* off) {
+  // the read order of HQSliceIO_VBR(istream), Slices.cpp:544-605: lengths are the only framing
+  if (!p || !off || n_slices < 0 || prefix < 0 || scalar < 1) return VC2_ERR_ARG;
+  size_t pos = 0;
+  for (int s = 0; s < n_slices; ++s) {
+    off[s] = (uint32_t)pos;
+    size_t q = pos + prefix + 1;   // after prefix and qindex
+    for (int c = 0; c < 3; ++c) {
+      if (q >= len) return VC2_ERR_STREAM;
+      q += 1 + (size_t)p[q] * scalar;
+    }
+    if (q > len) return VC2_ERR_STREAM;
+    pos = q;
+  }
+  off[n_slices] = (uint32_t)pos;
+  return VC2_OK;
+}
+
+extern "C" const char* vc2_status_message(int st) {
+  switch (st) {
+    case VC2_OK: return "";
+    case VC2_ERR_ARG: return "invalid argument";
+    case VC2_ERR_CUDA: return "CUDA error (no usable GPU or runtime failure); this library has no CPU fallback";
+    case VC2_ERR_SCALAR_TOO_SMALL: return "Slice scalar is too small, consider using a larger slice scalar.";
+    case VC2_ERR_QUANT_INDEX: return "quantization index exceeds maximum implemented value.";
+    case VC2_ERR_CBR_TOO_MANY_BYTES: return "SliceIO, HQ CBR mode: Too many bytes for the slice";
+    case VC2_ERR_CBR_COMPONENT_LENGTH:
+      return "Slice component length exceeds 1 byte when divided by slice size scalar. See above for suggestions to prevent this.";
+    case VC2_ERR_CAPACITY: return "output buffer too small";
+    case VC2_ERR_VLC_RANGE: return "quantised coefficient outside the 32-bit VLC range of the reference";
+    case VC2_ERR_STREAM: return "malformed or truncated slice data";
+    case VC2_ERR_LD_TOO_MANY_BYTES: return "SliceIO, LD mode: Too many bytes for the U and V slices";
+    default: return "unknown error";
+  }
+}
+
+extern "C" int vc2_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+// ================================================================================================
+// context
+// ================================================================================================
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    cudaError_t e = cudaMalloc(&p, n + 256);   // slack: the bit reader may touch 7 bytes past the data
+    if (e == cudaSuccess) cap = n;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct vc2_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  std::string err;
+  long launches = 0;
+  DevBuf tmp[8];   // scratch for the Library-surface (host pointer) calls
+};
+
+static int fail(vc2_ctx* c, int st, const char* extra = nullptr) {
+  if (c) {
+    c->err = vc2_status_message(st);
+    if (extra) { c->err += ": "; c->err += extra; }
+  }
+  return st;
+}
+static int cuda_fail(vc2_ctx* c, cudaError_t e) { return fail(c, VC2_ERR_CUDA, cudaGetErrorString(e)); }
+#define CU(call)                                         \
+  do {                                                   \
+    cudaError_t e_ = (call);                             \
+    if (e_ != cudaSuccess) return cuda_fail(ctx, e_);    \
+  } while (0)
+
+static void make_quant_tables(QuantTables& t) {
+  for (int q = 0; q < 128; ++q) {
+    const uint32_t d = (uint32_t)vc2_quant_factor(std::min(q, 119));
+    t.qf[q] = d;
+    t.qo[q] = (uint32_t)vc2_quant_offset(std::min(q, 119));
+    uint32_t l = 0;
+    while ((1ull << l) < d) ++l;   // ceil(log2 d); d >= 4 so l >= 2
+    t.ql[q] = l;
+    t.qm[q] = (uint32_t)(((1ull << 32) * ((1ull << l) - d)) / d + 1);
+  }
+}
+
+extern "C" vc2_ctx* vc2_create(int device) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n) return nullptr;
+  if (cudaSetDevice(device) != cudaSuccess) return nullptr;
+  vc2_ctx* c = new (std::nothrow) vc2_ctx();
+  if (!c) return nullptr;
+  c->device = device;
+  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return nullptr; }
+  c->own_stream = true;
+  QuantTables t;
+  make_quant_tables(t);
+  if (upload_quant_tables(t) != cudaSuccess) { cudaStreamDestroy(c->stream); delete c; return nullptr; }
+  return c;
+}
+
+extern "C" void vc2_destroy(vc2_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  for (auto& b : c->tmp) b.release();
+  if (c->own_stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+extern "C" int vc2_set_stream(vc2_ctx* c, void* s) {
+  if (!c) return VC2_ERR_ARG;
+  if (c->own_stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); c->own_stream = false; }
+  c->stream = reinterpret_cast<cudaStream_t>(s);
+  return VC2_OK;
+}
+
+extern "C" int vc2_synchronize(vc2_ctx* ctx) {
+  if (!ctx) return VC2_ERR_ARG;
+  CU(cudaStreamSynchronize(ctx->stream));
+  return VC2_OK;
+}
+
+extern "C" const char* vc2_last_error(vc2_ctx* c) { return c ? c->err.c_str() : "no context"; }
+
+extern "C" int vc2_kernel_launches(vc2_ctx* c, int reset) {
+  if (!c) return 0;
+  const long n = c->launches;
+  if (reset) c->launches = 0;
+  return (int)n;
+}
+
+// ================================================================================================
+// pipeline helpers shared by the Library-surface calls and the fused codec
+// ================================================================================================
+
+struct CompBuf {
+  PlaneGeom pg;
+  void* pix = nullptr;              // dense picture plane (int32 or raw)
+  long long pix_pic_stride = 0;     // elements (int32) or bytes (raw)
+  int pix_pitch = 0;
+  int32_t* planar = nullptr;        // planar-subband coefficients
+  long long planar_pic_stride = 0;
+  int32_t* scratch[2] = {nullptr, nullptr};
+  long long scratch_pic_stride[2] = {0, 0};
+  int sshift = 0, soffset = 0, clip_min = 0, clip_max = 0;
+};
+
+static PlaneGeom make_plane(int h, int w, int depth) {
+  PlaneGeom g;
+  g.h = h; g.w = w; g.depth = depth;
+  g.ph = vc2_padded_size(h, depth);
+  g.pw = vc2_padded_size(w, depth);
+  return g;
+}
+
+// all levels of the forward or inverse transform for ncomp components of npictures pictures
+static cudaError_t run_dwt(vc2_ctx* ctx, bool inverse, int kernel, int depth, int sample_kind, const CompBuf* cb, int ncomp,
+                           int npictures) {
+  for (int step = 0; step < depth; ++step) {
+    const int l = inverse ? depth - 1 - step : step;   // 0 = finest
+    const int L = depth - l;                           // VC-2 level of the bands touched
+    DwtParams p;
+    memset(&p, 0, sizeof(p));
+    p.ncomp = ncomp;
+    for (int c = 0; c < ncomp; ++c) {
+      const CompBuf& B = cb[c];
+      DwtComp& C = p.c[c];
+      C.lat_h = B.pg.ph >> l;
+      C.lat_w = B.pg.pw >> l;
+      if (l == 0) {
+        C.pix = B.pix; C.pix_pic_stride = B.pix_pic_stride; C.pix_h = B.pg.h; C.pix_w = B.pg.w; C.pix_pitch = B.pix_pitch;
+      } else {
+        C.pix = B.scratch[(l - 1) & 1]; C.pix_pic_stride = B.scratch_pic_stride[(l - 1) & 1];
+        C.pix_h = C.lat_h; C.pix_w = C.lat_w; C.pix_pitch = C.lat_w;
+      }
+      if (l == depth - 1) {
+        C.ll = B.planar; C.ll_pic_stride = B.planar_pic_stride;
+      } else {
+        C.ll = B.scratch[l & 1]; C.ll_pic_stride = B.scratch_pic_stride[l & 1];
+      }
+      C.ll_pitch = C.lat_w / 2;
+      C.hl = B.planar + B.pg.band_off(3 * (L - 1) + 1);
+      C.lh = B.planar + B.pg.band_off(3 * (L - 1) + 2);
+      C.hh = B.planar + B.pg.band_off(3 * (L - 1) + 3);
+      C.band_pic_stride = B.planar_pic_stride;
+      C.band_pitch = C.lat_w / 2;
+      C.sshift = B.sshift; C.soffset = B.soffset; C.clip_min = B.clip_min; C.clip_max = B.clip_max;
+    }
+    cudaError_t e = dwt_level_launch(ctx->stream, inverse, kernel, l == 0 ? sample_kind : SAMPLE_I32, p, npictures);
+    if (e != cudaSuccess) return e;
+    ctx->launches++;
+  }
+  return cudaSuccess;
+}
+
+static void fill_slice_geom(SliceGeom& g, const vc2_geom& vg, const int32_t* qmatrix) {
+  memset(&g, 0, sizeof(g));
+  g.depth = vg.depth;
+  g.nbands = 3 * vg.depth + 1;
+  g.slices_x = vg.slices_x; g.slices_y = vg.slices_y;
+  g.prefix = vg.prefix; g.scalar = vg.scalar;
+  g.plane[0] = make_plane(vg.luma_h, vg.luma_w, vg.depth);
+  g.plane[1] = g.plane[2] = make_plane(vg.chroma_h, vg.chroma_w, vg.depth);
+  long long off = 0;
+  for (int c = 0; c < 3; ++c) { g.plane_off[c] = off; off += g.plane[c].size(); }
+  g.coef_pic_stride = off;
+  int cs = 0;
+  for (int c = 0; c < 3; ++c) {
+    g.comp_start[c] = cs;
+    int bs = 0;
+    for (int b = 0; b < g.nbands; ++b) {
+      g.part_h[c][b] = g.plane[c].band_h(b) / g.slices_y;
+      g.part_w[c][b] = g.plane[c].band_w(b) / g.slices_x;
+      g.band_start[c][b] = bs;
+      bs += g.part_h[c][b] * g.part_w[c][b];
+    }
+    g.band_start[c][g.nbands] = bs;
+    cs += bs;
+  }
+  g.comp_start[3] = cs;
+  for (int b = 0; b < g.nbands; ++b) g.qmatrix[b] = qmatrix ? qmatrix[b] : 0;
+}
+
+static bool geom_ok(const vc2_geom* g) {
+  if (!g) return false;
+  if (g->depth < 1 || g->depth > VC2_MAX_DEPTH || g->kernel < 0 || g->kernel > VC2_DAUB97) return false;
+  if (g->luma_h < 1 || g->luma_w < 1 || g->chroma_h < 1 || g->chroma_w < 1) return false;
+  if (g->slices_x < 1 || g->slices_y < 1 || g->prefix < 0 || g->scalar < 1) return false;
+  const int cell = 1 << g->depth;
+  const int ph = vc2_padded_size(g->luma_h, g->depth), pw = vc2_padded_size(g->luma_w, g->depth);
+  const int ch = vc2_padded_size(g->chroma_h, g->depth), cw = vc2_padded_size(g->chroma_w, g->depth);
+  if (ph % g->slices_y || pw % g->slices_x || ch % g->slices_y || cw % g->slices_x) return false;
+  if ((ph / g->slices_y) % cell || (pw / g->slices_x) % cell || (ch / g->slices_y) % cell || (cw / g->slices_x) % cell) return false;
+  return true;
+}
+
+// worst-case payload of one slice: every coefficient at the 32-bit VLC limit, or the length-byte limit
+static int max_slice_bytes(const SliceGeom& g, int mode, const int32_t* slice_bytes) {
+  const int nslices = g.slices_x * g.slices_y;
+  int m = 0;
+  if (mode == VC2_HQ_CBR && slice_bytes) {
+    for (int i = 0; i < nslices; ++i) m = std::max(m, slice_bytes[i]);
+    m += g.prefix;
+  }
+  int v = g.prefix + 4;
+  for (int c = 0; c < 3; ++c) {
+    const int n = g.band_start[c][g.nbands];
+    const int by_bits = ((4 * n + g.scalar - 1) / g.scalar) * g.scalar;   // 32 bits per coefficient
+    v += std::min(by_bits, 255 * g.scalar);
+  }
+  return std::max(m, v);
+}
+
+static int flags_to_status(unsigned f) {
+  if (f & VC2_FLAG_QUANT_INDEX) return VC2_ERR_QUANT_INDEX;
+  if (f & VC2_FLAG_SCALAR_TOO_SMALL) return VC2_ERR_SCALAR_TOO_SMALL;
+  if (f & VC2_FLAG_CBR_TOO_MANY_BYTES) return VC2_ERR_CBR_TOO_MANY_BYTES;
+  if (f & VC2_FLAG_CBR_COMP_LENGTH) return VC2_ERR_CBR_COMPONENT_LENGTH;
+  if (f & VC2_FLAG_VLC_RANGE) return VC2_ERR_VLC_RANGE;
+  if (f & VC2_FLAG_STREAM) return VC2_ERR_STREAM;
+  return VC2_OK;
+}
+// reference throw order: rate control for every slice (raster) runs before any slice is written
+static int first_error(const uint32_t* flags, int n) {
+  for (int i = 0; i < n; ++i)
+    if (flags[i] & VC2_FLAG_SEARCH_PHASE) return flags_to_status(flags[i]);
+  for (int i = 0; i < n; ++i)
+    if (flags[i]) return flags_to_status(flags[i]);
+  return VC2_OK;
+}
+
+struct PackBuffers {
+  uint8_t* out; long long out_stride; long long out_capacity;
+  uint32_t* slice_off; uint32_t* err_flags; int32_t* qidx;
+  unsigned long long* tile_state; unsigned* ticket;
+  const int32_t* slice_bytes_dev; const uint32_t* fixed_off_dev;
+};
+
+static cudaError_t run_pack(vc2_ctx* ctx, const SliceGeom& g, const int32_t* coef, int npictures, int mode, int quantise,
+                            int search, int const_q, int emit, const PackBuffers& B, int img_bytes) {
+  PackParams p;
+  memset(&p, 0, sizeof(p));
+  p.g = g;
+  p.coef = coef;
+  p.mode = mode; p.quantise = quantise; p.search = search; p.const_q = const_q; p.emit = emit;
+  p.qidx = B.qidx; p.slice_bytes = B.slice_bytes_dev; p.fixed_off = B.fixed_off_dev;
+  p.out = B.out; p.out_pic_stride = B.out_stride; p.out_capacity = B.out_capacity;
+  p.slice_off = B.slice_off; p.err_flags = B.err_flags; p.tile_state = B.tile_state; p.ticket = B.ticket;
+  const int nslices = g.slices_x * g.slices_y;
+  p.coef_words = g.comp_start[3];
+  p.img_words = (img_bytes + 3) / 4 + 1;
+  const size_t per_warp = (size_t)(p.coef_words + p.img_words) * 4;
+  int W = 8;
+  while (W > 1 && per_warp * W > 200 * 1024) W >>= 1;
+  if (per_warp * W > 227 * 1024) return cudaErrorInvalidConfiguration;
+  p.warps_per_cta = W;
+  p.ctas_per_pic = (nslices + W - 1) / W;
+  cudaError_t e = cudaMemsetAsync(B.ticket, 0, sizeof(unsigned) * npictures, ctx->stream);
+  if (e != cudaSuccess) return e;
+  e = cudaMemsetAsync(B.tile_state, 0, sizeof(unsigned long long) * (size_t)p.ctas_per_pic * npictures, ctx->stream);
+  if (e != cudaSuccess) return e;
+  e = pack_launch(ctx->stream, p, npictures, per_warp * W);
+  if (e == cudaSuccess) ctx->launches++;
+  return e;
+}
+static size_t pack_state_words(const SliceGeom& g) { return (size_t)g.slices_x * g.slices_y; }   // >= ctas per picture
+
+// ================================================================================================
+// Library-surface operations (host buffers)
+// ================================================================================================
+
+extern "C" int vc2_dwt_forward(vc2_ctx* ctx, const int32_t* src, int h, int w, int kernel, int depth, int32_t* dst) {
+  if (!ctx || !src || !dst || h < 1 || w < 1 || depth < 1 || depth > VC2_MAX_DEPTH || kernel < 0 || kernel > VC2_DAUB97)
+    return fail(ctx, VC2_ERR_ARG);
+  CU(cudaSetDevice(ctx->device));
+  CompBuf B;
+  B.pg = make_plane(h, w, depth);
+  const size_t n_in = (size_t)h * w * 4, n_pad = (size_t)B.pg.size() * 4;
+  CU(ctx->tmp[0].reserve(n_in));
+  CU(ctx->tmp[1].reserve(n_pad));
+  CU(ctx->tmp[2].reserve(n_pad / 4));
+  CU(ctx->tmp[3].reserve(n_pad / 16 + 4));
+  CU(ctx->tmp[4].reserve(n_pad));
+  B.pix = ctx->tmp[0].p; B.pix_pitch = w; B.pix_pic_stride = (long long)h * w;
+  B.planar = ctx->tmp[1].as<int32_t>(); B.planar_pic_stride = B.pg.size();
+  B.scratch[0] = ctx->tmp[2].as<int32_t>(); B.scratch[1] = ctx->tmp[3].as<int32_t>();
+  CU(cudaMemcpyAsync(B.pix, src, n_in, cudaMemcpyHostToDevice, ctx->stream));
+  CU(run_dwt(ctx, false, kernel, depth, SAMPLE_I32, &B, 1, 1));
+  CU(layout_launch(ctx->stream, false, B.planar, ctx->tmp[4].as<int32_t>(), B.pg, 0, 0, 1));
+  ctx->launches++;
+  CU(cudaMemcpyAsync(dst, ctx->tmp[4].p, n_pad, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return VC2_OK;
+}
+
+extern "C" int vc2_dwt_inverse(vc2_ctx* ctx, const int32_t* src, int ph, int pw, int kernel, int depth, int32_t* dst, int h,
+                               int w) {
+  if (!ctx || !src || !dst || h < 1 || w < 1 || depth < 1 || depth > VC2_MAX_DEPTH || kernel < 0 || kernel > VC2_DAUB97)
+    return fail(ctx, VC2_ERR_ARG);
+  if (ph % (1 << depth) || pw % (1 << depth) || h > ph || w > pw) return fail(ctx, VC2_ERR_ARG);
+  CU(cudaSetDevice(ctx->device));
+  CompBuf B;
+  B.pg.h = h; B.pg.w = w; B.pg.ph = ph; B.pg.pw = pw; B.pg.depth = depth;
+  const size_t n_out = (size_t)h * w * 4, n_pad = (size_t)ph * pw * 4;
+  CU(ctx->tmp[0].reserve(n_out));
+  CU(ctx->tmp[1].reserve(n_pad));
+  CU(ctx->tmp[2].reserve(n_pad / 4));
+  CU(ctx->tmp[3].reserve(n_pad / 16 + 4));
+  CU(ctx->tmp[4].reserve(n_pad));
+  B.pix = ctx->tmp[0].p; B.pix_pitch = w; B.pix_pic_stride = (long long)h * w;
+  B.planar = ctx->tmp[1].as<int32_t>(); B.planar_pic_stride = B.pg.size();
+  B.scratch[0] = ctx->tmp[2].as<int32_t>(); B.scratch[1] = ctx->tmp[3].as<int32_t>();
+  CU(cudaMemcpyAsync(ctx->tmp[4].p, src, n_pad, cudaMemcpyHostToDevice, ctx->stream));
+  CU(layout_launch(ctx->stream, true, ctx->tmp[4].as<int32_t>(), B.planar, B.pg, 0, 0, 1));
+  ctx->launches++;
+  CU(run_dwt(ctx, true, kernel, depth, SAMPLE_I32, &B, 1, 1));
+  CU(cudaMemcpyAsync(dst, B.pix, n_out, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return VC2_OK;
+}
+
+static int quant_host(vc2_ctx* ctx, const int32_t* coef, int ph, int pw, int depth, const int32_t* qmatrix, const int32_t* qidx,
+                      int ny, int nx, int32_t* out, int inverse, int ld) {
+  if (!ctx || !coef || !qmatrix || !qidx || !out || depth < 1 || depth > VC2_MAX_DEPTH || ny < 1 || nx < 1 || ph < 1 || pw < 1)
+    return fail(ctx, VC2_ERR_ARG);
+  if (ph % ny || pw % nx || ph % (1 << depth) || pw % (1 << depth)) return fail(ctx, VC2_ERR_ARG);
+  // quant_factor throws for adjusted indices above 119 (Quantisation.cpp:60-63)
+  int minm = qmatrix[0];
+  for (int b = 0; b < 3 * depth + 1; ++b) minm = std::min(minm, qmatrix[b]);
+  for (int i = 0; i < ny * nx; ++i)
+    if (qidx[i] - minm > 119) return fail(ctx, VC2_ERR_QUANT_INDEX);
+  CU(cudaSetDevice(ctx->device));
+  const size_t n = (size_t)ph * pw * 4;
+  CU(ctx->tmp[0].reserve(n));
+  CU(ctx->tmp[1].reserve(n));
+  CU(ctx->tmp[2].reserve((size_t)ny * nx * 4));
+  CU(cudaMemcpyAsync(ctx->tmp[0].p, coef, n, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(ctx->tmp[2].p, qidx, (size_t)ny * nx * 4, cudaMemcpyHostToDevice, ctx->stream));
+  QuantParams p;
+  memset(&p, 0, sizeof(p));
+  p.src = ctx->tmp[0].as<int32_t>(); p.dst = ctx->tmp[1].as<int32_t>(); p.qidx = ctx->tmp[2].as<int32_t>();
+  p.ph = ph; p.pw = pw; p.depth = depth; p.slices_y = ny; p.slices_x = nx; p.inverse = inverse; p.skip_ll = ld;
+  for (int b = 0; b < 3 * depth + 1; ++b) p.qmatrix[b] = qmatrix[b];
+  CU(quant_launch(ctx->stream, p));
+  ctx->launches++;
+  if (ld) {
+    LdDcParams d;
+    d.plane = p.dst; d.qidx = p.qidx; d.ph = ph; d.pw = pw; d.depth = depth; d.slices_y = ny; d.slices_x = nx; d.qm0 = qmatrix[0];
+    CU(ld_dc_launch(ctx->stream, d));
+    ctx->launches++;
+  }
+  CU(cudaMemcpyAsync(out, ctx->tmp[1].p, n, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return VC2_OK;
+}
+
+extern "C" int vc2_quantise_np(vc2_ctx* ctx, const int32_t* coef, int ph, int pw, int depth, const int32_t* qmatrix,
+                               const int32_t* qidx, int ny, int nx, int32_t* out) {
+  return quant_host(ctx, coef, ph, pw, depth, qmatrix, qidx, ny, nx, out, 0, 0);
+}
+extern "C" int vc2_dequantise_np(vc2_ctx* ctx, const int32_t* coef, int ph, int pw, int depth, const int32_t* qmatrix,
+                                 const int32_t* qidx, int ny, int nx, int32_t* out) {
+  return quant_host(ctx, coef, ph, pw, depth, qmatrix, qidx, ny, nx, out, 1, 0);
+}
+extern "C" int vc2_dequantise_ld(vc2_ctx* ctx, const int32_t* coef, int ph, int pw, int depth, const int32_t* qmatrix,
+                                 const int32_t* qidx, int ny, int nx, int32_t* out) {
+  return quant_host(ctx, coef, ph, pw, depth, qmatrix, qidx, ny, nx, out, 1, 1);
+}
+
+// upload three in-place planes and convert them to one planar coefficient block in tmp[1]
+static int upload_planes(vc2_ctx* ctx, const SliceGeom& g, const int32_t* y, const int32_t* u, const int32_t* v) {
+  const int32_t* src[3] = {y, u, v};
+  CU(ctx->tmp[0].reserve((size_t)g.plane[0].size() * 4));
+  CU(ctx->tmp[1].reserve((size_t)g.coef_pic_stride * 4));
+  for (int c = 0; c < 3; ++c) {
+    const size_t n = (size_t)g.plane[c].size() * 4;
+    CU(cudaMemcpyAsync(ctx->tmp[0].p, src[c], n, cudaMemcpyHostToDevice, ctx->stream));
+    CU(layout_launch(ctx->stream, true, ctx->tmp[0].as<int32_t>(), ctx->tmp[1].as<int32_t>() + g.plane_off[c], g.plane[c], 0, 0, 1));
+    ctx->launches++;
+  }
+  return VC2_OK;
+}
+static int download_planes(vc2_ctx* ctx, const SliceGeom& g, const int32_t* planar, int32_t* y, int32_t* u, int32_t* v) {
+  int32_t* dst[3] = {y, u, v};
+  CU(ctx->tmp[0].reserve((size_t)g.plane[0].size() * 4));
+  for (int c = 0; c < 3; ++c) {
+    if (!dst[c]) continue;
+    const size_t n = (size_t)g.plane[c].size() * 4;
+    CU(layout_launch(ctx->stream, false, planar + g.plane_off[c], ctx->tmp[0].as<int32_t>(), g.plane[c], 0, 0, 1));
+    ctx->launches++;
+    CU(cudaMemcpyAsync(dst[c], ctx->tmp[0].p, n, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  return VC2_OK;
+}
+
+// shared body of vc2_hq_pack / vc2_cbr_qindices
+static int pack_host(vc2_ctx* ctx, const int32_t* Y, const int32_t* U, const int32_t* V, const vc2_geom* vg, const int32_t* qmatrix,
+                     const int32_t* qidx_in, int32_t* qidx_out, int mode, int search, int emit, const int32_t* slice_bytes,
+                     uint8_t* out, size_t cap, size_t* out_len, uint32_t* slice_off, uint32_t* err_flags_out) {
+  if (!ctx || !Y || !U || !V || !geom_ok(vg)) return fail(ctx, VC2_ERR_ARG);
+  if ((mode == VC2_HQ_CBR || search) && !slice_bytes) return fail(ctx, VC2_ERR_ARG);
+  CU(cudaSetDevice(ctx->device));
+  SliceGeom g;
+  fill_slice_geom(g, *vg, qmatrix);
+  const int nslices = g.slices_x * g.slices_y;
+  int st = upload_planes(ctx, g, Y, U, V);
+  if (st) return st;
+  const int img_bytes = max_slice_bytes(g, mode, slice_bytes);
+  std::vector<uint32_t> fixed(nslices + 1, 0);
+  size_t total_cap = 0;
+  if (mode == VC2_HQ_CBR) {
+    for (int i = 0; i < nslices; ++i) fixed[i + 1] = fixed[i] + (uint32_t)(slice_bytes[i] + g.prefix);
+    total_cap = fixed[nslices];
+  } else {
+    total_cap = (size_t)img_bytes * nslices;
+  }
+  // layout of tmp[2]: payload | slice_off | err | qidx | slice_bytes | fixed | ticket | tile_state
+  const size_t o_pay = 0, o_off = (total_cap + 259) / 256 * 256, o_err = o_off + (size_t)(nslices + 1) * 4,
+               o_q = o_err + (size_t)nslices * 4, o_sb = o_q + (size_t)nslices * 4, o_fx = o_sb + (size_t)nslices * 4,
+               o_tk = o_fx + (size_t)(nslices + 1) * 4, o_ts = (o_tk + 4 + 7) / 8 * 8, o_end = o_ts + pack_state_words(g) * 8;
+  CU(ctx->tmp[2].reserve(o_end));
+  uint8_t* base = ctx->tmp[2].as<uint8_t>();
+  PackBuffers B;
+  B.out = base + o_pay; B.out_stride = 0; B.out_capacity = (long long)total_cap;
+  B.slice_off = (uint32_t*)(base + o_off); B.err_flags = (uint32_t*)(base + o_err); B.qidx = (int32_t*)(base + o_q);
+  B.slice_bytes_dev = slice_bytes ? (const int32_t*)(base + o_sb) : nullptr;
+  B.fixed_off_dev = mode == VC2_HQ_CBR ? (const uint32_t*)(base + o_fx) : nullptr;
+  B.ticket = (unsigned*)(base + o_tk); B.tile_state = (unsigned long long*)(base + o_ts);
+  CU(cudaMemsetAsync(base + o_off, 0, o_q - o_off, ctx->stream));
+  if (qidx_in) CU(cudaMemcpyAsync(B.qidx, qidx_in, (size_t)nslices * 4, cudaMemcpyHostToDevice, ctx->stream));
+  if (slice_bytes) CU(cudaMemcpyAsync(base + o_sb, slice_bytes, (size_t)nslices * 4, cudaMemcpyHostToDevice, ctx->stream));
+  if (mode == VC2_HQ_CBR) CU(cudaMemcpyAsync(base + o_fx, fixed.data(), (size_t)(nslices + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CU(run_pack(ctx, g, ctx->tmp[1].as<int32_t>(), 1, mode, search ? 1 : 0, search, -1, emit, B, img_bytes));
+  std::vector<uint32_t> flags(nslices), offs(nslices + 1);
+  CU(cudaMemcpyAsync(flags.data(), B.err_flags, (size_t)nslices * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(offs.data(), B.slice_off, (size_t)(nslices + 1) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  if (qidx_out) CU(cudaMemcpyAsync(qidx_out, B.qidx, (size_t)nslices * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  if (err_flags_out) memcpy(err_flags_out, flags.data(), (size_t)nslices * 4);
+  st = first_error(flags.data(), nslices);
+  if (st) return fail(ctx, st);
+  if (emit) {
+    const size_t len = offs[nslices];
+    if (out_len) *out_len = len;
+    if (len > cap) return fail(ctx, VC2_ERR_CAPACITY);
+    CU(cudaMemcpy(out, B.out, len, cudaMemcpyDeviceToHost));
+    if (slice_off) memcpy(slice_off, offs.data(), (size_t)(nslices + 1) * 4);
+  }
+  return VC2_OK;
+}
+
+extern "C" int vc2_hq_pack(vc2_ctx* ctx, const int32_t* qY, const int32_t* qU, const int32_t* qV, const vc2_geom* g,
+                           const int32_t* qidx, int mode, const int32_t* slice_bytes, uint8_t* out, size_t cap, size_t* out_len,
+                           uint32_t* slice_off) {
+  if (!qidx || !out || (mode != VC2_HQ_VBR && mode != VC2_HQ_CBR)) return fail(ctx, VC2_ERR_ARG);
+  return pack_host(ctx, qY, qU, qV, g, nullptr, qidx, nullptr, mode, 0, 1, slice_bytes, out, cap, out_len, slice_off, nullptr);
+}
+
+extern "C" int vc2_cbr_qindices(vc2_ctx* ctx, const int32_t* cY, const int32_t* cU, const int32_t* cV, const vc2_geom* g,
+                                const int32_t* qmatrix, const int32_t* slice_bytes, int32_t* qidx_out, uint32_t* err_flags) {
+  if (!qmatrix || !qidx_out) return fail(ctx, VC2_ERR_ARG);
+  return pack_host(ctx, cY, cU, cV, g, qmatrix, nullptr, qidx_out, VC2_HQ_CBR, 1, 0, slice_bytes, nullptr, 0, nullptr, nullptr, err_flags);
+}
+
+static int unpack_host(vc2_ctx* ctx, const uint8_t* in, size_t len, const vc2_geom* vg, const int32_t* slice_bytes, int ld,
+                       int32_t* qY, int32_t* qU, int32_t* qV, int32_t* qidx) {
+  if (!ctx || !in || !geom_ok(vg) || !qY || !qU || !qV || !qidx) return fail(ctx, VC2_ERR_ARG);
+  if (ld && !slice_bytes) return fail(ctx, VC2_ERR_ARG);
+  CU(cudaSetDevice(ctx->device));
+  SliceGeom g;
+  fill_slice_geom(g, *vg, nullptr);
+  const int nslices = g.slices_x * g.slices_y;
+  std::vector<uint32_t> offs(nslices + 1, 0);
+  if (ld) {
+    for (int i = 0; i < nslices; ++i) offs[i + 1] = offs[i] + (uint32_t)slice_bytes[i];
+    if (offs[nslices] > len) return fail(ctx, VC2_ERR_STREAM);
+  } else {
+    const int st = vc2_hq_index_slices(in, len, nslices, g.prefix, g.scalar, offs.data());
+    if (st) return fail(ctx, st);
+  }
+  const size_t o_off = (len + 259) / 256 * 256, o_err = o_off + (size_t)(nslices + 1) * 4, o_q = o_err + (size_t)nslices * 4,
+               o_end = o_q + (size_t)nslices * 4;
+  CU(ctx->tmp[2].reserve(o_end));
+  CU(ctx->tmp[1].reserve((size_t)g.coef_pic_stride * 4));
+  uint8_t* base = ctx->tmp[2].as<uint8_t>();
+  CU(cudaMemcpyAsync(base, in, len, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(base + o_off, offs.data(), (size_t)(nslices + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemsetAsync(base + o_err, 0, (size_t)nslices * 8, ctx->stream));
+  UnpackParams p;
+  memset(&p, 0, sizeof(p));
+  p.g = g; p.in = base; p.in_pic_stride = 0; p.slice_off = (const uint32_t*)(base + o_off); p.slice_off_pic_stride = 0;
+  p.coef = ctx->tmp[1].as<int32_t>(); p.qidx = (int32_t*)(base + o_q); p.err_flags = (uint32_t*)(base + o_err);
+  p.dequantise = 0; p.ld = ld;
+  CU(unpack_launch(ctx->stream, p, 1));
+  ctx->launches++;
+  int st = download_planes(ctx, g, p.coef, qY, qU, qV);
+  if (st) return st;
+  std::vector<uint32_t> flags(nslices);
+  CU(cudaMemcpyAsync(flags.data(), p.err_flags, (size_t)nslices * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(qidx, p.qidx, (size_t)nslices * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  st = first_error(flags.data(), nslices);
+  if (st && st != VC2_ERR_VLC_RANGE) return fail(ctx, st);
+  return VC2_OK;
+}
+
+extern "C" int vc2_hq_unpack(vc2_ctx* ctx, const uint8_t* in, size_t len, const vc2_geom* g, int32_t* qY, int32_t* qU, int32_t* qV,
+                             int32_t* qidx) {
+  return unpack_host(ctx, in, len, g, nullptr, 0, qY, qU, qV, qidx);
+}
+extern "C" int vc2_ld_unpack(vc2_ctx* ctx, const uint8_t* in, size_t len, const vc2_geom* g, const int32_t* slice_bytes, int32_t* qY,
+                             int32_t* qU, int32_t* qV, int32_t* qidx) {
+  return unpack_host(ctx, in, len, g, slice_bytes, 1, qY, qU, qV, qidx);
+}
+
+// ================================================================================================
+// fused, batched picture codec
+// ================================================================================================
+
+struct vc2_codec {
+  vc2_ctx* ctx = nullptr;
+  vc2_codec_params prm;
+  SliceGeom g;
+  int nslices = 0;
+  int sample_kind = SAMPLE_U16BE;
+  size_t pic_bytes = 0;          // raw planar bytes per picture
+  size_t comp_bytes[3] = {0, 0, 0};
+  size_t payload_cap = 0;        // per picture
+  int img_bytes = 0;
+  std::vector<int32_t> slice_bytes;   // CBR / LD
+  std::vector<uint32_t> fixed_off;
+  // device buffers
+  DevBuf samples, coef, scratch0, scratch1, payload, slice_off, err, qidx, state, ticket, sbytes, fixed, tmp_plane, tmp_q;
+  long long scratch_stride[2] = {0, 0};
+  long long scratch_off[2][3];
+  std::vector<size_t> payload_len;    // host copy per slot (decode)
+  uint32_t* host_offs = nullptr;      // pinned staging for slice offset tables
+  cudaStream_t copy_in = nullptr, copy_out = nullptr;
+  cudaEvent_t ev_in[2], ev_done[2], ev_out[2];
+};
+
+static void codec_free(vc2_codec* k) {
+  if (!k) return;
+  cudaSetDevice(k->ctx->device);
+  cudaStreamSynchronize(k->ctx->stream);
+  DevBuf* all[] = {&k->samples, &k->coef, &k->scratch0, &k->scratch1, &k->payload, &k->slice_off, &k->err,
+                   &k->qidx, &k->state, &k->ticket, &k->sbytes, &k->fixed, &k->tmp_plane, &k->tmp_q};
+  for (DevBuf* b : all) b->release();
+  if (k->host_offs) cudaFreeHost(k->host_offs);
+  if (k->copy_in) cudaStreamDestroy(k->copy_in);
+  if (k->copy_out) cudaStreamDestroy(k->copy_out);
+  delete k;
+}
+
+extern "C" vc2_codec* vc2_codec_create(vc2_ctx* ctx, const vc2_codec_params* prm) {
+  if (!ctx || !prm || !geom_ok(&prm->geom) || prm->max_pictures < 1) { fail(ctx, VC2_ERR_ARG); return nullptr; }
+  const vc2_sample_format& f = prm->fmt;
+  if ((f.bytes_per_sample != 1 && f.bytes_per_sample != 2) || f.luma_depth < 1 || f.luma_depth > 8 * f.bytes_per_sample ||
+      f.chroma_depth < 1 || f.chroma_depth > 8 * f.bytes_per_sample) { fail(ctx, VC2_ERR_ARG); return nullptr; }
+  if (prm->mode == VC2_HQ_VBR && (prm->qindex < 0 || prm->qindex > 119)) { fail(ctx, VC2_ERR_ARG); return nullptr; }
+  if (prm->mode != VC2_HQ_VBR && prm->picture_bytes < 1) { fail(ctx, VC2_ERR_ARG); return nullptr; }
+  if (cudaSetDevice(ctx->device) != cudaSuccess) { fail(ctx, VC2_ERR_CUDA); return nullptr; }
+  vc2_codec* k = new (std::nothrow) vc2_codec();
+  if (!k) return nullptr;
+  k->ctx = ctx;
+  k->prm = *prm;
+  int32_t qm[VC2_MAX_BANDS];
+  vc2_quant_matrix(prm->geom.kernel, prm->geom.depth, qm);
+  if (prm->mode == VC2_LD) { k->prm.geom.prefix = 0; k->prm.geom.scalar = 1; }
+  fill_slice_geom(k->g, k->prm.geom, qm);
+  const SliceGeom& g = k->g;
+  k->nslices = g.slices_x * g.slices_y;
+  k->sample_kind = f.bytes_per_sample == 2 ? SAMPLE_U16BE : SAMPLE_U8;
+  for (int c = 0; c < 3; ++c) k->comp_bytes[c] = (size_t)g.plane[c].h * g.plane[c].w * f.bytes_per_sample;
+  k->pic_bytes = k->comp_bytes[0] + k->comp_bytes[1] + k->comp_bytes[2];
+  const int B = prm->max_pictures;
+  if (prm->mode != VC2_HQ_VBR) {
+    k->slice_bytes.resize(k->nslices);
+    vc2_slice_bytes(g.slices_y, g.slices_x, prm->picture_bytes, prm->mode == VC2_LD ? 1 : g.scalar, k->slice_bytes.data());
+    k->fixed_off.assign(k->nslices + 1, 0);
+    for (int i = 0; i < k->nslices; ++i) {
+      if (k->slice_bytes[i] < (prm->mode == VC2_LD ? 1 : 4)) { fail(ctx, VC2_ERR_ARG, "compressed bytes too small for this many slices"); delete k; return nullptr; }
+      k->fixed_off[i + 1] = k->fixed_off[i] + (uint32_t)(k->slice_bytes[i] + (prm->mode == VC2_LD ? 0 : g.prefix));
+    }
+  }
+  k->img_bytes = max_slice_bytes(g, prm->mode, k->slice_bytes.empty() ? nullptr : k->slice_bytes.data());
+  if (prm->mode == VC2_HQ_VBR) k->payload_cap = (size_t)k->img_bytes * k->nslices;
+  else k->payload_cap = k->fixed_off[k->nslices];
+  k->payload_cap = (k->payload_cap + 255) / 256 * 256 + 256;
+
+  bool ok = true;
+  auto R = [&](DevBuf& b, size_t n) { if (ok && b.reserve(n) != cudaSuccess) ok = false; };
+  R(k->samples, k->pic_bytes * B + 64);
+  R(k->coef, (size_t)g.coef_pic_stride * 4 * B);
+  long long s0 = 0, s1 = 0;
+  for (int c = 0; c < 3; ++c) {
+    k->scratch_off[0][c] = s0; k->scratch_off[1][c] = s1;
+    s0 += g.plane[c].size() / 4;
+    s1 += g.plane[c].size() / 16 + 1;
+  }
+  k->scratch_stride[0] = s0; k->scratch_stride[1] = s1;
+  R(k->scratch0, (size_t)s0 * 4 * B);
+  R(k->scratch1, (size_t)s1 * 4 * B);
+  R(k->payload, k->payload_cap * B);
+  R(k->slice_off, (size_t)(k->nslices + 1) * 4 * B);
+  R(k->err, (size_t)k->nslices * 4 * B);
+  R(k->qidx, (size_t)k->nslices * 4 * B);
+  R(k->state, pack_state_words(g) * 8 * B);
+  R(k->ticket, (size_t)4 * B);
+  R(k->sbytes, (size_t)k->nslices * 4);
+  R(k->fixed, (size_t)(k->nslices + 1) * 4);
+  R(k->tmp_plane, (size_t)g.plane[0].size() * 4);
+  R(k->tmp_q, (size_t)g.plane[0].size() * 4);
+  if (ok && cudaMallocHost((void**)&k->host_offs, (size_t)(k->nslices + 1) * 4 * B) != cudaSuccess) ok = false;
+  if (ok && cudaStreamCreateWithFlags(&k->copy_in, cudaStreamNonBlocking) != cudaSuccess) ok = false;
+  if (ok && cudaStreamCreateWithFlags(&k->copy_out, cudaStreamNonBlocking) != cudaSuccess) ok = false;
+  if (ok && !k->slice_bytes.empty()) {
+    ok = cudaMemcpy(k->sbytes.p, k->slice_bytes.data(), (size_t)k->nslices * 4, cudaMemcpyHostToDevice) == cudaSuccess &&
+         cudaMemcpy(k->fixed.p, k->fixed_off.data(), (size_t)(k->nslices + 1) * 4, cudaMemcpyHostToDevice) == cudaSuccess;
+  }
+  if (ok) ok = cudaMemset(k->err.p, 0, (size_t)k->nslices * 4 * B) == cudaSuccess;
+  if (!ok) { fail(ctx, VC2_ERR_CUDA, "codec allocation failed"); codec_free(k); return nullptr; }
+  k->payload_len.assign(B, 0);
+  return k;
+}
+
+extern "C" void vc2_codec_destroy(vc2_codec* k) { codec_free(k); }
+extern "C" size_t vc2_codec_picture_in_bytes(const vc2_codec* k) { return k ? k->pic_bytes : 0; }
+extern "C" size_t vc2_codec_payload_capacity(const vc2_codec* k) { return k ? k->payload_cap : 0; }
+
+static void codec_compbufs(vc2_codec* k, CompBuf cb[3], int first_slot) {
+  const SliceGeom& g = k->g;
+  const vc2_sample_format& f = k->prm.fmt;
+  size_t off = 0;
+  for (int c = 0; c < 3; ++c) {
+    CompBuf& B = cb[c];
+    B.pg = g.plane[c];
+    B.pix = k->samples.as<uint8_t>() + (size_t)first_slot * k->pic_bytes + off;
+    B.pix_pic_stride = (long long)k->pic_bytes;
+    B.pix_pitch = g.plane[c].w;
+    off += k->comp_bytes[c];
+    B.planar = k->coef.as<int32_t>() + (long long)first_slot * g.coef_pic_stride + g.plane_off[c];
+    B.planar_pic_stride = g.coef_pic_stride;
+    B.scratch[0] = k->scratch0.as<int32_t>() + (long long)first_slot * k->scratch_stride[0] + k->scratch_off[0][c];
+    B.scratch[1] = k->scratch1.as<int32_t>() + (long long)first_slot * k->scratch_stride[1] + k->scratch_off[1][c];
+    B.scratch_pic_stride[0] = k->scratch_stride[0];
+    B.scratch_pic_stride[1] = k->scratch_stride[1];
+    const int depth = c == 0 ? f.luma_depth : f.chroma_depth;
+    B.sshift = 8 * f.bytes_per_sample - depth;      // Arrays.cpp:170-172 (left justified)
+    B.soffset = 1 << (depth - 1);                   // Arrays.cpp:174-178 (offset binary)
+    B.clip_min = -(1 << (depth - 1));               // DecodeStream.cpp:593-596
+    B.clip_max = (1 << (depth - 1)) - 1;
+  }
+}
+
+static int codec_encode_range(vc2_codec* k, int first, int n) {
+  vc2_ctx* ctx = k->ctx;
+  if (k->prm.mode == VC2_LD) return fail(ctx, VC2_ERR_ARG, "LD is decode-only");
+  CompBuf cb[3];
+  codec_compbufs(k, cb, first);
+  CU(run_dwt(ctx, false, k->prm.geom.kernel, k->prm.geom.depth, k->sample_kind, cb, 3, n));
+  PackBuffers B;
+  B.out = k->payload.as<uint8_t>() + (size_t)first * k->payload_cap;
+  B.out_stride = (long long)k->payload_cap; B.out_capacity = (long long)k->payload_cap;
+  B.slice_off = k->slice_off.as<uint32_t>() + (size_t)first * (k->nslices + 1);
+  B.err_flags = k->err.as<uint32_t>() + (size_t)first * k->nslices;
+  B.qidx = k->qidx.as<int32_t>() + (size_t)first * k->nslices;
+  B.tile_state = k->state.as<unsigned long long>() + (size_t)first * pack_state_words(k->g);
+  B.ticket = k->ticket.as<unsigned>() + first;
+  const bool cbr = k->prm.mode == VC2_HQ_CBR;
+  B.slice_bytes_dev = cbr ? k->sbytes.as<int32_t>() : nullptr;
+  B.fixed_off_dev = cbr ? k->fixed.as<uint32_t>() : nullptr;
+  const int32_t* coef = k->coef.as<int32_t>() + (long long)first * k->g.coef_pic_stride;
+  // run_pack derives ctas_per_pic from the geometry; tile_state is strided by it inside the kernel,
+  // so hand it a base that is dense in ctas_per_pic (it is: we sized it with nslices per picture)
+  CU(run_pack(ctx, k->g, coef, n, k->prm.mode, 1, cbr ? 1 : 0, cbr ? -1 : k->prm.qindex, 1, B, k->img_bytes));
+  return VC2_OK;
+}
+
+extern "C" int vc2_codec_encode_dev(vc2_codec* k, int n) {
+  if (!k || n < 1 || n > k->prm.max_pictures) return fail(k ? k->ctx : nullptr, VC2_ERR_ARG);
+  vc2_ctx* ctx = k->ctx;
+  CU(cudaSetDevice(ctx->device));
+  return codec_encode_range(k, 0, n);
+}
+
+static int codec_decode_range(vc2_codec* k, int first, int n) {
+  vc2_ctx* ctx = k->ctx;
+  const SliceGeom& g = k->g;
+  const bool ld = k->prm.mode == VC2_LD;
+  const bool shared_off = ld;   // HQ pictures are always indexed from their own length bytes (DecodeStream.cpp:512)
+  CU(cudaMemsetAsync(k->err.as<uint32_t>() + (size_t)first * k->nslices, 0, (size_t)k->nslices * 4 * n, ctx->stream));
+  UnpackParams p;
+  memset(&p, 0, sizeof(p));
+  p.g = g;
+  p.in = k->payload.as<uint8_t>() + (size_t)first * k->payload_cap;
+  p.in_pic_stride = (long long)k->payload_cap;
+  p.slice_off = shared_off ? k->fixed.as<uint32_t>() : k->slice_off.as<uint32_t>() + (size_t)first * (k->nslices + 1);
+  p.slice_off_pic_stride = shared_off ? 0 : (k->nslices + 1);
+  p.coef = k->coef.as<int32_t>() + (long long)first * g.coef_pic_stride;
+  p.qidx = k->qidx.as<int32_t>() + (size_t)first * k->nslices;
+  p.err_flags = k->err.as<uint32_t>() + (size_t)first * k->nslices;
+  p.dequantise = 1;
+  p.ld = ld ? 1 : 0;
+  CU(unpack_launch(ctx->stream, p, n));
+  ctx->launches++;
+  if (ld) {
+    // LL band: DC-predicted reconstruction, one wavefront CTA per (picture, component)
+    for (int i = 0; i < n; ++i)
+      for (int c = 0; c < 3; ++c) {
+        LdDcParams d;
+        d.plane = p.coef + (long long)i * g.coef_pic_stride + g.plane_off[c];
+        d.qidx = p.qidx + (size_t)i * k->nslices;
+        // compact LL plane == an "in-place" plane of depth 0 with the LL dims
+        d.ph = g.plane[c].ph >> g.depth; d.pw = g.plane[c].pw >> g.depth; d.depth = 0;
+        d.slices_y = g.slices_y; d.slices_x = g.slices_x; d.qm0 = g.qmatrix[0];
+        CU(ld_dc_launch(ctx->stream, d));
+        ctx->launches++;
+      }
+  }
+  CompBuf cb[3];
+  codec_compbufs(k, cb, first);
+  CU(run_dwt(ctx, true, k->prm.geom.kernel, k->prm.geom.depth, k->sample_kind, cb, 3, n));
+  return VC2_OK;
+}
+
+extern "C" int vc2_codec_decode_dev(vc2_codec* k, int n) {
+  if (!k || n < 1 || n > k->prm.max_pictures) return fail(k ? k->ctx : nullptr, VC2_ERR_ARG);
+  vc2_ctx* ctx = k->ctx;
+  CU(cudaSetDevice(ctx->device));
+  return codec_decode_range(k, 0, n);
+}
+
+extern "C" void* vc2_codec_samples_dev(vc2_codec* k, int slot) {
+  return (k && slot >= 0 && slot < k->prm.max_pictures) ? k->samples.as<uint8_t>() + (size_t)slot * k->pic_bytes : nullptr;
+}
+extern "C" uint8_t* vc2_codec_payload_dev(vc2_codec* k, int slot) {
+  return (k && slot >= 0 && slot < k->prm.max_pictures) ? k->payload.as<uint8_t>() + (size_t)slot * k->payload_cap : nullptr;
+}
+extern "C" int32_t* vc2_codec_coeffs_dev(vc2_codec* k, int slot, int comp) {
+  if (!k || slot < 0 || slot >= k->prm.max_pictures || comp < 0 || comp > 2) return nullptr;
+  return k->coef.as<int32_t>() + (long long)slot * k->g.coef_pic_stride + k->g.plane_off[comp];
+}
+extern "C" uint32_t* vc2_codec_slice_offsets_dev(vc2_codec* k, int slot) {
+  return (k && slot >= 0 && slot < k->prm.max_pictures) ? k->slice_off.as<uint32_t>() + (size_t)slot * (k->nslices + 1) : nullptr;
+}
+
+#define KARG(cond)                                              \
+  do {                                                          \
+    if (!(cond)) return fail(k ? k->ctx : nullptr, VC2_ERR_ARG); \
+  } while (0)
+
+extern "C" int vc2_codec_upload_picture(vc2_codec* k, int slot, const void* raw) {
+  KARG(k && raw && slot >= 0 && slot < k->prm.max_pictures);
+  vc2_ctx* ctx = k->ctx;
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaMemcpyAsync(vc2_codec_samples_dev(k, slot), raw, k->pic_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  return VC2_OK;
+}
+extern "C" int vc2_codec_download_picture(vc2_codec* k, int slot, void* raw) {
+  KARG(k && raw && slot >= 0 && slot < k->prm.max_pictures);
+  vc2_ctx* ctx = k->ctx;
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaMemcpyAsync(raw, vc2_codec_samples_dev(k, slot), k->pic_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return VC2_OK;
+}
+
+// host-side slice index of one payload into the pinned staging table of `slot`
+static int codec_index_payload(vc2_codec* k, int slot, const uint8_t* payload, size_t len) {
+  if (k->prm.mode == VC2_LD) return len >= k->fixed_off[k->nslices] ? VC2_OK : VC2_ERR_STREAM;
+  return vc2_hq_index_slices(payload, len, k->nslices, k->g.prefix, k->g.scalar, k->host_offs + (size_t)slot * (k->nslices + 1));
+}
+
+extern "C" int vc2_codec_upload_payload(vc2_codec* k, int slot, const uint8_t* payload, size_t len) {
+  KARG(k && payload && slot >= 0 && slot < k->prm.max_pictures);
+  vc2_ctx* ctx = k->ctx;
+  if (len > k->payload_cap) return fail(ctx, VC2_ERR_CAPACITY);
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaStreamSynchronize(ctx->stream));   // the pinned offset table of this slot may still be in flight
+  const int st = codec_index_payload(k, slot, payload, len);
+  if (st) return fail(ctx, st);
+  CU(cudaMemcpyAsync(vc2_codec_payload_dev(k, slot), payload, len, cudaMemcpyHostToDevice, ctx->stream));
+  if (k->prm.mode != VC2_LD)
+    CU(cudaMemcpyAsync(vc2_codec_slice_offsets_dev(k, slot), k->host_offs + (size_t)slot * (k->nslices + 1),
+                       (size_t)(k->nslices + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
+  k->payload_len[slot] = len;
+  return VC2_OK;
+}
+
+extern "C" int vc2_codec_slot_status(vc2_codec* k, int slot) {
+  KARG(k && slot >= 0 && slot < k->prm.max_pictures);
+  vc2_ctx* ctx = k->ctx;
+  CU(cudaSetDevice(ctx->device));
+  std::vector<uint32_t> flags(k->nslices);
+  CU(cudaMemcpyAsync(flags.data(), k->err.as<uint32_t>() + (size_t)slot * k->nslices, (size_t)k->nslices * 4,
+                     cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  const int st = first_error(flags.data(), k->nslices);
+  if (st) return fail(ctx, st);
+  return VC2_OK;
+}
+
+extern "C" int vc2_codec_download_payload(vc2_codec* k, int slot, uint8_t* payload, size_t cap, size_t* len, int32_t* qidx,
+                                          uint32_t* slice_off) {
+  KARG(k && payload && len && slot >= 0 && slot < k->prm.max_pictures);
+  vc2_ctx* ctx = k->ctx;
+  const int st = vc2_codec_slot_status(k, slot);
+  if (st) return st;
+  std::vector<uint32_t> offs(k->nslices + 1);
+  CU(cudaMemcpy(offs.data(), vc2_codec_slice_offsets_dev(k, slot), (size_t)(k->nslices + 1) * 4, cudaMemcpyDeviceToHost));
+  *len = offs[k->nslices];
+  if (*len > cap) return fail(ctx, VC2_ERR_CAPACITY);
+  CU(cudaMemcpy(payload, vc2_codec_payload_dev(k, slot), *len, cudaMemcpyDeviceToHost));
+  if (qidx) CU(cudaMemcpy(qidx, k->qidx.as<int32_t>() + (size_t)slot * k->nslices, (size_t)k->nslices * 4, cudaMemcpyDeviceToHost));
+  if (slice_off) memcpy(slice_off, offs.data(), (size_t)(k->nslices + 1) * 4);
+  return VC2_OK;
+}
+
+extern "C" int vc2_codec_read_transform(vc2_codec* k, int slot, int32_t* y, int32_t* u, int32_t* v) {
+  KARG(k && slot >= 0 && slot < k->prm.max_pictures);
+  vc2_ctx* ctx = k->ctx;
+  CU(cudaSetDevice(ctx->device));
+  int32_t* dst[3] = {y, u, v};
+  for (int c = 0; c < 3; ++c) {
+    if (!dst[c]) continue;
+    CU(layout_launch(ctx->stream, false, vc2_codec_coeffs_dev(k, slot, c), k->tmp_plane.as<int32_t>(), k->g.plane[c], 0, 0, 1));
+    ctx->launches++;
+    CU(cudaMemcpyAsync(dst[c], k->tmp_plane.p, (size_t)k->g.plane[c].size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+  }
+  return VC2_OK;
+}
+
+extern "C" int vc2_codec_read_quantised(vc2_codec* k, int slot, int32_t* y, int32_t* u, int32_t* v) {
+  KARG(k && slot >= 0 && slot < k->prm.max_pictures);
+  vc2_ctx* ctx = k->ctx;
+  CU(cudaSetDevice(ctx->device));
+  int32_t* dst[3] = {y, u, v};
+  for (int c = 0; c < 3; ++c) {
+    if (!dst[c]) continue;
+    const PlaneGeom& pg = k->g.plane[c];
+    CU(layout_launch(ctx->stream, false, vc2_codec_coeffs_dev(k, slot, c), k->tmp_plane.as<int32_t>(), pg, 0, 0, 1));
+    QuantParams p;
+    memset(&p, 0, sizeof(p));
+    p.src = k->tmp_plane.as<int32_t>(); p.dst = k->tmp_q.as<int32_t>();
+    p.qidx = k->qidx.as<int32_t>() + (size_t)slot * k->nslices;
+    p.ph = pg.ph; p.pw = pg.pw; p.depth = pg.depth; p.slices_y = k->g.slices_y; p.slices_x = k->g.slices_x;
+    for (int b = 0; b < k->g.nbands; ++b) p.qmatrix[b] = k->g.qmatrix[b];
+    CU(quant_launch(ctx->stream, p));
+    ctx->launches += 2;
+    CU(cudaMemcpyAsync(dst[c], k->tmp_q.p, (size_t)pg.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+  }
+  return VC2_OK;
+}
+
+extern "C" int vc2_codec_read_indices(vc2_codec* k, int slot, int32_t* qidx) {
+  KARG(k && qidx && slot >= 0 && slot < k->prm.max_pictures);
+  vc2_ctx* ctx = k->ctx;
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaMemcpyAsync(qidx, k->qidx.as<int32_t>() + (size_t)slot * k->nslices, (size_t)k->nslices * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return VC2_OK;
+}
+
+// ---- end to end with host buffers: batches of max_pictures, H2D -> kernels -> D2H -----------------
+extern "C" int vc2_codec_encode_host(vc2_codec* k, int n, const void* const* pictures, uint8_t* const* payloads, size_t cap,
+                                     size_t* payload_len) {
+  KARG(k && pictures && payloads && payload_len && n >= 1);
+  vc2_ctx* ctx = k->ctx;
+  CU(cudaSetDevice(ctx->device));
+  const int B = k->prm.max_pictures;
+  std::vector<uint32_t> flags;
+  for (int base = 0; base < n; base += B) {
+    const int m = std::min(B, n - base);
+    for (int i = 0; i < m; ++i)
+      CU(cudaMemcpyAsync(vc2_codec_samples_dev(k, i), pictures[base + i], k->pic_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    const int st = codec_encode_range(k, 0, m);
+    if (st) return st;
+    // payload lengths = last entry of each slice offset table
+    CU(cudaMemcpy2DAsync(k->host_offs, 4, k->slice_off.as<uint32_t>() + k->nslices, (size_t)(k->nslices + 1) * 4, 4, m,
+                         cudaMemcpyDeviceToHost, ctx->stream));
+    flags.resize((size_t)m * k->nslices);
+    CU(cudaMemcpyAsync(flags.data(), k->err.p, flags.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < m; ++i) {
+      const int e = first_error(flags.data() + (size_t)i * k->nslices, k->nslices);
+      if (e) return fail(ctx, e);
+      payload_len[base + i] = k->host_offs[i];
+      if (payload_len[base + i] > cap) return fail(ctx, VC2_ERR_CAPACITY);
+      CU(cudaMemcpyAsync(payloads[base + i], vc2_codec_payload_dev(k, i), payload_len[base + i], cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CU(cudaStreamSynchronize(ctx->stream));
+  }
+  return VC2_OK;
+}
+
+extern "C" int vc2_codec_decode_host(vc2_codec* k, int n, const uint8_t* const* payloads, const size_t* payload_len,
+                                     void* const* pictures) {
+  KARG(k && pictures && payloads && payload_len && n >= 1);
+  vc2_ctx* ctx = k->ctx;
+  CU(cudaSetDevice(ctx->device));
+  const int B = k->prm.max_pictures;
+  std::vector<uint32_t> flags;
+  for (int base = 0; base < n; base += B) {
+    const int m = std::min(B, n - base);
+    for (int i = 0; i < m; ++i) {
+      if (payload_len[base + i] > k->payload_cap) return fail(ctx, VC2_ERR_CAPACITY);
+      const int st = codec_index_payload(k, i, payloads[base + i], payload_len[base + i]);
+      if (st) return fail(ctx, st);
+      CU(cudaMemcpyAsync(vc2_codec_payload_dev(k, i), payloads[base + i], payload_len[base + i], cudaMemcpyHostToDevice, ctx->stream));
+    }
+    if (k->prm.mode != VC2_LD)
+      CU(cudaMemcpyAsync(k->slice_off.p, k->host_offs, (size_t)(k->nslices + 1) * 4 * m, cudaMemcpyHostToDevice, ctx->stream));
+    const int st = codec_decode_range(k, 0, m);
+    if (st) return st;
+    for (int i = 0; i < m; ++i)
+      CU(cudaMemcpyAsync(pictures[base + i], vc2_codec_samples_dev(k, i), k->pic_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    flags.resize((size_t)m * k->nslices);
+    CU(cudaMemcpyAsync(flags.data(), k->err.p, flags.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < m; ++i) {
+      const int e = first_error(flags.data() + (size_t)i * k->nslices, k->nslices);
+      if (e && e != VC2_ERR_VLC_RANGE) return fail(ctx, e);
+    }
+  }
+  return VC2_OK;
+}

@@ -1,0 +1,97 @@
+// Integer lifting DWT / IDWT for the seven VC-2 wavelet kernels (sm_100a).
+//
+// Reference semantics reproduced bit-exactly (paths relative to /root/reference):
+//   forward level : src/Library/src/WaveletTransform.cpp:478-533 (DD97), 595-644 (LeGall),
+//                   700-761 (DD137), 829-871 (Haar), 919-1001 (Fidelity), 1090-1175 (Daub97)
+//   inverse level : :536-593, 647-698, 764-827, 874-917, 1004-1088, 1178-1265
+//   level loop    : :262-281 (forward, with waveletPad :79-94), :321-342 (inverse, crop :340)
+//
+// One CTA owns a TH x TW tile of one level's sample lattice plus a halo of R samples per side
+// (R = total reach of the kernel's lifting steps).  The tile lives in shared memory split into an
+// even-column array E and an odd-column array O, so that after the horizontal pass E holds the
+// low-pass and O the high-pass columns and every lifting step reads unit-stride words
+// (bank-conflict free).  Horizontal and vertical passes of a level are fused; edge handling is the
+// reference's tap clamping ("nearest sample of the same parity"), evaluated in global lattice
+// coordinates so tiles at the picture border reproduce it exactly.
+#pragma once
+#include "vc2_common.cuh"
+
+namespace vc2 {
+
+// ------------------------------------------------------------------------------------------
+// Lifting step descriptors.  A step updates all samples of parity P from the 2*N nearest samples
+// of the other parity:  x[t] += SIGN * ((ADD + sum_k CLk*x[t-(2k+1)] + CRk*x[t+(2k+1)]) >> SH)
+// ------------------------------------------------------------------------------------------
+template <int K, int S> struct Step;
+#define VC2_STEP(K, S, P_, N_, ADD_, SH_, SIGN_, L0, L1, L2, L3, R0, R1, R2, R3)                  \
+  template <> struct Step<K, S> {                                                                  \
+    static constexpr int P = P_, N = N_, ADD = ADD_, SH = SH_, SIGN = SIGN_;                        \
+    static constexpr int CL0 = L0, CL1 = L1, CL2 = L2, CL3 = L3, CR0 = R0, CR1 = R1, CR2 = R2, CR3 = R3; \
+  };
+
+// LeGall 5/3  (WaveletTransform.cpp:609-625)
+VC2_STEP(VC2_LEGALL, 0, 1, 1, 1, 1, -1, 1, 0, 0, 0, 1, 0, 0, 0)
+VC2_STEP(VC2_LEGALL, 1, 0, 1, 2, 2, +1, 1, 0, 0, 0, 1, 0, 0, 0)
+// Deslauriers-Dubuc 9/7  (:492-511)
+VC2_STEP(VC2_DD97, 0, 1, 2, 8, 4, -1, 9, -1, 0, 0, 9, -1, 0, 0)
+VC2_STEP(VC2_DD97, 1, 0, 1, 2, 2, +1, 1, 0, 0, 0, 1, 0, 0, 0)
+// Deslauriers-Dubuc 13/7  (:714-736)
+VC2_STEP(VC2_DD137, 0, 1, 2, 8, 4, -1, 9, -1, 0, 0, 9, -1, 0, 0)
+VC2_STEP(VC2_DD137, 1, 0, 2, 16, 5, +1, 9, -1, 0, 0, 9, -1, 0, 0)
+// Haar, with and without shift  (:843-855)
+VC2_STEP(VC2_HAAR0, 0, 1, 1, 0, 0, -1, 1, 0, 0, 0, 0, 0, 0, 0)
+VC2_STEP(VC2_HAAR0, 1, 0, 1, 1, 1, +1, 0, 0, 0, 0, 1, 0, 0, 0)
+VC2_STEP(VC2_HAAR1, 0, 1, 1, 0, 0, -1, 1, 0, 0, 0, 0, 0, 0, 0)
+VC2_STEP(VC2_HAAR1, 1, 0, 1, 1, 1, +1, 0, 0, 0, 0, 1, 0, 0, 0)
+// Fidelity: update first, then predict  (:933-964)
+VC2_STEP(VC2_FIDELITY, 0, 0, 4, 128, 8, +1, 161, -46, 21, -8, 161, -46, 21, -8)
+VC2_STEP(VC2_FIDELITY, 1, 1, 4, 128, 8, -1, 81, -25, 10, -2, 81, -25, 10, -2)
+// Daubechies 9/7 integer approximation  (:1104-1137)
+VC2_STEP(VC2_DAUB97, 0, 1, 1, 2048, 12, -1, 6497, 0, 0, 0, 6497, 0, 0, 0)
+VC2_STEP(VC2_DAUB97, 1, 0, 1, 2048, 12, -1, 217, 0, 0, 0, 217, 0, 0, 0)
+VC2_STEP(VC2_DAUB97, 2, 1, 1, 2048, 12, +1, 3616, 0, 0, 0, 3616, 0, 0, 0)
+VC2_STEP(VC2_DAUB97, 3, 0, 1, 2048, 12, +1, 1817, 0, 0, 0, 1817, 0, 0, 0)
+#undef VC2_STEP
+
+// number of lifting steps, accuracy shift (WaveletTransform.cpp:224-260) and halo per side
+template <int K> struct Wavelet;
+template <> struct Wavelet<VC2_DD97>     { static constexpr int NSTEPS = 2, SHIFT = 1, R = 4; };
+template <> struct Wavelet<VC2_LEGALL>   { static constexpr int NSTEPS = 2, SHIFT = 1, R = 2; };
+template <> struct Wavelet<VC2_DD137>    { static constexpr int NSTEPS = 2, SHIFT = 1, R = 6; };
+template <> struct Wavelet<VC2_HAAR0>    { static constexpr int NSTEPS = 2, SHIFT = 0, R = 0; };
+template <> struct Wavelet<VC2_HAAR1>    { static constexpr int NSTEPS = 2, SHIFT = 1, R = 0; };
+template <> struct Wavelet<VC2_FIDELITY> { static constexpr int NSTEPS = 2, SHIFT = 0, R = 14; };
+template <> struct Wavelet<VC2_DAUB97>   { static constexpr int NSTEPS = 4, SHIFT = 1, R = 4; };
+
+// ------------------------------------------------------------------------------------------
+// kernel parameter blocks
+// ------------------------------------------------------------------------------------------
+enum SampleKind { SAMPLE_I32 = 0, SAMPLE_U16BE = 1, SAMPLE_U8 = 2 };
+
+struct DwtComp {
+  // level input (forward) / level output (inverse): a dense plane per picture
+  void* pix;                 // int32 plane, or raw sample bytes at level 0 on the fused path
+  long long pix_pic_stride;  // elements (int32) or bytes (raw) between consecutive pictures
+  int pix_h, pix_w;          // valid dims of that plane (level 0: unpadded picture; deeper: lattice)
+  int pix_pitch;             // elements per row
+  int lat_h, lat_w;          // lattice dims at this level = padded dims >> level
+  // the four subbands of this level, dense planes of (lat_h/2 x lat_w/2) with pitch band_pitch
+  int32_t* ll;               // forward: output LL (next level's input, or band 0 at the last level)
+  long long ll_pic_stride;
+  int ll_pitch;
+  int32_t* hl;
+  int32_t* lh;
+  int32_t* hh;
+  long long band_pic_stride;
+  int band_pitch;
+  // raw sample conversion (Arrays.cpp:351-376, 396-397): v = (word >> sshift) - soffset
+  int sshift, soffset;
+  int clip_min, clip_max;    // inverse level 0 on the fused path (Picture.cpp:284-292)
+};
+
+struct DwtParams {
+  DwtComp c[3];
+  int ncomp;
+};
+
+}  // namespace vc2

@@ -1,0 +1,91 @@
+// HQ / LD slice coding kernels: dead-zone quantisation, interleaved exp-Golomb packing and
+// parsing, HQ_CBR rate control.  Reference semantics (paths relative to /root/reference):
+//   quant / scale            src/Library/src/Quantisation.cpp:40-95
+//   component_slice_bytes    src/Library/src/Slices.cpp:97-119
+//   HQ slice writers/readers src/Library/src/Slices.cpp:305-382 (CBR), 469-533 (VBR), 535-612 (read)
+//   LD slice reader          src/Library/src/Slices.cpp:246-303
+//   SignedVLC / bounded IO   src/Library/src/VLC.cpp:21-94, 151-213, 229-257
+//   quantIndicesCBR          src/EncodeStream/EncodeStream.cpp:73-125 ; yss_for_slice Quantisation.cpp:627-642
+#pragma once
+#include "vc2_common.cuh"
+
+namespace vc2 {
+
+struct SliceGeom {
+  PlaneGeom plane[3];        // Y, C1, C2 (planar-subband planes)
+  long long plane_off[3];    // element offset of each component inside one picture's coefficient block
+  long long coef_pic_stride; // elements between pictures
+  int depth, nbands;
+  int slices_x, slices_y;
+  int prefix, scalar;
+  int qmatrix[VC2_MAX_BANDS];
+  // per component class: slice part of each band (rows x cols) and scan-order start of each band
+  int part_h[3][VC2_MAX_BANDS];
+  int part_w[3][VC2_MAX_BANDS];
+  int band_start[3][VC2_MAX_BANDS + 1];  // band_start[c][nbands] = coefficients per slice component
+  int comp_start[4];                     // start of each component in the per-slice coefficient list
+};
+
+struct PackParams {
+  SliceGeom g;
+  const int32_t* coef;          // planar coefficients [pic]
+  int mode;                     // VC2_HQ_VBR / VC2_HQ_CBR
+  int quantise;                 // 1: coefficients are unquantised, apply quant(); 0: already quantised
+  int search;                   // 1: run quantIndicesCBR per slice and use (and store) its result
+  int const_q;                  // >= 0: every slice uses this index (HQ_ConstQ); < 0: read qidx[]
+  int emit;                     // 0: rate control only (vc2_cbr_qindices)
+  int32_t* qidx;                // [pic][slices] in (search == 0 && const_q < 0) or out
+  const int32_t* slice_bytes;   // [slices] per-slice byte budget (CBR), same for every picture
+  const uint32_t* fixed_off;    // [slices + 1] slice offsets when they are known a priori (CBR) else NULL
+  uint8_t* out;                 // payload [pic]
+  long long out_pic_stride;
+  long long out_capacity;       // bytes available per picture
+  uint32_t* slice_off;          // [pic][slices + 1] out
+  uint32_t* err_flags;          // [pic][slices] out (VC2_FLAG_*)
+  unsigned long long* tile_state;  // [pic][ctas] decoupled look-back state, zeroed before launch
+  unsigned* ticket;             // [pic] zeroed before launch
+  int ctas_per_pic;
+  int warps_per_cta;
+  int img_words;                // shared-memory slice image capacity per warp (32-bit words)
+  int coef_words;               // shared-memory coefficient words per warp
+};
+
+struct UnpackParams {
+  SliceGeom g;
+  const uint8_t* in;            // payload [pic]
+  long long in_pic_stride;
+  const uint32_t* slice_off;    // [pic][slices + 1]
+  long long slice_off_pic_stride;  // 0 when every picture shares one table (CBR / LD)
+  int32_t* coef;                // planar coefficients out [pic]
+  int32_t* qidx;                // [pic][slices] out
+  uint32_t* err_flags;          // [pic][slices]
+  int dequantise;               // 1: store scale(v, q'); 0: store the quantised value
+  int ld;                       // 1: LD slice syntax (Slices.cpp:246-303); LL band left quantised
+};
+
+struct QuantParams {            // stand-alone quantise / dequantise on IN-PLACE ordered planes
+  const int32_t* src;
+  int32_t* dst;
+  const int32_t* qidx;          // [slices_y][slices_x]
+  int ph, pw, depth;
+  int slices_y, slices_x;
+  int qmatrix[VC2_MAX_BANDS];
+  int inverse;                  // 0: quant, 1: scale
+  int skip_ll;                  // LD: leave the LL band to the DC-prediction kernel
+};
+
+struct LdDcParams {             // LD LL-band reconstruction with DC prediction (Quantisation.cpp:287-306)
+  int32_t* plane;               // IN-PLACE ordered plane; LL samples at multiples of 2^depth
+  const int32_t* qidx;
+  int ph, pw, depth;
+  int slices_y, slices_x;
+  int qm0;
+};
+
+cudaError_t upload_quant_tables(const QuantTables& t);
+cudaError_t pack_launch(cudaStream_t s, const PackParams& p, int npictures, size_t smem_bytes);
+cudaError_t unpack_launch(cudaStream_t s, const UnpackParams& p, int npictures);
+cudaError_t quant_launch(cudaStream_t s, const QuantParams& p);
+cudaError_t ld_dc_launch(cudaStream_t s, const LdDcParams& p);
+
+}  // namespace vc2
