@@ -101,6 +101,21 @@ const char* vc2_status_message(int status);         /* same text, by status code
 int vc2_device_count(void);
 int vc2_kernel_launches(vc2_ctx* ctx, int reset);   /* kernels launched through this context    */
 
+/* per-kernel timing for the roofline report: CUDA events recorded on the launch stream around every
+ * kernel launched through this context (no reference counterpart; measurement only) */
+enum vc2_stage {
+  VC2_STAGE_DWT_L0 = 0,    /* forward lifting, finest level (reads the picture)          */
+  VC2_STAGE_DWT_DEEP = 1,  /* forward lifting, remaining levels                          */
+  VC2_STAGE_PACK = 2,      /* quantise + [CBR search] + exp-Golomb slice packing         */
+  VC2_STAGE_UNPACK = 3,    /* slice parsing + inverse quantisation                       */
+  VC2_STAGE_IDWT_DEEP = 4, /* inverse lifting, coarse levels                             */
+  VC2_STAGE_IDWT_L0 = 5,   /* inverse lifting, finest level (writes the picture)         */
+  VC2_STAGE_LD_DC = 6,     /* LD LL-band DC prediction wavefront                         */
+  VC2_NUM_STAGES = 7
+};
+int vc2_profile_enable(vc2_ctx* ctx, int on);
+int vc2_profile_read(vc2_ctx* ctx, float* ms, int* launches, int nstages);
+
 /* ---- host-side helpers (pure host code, no GPU needed) ---------------------- */
 
 /* paddedSize  - WaveletTransform.cpp:74-77 */
@@ -182,7 +197,8 @@ int vc2_codec_encode_dev(vc2_codec*, int n_pictures);
 int vc2_codec_decode_dev(vc2_codec*, int n_pictures);
 
 /* device buffers owned by the codec (for device-resident use and for tests) */
-void* vc2_codec_samples_dev(vc2_codec*, int slot);       /* raw planar picture bytes (in for encode, out for decode) */
+void* vc2_codec_samples_dev(vc2_codec*, int slot);       /* raw planar picture bytes: encoder input   */
+void* vc2_codec_recon_dev(vc2_codec*, int slot);         /* raw planar picture bytes: decoder output  */
 uint8_t* vc2_codec_payload_dev(vc2_codec*, int slot);    /* slice payload                                   */
 int32_t* vc2_codec_coeffs_dev(vc2_codec*, int slot, int comp); /* planar-subband coefficient plane        */
 uint32_t* vc2_codec_slice_offsets_dev(vc2_codec*, int slot);   /* n_slices+1                              */

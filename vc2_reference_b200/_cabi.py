@@ -44,6 +44,8 @@ def _load():
         "vc2_status_message": (C.c_char_p, [C.c_int]),
         "vc2_device_count": (C.c_int, []),
         "vc2_kernel_launches": (C.c_int, [vp, C.c_int]),
+        "vc2_profile_enable": (C.c_int, [vp, C.c_int]),
+        "vc2_profile_read": (C.c_int, [vp, C.POINTER(C.c_float), C.POINTER(C.c_int), C.c_int]),
         "vc2_padded_size": (C.c_int, [C.c_int, C.c_int]),
         "vc2_slice_size_is_valid": (C.c_int, [C.c_int] * 4),
         "vc2_quant_matrix": (C.c_int, [C.c_int, C.c_int, i32p]),
@@ -68,6 +70,7 @@ def _load():
         "vc2_codec_encode_dev": (C.c_int, [vp, C.c_int]),
         "vc2_codec_decode_dev": (C.c_int, [vp, C.c_int]),
         "vc2_codec_samples_dev": (vp, [vp, C.c_int]),
+        "vc2_codec_recon_dev": (vp, [vp, C.c_int]),
         "vc2_codec_payload_dev": (vp, [vp, C.c_int]),
         "vc2_codec_coeffs_dev": (vp, [vp, C.c_int, C.c_int]),
         "vc2_codec_slice_offsets_dev": (vp, [vp, C.c_int]),

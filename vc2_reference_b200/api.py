@@ -90,6 +90,18 @@ class Context:
     def kernel_launches(self, reset=False):
         return lib.vc2_kernel_launches(self.h, 1 if reset else 0)
 
+    STAGES = ["dwt_l0", "dwt_deep", "pack", "unpack", "idwt_deep", "idwt_l0", "ld_dc"]
+
+    def profile_enable(self, on=True):
+        _check(lib.vc2_profile_enable(self.h, 1 if on else 0), self.h)
+
+    def profile_read(self):
+        n = len(self.STAGES)
+        ms = (C.c_float * n)()
+        cnt = (C.c_int * n)()
+        _check(lib.vc2_profile_read(self.h, ms, cnt, n), self.h)
+        return {s: (ms[i], cnt[i]) for i, s in enumerate(self.STAGES)}
+
     # waveletTransform / inverseWaveletTransform
     def waveletTransform(self, picture, kernel, depth):
         src = _i32(picture)

@@ -215,6 +215,28 @@ struct vc2_ctx {
   std::string err;
   long launches = 0;
   DevBuf tmp[8];   // scratch for the Library-surface (host pointer) calls
+  // optional per-kernel timing with CUDA events on the launch stream (vc2_profile_*)
+  bool profiling = false;
+  struct Span { int stage; cudaEvent_t a, b; };
+  std::vector<Span> spans;
+  std::vector<cudaEvent_t> event_pool;
+};
+
+static cudaEvent_t prof_event(vc2_ctx* c) {
+  cudaEvent_t e = nullptr;
+  if (!c->event_pool.empty()) { e = c->event_pool.back(); c->event_pool.pop_back(); }
+  else cudaEventCreate(&e);
+  return e;
+}
+struct ProfScope {
+  vc2_ctx* c; int idx = -1;
+  ProfScope(vc2_ctx* c_, int stage) : c(c_) {
+    if (!c->profiling) return;
+    vc2_ctx::Span sp; sp.stage = stage; sp.a = prof_event(c); sp.b = prof_event(c);
+    cudaEventRecord(sp.a, c->stream);
+    c->spans.push_back(sp); idx = (int)c->spans.size() - 1;
+  }
+  ~ProfScope() { if (idx >= 0) cudaEventRecord(c->spans[idx].b, c->stream); }
 };
 
 static int fail(vc2_ctx* c, int st, const char* extra = nullptr) {
@@ -263,6 +285,8 @@ extern "C" void vc2_destroy(vc2_ctx* c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   for (auto& b : c->tmp) b.release();
+  for (auto& sp : c->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
+  for (auto e : c->event_pool) cudaEventDestroy(e);
   if (c->own_stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -287,6 +311,28 @@ extern "C" int vc2_kernel_launches(vc2_ctx* c, int reset) {
   const long n = c->launches;
   if (reset) c->launches = 0;
   return (int)n;
+}
+
+extern "C" int vc2_profile_enable(vc2_ctx* ctx, int on) {
+  if (!ctx) return VC2_ERR_ARG;
+  ctx->profiling = on != 0;
+  return VC2_OK;
+}
+
+// sum of CUDA-event durations (ms) and launch counts per stage since the last read; synchronises the stream
+extern "C" int vc2_profile_read(vc2_ctx* ctx, float* ms, int* launches, int nstages) {
+  if (!ctx || !ms || !launches) return VC2_ERR_ARG;
+  CU(cudaStreamSynchronize(ctx->stream));
+  for (int i = 0; i < nstages; ++i) { ms[i] = 0.f; launches[i] = 0; }
+  for (auto& sp : ctx->spans) {
+    float t = 0.f;
+    cudaEventElapsedTime(&t, sp.a, sp.b);
+    if (sp.stage >= 0 && sp.stage < nstages) { ms[sp.stage] += t; launches[sp.stage]++; }
+    ctx->event_pool.push_back(sp.a);
+    ctx->event_pool.push_back(sp.b);
+  }
+  ctx->spans.clear();
+  return VC2_OK;
 }
 
 // ================================================================================================
@@ -346,6 +392,7 @@ static cudaError_t run_dwt(vc2_ctx* ctx, bool inverse, int kernel, int depth, in
       C.band_pitch = C.lat_w / 2;
       C.sshift = B.sshift; C.soffset = B.soffset; C.clip_min = B.clip_min; C.clip_max = B.clip_max;
     }
+    ProfScope ps(ctx, inverse ? (l == 0 ? VC2_STAGE_IDWT_L0 : VC2_STAGE_IDWT_DEEP) : (l == 0 ? VC2_STAGE_DWT_L0 : VC2_STAGE_DWT_DEEP));
     cudaError_t e = dwt_level_launch(ctx->stream, inverse, kernel, l == 0 ? sample_kind : SAMPLE_I32, p, npictures);
     if (e != cudaSuccess) return e;
     ctx->launches++;
@@ -459,7 +506,10 @@ static cudaError_t run_pack(vc2_ctx* ctx, const SliceGeom& g, const int32_t* coe
   if (e != cudaSuccess) return e;
   e = cudaMemsetAsync(B.tile_state, 0, sizeof(unsigned long long) * (size_t)p.ctas_per_pic * npictures, ctx->stream);
   if (e != cudaSuccess) return e;
-  e = pack_launch(ctx->stream, p, npictures, per_warp * W);
+  {
+    ProfScope ps(ctx, VC2_STAGE_PACK);
+    e = pack_launch(ctx->stream, p, npictures, per_warp * W);
+  }
   if (e == cudaSuccess) ctx->launches++;
   return e;
 }
@@ -730,7 +780,7 @@ struct vc2_codec {
   std::vector<int32_t> slice_bytes;   // CBR / LD
   std::vector<uint32_t> fixed_off;
   // device buffers
-  DevBuf samples, coef, scratch0, scratch1, payload, slice_off, err, qidx, state, ticket, sbytes, fixed, tmp_plane, tmp_q;
+  DevBuf samples, recon, coef, scratch0, scratch1, payload, slice_off, err, qidx, state, ticket, sbytes, fixed, tmp_plane, tmp_q;
   long long scratch_stride[2] = {0, 0};
   long long scratch_off[2][3];
   std::vector<size_t> payload_len;    // host copy per slot (decode)
@@ -743,7 +793,7 @@ static void codec_free(vc2_codec* k) {
   if (!k) return;
   cudaSetDevice(k->ctx->device);
   cudaStreamSynchronize(k->ctx->stream);
-  DevBuf* all[] = {&k->samples, &k->coef, &k->scratch0, &k->scratch1, &k->payload, &k->slice_off, &k->err,
+  DevBuf* all[] = {&k->samples, &k->recon, &k->coef, &k->scratch0, &k->scratch1, &k->payload, &k->slice_off, &k->err,
                    &k->qidx, &k->state, &k->ticket, &k->sbytes, &k->fixed, &k->tmp_plane, &k->tmp_q};
   for (DevBuf* b : all) b->release();
   if (k->host_offs) cudaFreeHost(k->host_offs);
@@ -791,6 +841,7 @@ extern "C" vc2_codec* vc2_codec_create(vc2_ctx* ctx, const vc2_codec_params* prm
   bool ok = true;
   auto R = [&](DevBuf& b, size_t n) { if (ok && b.reserve(n) != cudaSuccess) ok = false; };
   R(k->samples, k->pic_bytes * B + 64);
+  R(k->recon, k->pic_bytes * B + 64);
   R(k->coef, (size_t)g.coef_pic_stride * 4 * B);
   long long s0 = 0, s1 = 0;
   for (int c = 0; c < 3; ++c) {
@@ -828,14 +879,14 @@ extern "C" void vc2_codec_destroy(vc2_codec* k) { codec_free(k); }
 extern "C" size_t vc2_codec_picture_in_bytes(const vc2_codec* k) { return k ? k->pic_bytes : 0; }
 extern "C" size_t vc2_codec_payload_capacity(const vc2_codec* k) { return k ? k->payload_cap : 0; }
 
-static void codec_compbufs(vc2_codec* k, CompBuf cb[3], int first_slot) {
+static void codec_compbufs(vc2_codec* k, CompBuf cb[3], int first_slot, bool recon) {
   const SliceGeom& g = k->g;
   const vc2_sample_format& f = k->prm.fmt;
   size_t off = 0;
   for (int c = 0; c < 3; ++c) {
     CompBuf& B = cb[c];
     B.pg = g.plane[c];
-    B.pix = k->samples.as<uint8_t>() + (size_t)first_slot * k->pic_bytes + off;
+    B.pix = (recon ? k->recon : k->samples).as<uint8_t>() + (size_t)first_slot * k->pic_bytes + off;
     B.pix_pic_stride = (long long)k->pic_bytes;
     B.pix_pitch = g.plane[c].w;
     off += k->comp_bytes[c];
@@ -857,7 +908,7 @@ static int codec_encode_range(vc2_codec* k, int first, int n) {
   vc2_ctx* ctx = k->ctx;
   if (k->prm.mode == VC2_LD) return fail(ctx, VC2_ERR_ARG, "LD is decode-only");
   CompBuf cb[3];
-  codec_compbufs(k, cb, first);
+  codec_compbufs(k, cb, first, false);
   CU(run_dwt(ctx, false, k->prm.geom.kernel, k->prm.geom.depth, k->sample_kind, cb, 3, n));
   PackBuffers B;
   B.out = k->payload.as<uint8_t>() + (size_t)first * k->payload_cap;
@@ -902,7 +953,10 @@ static int codec_decode_range(vc2_codec* k, int first, int n) {
   p.err_flags = k->err.as<uint32_t>() + (size_t)first * k->nslices;
   p.dequantise = 1;
   p.ld = ld ? 1 : 0;
-  CU(unpack_launch(ctx->stream, p, n));
+  {
+    ProfScope ps(ctx, VC2_STAGE_UNPACK);
+    CU(unpack_launch(ctx->stream, p, n));
+  }
   ctx->launches++;
   if (ld) {
     // LL band: DC-predicted reconstruction, one wavefront CTA per (picture, component)
@@ -914,12 +968,13 @@ static int codec_decode_range(vc2_codec* k, int first, int n) {
         // compact LL plane == an "in-place" plane of depth 0 with the LL dims
         d.ph = g.plane[c].ph >> g.depth; d.pw = g.plane[c].pw >> g.depth; d.depth = 0;
         d.slices_y = g.slices_y; d.slices_x = g.slices_x; d.qm0 = g.qmatrix[0];
+        ProfScope ps(ctx, VC2_STAGE_LD_DC);
         CU(ld_dc_launch(ctx->stream, d));
         ctx->launches++;
       }
   }
   CompBuf cb[3];
-  codec_compbufs(k, cb, first);
+  codec_compbufs(k, cb, first, true);
   CU(run_dwt(ctx, true, k->prm.geom.kernel, k->prm.geom.depth, k->sample_kind, cb, 3, n));
   return VC2_OK;
 }
@@ -933,6 +988,9 @@ extern "C" int vc2_codec_decode_dev(vc2_codec* k, int n) {
 
 extern "C" void* vc2_codec_samples_dev(vc2_codec* k, int slot) {
   return (k && slot >= 0 && slot < k->prm.max_pictures) ? k->samples.as<uint8_t>() + (size_t)slot * k->pic_bytes : nullptr;
+}
+extern "C" void* vc2_codec_recon_dev(vc2_codec* k, int slot) {
+  return (k && slot >= 0 && slot < k->prm.max_pictures) ? k->recon.as<uint8_t>() + (size_t)slot * k->pic_bytes : nullptr;
 }
 extern "C" uint8_t* vc2_codec_payload_dev(vc2_codec* k, int slot) {
   return (k && slot >= 0 && slot < k->prm.max_pictures) ? k->payload.as<uint8_t>() + (size_t)slot * k->payload_cap : nullptr;
@@ -961,7 +1019,7 @@ extern "C" int vc2_codec_download_picture(vc2_codec* k, int slot, void* raw) {
   KARG(k && raw && slot >= 0 && slot < k->prm.max_pictures);
   vc2_ctx* ctx = k->ctx;
   CU(cudaSetDevice(ctx->device));
-  CU(cudaMemcpyAsync(raw, vc2_codec_samples_dev(k, slot), k->pic_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(raw, vc2_codec_recon_dev(k, slot), k->pic_bytes, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   return VC2_OK;
 }
@@ -1116,7 +1174,7 @@ extern "C" int vc2_codec_decode_host(vc2_codec* k, int n, const uint8_t* const* 
     const int st = codec_decode_range(k, 0, m);
     if (st) return st;
     for (int i = 0; i < m; ++i)
-      CU(cudaMemcpyAsync(pictures[base + i], vc2_codec_samples_dev(k, i), k->pic_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+      CU(cudaMemcpyAsync(pictures[base + i], vc2_codec_recon_dev(k, i), k->pic_bytes, cudaMemcpyDeviceToHost, ctx->stream));
     flags.resize((size_t)m * k->nslices);
     CU(cudaMemcpyAsync(flags.data(), k->err.p, flags.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
