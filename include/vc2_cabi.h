@@ -200,7 +200,7 @@ int vc2_codec_decode_dev(vc2_codec*, int n_pictures);
 void* vc2_codec_samples_dev(vc2_codec*, int slot);       /* raw planar picture bytes: encoder input   */
 void* vc2_codec_recon_dev(vc2_codec*, int slot);         /* raw planar picture bytes: decoder output  */
 uint8_t* vc2_codec_payload_dev(vc2_codec*, int slot);    /* slice payload                                   */
-int32_t* vc2_codec_coeffs_dev(vc2_codec*, int slot, int comp); /* planar-subband coefficient plane        */
+int32_t* vc2_codec_coeffs_dev(vc2_codec*, int slot, int comp); /* slice-major block: slot base + comp start  */
 uint32_t* vc2_codec_slice_offsets_dev(vc2_codec*, int slot);   /* n_slices+1                              */
 
 /* host <-> slot transfers (pinned staging inside; asynchronous, ordered on the context stream) */

@@ -15,8 +15,6 @@
 
 namespace vc2 {
 cudaError_t dwt_level_launch(cudaStream_t s, bool inverse, int kernel, int sample_kind, const DwtParams& p, int npictures);
-cudaError_t layout_launch(cudaStream_t s, bool to_planar, const int32_t* src, int32_t* dst, const PlaneGeom& g,
-                          long long src_pic_stride, long long dst_pic_stride, int npictures);
 }  // namespace vc2
 
 using namespace vc2;
@@ -344,8 +342,9 @@ struct CompBuf {
   void* pix = nullptr;              // dense picture plane (int32 or raw)
   long long pix_pic_stride = 0;     // elements (int32) or bytes (raw)
   int pix_pitch = 0;
-  int32_t* planar = nullptr;        // planar-subband coefficients
-  long long planar_pic_stride = 0;
+  int comp = 0;                     // component index inside the slice-major block
+  int32_t* coef = nullptr;          // slice-major coefficient block of picture 0
+  long long coef_pic_stride = 0;
   int32_t* scratch[2] = {nullptr, nullptr};
   long long scratch_pic_stride[2] = {0, 0};
   int sshift = 0, soffset = 0, clip_min = 0, clip_max = 0;
@@ -360,8 +359,15 @@ static PlaneGeom make_plane(int h, int w, int depth) {
 }
 
 // all levels of the forward or inverse transform for ncomp components of npictures pictures
-static cudaError_t run_dwt(vc2_ctx* ctx, bool inverse, int kernel, int depth, int sample_kind, const CompBuf* cb, int ncomp,
-                           int npictures) {
+static int ilog2_or_neg(int v) {
+  if (v <= 0 || (v & (v - 1))) return -1;
+  int l = 0;
+  while ((1 << l) < v) ++l;
+  return l;
+}
+
+static cudaError_t run_dwt(vc2_ctx* ctx, bool inverse, int kernel, int depth, int sample_kind, const SliceGeom& g, const CompBuf* cb,
+                           int ncomp, int npictures) {
   for (int step = 0; step < depth; ++step) {
     const int l = inverse ? depth - 1 - step : step;   // 0 = finest
     const int L = depth - l;                           // VC-2 level of the bands touched
@@ -380,16 +386,20 @@ static cudaError_t run_dwt(vc2_ctx* ctx, bool inverse, int kernel, int depth, in
         C.pix_h = C.lat_h; C.pix_w = C.lat_w; C.pix_pitch = C.lat_w;
       }
       if (l == depth - 1) {
-        C.ll = B.planar; C.ll_pic_stride = B.planar_pic_stride;
+        C.ll = nullptr; C.ll_pic_stride = 0;   // LL of the last level is band 0 of the coefficient block
       } else {
         C.ll = B.scratch[l & 1]; C.ll_pic_stride = B.scratch_pic_stride[l & 1];
       }
       C.ll_pitch = C.lat_w / 2;
-      C.hl = B.planar + B.pg.band_off(3 * (L - 1) + 1);
-      C.lh = B.planar + B.pg.band_off(3 * (L - 1) + 2);
-      C.hh = B.planar + B.pg.band_off(3 * (L - 1) + 3);
-      C.band_pic_stride = B.planar_pic_stride;
-      C.band_pitch = C.lat_w / 2;
+      const int cc = B.comp, bhl = 3 * (L - 1) + 1;
+      C.coef = B.coef; C.coef_pic_stride = B.coef_pic_stride;
+      C.bh = g.part_h[cc][bhl]; C.bw = g.part_w[cc][bhl];
+      C.lgbh = ilog2_or_neg(C.bh); C.lgbw = ilog2_or_neg(C.bw);
+      C.nx = g.slices_x; C.NC = g.comp_start[3];
+      C.base_ll = g.comp_start[cc] + g.band_start[cc][0];
+      C.base_hl = g.comp_start[cc] + g.band_start[cc][bhl];
+      C.base_lh = g.comp_start[cc] + g.band_start[cc][bhl + 1];
+      C.base_hh = g.comp_start[cc] + g.band_start[cc][bhl + 2];
       C.sshift = B.sshift; C.soffset = B.soffset; C.clip_min = B.clip_min; C.clip_max = B.clip_max;
     }
     ProfScope ps(ctx, inverse ? (l == 0 ? VC2_STAGE_IDWT_L0 : VC2_STAGE_IDWT_DEEP) : (l == 0 ? VC2_STAGE_DWT_L0 : VC2_STAGE_DWT_DEEP));
@@ -408,16 +418,15 @@ static void fill_slice_geom(SliceGeom& g, const vc2_geom& vg, const int32_t* qma
   g.prefix = vg.prefix; g.scalar = vg.scalar;
   g.plane[0] = make_plane(vg.luma_h, vg.luma_w, vg.depth);
   g.plane[1] = g.plane[2] = make_plane(vg.chroma_h, vg.chroma_w, vg.depth);
-  long long off = 0;
-  for (int c = 0; c < 3; ++c) { g.plane_off[c] = off; off += g.plane[c].size(); }
-  g.coef_pic_stride = off;
+  g.coef_pic_stride = g.plane[0].size() + 2 * g.plane[1].size();
   int cs = 0;
   for (int c = 0; c < 3; ++c) {
     g.comp_start[c] = cs;
     int bs = 0;
     for (int b = 0; b < g.nbands; ++b) {
-      g.part_h[c][b] = g.plane[c].band_h(b) / g.slices_y;
-      g.part_w[c][b] = g.plane[c].band_w(b) / g.slices_x;
+      const int lev = b == 0 ? g.depth : g.depth - ((b - 1) / 3 + 1) + 1;   // band dims = padded dims >> lev
+      g.part_h[c][b] = (g.plane[c].ph >> lev) / g.slices_y;
+      g.part_w[c][b] = (g.plane[c].pw >> lev) / g.slices_x;
       g.band_start[c][b] = bs;
       bs += g.part_h[c][b] * g.part_w[c][b];
     }
@@ -426,6 +435,31 @@ static void fill_slice_geom(SliceGeom& g, const vc2_geom& vg, const int32_t* qma
   }
   g.comp_start[3] = cs;
   for (int b = 0; b < g.nbands; ++b) g.qmatrix[b] = qmatrix ? qmatrix[b] : 0;
+}
+
+// one plane treated as a single component made of a single slice (stand-alone transforms)
+static void fill_plane_geom(SliceGeom& g, int h, int w, int ph, int pw, int depth) {
+  memset(&g, 0, sizeof(g));
+  g.depth = depth;
+  g.nbands = 3 * depth + 1;
+  g.slices_x = g.slices_y = 1;
+  g.scalar = 1;
+  g.plane[0].h = h; g.plane[0].w = w; g.plane[0].ph = ph; g.plane[0].pw = pw; g.plane[0].depth = depth;
+  g.plane[1] = g.plane[2] = g.plane[0];
+  g.plane[1].h = g.plane[1].w = g.plane[1].ph = g.plane[1].pw = 0;
+  g.plane[2] = g.plane[1];
+  int bs = 0;
+  for (int b = 0; b < g.nbands; ++b) {
+    const int lev = b == 0 ? depth : depth - ((b - 1) / 3 + 1) + 1;
+    g.part_h[0][b] = ph >> lev;
+    g.part_w[0][b] = pw >> lev;
+    g.band_start[0][b] = bs;
+    bs += g.part_h[0][b] * g.part_w[0][b];
+  }
+  g.band_start[0][g.nbands] = bs;
+  g.comp_start[0] = 0;
+  g.comp_start[1] = g.comp_start[2] = g.comp_start[3] = bs;
+  g.coef_pic_stride = bs;
 }
 
 static bool geom_ok(const vc2_geom* g) {
@@ -494,8 +528,16 @@ static cudaError_t run_pack(vc2_ctx* ctx, const SliceGeom& g, const int32_t* coe
   p.out = B.out; p.out_pic_stride = B.out_stride; p.out_capacity = B.out_capacity;
   p.slice_off = B.slice_off; p.err_flags = B.err_flags; p.tile_state = B.tile_state; p.ticket = B.ticket;
   const int nslices = g.slices_x * g.slices_y;
-  p.coef_words = g.comp_start[3];
-  p.img_words = (img_bytes + 3) / 4 + 1;
+  int words = 0;
+  for (int c = 0; c < 3; ++c) {
+    const int n = g.band_start[c][g.nbands];
+    p.run_len[c] = (n + 31) / 32;
+    p.run_stride[c] = p.run_len[c] | 1;
+    p.run_base[c] = words;
+    words += 32 * p.run_stride[c];
+  }
+  p.coef_words = words;
+  p.img_words = (img_bytes + 3) / 4 + 4;
   const size_t per_warp = (size_t)(p.coef_words + p.img_words) * 4;
   int W = 8;
   while (W > 1 && per_warp * W > 200 * 1024) W >>= 1;
@@ -532,11 +574,13 @@ extern "C" int vc2_dwt_forward(vc2_ctx* ctx, const int32_t* src, int h, int w, i
   CU(ctx->tmp[3].reserve(n_pad / 16 + 4));
   CU(ctx->tmp[4].reserve(n_pad));
   B.pix = ctx->tmp[0].p; B.pix_pitch = w; B.pix_pic_stride = (long long)h * w;
-  B.planar = ctx->tmp[1].as<int32_t>(); B.planar_pic_stride = B.pg.size();
+  SliceGeom g;
+  fill_plane_geom(g, h, w, B.pg.ph, B.pg.pw, depth);
+  B.coef = ctx->tmp[1].as<int32_t>(); B.coef_pic_stride = B.pg.size(); B.comp = 0;
   B.scratch[0] = ctx->tmp[2].as<int32_t>(); B.scratch[1] = ctx->tmp[3].as<int32_t>();
   CU(cudaMemcpyAsync(B.pix, src, n_in, cudaMemcpyHostToDevice, ctx->stream));
-  CU(run_dwt(ctx, false, kernel, depth, SAMPLE_I32, &B, 1, 1));
-  CU(layout_launch(ctx->stream, false, B.planar, ctx->tmp[4].as<int32_t>(), B.pg, 0, 0, 1));
+  CU(run_dwt(ctx, false, kernel, depth, SAMPLE_I32, g, &B, 1, 1));
+  CU(layout_launch(ctx->stream, false, B.coef, ctx->tmp[4].as<int32_t>(), g, 0));
   ctx->launches++;
   CU(cudaMemcpyAsync(dst, ctx->tmp[4].p, n_pad, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
@@ -558,12 +602,14 @@ extern "C" int vc2_dwt_inverse(vc2_ctx* ctx, const int32_t* src, int ph, int pw,
   CU(ctx->tmp[3].reserve(n_pad / 16 + 4));
   CU(ctx->tmp[4].reserve(n_pad));
   B.pix = ctx->tmp[0].p; B.pix_pitch = w; B.pix_pic_stride = (long long)h * w;
-  B.planar = ctx->tmp[1].as<int32_t>(); B.planar_pic_stride = B.pg.size();
+  SliceGeom g;
+  fill_plane_geom(g, h, w, ph, pw, depth);
+  B.coef = ctx->tmp[1].as<int32_t>(); B.coef_pic_stride = B.pg.size(); B.comp = 0;
   B.scratch[0] = ctx->tmp[2].as<int32_t>(); B.scratch[1] = ctx->tmp[3].as<int32_t>();
   CU(cudaMemcpyAsync(ctx->tmp[4].p, src, n_pad, cudaMemcpyHostToDevice, ctx->stream));
-  CU(layout_launch(ctx->stream, true, ctx->tmp[4].as<int32_t>(), B.planar, B.pg, 0, 0, 1));
+  CU(layout_launch(ctx->stream, true, ctx->tmp[4].as<int32_t>(), B.coef, g, 0));
   ctx->launches++;
-  CU(run_dwt(ctx, true, kernel, depth, SAMPLE_I32, &B, 1, 1));
+  CU(run_dwt(ctx, true, kernel, depth, SAMPLE_I32, g, &B, 1, 1));
   CU(cudaMemcpyAsync(dst, B.pix, n_out, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   return VC2_OK;
@@ -595,7 +641,10 @@ static int quant_host(vc2_ctx* ctx, const int32_t* coef, int ph, int pw, int dep
   ctx->launches++;
   if (ld) {
     LdDcParams d;
-    d.plane = p.dst; d.qidx = p.qidx; d.ph = ph; d.pw = pw; d.depth = depth; d.slices_y = ny; d.slices_x = nx; d.qm0 = qmatrix[0];
+    memset(&d, 0, sizeof(d));
+    d.base = p.dst; d.qidx = p.qidx; d.H = ph >> depth; d.W = pw >> depth; d.bh = d.H; d.bw = d.W;
+    d.A = 0; d.B = (long long)pw << depth; d.C = 0; d.D = 1ll << depth;
+    d.slices_y = ny; d.slices_x = nx; d.qm0 = qmatrix[0];
     CU(ld_dc_launch(ctx->stream, d));
     ctx->launches++;
   }
@@ -617,7 +666,7 @@ extern "C" int vc2_dequantise_ld(vc2_ctx* ctx, const int32_t* coef, int ph, int 
   return quant_host(ctx, coef, ph, pw, depth, qmatrix, qidx, ny, nx, out, 1, 1);
 }
 
-// upload three in-place planes and convert them to one planar coefficient block in tmp[1]
+// upload three in-place planes and convert them to one slice-major coefficient block in tmp[1]
 static int upload_planes(vc2_ctx* ctx, const SliceGeom& g, const int32_t* y, const int32_t* u, const int32_t* v) {
   const int32_t* src[3] = {y, u, v};
   CU(ctx->tmp[0].reserve((size_t)g.plane[0].size() * 4));
@@ -625,18 +674,18 @@ static int upload_planes(vc2_ctx* ctx, const SliceGeom& g, const int32_t* y, con
   for (int c = 0; c < 3; ++c) {
     const size_t n = (size_t)g.plane[c].size() * 4;
     CU(cudaMemcpyAsync(ctx->tmp[0].p, src[c], n, cudaMemcpyHostToDevice, ctx->stream));
-    CU(layout_launch(ctx->stream, true, ctx->tmp[0].as<int32_t>(), ctx->tmp[1].as<int32_t>() + g.plane_off[c], g.plane[c], 0, 0, 1));
+    CU(layout_launch(ctx->stream, true, ctx->tmp[0].as<int32_t>(), ctx->tmp[1].as<int32_t>(), g, c));
     ctx->launches++;
   }
   return VC2_OK;
 }
-static int download_planes(vc2_ctx* ctx, const SliceGeom& g, const int32_t* planar, int32_t* y, int32_t* u, int32_t* v) {
+static int download_planes(vc2_ctx* ctx, const SliceGeom& g, const int32_t* coef, int32_t* y, int32_t* u, int32_t* v) {
   int32_t* dst[3] = {y, u, v};
   CU(ctx->tmp[0].reserve((size_t)g.plane[0].size() * 4));
   for (int c = 0; c < 3; ++c) {
     if (!dst[c]) continue;
     const size_t n = (size_t)g.plane[c].size() * 4;
-    CU(layout_launch(ctx->stream, false, planar + g.plane_off[c], ctx->tmp[0].as<int32_t>(), g.plane[c], 0, 0, 1));
+    CU(layout_launch(ctx->stream, false, coef, ctx->tmp[0].as<int32_t>(), g, c));
     ctx->launches++;
     CU(cudaMemcpyAsync(dst[c], ctx->tmp[0].p, n, cudaMemcpyDeviceToHost, ctx->stream));
   }
@@ -890,8 +939,9 @@ static void codec_compbufs(vc2_codec* k, CompBuf cb[3], int first_slot, bool rec
     B.pix_pic_stride = (long long)k->pic_bytes;
     B.pix_pitch = g.plane[c].w;
     off += k->comp_bytes[c];
-    B.planar = k->coef.as<int32_t>() + (long long)first_slot * g.coef_pic_stride + g.plane_off[c];
-    B.planar_pic_stride = g.coef_pic_stride;
+    B.comp = c;
+    B.coef = k->coef.as<int32_t>() + (long long)first_slot * g.coef_pic_stride;
+    B.coef_pic_stride = g.coef_pic_stride;
     B.scratch[0] = k->scratch0.as<int32_t>() + (long long)first_slot * k->scratch_stride[0] + k->scratch_off[0][c];
     B.scratch[1] = k->scratch1.as<int32_t>() + (long long)first_slot * k->scratch_stride[1] + k->scratch_off[1][c];
     B.scratch_pic_stride[0] = k->scratch_stride[0];
@@ -909,7 +959,7 @@ static int codec_encode_range(vc2_codec* k, int first, int n) {
   if (k->prm.mode == VC2_LD) return fail(ctx, VC2_ERR_ARG, "LD is decode-only");
   CompBuf cb[3];
   codec_compbufs(k, cb, first, false);
-  CU(run_dwt(ctx, false, k->prm.geom.kernel, k->prm.geom.depth, k->sample_kind, cb, 3, n));
+  CU(run_dwt(ctx, false, k->prm.geom.kernel, k->prm.geom.depth, k->sample_kind, k->g, cb, 3, n));
   PackBuffers B;
   B.out = k->payload.as<uint8_t>() + (size_t)first * k->payload_cap;
   B.out_stride = (long long)k->payload_cap; B.out_capacity = (long long)k->payload_cap;
@@ -963,10 +1013,12 @@ static int codec_decode_range(vc2_codec* k, int first, int n) {
     for (int i = 0; i < n; ++i)
       for (int c = 0; c < 3; ++c) {
         LdDcParams d;
-        d.plane = p.coef + (long long)i * g.coef_pic_stride + g.plane_off[c];
+        memset(&d, 0, sizeof(d));
+        d.base = p.coef + (long long)i * g.coef_pic_stride + g.comp_start[c];   // band 0 starts each component
         d.qidx = p.qidx + (size_t)i * k->nslices;
-        // compact LL plane == an "in-place" plane of depth 0 with the LL dims
-        d.ph = g.plane[c].ph >> g.depth; d.pw = g.plane[c].pw >> g.depth; d.depth = 0;
+        d.H = g.plane[c].ph >> g.depth; d.W = g.plane[c].pw >> g.depth;
+        d.bh = g.part_h[c][0]; d.bw = g.part_w[c][0];
+        d.A = (long long)g.slices_x * g.comp_start[3]; d.B = d.bw; d.C = g.comp_start[3]; d.D = 1;
         d.slices_y = g.slices_y; d.slices_x = g.slices_x; d.qm0 = g.qmatrix[0];
         ProfScope ps(ctx, VC2_STAGE_LD_DC);
         CU(ld_dc_launch(ctx->stream, d));
@@ -975,7 +1027,7 @@ static int codec_decode_range(vc2_codec* k, int first, int n) {
   }
   CompBuf cb[3];
   codec_compbufs(k, cb, first, true);
-  CU(run_dwt(ctx, true, k->prm.geom.kernel, k->prm.geom.depth, k->sample_kind, cb, 3, n));
+  CU(run_dwt(ctx, true, k->prm.geom.kernel, k->prm.geom.depth, k->sample_kind, k->g, cb, 3, n));
   return VC2_OK;
 }
 
@@ -997,7 +1049,7 @@ extern "C" uint8_t* vc2_codec_payload_dev(vc2_codec* k, int slot) {
 }
 extern "C" int32_t* vc2_codec_coeffs_dev(vc2_codec* k, int slot, int comp) {
   if (!k || slot < 0 || slot >= k->prm.max_pictures || comp < 0 || comp > 2) return nullptr;
-  return k->coef.as<int32_t>() + (long long)slot * k->g.coef_pic_stride + k->g.plane_off[comp];
+  return k->coef.as<int32_t>() + (long long)slot * k->g.coef_pic_stride + k->g.comp_start[comp];
 }
 extern "C" uint32_t* vc2_codec_slice_offsets_dev(vc2_codec* k, int slot) {
   return (k && slot >= 0 && slot < k->prm.max_pictures) ? k->slice_off.as<uint32_t>() + (size_t)slot * (k->nslices + 1) : nullptr;
@@ -1082,7 +1134,7 @@ extern "C" int vc2_codec_read_transform(vc2_codec* k, int slot, int32_t* y, int3
   int32_t* dst[3] = {y, u, v};
   for (int c = 0; c < 3; ++c) {
     if (!dst[c]) continue;
-    CU(layout_launch(ctx->stream, false, vc2_codec_coeffs_dev(k, slot, c), k->tmp_plane.as<int32_t>(), k->g.plane[c], 0, 0, 1));
+    CU(layout_launch(ctx->stream, false, vc2_codec_coeffs_dev(k, slot, 0), k->tmp_plane.as<int32_t>(), k->g, c));
     ctx->launches++;
     CU(cudaMemcpyAsync(dst[c], k->tmp_plane.p, (size_t)k->g.plane[c].size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
@@ -1098,7 +1150,7 @@ extern "C" int vc2_codec_read_quantised(vc2_codec* k, int slot, int32_t* y, int3
   for (int c = 0; c < 3; ++c) {
     if (!dst[c]) continue;
     const PlaneGeom& pg = k->g.plane[c];
-    CU(layout_launch(ctx->stream, false, vc2_codec_coeffs_dev(k, slot, c), k->tmp_plane.as<int32_t>(), pg, 0, 0, 1));
+    CU(layout_launch(ctx->stream, false, vc2_codec_coeffs_dev(k, slot, 0), k->tmp_plane.as<int32_t>(), k->g, c));
     QuantParams p;
     memset(&p, 0, sizeof(p));
     p.src = k->tmp_plane.as<int32_t>(); p.dst = k->tmp_q.as<int32_t>();

@@ -1,313 +1,401 @@
-// Forward / inverse lifting level kernels and the in-place <-> planar layout kernels.
+// Forward / inverse lifting level kernels and the in-place <-> slice-major layout kernels.
 // See dwt.cuh for the reference line citations and the tiling scheme.
 #include "dwt.cuh"
+#include "slices.cuh"
 
 namespace vc2 {
 
 namespace {
 
-constexpr int TH = 64;    // tile rows (lattice samples)
-constexpr int TW = 128;   // tile columns (lattice samples)
-constexpr int BX = 32;    // blockDim.x : lanes run along a row (unit-stride shared memory)
-constexpr int BY = 8;     // blockDim.y
+constexpr unsigned FULL = 0xFFFFFFFFu;
+constexpr int TH = 64;      // useful tile rows (lattice samples)
+constexpr int RW = 128;     // region columns: one warp row segment, 4 samples per lane
+constexpr int RP = RW / 2;  // pairs per region row = shared-memory row pitch of E and O
+constexpr int NT = 256;     // threads per CTA (8 warps)
 
-__device__ __forceinline__ int clampi(int v, int lo, int hi) { return min(max(v, lo), hi); }
-
-// One lifting step on one target sample.
-//   tgt    : the sample being updated (parity Step::P)
-//   oth    : other-parity sequence, element ii at oth[ii * stride]
-//   idx    : pair index of the target; [lo, hi] = valid pair indices (reference tap clamping)
-template <int K, int S, int DIR>
-__device__ __forceinline__ void lift(int* tgt, const int* oth, int stride, int idx, int lo, int hi) {
-  using ST = Step<K, S>;
-  unsigned sum = (unsigned)ST::ADD;
-#define VC2_TAPL(k) ((unsigned)oth[clampi(idx - (ST::P ? (k) : (k) + 1), lo, hi) * stride])
-#define VC2_TAPR(k) ((unsigned)oth[clampi(idx + (ST::P ? (k) + 1 : (k)), lo, hi) * stride])
-  if (ST::CL0 != 0) sum += (unsigned)ST::CL0 * VC2_TAPL(0);
-  if (ST::CR0 != 0) sum += (unsigned)ST::CR0 * VC2_TAPR(0);
-  if (ST::N > 1) {
-    if (ST::CL1 != 0) sum += (unsigned)ST::CL1 * VC2_TAPL(1);
-    if (ST::CR1 != 0) sum += (unsigned)ST::CR1 * VC2_TAPR(1);
-  }
-  if (ST::N > 2) {
-    if (ST::CL2 != 0) sum += (unsigned)ST::CL2 * VC2_TAPL(2);
-    if (ST::CR2 != 0) sum += (unsigned)ST::CR2 * VC2_TAPR(2);
-    if (ST::CL3 != 0) sum += (unsigned)ST::CL3 * VC2_TAPL(3);
-    if (ST::CR3 != 0) sum += (unsigned)ST::CR3 * VC2_TAPR(3);
-  }
-#undef VC2_TAPL
-#undef VC2_TAPR
-  const int delta = ((int)sum) >> ST::SH;
-  if (ST::SIGN * DIR > 0) *tgt = (int)((unsigned)*tgt + (unsigned)delta);
-  else *tgt = (int)((unsigned)*tgt - (unsigned)delta);
-}
-
-// Shared-memory tile: E = even columns, O = odd columns; RH rows, RP pairs per row.
 template <int K>
 struct Tile {
-  static constexpr int R = Wavelet<K>::R;
+  static constexpr int R = Wavelet<K>::R, HX = Wavelet<K>::HX;
   static constexpr int RH = TH + 2 * R;
-  static constexpr int RP = (TW + 2 * R) / 2;
+  static constexpr int TWU = RW - 2 * HX;   // useful columns per tile
   static constexpr int BYTES = 2 * RH * RP * (int)sizeof(int);
 };
 
-// horizontal pass of one step over rows [r0, r1), pairs [jlo, jhi]
+// reach of one lifting step along the lifted axis, and the reach still to come after / before it
+template <int K, int S> __host__ __device__ constexpr int step_reach() { return Wavelet<K>::R == 0 ? 0 : 2 * Step<K, S>::N - 1; }
+template <int K, int S> __host__ __device__ constexpr int reach_after() {   // forward order: steps S+1 .. NSTEPS-1
+  if constexpr (S + 1 >= Wavelet<K>::NSTEPS) return 0;
+  else return step_reach<K, S + 1>() + reach_after<K, S + 1>();
+}
+template <int K, int S> __host__ __device__ constexpr int reach_before() {  // inverse order: steps S-1 .. 0
+  if constexpr (S == 0) return 0;
+  else return step_reach<K, S - 1>() + reach_before<K, S - 1>();
+}
+
+// ---- horizontal lifting step in registers ------------------------------------------------------
+// A lane holds pairs 2*lane and 2*lane+1 of a 64-pair row segment: e[a] / o[a] = even / odd sample
+// of pair 2*lane+a.  Neighbouring pairs come from other lanes by shuffle.  When the segment
+// touches the left/right edge of the lattice (hedge), the source-parity sequence is first extended
+// beyond [plo, phi] with its edge value = the reference's tap clamping.
 template <int K, int S, int DIR>
-__device__ __forceinline__ void hpass(int* E, int* O, int r0, int r1, int jlo, int jhi) {
-  constexpr int RP = Tile<K>::RP;
-  for (int r = r0 + threadIdx.y; r < r1; r += BY) {
-    int* tg = (Step<K, S>::P ? O : E) + r * RP;
-    const int* ot = (Step<K, S>::P ? E : O) + r * RP;
-    for (int j = jlo + threadIdx.x; j <= jhi; j += BX) lift<K, S, DIR>(tg + j, ot, 1, j, jlo, jhi);
+__device__ __forceinline__ void hstep(int (&e)[2], int (&o)[2], int lane, bool hedge, int plo, int phi) {
+  using ST = Step<K, S>;
+  constexpr int P = ST::P, N = ST::N;
+  int (&src)[2] = P ? e : o;
+  int (&tgt)[2] = P ? o : e;
+  if (hedge) {
+    const int vlo = __shfl_sync(FULL, (plo & 1) ? src[1] : src[0], plo >> 1);
+    const int vhi = __shfl_sync(FULL, (phi & 1) ? src[1] : src[0], phi >> 1);
+    const int p0 = 2 * lane;
+    if (p0 < plo) src[0] = vlo; else if (p0 > phi) src[0] = vhi;
+    if (p0 + 1 < plo) src[1] = vlo; else if (p0 + 1 > phi) src[1] = vhi;
+  }
+  constexpr int QMIN = -(P ? N - 1 : N), QMAX = 1 + (P ? N : N - 1);
+  int nb[QMAX - QMIN + 1];   // source values at pair offsets QMIN..QMAX from pair 2*lane
+#pragma unroll
+  for (int q = QMIN; q <= QMAX; ++q) {
+    const int r = q & 1, dl = (q - r) / 2;
+    nb[q - QMIN] = dl == 0 ? src[r] : __shfl_sync(FULL, src[r], lane + dl);
+  }
+#pragma unroll
+  for (int a = 0; a < 2; ++a) {
+    unsigned sum = (unsigned)ST::ADD;
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      if (ST::cl(k) != 0) sum += (unsigned)ST::cl(k) * (unsigned)nb[a - (P ? k : k + 1) - QMIN];
+      if (ST::cr(k) != 0) sum += (unsigned)ST::cr(k) * (unsigned)nb[a + (P ? k + 1 : k) - QMIN];
+    }
+    const int delta = ((int)sum) >> ST::SH;
+    tgt[a] = (ST::SIGN * DIR > 0) ? (int)((unsigned)tgt[a] + (unsigned)delta) : (int)((unsigned)tgt[a] - (unsigned)delta);
   }
 }
 
-// vertical pass of one step over row pairs [ilo, ihi], pair columns [j0, j1) of both E and O
+template <int K, int DIR>
+__device__ __forceinline__ void hsteps(int (&e)[2], int (&o)[2], int lane, bool hedge, int plo, int phi) {
+  constexpr int N = Wavelet<K>::NSTEPS;
+  if constexpr (DIR > 0) {
+    hstep<K, 0, DIR>(e, o, lane, hedge, plo, phi);
+    hstep<K, 1, DIR>(e, o, lane, hedge, plo, phi);
+    if constexpr (N == 4) {
+      hstep<K, 2, DIR>(e, o, lane, hedge, plo, phi);
+      hstep<K, 3, DIR>(e, o, lane, hedge, plo, phi);
+    }
+  } else {
+    if constexpr (N == 4) {
+      hstep<K, 3, DIR>(e, o, lane, hedge, plo, phi);
+      hstep<K, 2, DIR>(e, o, lane, hedge, plo, phi);
+    }
+    hstep<K, 1, DIR>(e, o, lane, hedge, plo, phi);
+    hstep<K, 0, DIR>(e, o, lane, hedge, plo, phi);
+  }
+}
+
+// ---- vertical lifting step on the shared-memory tile ---------------------------------------------
+// x points at the target sample X[r][j]; taps sit at fixed row offsets (row pitch RP)
 template <int K, int S, int DIR>
-__device__ __forceinline__ void vpass(int* E, int* O, int ilo, int ihi, int j0, int j1) {
-  constexpr int RP = Tile<K>::RP;
-  constexpr int P = Step<K, S>::P;
-  const int nj = j1 - j0;
-  for (int i = ilo + threadIdx.y; i <= ihi; i += BY) {
-    for (int c = threadIdx.x; c < 2 * nj; c += BX) {
-      int* X = (c < nj) ? E : O;
-      const int j = j0 + ((c < nj) ? c : c - nj);
-      lift<K, S, DIR>(X + (2 * i + P) * RP + j, X + (1 - P) * RP + j, 2 * RP, i, ilo, ihi);
+__device__ __forceinline__ int vlift(const int* x) {
+  using ST = Step<K, S>;
+  unsigned sum = (unsigned)ST::ADD;
+#pragma unroll
+  for (int k = 0; k < ST::N; ++k) {
+    if (ST::cl(k) != 0) sum += (unsigned)ST::cl(k) * (unsigned)x[-(2 * k + 1) * RP];
+    if (ST::cr(k) != 0) sum += (unsigned)ST::cr(k) * (unsigned)x[(2 * k + 1) * RP];
+  }
+  const int delta = ((int)sum) >> ST::SH;
+  return (ST::SIGN * DIR > 0) ? (int)((unsigned)x[0] + (unsigned)delta) : (int)((unsigned)x[0] - (unsigned)delta);
+}
+
+// copy the first / last valid row of parity q into the out-of-lattice halo rows of that parity
+// (rows [0, rlo) and (rhi, RH)); only CTAs at the top / bottom edge of the lattice have any
+__device__ __forceinline__ void extend_rows(int* E, int* O, int q, int rlo, int rhi, int RH) {
+  const int col = threadIdx.x & 127, half = threadIdx.x >> 7;
+  int* X = (col < RP ? E : O) + (col & (RP - 1));
+  const int first = rlo + q, last = rhi - (1 - q);
+  for (int r = q + 2 * half; r < rlo; r += 4) X[r * RP] = X[first * RP];
+  for (int r = last + 2 + 2 * half; r < RH; r += 4) X[r * RP] = X[last * RP];
+}
+
+struct BandAddr {   // slice-major addressing of one lattice column / row (see vc2_common.cuh)
+  int bh, bw, lgbh, lgbw, nx, NC;
+  __device__ __forceinline__ int col(int bx) const {   // part that depends on the band column
+    const int sx = lgbw >= 0 ? (bx >> lgbw) : (bx / bw);
+    return sx * NC + (bx - sx * bw);
+  }
+  __device__ __forceinline__ int row(int by) const {   // part that depends on the band row
+    const int sy = lgbh >= 0 ? (by >> lgbh) : (by / bh);
+    return sy * nx * NC + (by - sy * bh) * bw;
+  }
+};
+
+__device__ __forceinline__ int sample_u16be(unsigned w, int sshift, int soffset) {
+  return (int)((((w >> 8) | (w << 8)) & 0xFFFFu) >> sshift) - soffset;
+}
+
+// ------------------------------------------------------------------------------------------
+// forward level:  pix (dense plane)  ->  LL (compact plane or band 0), HL, LH, HH (slice-major)
+// ------------------------------------------------------------------------------------------
+template <int K, int S>
+__device__ __forceinline__ void fwd_vstep(int* E, int* O, const DwtComp& C, int pic, int ys, int rlo, int rhi, int xs, int phi,
+                                          bool vedge) {
+  using T = Tile<K>;
+  using ST = Step<K, S>;
+  constexpr int R = T::R, RH = T::RH, P = ST::P, NS = Wavelet<K>::NSTEPS;
+  constexpr bool LAST = (S == NS - 1);
+  constexpr bool FINAL_FOR_PARITY = (S >= NS - 2);   // steps alternate parity: the last two finish one parity each
+  if (vedge) {
+    extend_rows(E, O, 1 - P, rlo, rhi, RH);
+    __syncthreads();
+  }
+  constexpr int RA = reach_after<K, S>();
+  const int tlo = max(R - RA, rlo), thi = min(R + TH - 1 + RA, rhi);
+  const int col = threadIdx.x & 127, half = threadIdx.x >> 7;
+  const int j = col & (RP - 1);
+  const bool isO = col >= RP;
+  if (j >= T::HX / 2 && j < T::HX / 2 + T::TWU / 2 && j <= phi) {
+    int* X = (isO ? O : E) + j;
+    const int bx = (xs >> 1) + j;
+    const BandAddr ba = {C.bh, C.bw, C.lgbh, C.lgbw, C.nx, C.NC};
+    const int coff = ba.col(bx);
+    int32_t* coef = C.coef + (long long)pic * C.coef_pic_stride;
+    int t0 = tlo + ((tlo & 1) != P ? 1 : 0);
+    for (int r = t0 + 2 * half; r <= thi; r += 4) {
+      const int v = vlift<K, S, +1>(X + r * RP);
+      if (!LAST) X[r * RP] = v;
+      if (FINAL_FOR_PARITY && r >= R && r < R + TH) {
+        const int by = (ys + r) >> 1;
+        if (P == 0 && !isO && C.ll) {
+          C.ll[(long long)pic * C.ll_pic_stride + (long long)by * C.ll_pitch + bx] = v;
+        } else {
+          const int base = P ? (isO ? C.base_hh : C.base_lh) : (isO ? C.base_hl : C.base_ll);
+          coef[base + ba.row(by) + coff] = v;
+        }
+      }
     }
   }
+  if (!LAST) __syncthreads();
 }
 
-template <int K, int DIR, bool HORIZ>
-__device__ __forceinline__ void all_steps(int* E, int* O, int a0, int a1, int b0, int b1) {
-  // forward: steps 0..N-1 ; inverse: N-1..0 with the sign flipped
-  constexpr int N = Wavelet<K>::NSTEPS;
-#define VC2_RUN(S)                                                    \
-  {                                                                   \
-    if (HORIZ) hpass<K, S, DIR>(E, O, a0, a1, b0, b1);                \
-    else vpass<K, S, DIR>(E, O, a0, a1, b0, b1);                      \
-    __syncthreads();                                                  \
-  }
-  if (DIR > 0) {
-    VC2_RUN(0) VC2_RUN(1)
-    if (N == 4) { VC2_RUN((N == 4 ? 2 : 0)) VC2_RUN((N == 4 ? 3 : 1)) }
-  } else {
-    if (N == 4) { VC2_RUN((N == 4 ? 3 : 1)) VC2_RUN((N == 4 ? 2 : 0)) }
-    VC2_RUN(1) VC2_RUN(0)
-  }
-#undef VC2_RUN
-}
-
-__device__ __forceinline__ int load_sample_u16be(const uint16_t* p, int sshift, int soffset) {
-  const unsigned w = *p;
-  const unsigned v = ((w >> 8) | (w << 8)) & 0xFFFFu;
-  return (int)(v >> sshift) - soffset;
-}
-
-// ------------------------------------------------------------------------------------------
-// forward level:  pix (dense plane)  ->  LL, HL, LH, HH
-// ------------------------------------------------------------------------------------------
 template <int K, int KIND>
-__global__ void __launch_bounds__(BX* BY) dwt_fwd_kernel(const DwtParams p) {
+__global__ void __launch_bounds__(NT) dwt_fwd_kernel(const DwtParams p) {
   using T = Tile<K>;
-  constexpr int R = T::R, RH = T::RH, RP = T::RP, SHIFT = Wavelet<K>::SHIFT;
+  constexpr int R = T::R, RH = T::RH, HX = T::HX, SHIFT = Wavelet<K>::SHIFT, NS = Wavelet<K>::NSTEPS;
   extern __shared__ int smem[];
   int* E = smem;
   int* O = smem + RH * RP;
 
-  const int comp = blockIdx.z % p.ncomp;
-  const int pic = blockIdx.z / p.ncomp;
+  const int comp = blockIdx.z % p.ncomp, pic = blockIdx.z / p.ncomp;
   const DwtComp& C = p.c[comp];
-  const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
+  const int x0 = blockIdx.x * T::TWU, y0 = blockIdx.y * TH;
   if (x0 >= C.lat_w || y0 >= C.lat_h) return;
-  const int gx0 = x0 - R, gy0 = y0 - R;
+  const int xs = x0 - HX, ys = y0 - R;
+  const int plo = max(0, -xs / 2), phi = min(RP - 1, (C.lat_w - 2 - xs) / 2);
+  const bool hedge = xs < 0 || xs + RW > C.lat_w;
+  const int rlo = max(0, -ys), rhi = min(RH - 1, C.lat_h - 1 - ys);
+  const bool vedge = ys < 0 || ys + RH > C.lat_h;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
-  // valid local ranges (pairs / rows / row pairs) = region intersected with the lattice
-  const int jlo = max(0, -gx0 / 2), jhi = min(RP - 1, (C.lat_w - 2 - gx0) / 2);
-  const int rlo = max(0, -gy0), rhi = min(RH - 1, C.lat_h - 1 - gy0);   // rows (inclusive)
-  const int ilo = rlo / 2, ihi = (rhi - 1) / 2;                         // row pairs (inclusive)
-
-  // ---- load (edge replicate = waveletPad, WaveletTransform.cpp:79-94) and accuracy shift
+  // ---- phase 1: load a row segment, accuracy shift, horizontal lifting in registers, park in the tile
   {
-    const bool vec = ((C.pix_pitch & 1) == 0) && ((C.pix_pic_stride & 1) == 0);
-    for (int r = rlo + threadIdx.y; r <= rhi; r += BY) {
-      const int sy = min(gy0 + r, C.pix_h - 1);
-      for (int j = jlo + threadIdx.x; j <= jhi; j += BX) {
-        const int gx = gx0 + 2 * j;
-        int e, o;
-        if (KIND == SAMPLE_I32) {
-          const int* src = (const int*)C.pix + (long long)pic * C.pix_pic_stride + (long long)sy * C.pix_pitch;
-          if (vec && gx + 1 < C.pix_w) {
-            const int2 v = *reinterpret_cast<const int2*>(src + gx);
-            e = v.x; o = v.y;
-          } else {
-            e = src[min(gx, C.pix_w - 1)];
-            o = src[min(gx + 1, C.pix_w - 1)];
-          }
-        } else if (KIND == SAMPLE_U16BE) {
-          const uint16_t* src = (const uint16_t*)((const uint8_t*)C.pix + (long long)pic * C.pix_pic_stride) +
-                                (long long)sy * C.pix_pitch;
-          if (vec && gx + 1 < C.pix_w) {
-            const unsigned w = *reinterpret_cast<const unsigned*>(src + gx);   // bytes: e_hi e_lo o_hi o_lo
-            const unsigned ev = __byte_perm(w, 0, 0x4401), ov = __byte_perm(w, 0, 0x4423);
-            e = (int)(ev >> C.sshift) - C.soffset;
-            o = (int)(ov >> C.sshift) - C.soffset;
-          } else {
-            e = load_sample_u16be(src + min(gx, C.pix_w - 1), C.sshift, C.soffset);
-            o = load_sample_u16be(src + min(gx + 1, C.pix_w - 1), C.sshift, C.soffset);
-          }
+    const int gx = xs + 4 * lane;
+    const bool inside = gx >= 0 && gx + 3 < C.pix_w;   // all four samples are real picture samples
+    for (int r = rlo + warp; r <= rhi; r += NT / 32) {
+      const int sy = min(ys + r, C.pix_h - 1);          // waveletPad: replicate the last row (WaveletTransform.cpp:88)
+      int v[4];
+      if (KIND == SAMPLE_I32) {
+        const int* row = (const int*)C.pix + (long long)pic * C.pix_pic_stride + (long long)sy * C.pix_pitch;
+        if (inside && ((reinterpret_cast<uintptr_t>(row + gx) & 15) == 0)) {
+          const int4 q = *reinterpret_cast<const int4*>(row + gx);
+          v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
         } else {
-          const uint8_t* src = (const uint8_t*)C.pix + (long long)pic * C.pix_pic_stride + (long long)sy * C.pix_pitch;
-          e = (int)((unsigned)src[min(gx, C.pix_w - 1)] >> C.sshift) - C.soffset;
-          o = (int)((unsigned)src[min(gx + 1, C.pix_w - 1)] >> C.sshift) - C.soffset;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) v[k] = row[min(max(gx + k, 0), C.pix_w - 1)];   // :89 replicate the last column
         }
-        E[r * RP + j] = (int)((unsigned)e << SHIFT);
-        O[r * RP + j] = (int)((unsigned)o << SHIFT);
+      } else if (KIND == SAMPLE_U16BE) {
+        const uint16_t* row = (const uint16_t*)((const uint8_t*)C.pix + (long long)pic * C.pix_pic_stride) + (long long)sy * C.pix_pitch;
+        if (inside && ((reinterpret_cast<uintptr_t>(row + gx) & 7) == 0)) {
+          const uint2 q = *reinterpret_cast<const uint2*>(row + gx);
+          v[0] = sample_u16be(q.x & 0xFFFFu, C.sshift, C.soffset);
+          v[1] = sample_u16be(q.x >> 16, C.sshift, C.soffset);
+          v[2] = sample_u16be(q.y & 0xFFFFu, C.sshift, C.soffset);
+          v[3] = sample_u16be(q.y >> 16, C.sshift, C.soffset);
+        } else {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) v[k] = sample_u16be(row[min(max(gx + k, 0), C.pix_w - 1)], C.sshift, C.soffset);
+        }
+      } else {
+        const uint8_t* row = (const uint8_t*)C.pix + (long long)pic * C.pix_pic_stride + (long long)sy * C.pix_pitch;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] = (int)((unsigned)row[min(max(gx + k, 0), C.pix_w - 1)] >> C.sshift) - C.soffset;
       }
+      int e[2] = {(int)((unsigned)v[0] << SHIFT), (int)((unsigned)v[2] << SHIFT)};
+      int o[2] = {(int)((unsigned)v[1] << SHIFT), (int)((unsigned)v[3] << SHIFT)};
+      hsteps<K, +1>(e, o, lane, hedge, plo, phi);
+      *reinterpret_cast<int2*>(E + r * RP + 2 * lane) = make_int2(e[0], e[1]);
+      *reinterpret_cast<int2*>(O + r * RP + 2 * lane) = make_int2(o[0], o[1]);
     }
   }
   __syncthreads();
 
-  // ---- horizontal lifting on every region row, then vertical lifting on the tile's own columns
-  all_steps<K, +1, true>(E, O, rlo, rhi + 1, jlo, jhi);
-  const int tj0 = R / 2, tj1 = min(R / 2 + TW / 2, jhi + 1);
-  all_steps<K, +1, false>(E, O, ilo, ihi, tj0, tj1);
-
-  // ---- store the four subbands (dense rows)
-  {
-    int32_t* ll = C.ll + (long long)pic * C.ll_pic_stride;
-    int32_t* hl = C.hl + (long long)pic * C.band_pic_stride;
-    int32_t* lh = C.lh + (long long)pic * C.band_pic_stride;
-    int32_t* hh = C.hh + (long long)pic * C.band_pic_stride;
-    const int ny = min(TH, C.lat_h - y0), nj = min(TW, C.lat_w - x0) / 2;
-    for (int yy = threadIdx.y; yy < ny; yy += BY) {
-      const int r = R + yy, by = (y0 + yy) >> 1;
-      const bool odd = yy & 1;
-      int32_t* de = odd ? (lh + (long long)by * C.band_pitch) : (ll + (long long)by * C.ll_pitch);
-      int32_t* dO = (odd ? hh : hl) + (long long)by * C.band_pitch;
-      for (int jj = threadIdx.x; jj < nj; jj += BX) {
-        const int bx = (x0 >> 1) + jj;
-        de[bx] = E[r * RP + R / 2 + jj];
-        dO[bx] = O[r * RP + R / 2 + jj];
-      }
-    }
+  // ---- phase 2: vertical lifting on the tile, results straight to global memory
+  fwd_vstep<K, 0>(E, O, C, pic, ys, rlo, rhi, xs, phi, vedge);
+  fwd_vstep<K, 1>(E, O, C, pic, ys, rlo, rhi, xs, phi, vedge);
+  if constexpr (NS == 4) {
+    fwd_vstep<K, 2>(E, O, C, pic, ys, rlo, rhi, xs, phi, vedge);
+    fwd_vstep<K, 3>(E, O, C, pic, ys, rlo, rhi, xs, phi, vedge);
   }
 }
 
 // ------------------------------------------------------------------------------------------
 // inverse level:  LL, HL, LH, HH  ->  pix (dense plane; cropped / clipped / packed at level 0)
 // ------------------------------------------------------------------------------------------
-template <int K, int KIND>
-__global__ void __launch_bounds__(BX* BY) dwt_inv_kernel(const DwtParams p) {
+template <int K, int S>
+__device__ __forceinline__ void inv_vstep(int* E, int* O, int rlo, int rhi, int plo, int phi, bool vedge) {
   using T = Tile<K>;
-  constexpr int R = T::R, RH = T::RH, RP = T::RP, SHIFT = Wavelet<K>::SHIFT;
+  using ST = Step<K, S>;
+  constexpr int R = T::R, RH = T::RH, P = ST::P;
+  if (vedge) {
+    extend_rows(E, O, 1 - P, rlo, rhi, RH);
+    __syncthreads();
+  }
+  constexpr int RA = reach_before<K, S>();
+  const int tlo = max(R - RA, rlo), thi = min(R + TH - 1 + RA, rhi);
+  const int col = threadIdx.x & 127, half = threadIdx.x >> 7;
+  const int j = col & (RP - 1);
+  if (j >= plo && j <= phi) {
+    int* X = (col >= RP ? O : E) + j;
+    const int t0 = tlo + ((tlo & 1) != P ? 1 : 0);
+    for (int r = t0 + 2 * half; r <= thi; r += 4) X[r * RP] = vlift<K, S, -1>(X + r * RP);
+  }
+  __syncthreads();
+}
+
+template <int K, int KIND>
+__global__ void __launch_bounds__(NT) dwt_inv_kernel(const DwtParams p) {
+  using T = Tile<K>;
+  constexpr int R = T::R, RH = T::RH, HX = T::HX, SHIFT = Wavelet<K>::SHIFT, NS = Wavelet<K>::NSTEPS;
   extern __shared__ int smem[];
   int* E = smem;
   int* O = smem + RH * RP;
 
-  const int comp = blockIdx.z % p.ncomp;
-  const int pic = blockIdx.z / p.ncomp;
+  const int comp = blockIdx.z % p.ncomp, pic = blockIdx.z / p.ncomp;
   const DwtComp& C = p.c[comp];
-  const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
+  const int x0 = blockIdx.x * T::TWU, y0 = blockIdx.y * TH;
   if (x0 >= C.lat_w || y0 >= C.lat_h) return;
-  // nothing of this tile survives the crop (WaveletTransform.cpp:340)
-  if (x0 >= C.pix_w || y0 >= C.pix_h) return;
-  const int gx0 = x0 - R, gy0 = y0 - R;
-  const int jlo = max(0, -gx0 / 2), jhi = min(RP - 1, (C.lat_w - 2 - gx0) / 2);
-  const int rlo = max(0, -gy0), rhi = min(RH - 1, C.lat_h - 1 - gy0);
-  const int ilo = rlo / 2, ihi = (rhi - 1) / 2;
+  if (x0 >= C.pix_w || y0 >= C.pix_h) return;   // nothing of this tile survives the crop (WaveletTransform.cpp:340)
+  const int xs = x0 - HX, ys = y0 - R;
+  const int plo = max(0, -xs / 2), phi = min(RP - 1, (C.lat_w - 2 - xs) / 2);
+  const bool hedge = xs < 0 || xs + RW > C.lat_w;
+  const int rlo = max(0, -ys), rhi = min(RH - 1, C.lat_h - 1 - ys);
+  const bool vedge = ys < 0 || ys + RH > C.lat_h;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
+  // ---- phase 1: gather the four subbands into the tile
   {
-    const int32_t* ll = C.ll + (long long)pic * C.ll_pic_stride;
-    const int32_t* hl = C.hl + (long long)pic * C.band_pic_stride;
-    const int32_t* lh = C.lh + (long long)pic * C.band_pic_stride;
-    const int32_t* hh = C.hh + (long long)pic * C.band_pic_stride;
-    for (int r = rlo + threadIdx.y; r <= rhi; r += BY) {
-      const int gy = gy0 + r, by = gy >> 1;
-      const bool odd = gy & 1;
-      const int32_t* se = odd ? (lh + (long long)by * C.band_pitch) : (ll + (long long)by * C.ll_pitch);
-      const int32_t* so = (odd ? hh : hl) + (long long)by * C.band_pitch;
-      for (int j = jlo + threadIdx.x; j <= jhi; j += BX) {
-        const int bx = (gx0 >> 1) + j;   // gx0 is even; arithmetic shift is exact
-        E[r * RP + j] = se[bx];
-        O[r * RP + j] = so[bx];
+    const int col = threadIdx.x & 127, half = threadIdx.x >> 7;
+    const int j = col & (RP - 1);
+    const bool isO = col >= RP;
+    if (j >= plo && j <= phi) {
+      int* X = (isO ? O : E) + j;
+      const int bx = (xs >> 1) + j;
+      const BandAddr ba = {C.bh, C.bw, C.lgbh, C.lgbw, C.nx, C.NC};
+      const int coff = ba.col(bx);
+      const int32_t* coef = C.coef + (long long)pic * C.coef_pic_stride;
+      for (int r = rlo + half; r <= rhi; r += 2) {
+        const int gy = ys + r, by = gy >> 1;
+        int v;
+        if (!(gy & 1) && !isO && C.ll) v = C.ll[(long long)pic * C.ll_pic_stride + (long long)by * C.ll_pitch + bx];
+        else {
+          const int base = (gy & 1) ? (isO ? C.base_hh : C.base_lh) : (isO ? C.base_hl : C.base_ll);
+          v = coef[base + ba.row(by) + coff];
+        }
+        X[r * RP] = v;
       }
     }
   }
   __syncthreads();
 
-  // vertical inverse on every region column, then horizontal inverse on the tile's own rows
-  all_steps<K, -1, false>(E, O, ilo, ihi, jlo, jhi + 1);
-  const int tr0 = R, tr1 = min(R + TH, rhi + 1);
-  all_steps<K, -1, true>(E, O, tr0, tr1, jlo, jhi);
+  // ---- phase 2: vertical inverse lifting (steps in reverse order, sign flipped)
+  if constexpr (NS == 4) {
+    inv_vstep<K, 3>(E, O, rlo, rhi, plo, phi, vedge);
+    inv_vstep<K, 2>(E, O, rlo, rhi, plo, phi, vedge);
+  }
+  inv_vstep<K, 1>(E, O, rlo, rhi, plo, phi, vedge);
+  inv_vstep<K, 0>(E, O, rlo, rhi, plo, phi, vedge);
 
+  // ---- phase 3: horizontal inverse lifting in registers, rounding, crop, clip, pack, store
   {
-    const int ny = min(TH, C.pix_h - y0);
-    const int nx = min(TW, C.pix_w - x0);   // may be odd after the crop
+    const int gx = xs + 4 * lane;
+    const bool mine = gx >= x0 && gx < x0 + T::TWU && gx < C.pix_w;   // lane groups are wholly useful or wholly halo
     const int rnd = SHIFT ? (1 << (SHIFT - 1)) : 0;
-    for (int yy = threadIdx.y; yy < ny; yy += BY) {
-      const int r = R + yy;
-      const long long row = (long long)(y0 + yy) * C.pix_pitch;
-      for (int jj = threadIdx.x; 2 * jj < nx; jj += BX) {
-        int e = E[r * RP + R / 2 + jj], o = O[r * RP + R / 2 + jj];
-        if (SHIFT) {
-          e = (e + rnd) >> SHIFT;
-          o = (o + rnd) >> SHIFT;
+    const int rend = min(R + TH - 1, min(rhi, C.pix_h - 1 - ys));
+    for (int r = R + warp; r <= rend; r += NT / 32) {
+      const int2 ev = *reinterpret_cast<const int2*>(E + r * RP + 2 * lane);
+      const int2 ov = *reinterpret_cast<const int2*>(O + r * RP + 2 * lane);
+      int e[2] = {ev.x, ev.y}, o[2] = {ov.x, ov.y};
+      hsteps<K, -1>(e, o, lane, hedge, plo, phi);
+      if (!mine) continue;
+      int v[4] = {e[0], o[0], e[1], o[1]};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (SHIFT) v[k] = (v[k] + rnd) >> SHIFT;
+        if (KIND != SAMPLE_I32) v[k] = (int)((unsigned)(min(max(v[k], C.clip_min), C.clip_max) + C.soffset) << C.sshift);
+      }
+      const long long rowoff = (long long)(ys + r) * C.pix_pitch;
+      const bool whole = gx + 3 < C.pix_w;
+      if (KIND == SAMPLE_I32) {
+        int* dst = (int*)C.pix + (long long)pic * C.pix_pic_stride + rowoff + gx;
+        if (whole && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) *reinterpret_cast<int4*>(dst) = make_int4(v[0], v[1], v[2], v[3]);
+        else {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) if (gx + k < C.pix_w) dst[k] = v[k];
         }
-        const int x = x0 + 2 * jj;
-        const bool has_o = (2 * jj + 1) < nx;
-        if (KIND == SAMPLE_I32) {
-          int* dst = (int*)C.pix + (long long)pic * C.pix_pic_stride + row;
-          dst[x] = e;
-          if (has_o) dst[x + 1] = o;
-        } else {
-          // clip (Picture.cpp:284-292), offset binary, MSB justify, big endian (Arrays.cpp:396-414)
-          e = min(max(e, C.clip_min), C.clip_max);
-          o = min(max(o, C.clip_min), C.clip_max);
-          const unsigned ev = (unsigned)(e + C.soffset) << C.sshift;
-          const unsigned ov = (unsigned)(o + C.soffset) << C.sshift;
-          if (KIND == SAMPLE_U16BE) {
-            uint16_t* dst = (uint16_t*)((uint8_t*)C.pix + (long long)pic * C.pix_pic_stride) + row;
-            dst[x] = (uint16_t)(((ev >> 8) & 0xFF) | ((ev & 0xFF) << 8));
-            if (has_o) dst[x + 1] = (uint16_t)(((ov >> 8) & 0xFF) | ((ov & 0xFF) << 8));
-          } else {
-            uint8_t* dst = (uint8_t*)C.pix + (long long)pic * C.pix_pic_stride + row;
-            dst[x] = (uint8_t)ev;
-            if (has_o) dst[x + 1] = (uint8_t)ov;
-          }
+      } else if (KIND == SAMPLE_U16BE) {
+        // offset binary, MSB justified, big endian (Arrays.cpp:396-414)
+        uint16_t* dst = (uint16_t*)((uint8_t*)C.pix + (long long)pic * C.pix_pic_stride) + rowoff + gx;
+        unsigned h[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) h[k] = __byte_perm((unsigned)v[k], 0, 0x4401);
+        if (whole && ((reinterpret_cast<uintptr_t>(dst) & 7) == 0)) *reinterpret_cast<uint2*>(dst) = make_uint2(h[0] | (h[1] << 16), h[2] | (h[3] << 16));
+        else {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) if (gx + k < C.pix_w) dst[k] = (uint16_t)h[k];
         }
+      } else {
+        uint8_t* dst = (uint8_t*)C.pix + (long long)pic * C.pix_pic_stride + rowoff + gx;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) if (gx + k < C.pix_w) dst[k] = (uint8_t)v[k];
       }
     }
   }
 }
 
 // ------------------------------------------------------------------------------------------
-// layout kernels: reference in-place interleaved order <-> planar subbands
+// layout kernels: reference in-place interleaved plane <-> slice-major coefficient block
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ long long planar_index(const PlaneGeom& g, int y, int x) {
+__device__ __forceinline__ long long slice_major_index(const SliceGeom& g, int c, int y, int x) {
   const int d = g.depth;
   const int t = (y | x) & ((1 << d) - 1);
-  if (t == 0) return (long long)(y >> d) * (g.pw >> d) + (x >> d);
-  const int l = __ffs(t) - 1;          // 0 = finest level
-  const int L = d - l;                 // VC-2 level number
-  const int hx = (x >> l) & 1, hy = (y >> l) & 1;
-  const int type = hx ? (hy ? 3 : 1) : 2;
-  const long long n0 = (long long)(g.ph >> d) * (g.pw >> d);
-  const long long off = (n0 << (2 * (L - 1))) * type;
-  return off + (long long)(y >> (l + 1)) * (g.pw >> (l + 1)) + (x >> (l + 1));
+  int b, by, bx;
+  if (t == 0) { b = 0; by = y >> d; bx = x >> d; }
+  else {
+    const int l = __ffs(t) - 1;          // 0 = finest level
+    const int L = d - l;                 // VC-2 level number
+    const int hx = (x >> l) & 1, hy = (y >> l) & 1;
+    b = 3 * (L - 1) + (hx ? (hy ? 3 : 1) : 2);
+    by = y >> (l + 1); bx = x >> (l + 1);
+  }
+  const int bh = g.part_h[c][b], bw = g.part_w[c][b];
+  const int sy = by / bh, sx = bx / bw;
+  return (long long)(sy * g.slices_x + sx) * g.comp_start[3] + g.comp_start[c] + g.band_start[c][b] + (by - sy * bh) * bw + (bx - sx * bw);
 }
 
-__global__ void inplace_to_planar_kernel(const int32_t* __restrict__ src, int32_t* __restrict__ dst, PlaneGeom g,
-                                         long long src_pic_stride, long long dst_pic_stride) {
+__global__ void layout_kernel(const int32_t* __restrict__ src, int32_t* __restrict__ dst, const SliceGeom g, int c, bool to_slice_major) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
-  if (x >= g.pw || y >= g.ph) return;
-  dst[blockIdx.z * dst_pic_stride + planar_index(g, y, x)] = src[blockIdx.z * src_pic_stride + (long long)y * g.pw + x];
-}
-
-__global__ void planar_to_inplace_kernel(const int32_t* __restrict__ src, int32_t* __restrict__ dst, PlaneGeom g,
-                                         long long src_pic_stride, long long dst_pic_stride) {
-  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
-  if (x >= g.pw || y >= g.ph) return;
-  dst[blockIdx.z * dst_pic_stride + (long long)y * g.pw + x] = src[blockIdx.z * src_pic_stride + planar_index(g, y, x)];
+  const PlaneGeom& pg = g.plane[c];
+  if (x >= pg.pw || y >= pg.ph) return;
+  const long long a = (long long)y * pg.pw + x, b = slice_major_index(g, c, y, x);
+  if (to_slice_major) dst[b] = src[a];
+  else dst[a] = src[b];
 }
 
 template <int K, int KIND>
@@ -318,7 +406,7 @@ cudaError_t launch_fwd(cudaStream_t s, const DwtParams& p, dim3 grid) {
     if (e != cudaSuccess) return e;
     attr_done = true;
   }
-  dwt_fwd_kernel<K, KIND><<<grid, dim3(BX, BY), Tile<K>::BYTES, s>>>(p);
+  dwt_fwd_kernel<K, KIND><<<grid, NT, Tile<K>::BYTES, s>>>(p);
   return cudaGetLastError();
 }
 template <int K, int KIND>
@@ -329,13 +417,24 @@ cudaError_t launch_inv(cudaStream_t s, const DwtParams& p, dim3 grid) {
     if (e != cudaSuccess) return e;
     attr_done = true;
   }
-  dwt_inv_kernel<K, KIND><<<grid, dim3(BX, BY), Tile<K>::BYTES, s>>>(p);
+  dwt_inv_kernel<K, KIND><<<grid, NT, Tile<K>::BYTES, s>>>(p);
   return cudaGetLastError();
 }
 
+template <int K, int KIND>
+cudaError_t launch_level(cudaStream_t s, bool inverse, const DwtParams& p, int npictures) {
+  int mw = 0, mh = 0;
+  for (int c = 0; c < p.ncomp; ++c) {
+    mw = p.c[c].lat_w > mw ? p.c[c].lat_w : mw;
+    mh = p.c[c].lat_h > mh ? p.c[c].lat_h : mh;
+  }
+  const dim3 grid((mw + Tile<K>::TWU - 1) / Tile<K>::TWU, (mh + TH - 1) / TH, npictures * p.ncomp);
+  return inverse ? launch_inv<K, KIND>(s, p, grid) : launch_fwd<K, KIND>(s, p, grid);
+}
+
 template <int KIND>
-cudaError_t dispatch(cudaStream_t s, bool inverse, int kernel, const DwtParams& p, dim3 grid) {
-#define VC2_CASE(K) case K: return inverse ? launch_inv<K, KIND>(s, p, grid) : launch_fwd<K, KIND>(s, p, grid);
+cudaError_t dispatch(cudaStream_t s, bool inverse, int kernel, const DwtParams& p, int npictures) {
+#define VC2_CASE(K) case K: return launch_level<K, KIND>(s, inverse, p, npictures);
   switch (kernel) {
     VC2_CASE(VC2_DD97) VC2_CASE(VC2_LEGALL) VC2_CASE(VC2_DD137) VC2_CASE(VC2_HAAR0)
     VC2_CASE(VC2_HAAR1) VC2_CASE(VC2_FIDELITY) VC2_CASE(VC2_DAUB97)
@@ -346,31 +445,20 @@ cudaError_t dispatch(cudaStream_t s, bool inverse, int kernel, const DwtParams& 
 
 }  // namespace
 
-// grid covering the largest component lattice, z = pictures * components
-static dim3 level_grid(const DwtParams& p, int npictures) {
-  int mw = 0, mh = 0;
-  for (int c = 0; c < p.ncomp; ++c) {
-    mw = p.c[c].lat_w > mw ? p.c[c].lat_w : mw;
-    mh = p.c[c].lat_h > mh ? p.c[c].lat_h : mh;
-  }
-  return dim3((mw + TW - 1) / TW, (mh + TH - 1) / TH, npictures * p.ncomp);
-}
-
 cudaError_t dwt_level_launch(cudaStream_t s, bool inverse, int kernel, int sample_kind, const DwtParams& p, int npictures) {
-  const dim3 grid = level_grid(p, npictures);
   switch (sample_kind) {
-    case SAMPLE_I32: return dispatch<SAMPLE_I32>(s, inverse, kernel, p, grid);
-    case SAMPLE_U16BE: return dispatch<SAMPLE_U16BE>(s, inverse, kernel, p, grid);
-    case SAMPLE_U8: return dispatch<SAMPLE_U8>(s, inverse, kernel, p, grid);
+    case SAMPLE_I32: return dispatch<SAMPLE_I32>(s, inverse, kernel, p, npictures);
+    case SAMPLE_U16BE: return dispatch<SAMPLE_U16BE>(s, inverse, kernel, p, npictures);
+    case SAMPLE_U8: return dispatch<SAMPLE_U8>(s, inverse, kernel, p, npictures);
     default: return cudaErrorInvalidValue;
   }
 }
 
-cudaError_t layout_launch(cudaStream_t s, bool to_planar, const int32_t* src, int32_t* dst, const PlaneGeom& g,
-                          long long src_pic_stride, long long dst_pic_stride, int npictures) {
-  const dim3 block(32, 8), grid((g.pw + 31) / 32, (g.ph + 7) / 8, npictures);
-  if (to_planar) inplace_to_planar_kernel<<<grid, block, 0, s>>>(src, dst, g, src_pic_stride, dst_pic_stride);
-  else planar_to_inplace_kernel<<<grid, block, 0, s>>>(src, dst, g, src_pic_stride, dst_pic_stride);
+// src/dst: one in-place plane (ph x pw) and one picture's slice-major block
+cudaError_t layout_launch(cudaStream_t s, bool to_slice_major, const int32_t* src, int32_t* dst, const SliceGeom& g, int c) {
+  const PlaneGeom& pg = g.plane[c];
+  const dim3 block(32, 8), grid((pg.pw + 31) / 32, (pg.ph + 7) / 8);
+  layout_kernel<<<grid, block, 0, s>>>(src, dst, g, c, to_slice_major);
   return cudaGetLastError();
 }
 

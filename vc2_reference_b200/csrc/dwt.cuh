@@ -6,13 +6,14 @@
 //   inverse level : :536-593, 647-698, 764-827, 874-917, 1004-1088, 1178-1265
 //   level loop    : :262-281 (forward, with waveletPad :79-94), :321-342 (inverse, crop :340)
 //
-// One CTA owns a TH x TW tile of one level's sample lattice plus a halo of R samples per side
-// (R = total reach of the kernel's lifting steps).  The tile lives in shared memory split into an
-// even-column array E and an odd-column array O, so that after the horizontal pass E holds the
-// low-pass and O the high-pass columns and every lifting step reads unit-stride words
-// (bank-conflict free).  Horizontal and vertical passes of a level are fused; edge handling is the
-// reference's tap clamping ("nearest sample of the same parity"), evaluated in global lattice
-// coordinates so tiles at the picture border reproduce it exactly.
+// One CTA owns a tile of one level's sample lattice plus a halo (the total reach of the kernel's
+// lifting steps).  Horizontal lifting runs in REGISTERS: a warp holds one 128-sample row segment,
+// four samples per lane, and fetches neighbours with warp shuffles.  Vertical lifting runs on a
+// shared-memory tile split into even-column (E) and odd-column (O) arrays, one thread per column,
+// taps at fixed row offsets.  The reference's edge rule - a tap that falls outside the array uses
+// the nearest sample of the same parity - is implemented by EXTENDING the source-parity sequence
+// into the halo (registers for rows, halo rows of the tile for columns) before each step, which
+// is the same thing as clamping every tap index and leaves the inner loops free of index math.
 #pragma once
 #include "vc2_common.cuh"
 
@@ -26,7 +27,8 @@ template <int K, int S> struct Step;
 #define VC2_STEP(K, S, P_, N_, ADD_, SH_, SIGN_, L0, L1, L2, L3, R0, R1, R2, R3)                  \
   template <> struct Step<K, S> {                                                                  \
     static constexpr int P = P_, N = N_, ADD = ADD_, SH = SH_, SIGN = SIGN_;                        \
-    static constexpr int CL0 = L0, CL1 = L1, CL2 = L2, CL3 = L3, CR0 = R0, CR1 = R1, CR2 = R2, CR3 = R3; \
+    __host__ __device__ static constexpr int cl(int k) { return k == 0 ? L0 : k == 1 ? L1 : k == 2 ? L2 : L3; } \
+    __host__ __device__ static constexpr int cr(int k) { return k == 0 ? R0 : k == 1 ? R1 : k == 2 ? R2 : R3; } \
   };
 
 // LeGall 5/3  (WaveletTransform.cpp:609-625)
@@ -53,15 +55,16 @@ VC2_STEP(VC2_DAUB97, 2, 1, 1, 2048, 12, +1, 3616, 0, 0, 0, 3616, 0, 0, 0)
 VC2_STEP(VC2_DAUB97, 3, 0, 1, 2048, 12, +1, 1817, 0, 0, 0, 1817, 0, 0, 0)
 #undef VC2_STEP
 
-// number of lifting steps, accuracy shift (WaveletTransform.cpp:224-260) and halo per side
+// number of lifting steps, accuracy shift (WaveletTransform.cpp:224-260), halo per side (R) and the
+// horizontal halo rounded up to whole 4-sample lane groups (HX)
 template <int K> struct Wavelet;
-template <> struct Wavelet<VC2_DD97>     { static constexpr int NSTEPS = 2, SHIFT = 1, R = 4; };
-template <> struct Wavelet<VC2_LEGALL>   { static constexpr int NSTEPS = 2, SHIFT = 1, R = 2; };
-template <> struct Wavelet<VC2_DD137>    { static constexpr int NSTEPS = 2, SHIFT = 1, R = 6; };
-template <> struct Wavelet<VC2_HAAR0>    { static constexpr int NSTEPS = 2, SHIFT = 0, R = 0; };
-template <> struct Wavelet<VC2_HAAR1>    { static constexpr int NSTEPS = 2, SHIFT = 1, R = 0; };
-template <> struct Wavelet<VC2_FIDELITY> { static constexpr int NSTEPS = 2, SHIFT = 0, R = 14; };
-template <> struct Wavelet<VC2_DAUB97>   { static constexpr int NSTEPS = 4, SHIFT = 1, R = 4; };
+template <> struct Wavelet<VC2_DD97>     { static constexpr int NSTEPS = 2, SHIFT = 1, R = 4,  HX = 4; };
+template <> struct Wavelet<VC2_LEGALL>   { static constexpr int NSTEPS = 2, SHIFT = 1, R = 2,  HX = 4; };
+template <> struct Wavelet<VC2_DD137>    { static constexpr int NSTEPS = 2, SHIFT = 1, R = 6,  HX = 8; };
+template <> struct Wavelet<VC2_HAAR0>    { static constexpr int NSTEPS = 2, SHIFT = 0, R = 0,  HX = 0; };
+template <> struct Wavelet<VC2_HAAR1>    { static constexpr int NSTEPS = 2, SHIFT = 1, R = 0,  HX = 0; };
+template <> struct Wavelet<VC2_FIDELITY> { static constexpr int NSTEPS = 2, SHIFT = 0, R = 14, HX = 16; };
+template <> struct Wavelet<VC2_DAUB97>   { static constexpr int NSTEPS = 4, SHIFT = 1, R = 4,  HX = 4; };
 
 // ------------------------------------------------------------------------------------------
 // kernel parameter blocks
@@ -69,21 +72,22 @@ template <> struct Wavelet<VC2_DAUB97>   { static constexpr int NSTEPS = 4, SHIF
 enum SampleKind { SAMPLE_I32 = 0, SAMPLE_U16BE = 1, SAMPLE_U8 = 2 };
 
 struct DwtComp {
-  // level input (forward) / level output (inverse): a dense plane per picture
+  // dense plane per picture: level input (forward) / level output (inverse)
   void* pix;                 // int32 plane, or raw sample bytes at level 0 on the fused path
   long long pix_pic_stride;  // elements (int32) or bytes (raw) between consecutive pictures
   int pix_h, pix_w;          // valid dims of that plane (level 0: unpadded picture; deeper: lattice)
   int pix_pitch;             // elements per row
   int lat_h, lat_w;          // lattice dims at this level = padded dims >> level
-  // the four subbands of this level, dense planes of (lat_h/2 x lat_w/2) with pitch band_pitch
-  int32_t* ll;               // forward: output LL (next level's input, or band 0 at the last level)
+  // slice-major coefficient block (see vc2_common.cuh) holding this level's HL, LH, HH (and LL at the last level)
+  int32_t* coef;
+  long long coef_pic_stride;
+  int bh, bw, lgbh, lgbw;    // this level's band part per slice (rows, cols); lg = log2 or -1 if not a power of two
+  int nx, NC;                // slices per row, coefficients per slice
+  int base_ll, base_hl, base_lh, base_hh;   // comp_start + band_start of the four bands inside a slice
+  // compact LL plane (next level's input / previous level's output); NULL at the last level (LL = band 0 in coef)
+  int32_t* ll;
   long long ll_pic_stride;
   int ll_pitch;
-  int32_t* hl;
-  int32_t* lh;
-  int32_t* hh;
-  long long band_pic_stride;
-  int band_pitch;
   // raw sample conversion (Arrays.cpp:351-376, 396-397): v = (word >> sshift) - soffset
   int sshift, soffset;
   int clip_min, clip_max;    // inverse level 0 on the fused path (Picture.cpp:284-292)

@@ -98,6 +98,7 @@ __device__ __forceinline__ unsigned warp_sum_u(unsigned v) {
   return v;
 }
 
+
 // Per-warp band table: quantiser parameters of every band for the slice's current index.
 struct BandQ {
   uint32_t qm, ql, qf, qo;
@@ -107,6 +108,7 @@ struct BandQ {
 // would throw "quantization index exceeds maximum implemented value" (Quantisation.cpp:60-63)
 __device__ __forceinline__ bool fill_bandq(BandQ* bq, const SliceGeom& g, int q, int lane) {
   bool ok = true;
+  __syncwarp();
   if (lane < g.nbands) {
     const int aq = max(q - g.qmatrix[lane], 0);
     ok = aq <= 119;
@@ -118,30 +120,34 @@ __device__ __forceinline__ bool fill_bandq(BandQ* bq, const SliceGeom& g, int q,
   return ok;
 }
 
-// One pass over a slice component held in shared memory in coding (subband) order.
+// One pass over a slice component held in shared memory as 32 lane runs (run-major, odd stride):
+// lane L owns coefficients [L*rl, min(n, (L+1)*rl)) of the component's coding order.
 //  MODE 0: length only, coefficients stay unquantised (rate-control probe)
 //  MODE 1: length, and the quantised values replace the coefficients (final pass)
 //  MODE 2: luma squared error of quantise + inverse quantise (yss_for_slice); returns 0
 // Returns component_slice_bytes' "count" = bits up to and including the last non-zero coefficient;
 // lane_off = this lane's bit offset; range_err set if |quantised| >= 65535.
 template <int MODE, bool QUANT>
-__device__ __forceinline__ int comp_pass(int* cf, int n, const int* bstart, int nbands, const BandQ* bq, int lane,
+__device__ __forceinline__ int comp_pass(int* run, int rl, int n, const int* bstart, int nbands, const BandQ* bq, int lane,
                                          int& lane_off, bool& range_err, long long& sse) {
-  const int rl = (n + 31) >> 5;
   const int i0 = min(lane * rl, n), i1 = min(i0 + rl, n);
   int b = 0;
-  while (b + 1 < nbands && i0 >= bstart[b + 1]) ++b;
-  int bend = bstart[b + 1];
-  BandQ q = bq[b];
+  BandQ q;
+  int bend = 0;
+  if (QUANT) {
+    while (b + 1 < nbands && i0 >= bstart[b + 1]) ++b;
+    bend = bstart[b + 1];
+    q = bq[b];
+  }
   int bits = 0, last = 0;
   long long acc = 0;
   for (int i = i0; i < i1; ++i) {
-    if (i >= bend) {
+    if (QUANT && i >= bend) {
       ++b;
       bend = bstart[b + 1];
       q = bq[b];
     }
-    const int v = cf[i];
+    const int v = run[i - i0];
     int qv = QUANT ? quant_one(v, q.qm, q.ql) : v;
     if (MODE == 2) {
       const int d = v - scale_one(qv, q.qf, q.qo);
@@ -154,7 +160,7 @@ __device__ __forceinline__ int comp_pass(int* cf, int n, const int* bstart, int 
       const int nb = vlc_bits(qv);
       bits += nb;
       if (nb > 1) last = bits;
-      if (MODE == 1) cf[i] = qv;
+      if (MODE == 1) run[i - i0] = qv;
     }
   }
   if (MODE == 2) {
@@ -183,18 +189,16 @@ __device__ __forceinline__ void img_put_byte(uint32_t* img, int byte_pos, uint32
   atomicOr(&img[byte_pos >> 2], (value & 0xFFu) << (24 - 8 * (byte_pos & 3)));
 }
 
-// write the VLC codes of this lane's run at bit position base + lane_off; bits >= endbit are dropped
+// write the VLC codes of this lane's run at bit position startbit; bits >= endbit are dropped
 // (they can only be the '1' codes of trailing zeros, VLC.cpp:151-155)
-__device__ __forceinline__ void emit_run(uint32_t* img, const int* cf, int n, int lane, int startbit, int endbit) {
-  const int rl = (n + 31) >> 5;
-  const int i0 = min(lane * rl, n), i1 = min(i0 + rl, n);
+__device__ __forceinline__ void emit_run(uint32_t* img, const int* run, int cnt, int startbit, int endbit) {
   int w = startbit >> 5;
   int nacc = startbit & 31;
   unsigned long long acc = 0;
-  for (int i = i0; i < i1; ++i) {
+  for (int i = 0; i < cnt; ++i) {
     uint32_t code;
     int nb;
-    vlc_code(cf[i], code, nb);
+    vlc_code(run[i], code, nb);
     acc = (acc << nb) | code;
     nacc += nb;
     if (nacc >= 32) {
@@ -213,9 +217,9 @@ __device__ __forceinline__ unsigned long long ld_state(const unsigned long long*
 
 // ------------------------------------------------------------------------------------------
 // HQ slice encoder: one warp per slice.
-//   load slice coefficients (coding order) -> [quantIndicesCBR] -> quantise + lengths ->
-//   bit-pack into a shared-memory slice image -> global offset (decoupled look-back over
-//   CTAs, or a priori for CBR) -> copy out.
+//   stream the slice's coefficients (contiguous in the slice-major layout) -> quantise ->
+//   [quantIndicesCBR] -> per-lane code lengths + warp scan -> bit-pack into a shared-memory
+//   slice image -> global offset (decoupled look-back over CTAs, or a priori for CBR) -> copy out.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) hq_pack_kernel(const PackParams p) {
   extern __shared__ uint32_t smem[];
@@ -247,27 +251,28 @@ __global__ void __launch_bounds__(256) hq_pack_kernel(const PackParams p) {
   int loff[3] = {0, 0, 0};
 
   if (active) {
-    const int sy = s / g.slices_x, sx = s - sy * g.slices_x;
-    // ---- gather the slice's coefficients in coding order: component, band, raster (WaveletTransform.cpp:428-450)
-    const int32_t* cbase = p.coef + (long long)pic * g.coef_pic_stride;
+    if (!p.search) qi = p.const_q >= 0 ? p.const_q : p.qidx[(long long)pic * nslices + s];
+    const bool quant_on_load = p.quantise && !p.search;
+    if (quant_on_load && !fill_bandq(bq, g, qi, lane)) flags |= VC2_FLAG_QUANT_INDEX;
+
+    // ---- stream the slice in: coefficient i of component c -> run i / rl, slot i % rl (conflict-free both ways)
+    const int32_t* src = p.coef + (long long)pic * g.coef_pic_stride + (long long)s * g.comp_start[3];
     for (int c = 0; c < 3; ++c) {
-      const PlaneGeom& pg = g.plane[c];
-      const int32_t* pl = cbase + g.plane_off[c];
-      for (int b = 0; b < g.nbands; ++b) {
-        const int bh = g.part_h[c][b], bw = g.part_w[c][b];
-        const int BW = pg.band_w(b);
-        const int32_t* src = pl + pg.band_off(b) + (long long)(sy * bh) * BW + sx * bw;
-        int* dst = cf + g.comp_start[c] + g.band_start[c][b];
-        const int n = bh * bw;
-        if ((bw & (bw - 1)) == 0) {
-          const int lg = 31 - __clz(bw);
-          for (int i = lane; i < n; i += 32) dst[i] = src[(long long)(i >> lg) * BW + (i & (bw - 1))];
-        } else {
-          for (int i = lane; i < n; i += 32) {
-            const int y = i / bw;
-            dst[i] = src[(long long)y * BW + (i - y * bw)];
-          }
+      const int n = g.band_start[c][g.nbands];
+      const int rl = p.run_len[c], rs = p.run_stride[c];
+      const int lg = (rl & (rl - 1)) == 0 ? 31 - __clz(rl) : -1;
+      int* dst = cf + p.run_base[c];
+      const int32_t* sc = src + g.comp_start[c];
+      int b = 0, bend = g.band_start[c][1];
+      BandQ q = bq[0];
+      for (int i = lane; i < n; i += 32) {
+        int v = sc[i];
+        if (quant_on_load) {
+          while (i >= bend) { ++b; bend = g.band_start[c][b + 1]; q = bq[b]; }
+          v = quant_one(v, q.qm, q.ql);
         }
+        const int r = lg >= 0 ? (i >> lg) : (i / rl);
+        dst[r * rs + (i - r * rl)] = v;
       }
     }
     __syncwarp();
@@ -288,27 +293,27 @@ __global__ void __launch_bounds__(256) hq_pack_kernel(const PackParams p) {
         bool too_big = false;
         for (int c = 0; c < 3; ++c) {
           const int n = g.band_start[c][g.nbands];
-          const int count = comp_pass<0, true>(cf + g.comp_start[c], n, g.band_start[c], g.nbands, bq, lane, lane_off, range_err, sse);
+          const int count = comp_pass<0, true>(cf + p.run_base[c] + lane * p.run_stride[c], p.run_len[c], n, g.band_start[c], g.nbands,
+                                               bq, lane, lane_off, range_err, sse);
           need += scaled_bytes(count, g.scalar, too_big);
         }
         if (too_big) { flags |= VC2_FLAG_SCALAR_TOO_SMALL | VC2_FLAG_SEARCH_PHASE; dead = true; break; }
         if (need <= avail) { if (trialQ < q) q = trialQ; trialQ -= delta; }
         else trialQ += delta;
-        __syncwarp();
       }
       if (!dead) {
         // "try a few higher quantisers": keep going while the luma squared error strictly drops
         trialQ = q;
         const int ny = g.band_start[0][g.nbands];
+        int* yrun = cf + p.run_base[0] + lane * p.run_stride[0];
         if (!fill_bandq(bq, g, trialQ, lane)) { flags |= VC2_FLAG_QUANT_INDEX | VC2_FLAG_SEARCH_PHASE; dead = true; }
         long long prev = 0;
-        if (!dead) { comp_pass<2, true>(cf + g.comp_start[0], ny, g.band_start[0], g.nbands, bq, lane, lane_off, range_err, prev); }
+        if (!dead) comp_pass<2, true>(yrun, p.run_len[0], ny, g.band_start[0], g.nbands, bq, lane, lane_off, range_err, prev);
         while (!dead) {
           ++trialQ;
-          __syncwarp();
           if (!fill_bandq(bq, g, trialQ, lane)) { flags |= VC2_FLAG_QUANT_INDEX | VC2_FLAG_SEARCH_PHASE; dead = true; break; }
           long long cur;
-          comp_pass<2, true>(cf + g.comp_start[0], ny, g.band_start[0], g.nbands, bq, lane, lane_off, range_err, cur);
+          comp_pass<2, true>(yrun, p.run_len[0], ny, g.band_start[0], g.nbands, bq, lane, lane_off, range_err, cur);
           const long long d = cur - prev;
           prev = cur;
           if (!(d < 0)) break;
@@ -317,24 +322,21 @@ __global__ void __launch_bounds__(256) hq_pack_kernel(const PackParams p) {
       }
       qi = dead ? 0 : q;
       range_err = false;
-      __syncwarp();
-    } else {
-      qi = p.const_q >= 0 ? p.const_q : p.qidx[(long long)pic * nslices + s];
     }
     if ((p.search || p.const_q >= 0) && lane == 0) p.qidx[(long long)pic * nslices + s] = qi;
 
     if (p.emit) {
-      // ---- final quantisation and component lengths
-      if (p.quantise) {
-        if (!fill_bandq(bq, g, qi, lane)) flags |= VC2_FLAG_QUANT_INDEX;
-      }
+      // ---- final quantisation (CBR: the staged coefficients are still raw) and component lengths
+      const bool quant_now = p.quantise && p.search;
+      if (quant_now && !fill_bandq(bq, g, qi, lane)) flags |= VC2_FLAG_QUANT_INDEX;
       bool too_big = false;
       int need[3];
       for (int c = 0; c < 3; ++c) {
         const int n = g.band_start[c][g.nbands];
+        int* run = cf + p.run_base[c] + lane * p.run_stride[c];
         int count;
-        if (p.quantise) count = comp_pass<1, true>(cf + g.comp_start[c], n, g.band_start[c], g.nbands, bq, lane, lane_off, range_err, sse);
-        else count = comp_pass<1, false>(cf + g.comp_start[c], n, g.band_start[c], g.nbands, bq, lane, lane_off, range_err, sse);
+        if (quant_now) count = comp_pass<1, true>(run, p.run_len[c], n, g.band_start[c], g.nbands, bq, lane, lane_off, range_err, sse);
+        else count = comp_pass<1, false>(run, p.run_len[c], n, g.band_start[c], g.nbands, bq, lane, lane_off, range_err, sse);
         loff[c] = lane_off;
         need[c] = scaled_bytes(count, g.scalar, too_big);
         Lc[c] = need[c];
@@ -349,14 +351,14 @@ __global__ void __launch_bounds__(256) hq_pack_kernel(const PackParams p) {
         Lc[2] = max(vBytes, 0);
       }
       total = g.prefix + 4 + Lc[0] + Lc[1] + Lc[2];
-      if (total > p.img_words * 4) {   // cannot happen for well-formed parameters; keep shared memory safe
+      if (total > p.img_words * 4 - 8) {   // cannot happen for well-formed parameters; keep shared memory safe
         flags |= VC2_FLAG_SCALAR_TOO_SMALL;
         total = 0;
       }
-      if (flags) total = (p.mode == VC2_HQ_CBR && p.fixed_off) ? total : 0;
+      if (flags & ~VC2_FLAG_VLC_RANGE) total = (p.mode == VC2_HQ_CBR && p.fixed_off) ? total : 0;
 
       // ---- build the slice image: prefix | qindex | len Y | Y | len U | U | len V | V   (Slices.cpp:478-530)
-      const int words = (total + 3) >> 2;
+      const int words = ((total + 3) >> 2) + 2;
       for (int w = lane; w < words; w += 32) img[w] = 0;
       __syncwarp();
       if (total > 0 && !(flags & ~VC2_FLAG_VLC_RANGE)) {
@@ -367,7 +369,9 @@ __global__ void __launch_bounds__(256) hq_pack_kernel(const PackParams p) {
           if (lane == 0) img_put_byte(img, pos, (uint32_t)(Lc[c] / g.scalar));
           ++pos;
           const int n = g.band_start[c][g.nbands];
-          emit_run(img, cf + g.comp_start[c], n, lane, 8 * pos + loff[c], 8 * (pos + Lc[c]));
+          const int rl = p.run_len[c];
+          const int i0 = min(lane * rl, n), cnt = min(i0 + rl, n) - i0;
+          emit_run(img, cf + p.run_base[c] + lane * p.run_stride[c], cnt, 8 * pos + loff[c], 8 * (pos + Lc[c]));
           pos += Lc[c];
         }
       }
@@ -403,7 +407,7 @@ __global__ void __launch_bounds__(256) hq_pack_kernel(const PackParams p) {
           const int idx = pos - lane;
           const unsigned long long val = idx >= 0 ? ld_state(&st[idx]) : (2ull << 32);
           const unsigned f = (unsigned)(val >> 32);
-          if (__any_sync(FULL, f == 0)) continue;
+          if (__any_sync(FULL, f == 0)) { __nanosleep(40); continue; }
           const unsigned m = __ballot_sync(FULL, f == 2);
           const int first = m ? (__ffs(m) - 1) : 32;
           prefix += warp_sum_u(lane <= first ? (unsigned)val : 0u);
@@ -426,164 +430,247 @@ __global__ void __launch_bounds__(256) hq_pack_kernel(const PackParams p) {
     }
     if ((long long)offset + total > p.out_capacity) {
       if (lane == 0) p.err_flags[(long long)pic * nslices + s] = flags | VC2_FLAG_STREAM;
-    } else {
+    } else if (total > 0) {
+      // copy out: head bytes up to 4-byte alignment, aligned 32-bit words, tail bytes
       uint8_t* dst = p.out + (long long)pic * p.out_pic_stride + offset;
-      for (int i = lane; i < total; i += 32) dst[i] = (uint8_t)(img[i >> 2] >> (24 - 8 * (i & 3)));
+      const int head = min((int)((4 - (reinterpret_cast<uintptr_t>(dst) & 3)) & 3), total);
+      if (lane < head) dst[lane] = (uint8_t)(img[0] >> (24 - 8 * lane));
+      const int nwords = (total - head) >> 2;
+      uint32_t* dw = reinterpret_cast<uint32_t*>(dst + head);
+      for (int m = lane; m < nwords; m += 32) {
+        const int qb = head + 4 * m;   // image byte index; qb & 3 == head
+        const uint32_t be = __funnelshift_l(img[(qb >> 2) + 1], img[qb >> 2], 8 * head);
+        dw[m] = __byte_perm(be, 0, 0x0123);
+      }
+      const int done = head + 4 * nwords, tail = total - done;
+      if (lane < tail) {
+        const int i = done + lane;
+        dst[i] = (uint8_t)(img[i >> 2] >> (24 - 8 * (i & 3)));
+      }
     }
   }
 }
 
 // ------------------------------------------------------------------------------------------
-// Bit reader over a byte-aligned global buffer, MSB first, 32-bit window, bounded:
-// bits at or beyond `endbit` read as '1' (VLC.cpp:182-185).
+// Bit reader over shared memory, MSB first: 64-bit buffer refilled 32 bits at a time;
+// bytes at or beyond the component length read as 0xFF (VLC.cpp:182-185).
 // ------------------------------------------------------------------------------------------
 struct BitReader {
-  const uint32_t* wp;   // aligned words
-  uint32_t w0, w1;      // big-endian words at word index wi, wi + 1
-  int wi;
-  int bp;               // bit position relative to wp
-  int endbit;
-  __device__ __forceinline__ void init(const uint8_t* base, long long byte_pos, int nbits_) {
-    const uintptr_t a = reinterpret_cast<uintptr_t>(base) + (uintptr_t)byte_pos;
-    wp = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
-    bp = (int)(a & 3) * 8;
-    endbit = bp + nbits_;
-    wi = 0;
-    w0 = __byte_perm(wp[0], 0, 0x0123);
-    w1 = __byte_perm(wp[1], 0, 0x0123);
+  const uint32_t* words;   // aligned words containing the data (shared or global)
+  unsigned long long buf;  // valid bits are the top nb bits
+  int nb;
+  int nextw;               // index of the next aligned word to load
+  int sh;                  // 8 * (start byte & 3): data is shifted inside the aligned words
+  int pos;                 // bytes of data already pulled into buf (multiple of 4)
+  int len;                 // bytes of real data
+  uint32_t carry;          // previous aligned word (big endian)
+  int bits_left;           // BOUNDED reads only (LD blocks end on arbitrary bits): readable bits from here
+
+  __device__ __forceinline__ uint32_t ldw(int i) const { return __byte_perm(words[i], 0, 0x0123); }
+
+  __device__ __forceinline__ void init(const uint32_t* aligned_base, int start_byte, int nbytes) {
+    words = aligned_base;
+    nextw = start_byte >> 2;
+    sh = 8 * (start_byte & 3);
+    len = nbytes;
+    pos = 0;
+    buf = 0;
+    nb = 0;
+    carry = ldw(nextw++);
+    refill();
+    refill();
   }
-  __device__ __forceinline__ uint32_t peek() const {
-    const int s = bp & 31;
-    uint32_t w = __funnelshift_l(w1, w0, s);
-    const int left = endbit - bp;
-    if (left < 32) w |= (left <= 0) ? 0xFFFFFFFFu : (0xFFFFFFFFu >> left);
+  // next 32 data bits (big endian), 0xFF beyond len
+  __device__ __forceinline__ uint32_t next32() {
+    uint32_t w;
+    if (pos >= len) w = 0xFFFFFFFFu;
+    else {
+      const uint32_t nw = ldw(nextw++);
+      w = __funnelshift_l(nw, carry, sh);
+      carry = nw;
+      const int left = len - pos;
+      if (left < 4) w |= 0xFFFFFFFFu >> (8 * left);
+    }
+    pos += 4;
     return w;
   }
-  __device__ __forceinline__ void skip(int n) {
-    bp += n;
-    const int nwi = bp >> 5;
-    if (nwi != wi) {
-      // at most one word per call as n <= 32 (two when n == 32 and alignment conspires: handle generally)
-      if (nwi == wi + 1) { w0 = w1; }
-      else { w0 = __byte_perm(wp[nwi], 0, 0x0123); }
-      wi = nwi;
-      w1 = (bp < endbit) ? __byte_perm(wp[nwi + 1], 0, 0x0123) : 0xFFFFFFFFu;
+  __device__ __forceinline__ void refill() {
+    if (nb <= 32) {
+      buf |= (unsigned long long)next32() << (32 - nb);
+      nb += 32;
     }
   }
-  // one signed interleaved exp-Golomb value (VLC.cpp:283-317)
+  __device__ __forceinline__ uint32_t peek() const { return (uint32_t)(buf >> 32); }
+  __device__ __forceinline__ void skip(int n) { buf <<= n; nb -= n; }
+  // one signed interleaved exp-Golomb value (VLC.cpp:283-317); nb >= 32 on entry.
+  // BOUNDED: bits beyond bits_left read as ones (vlc::bounded, VLC.cpp:182-185)
+  template <bool BOUNDED>
   __device__ __forceinline__ int get_vlc(bool& range_err) {
-    const uint32_t w = peek();
+    uint32_t w = peek();
+    if (BOUNDED && bits_left < 32) w |= bits_left <= 0 ? 0xFFFFFFFFu : (0xFFFFFFFFu >> bits_left);
     const uint32_t f = w & 0xAAAAAAAAu;
     if (f == 0) {   // more than 16 magnitude bits: outside the reference's 32-bit VLC domain
       range_err = true;
       skip(32);
+      if (BOUNDED) bits_left -= 32;
       return 0;
     }
     const int k = __clz(f) >> 1;
-    if (k == 0) { skip(1); return 0; }
+    if (k == 0) { skip(1); if (BOUNDED) bits_left -= 1; return 0; }
     const uint32_t t = w >> (32 - 2 * k);
     const uint32_t m = (1u << k) | compress16(t);
     const int v = (int)m - 1;
     const int neg = (w >> (30 - 2 * k)) & 1u;
     skip(2 * k + 2);
+    if (BOUNDED) bits_left -= 2 * k + 2;
     return neg ? -v : v;
   }
-  __device__ __forceinline__ uint32_t get_bits(int n) {   // n in 1..32
+  __device__ __forceinline__ uint32_t get_bits(int n) {   // n in 1..32, nb >= 32
     const uint32_t w = peek();
     skip(n);
     return n == 32 ? w : (w >> (32 - n));
   }
 };
 
+// 8-bit prefix table: entry = (value << 4) | length for codes of at most 8 bits, 0 when the code is longer
+__device__ __forceinline__ int16_t vlc_lut_entry(int idx) {
+  const uint32_t w = (uint32_t)idx << 24;
+  const uint32_t f = w & 0xAA000000u;
+  if (f == 0) return 0;
+  const int k = __clz(f) >> 1;
+  if (k == 0) return 1;                  // value 0, 1 bit
+  const int nbits = 2 * k + 2;
+  if (nbits > 8) return 0;
+  const uint32_t t = w >> (32 - 2 * k);
+  const int v = (int)((1u << k) | compress16(t)) - 1;
+  const int neg = (w >> (30 - 2 * k)) & 1u;
+  return (int16_t)(((neg ? -v : v) << 4) | nbits);
+}
+
 // ------------------------------------------------------------------------------------------
-// HQ / LD slice decoder: one thread per (slice, component bitstream).  Threads of a warp own
-// the same component of 32 consecutive slices, so the decode loop is divergence free
-// (every stream yields the same number of coefficients).
+// HQ / LD slice decoder.  A CTA takes G = 32 consecutive slices: their bytes are one contiguous
+// run of the payload and are staged in shared memory with coalesced loads.  One thread decodes one
+// (slice, component) bitstream; a warp owns the same component of the 32 slices, so every thread
+// of a warp decodes the same number of coefficients (no divergence on the loop structure).
+// Output is contiguous per thread in the slice-major layout: 128-bit stores.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) slice_unpack_kernel(const UnpackParams p) {
+constexpr int UNPACK_G = 32;
+
+template <bool LD>
+__global__ void __launch_bounds__(96) slice_unpack_kernel(const UnpackParams p, int stage_bytes) {
+  extern __shared__ uint32_t stage[];
+  __shared__ int16_t s_lut[256];
   const SliceGeom& g = p.g;
   const int nslices = g.slices_x * g.slices_y;
-  const int blocks_per_comp = (nslices + blockDim.x - 1) / blockDim.x;
-  const int nstreams = p.ld ? 2 : 3;                 // LD: luma stream + interleaved chroma stream
-  const int strm = blockIdx.x / blocks_per_comp;
-  const int s = (blockIdx.x - strm * blocks_per_comp) * blockDim.x + threadIdx.x;
   const int pic = blockIdx.y;
-  if (strm >= nstreams || s >= nslices) return;
-  const int sy = s / g.slices_x, sx = s - sy * g.slices_x;
+  const int s0 = blockIdx.x * UNPACK_G;
+  const int lane = threadIdx.x & 31, strm = threadIdx.x >> 5;   // warp = stream class: Y,U,V (HQ) / Y,UV (LD)
+  const int nact = min(UNPACK_G, nslices - s0);
+
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) s_lut[i] = vlc_lut_entry(i);
 
   const uint32_t* so = p.slice_off + (long long)pic * p.slice_off_pic_stride;
-  const uint32_t off = so[s], next = so[s + 1];
+  const uint32_t r0 = so[s0], r1 = so[s0 + nact];
   const uint8_t* base = p.in + (long long)pic * p.in_pic_stride;
-  int32_t* cbase = p.coef + (long long)pic * g.coef_pic_stride;
+  // stage [r0, r1) at its own 4-byte phase so that aligned global words map to aligned shared words
+  const uintptr_t ga = reinterpret_cast<uintptr_t>(base) + r0;
+  const int phase = (int)(ga & 3);
+  const uint32_t* gw = reinterpret_cast<const uint32_t*>(ga - phase);
+  const int nwords = (int)((phase + (r1 - r0) + 3) >> 2) + 2;   // + slack for the reader's look-ahead (buffer has slack too)
+  const bool staged = nwords * 4 <= stage_bytes;
+  if (staged)
+    for (int i = threadIdx.x; i < nwords; i += blockDim.x) stage[i] = gw[i];
+  __syncthreads();
+  const uint32_t* words = staged ? stage : gw;
+
+  const int s = s0 + lane;
+  if (s >= nslices || strm >= (LD ? 2 : 3)) return;
+  const int off = phase + (int)(so[s] - r0), size = (int)(so[s + 1] - so[s]);
+  const uint8_t* bytes = reinterpret_cast<const uint8_t*>(words);
+  int32_t* out = p.coef + (long long)pic * g.coef_pic_stride + (long long)s * g.comp_start[3];
   unsigned flags = 0;
   bool range_err = false;
   int qi;
-
   BitReader br;
-  BitReader br2;   // unused for HQ
-  int ncomp_here = 1, c0 = strm;
-  if (!p.ld) {
+  int c0 = strm, ncomp_here = 1;
+
+  if (!LD) {
     // prefix | qindex | len | data | len | data | len | data   (Slices.cpp:544-605)
-    const int size = (int)(next - off);
     int pos = g.prefix;
     int len = 0, start = 0;
     bool bad = size < g.prefix + 4;
-    qi = bad ? 0 : base[off + pos];
+    qi = bad ? 0 : bytes[off + pos];
     ++pos;
     for (int c = 0; c <= strm && !bad; ++c) {
-      len = base[off + pos] * g.scalar;
+      len = bytes[off + pos] * g.scalar;
       start = pos + 1;
       pos = start + len;
       if (pos + (2 - c) > size) bad = true;
     }
     if (bad) { flags |= VC2_FLAG_STREAM; len = 0; start = 0; }
-    br.init(base, (long long)off + start, 8 * len);
+    br.init(words, off + start, len);
   } else {
     // qindex (7 bits) | luma length | luma (bounded) | U/V interleaved (bounded)   (Slices.cpp:253-296)
-    const int bytes = (int)(next - off);
-    br.init(base, off, 8 * bytes);
+    br.init(words, off, size);
     qi = (int)br.get_bits(7);
-    int lb = 0;   // utils::intlog2(8*bytes-7): bits needed to express the value
-    { int v = 8 * bytes - 7; while ((1 << lb) < v) ++lb; }
+    br.refill();
+    int lb = 0;   // utils::intlog2(8*bytes-7)
+    { const int v = 8 * size - 7; while ((1 << lb) < v) ++lb; }
     const int ybits = (int)br.get_bits(lb);
-    const int uvbits = 8 * bytes - 7 - lb - ybits;
+    const int uvbits = 8 * size - 7 - lb - ybits;
     if (uvbits < 0) flags |= VC2_FLAG_STREAM;
-    if (strm == 0) {
-      br.endbit = br.bp + ybits;
-    } else {
-      br.skip(min(ybits, 8 * bytes));   // vlc::flush moves to the end of the luma block (VLC.cpp:238-243)
-      // re-prime the reader at the new position
-      const int bpn = br.bp;
-      br.wi = bpn >> 5;
-      br.w0 = __byte_perm(br.wp[br.wi], 0, 0x0123);
-      br.w1 = __byte_perm(br.wp[br.wi + 1], 0, 0x0123);
-      br.endbit = br.bp + max(uvbits, 0);
-      ncomp_here = 2;
-      c0 = 1;
-    }
+    // the two blocks end on arbitrary bits: restart the reader at the byte holding the block's first bit,
+    // drop the leading bits, and bound the readable bits (everything beyond reads as ones)
+    const int ystart = 7 + lb;
+    const int bstart = strm == 0 ? ystart : ystart + ybits, bbits = strm == 0 ? ybits : max(uvbits, 0);
+    const int rb = min(bstart >> 3, size);
+    br.init(words, off + rb, size - rb);
+    br.skip(bstart & 7);
+    br.refill();
+    br.bits_left = bbits;
+    if (strm == 1) { ncomp_here = 2; c0 = 1; }
   }
   if (strm == 0) p.qidx[(long long)pic * nslices + s] = qi;
+
+  int32_t* dstc[2];
+  dstc[0] = out + g.comp_start[c0];
+  dstc[1] = ncomp_here == 2 ? out + g.comp_start[2] : dstc[0];
 
   for (int b = 0; b < g.nbands; ++b) {
     const int aq = max(qi - g.qmatrix[b], 0);
     if (aq > 119 && p.dequantise) flags |= VC2_FLAG_QUANT_INDEX;
     const QParam qp = qparam(aq);
-    const bool deq = p.dequantise && !(p.ld && b == 0);
-    const int bh = g.part_h[c0][b], bw = g.part_w[c0][b];
-    int32_t* dst[2];
-    int BW = 0;
-    for (int k = 0; k < ncomp_here; ++k) {
-      const PlaneGeom& pg = g.plane[c0 + k];
-      BW = pg.band_w(b);
-      dst[k] = cbase + g.plane_off[c0 + k] + pg.band_off(b) + (long long)(sy * bh) * BW + sx * bw;
-    }
-    for (int y = 0; y < bh; ++y) {
-      for (int x = 0; x < bw; ++x) {
-        for (int k = 0; k < ncomp_here; ++k) {
-          int v = br.get_vlc(range_err);
-          if (deq) v = scale_one(v, qp.qf, qp.qo);
-          dst[k][(long long)y * BW + x] = v;
+    const bool deq = p.dequantise && !(LD && b == 0);
+    const int n = g.band_start[c0][b + 1] - g.band_start[c0][b];
+    int i = g.band_start[c0][b];
+    const int iend = i + n;
+    auto one = [&]() -> int {
+      br.refill();
+      int v;
+      if (LD) {
+        v = br.get_vlc<true>(range_err);
+      } else {
+        const int ent = s_lut[br.peek() >> 24];
+        if (ent) { v = ent >> 4; br.skip(ent & 15); }
+        else v = br.get_vlc<false>(range_err);
+      }
+      return deq ? scale_one(v, qp.qf, qp.qo) : v;
+    };
+    if (ncomp_here == 1) {
+      // vector part when the band start is 16-byte aligned inside the slice block
+      if (((i | n) & 3) == 0 && ((g.comp_start[3] | g.comp_start[c0]) & 3) == 0) {
+        for (; i < iend; i += 4) {
+          int4 q;
+          q.x = one(); q.y = one(); q.z = one(); q.w = one();
+          *reinterpret_cast<int4*>(dstc[0] + i) = q;
         }
+      } else {
+        for (; i < iend; ++i) dstc[0][i] = one();
+      }
+    } else {
+      for (; i < iend; ++i) {   // LD chroma: u0 v0 u1 v1 ... (Slices.cpp:287-294)
+        dstc[0][i] = one();
+        dstc[1][i] = one();
       }
     }
   }
@@ -620,23 +707,25 @@ __global__ void quant_kernel(const QuantParams p) {
 // the anti-diagonal wavefront: element (y, x) depends on (y-1, x-1), (y-1, x), (y, x-1).
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) ld_dc_kernel(const LdDcParams p) {
-  const int d = p.depth;
-  const int H = p.ph >> d, Wd = p.pw >> d;
-  const long long pitch = (long long)p.pw << d;   // rows of the LL lattice inside the in-place plane
+  const int H = p.H, Wd = p.W;
+  auto at = [&](int y, int x) -> int32_t* {
+    const int sy = y / p.bh, sx = x / p.bw;
+    return p.base + sy * p.A + (y - sy * p.bh) * p.B + sx * p.C + (x - sx * p.bw) * p.D;
+  };
   for (int diag = 0; diag < H + Wd - 1; ++diag) {
     const int ylo = max(0, diag - (Wd - 1)), yhi = min(H - 1, diag);
     for (int y = ylo + (int)threadIdx.x; y <= yhi; y += blockDim.x) {
       const int x = diag - y;
-      int32_t* e = p.plane + y * pitch + ((long long)x << d);
+      int32_t* e = at(y, x);
       const int yb = ((y + 1) * p.slices_y - 1) / H, xb = ((x + 1) * p.slices_x - 1) / Wd;
       const int q = max(p.qidx[yb * p.slices_x + xb] - p.qm0, 0);
       const QParam qp = qparam(q);
       int pred;
       if (y > 0 && x > 0) {
-        const int sum = e[-pitch - (1 << d)] + e[-pitch] + e[-(1 << d)];
+        const int sum = *at(y - 1, x - 1) + *at(y - 1, x) + *at(y, x - 1);
         pred = sum >= 0 ? (sum + 1) / 3 : (sum - 1) / 3;
-      } else if (y > 0) pred = e[-pitch];
-      else if (x > 0) pred = e[-(1 << d)];
+      } else if (y > 0) pred = *at(y - 1, x);
+      else if (x > 0) pred = *at(y, x - 1);
       else pred = 0;
       *e = scale_one(*e, qp.qf, qp.qo) + pred;
     }
@@ -659,9 +748,17 @@ cudaError_t pack_launch(cudaStream_t s, const PackParams& p, int npictures, size
 
 cudaError_t unpack_launch(cudaStream_t s, const UnpackParams& p, int npictures) {
   const int nslices = p.g.slices_x * p.g.slices_y;
-  const int threads = 128;
-  const int bpc = (nslices + threads - 1) / threads;
-  slice_unpack_kernel<<<dim3(bpc * (p.ld ? 2 : 3), npictures), threads, 0, s>>>(p);
+  const int stage_bytes = 40 * 1024;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(slice_unpack_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, stage_bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(slice_unpack_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, stage_bytes);
+    if (e != cudaSuccess) return e;
+    attr_done = true;
+  }
+  const dim3 grid((nslices + UNPACK_G - 1) / UNPACK_G, npictures);
+  if (p.ld) slice_unpack_kernel<true><<<grid, 96, stage_bytes, s>>>(p, stage_bytes);
+  else slice_unpack_kernel<false><<<grid, 96, stage_bytes, s>>>(p, stage_bytes);
   return cudaGetLastError();
 }
 

@@ -12,9 +12,8 @@
 namespace vc2 {
 
 struct SliceGeom {
-  PlaneGeom plane[3];        // Y, C1, C2 (planar-subband planes)
-  long long plane_off[3];    // element offset of each component inside one picture's coefficient block
-  long long coef_pic_stride; // elements between pictures
+  PlaneGeom plane[3];        // Y, C1, C2 padded plane geometry
+  long long coef_pic_stride; // elements between pictures = slices * comp_start[3]
   int depth, nbands;
   int slices_x, slices_y;
   int prefix, scalar;
@@ -28,7 +27,7 @@ struct SliceGeom {
 
 struct PackParams {
   SliceGeom g;
-  const int32_t* coef;          // planar coefficients [pic]
+  const int32_t* coef;          // slice-major coefficients [pic]
   int mode;                     // VC2_HQ_VBR / VC2_HQ_CBR
   int quantise;                 // 1: coefficients are unquantised, apply quant(); 0: already quantised
   int search;                   // 1: run quantIndicesCBR per slice and use (and store) its result
@@ -47,7 +46,10 @@ struct PackParams {
   int ctas_per_pic;
   int warps_per_cta;
   int img_words;                // shared-memory slice image capacity per warp (32-bit words)
-  int coef_words;               // shared-memory coefficient words per warp
+  int coef_words;               // shared-memory coefficient words per warp (run-major, padded)
+  int run_len[3];               // coefficients per lane run = ceil(n / 32), per component
+  int run_stride[3];            // run_len | 1 : odd stride keeps the 32 runs on distinct banks
+  int run_base[3];              // start of each component's runs inside the per-warp coefficient area
 };
 
 struct UnpackParams {
@@ -56,7 +58,7 @@ struct UnpackParams {
   long long in_pic_stride;
   const uint32_t* slice_off;    // [pic][slices + 1]
   long long slice_off_pic_stride;  // 0 when every picture shares one table (CBR / LD)
-  int32_t* coef;                // planar coefficients out [pic]
+  int32_t* coef;                // slice-major coefficients out [pic]
   int32_t* qidx;                // [pic][slices] out
   uint32_t* err_flags;          // [pic][slices]
   int dequantise;               // 1: store scale(v, q'); 0: store the quantised value
@@ -75,9 +77,11 @@ struct QuantParams {            // stand-alone quantise / dequantise on IN-PLACE
 };
 
 struct LdDcParams {             // LD LL-band reconstruction with DC prediction (Quantisation.cpp:287-306)
-  int32_t* plane;               // IN-PLACE ordered plane; LL samples at multiples of 2^depth
-  const int32_t* qidx;
-  int ph, pw, depth;
+  int32_t* base;                // LL sample (y, x) lives at base + (y/bh)*A + (y%bh)*B + (x/bw)*C + (x%bw)*D
+  const int32_t* qidx;          //   in-place plane: bh = H, bw = W, B = pw << depth, D = 1 << depth
+  int H, W;                     //   slice-major   : bh, bw = LL part of a slice, A = nx*NC, B = bw, C = NC, D = 1
+  int bh, bw;
+  long long A, B, C, D;
   int slices_y, slices_x;
   int qm0;
 };
@@ -85,6 +89,7 @@ struct LdDcParams {             // LD LL-band reconstruction with DC prediction 
 cudaError_t upload_quant_tables(const QuantTables& t);
 cudaError_t pack_launch(cudaStream_t s, const PackParams& p, int npictures, size_t smem_bytes);
 cudaError_t unpack_launch(cudaStream_t s, const UnpackParams& p, int npictures);
+cudaError_t layout_launch(cudaStream_t s, bool to_slice_major, const int32_t* src, int32_t* dst, const SliceGeom& g, int c);
 cudaError_t quant_launch(cudaStream_t s, const QuantParams& p);
 cudaError_t ld_dc_launch(cudaStream_t s, const LdDcParams& p);
 

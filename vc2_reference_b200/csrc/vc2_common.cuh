@@ -10,17 +10,19 @@
 namespace vc2 {
 
 // ---------------------------------------------------------------------------------------------
-// Planar-subband coefficient layout used INSIDE the device pipeline.
+// SLICE-MAJOR coefficient layout used INSIDE the device pipeline.
 //
-// A padded component plane (ph x pw, both multiples of 2^depth) is stored as 3*depth+1 compact
-// subband planes back to back: band 0 = LL (ph>>d x pw>>d); VC-2 level L = 1..d (L = d finest)
-// contributes HL, LH, HH (bands 3(L-1)+1..3), each (ph >> (d-L+1)) x (pw >> (d-L+1)).
-// Everything before level L sums to n0*4^(L-1) elements (n0 = LL size), so
-//   offset(L, type) = n0 * 4^(L-1) * type,  type = 1 (HL), 2 (LH), 3 (HH).
-// This is exactly the order in which a slice's coefficients are coded
-// (reference split_into_subbands, WaveletTransform.cpp:428-450), so slice coding reads contiguous
-// band rows, and every DWT level reads/writes dense rows.  The reference's in-place interleaved
-// Array2D order is produced/consumed only at the Library boundary (layout kernels in dwt.cu).
+// One picture's coefficients (all three padded component planes) are stored slice by slice, in
+// raster slice order; inside a slice: Y, C1, C2; inside a component: subbands in coding order
+// (band 0 = LL, then VC-2 level L = 1..depth: HL, LH, HH = bands 3(L-1)+1..3), each subband's
+// part of the slice in raster order - i.e. exactly the order in which the reference codes a
+// slice (split_into_subbands, WaveletTransform.cpp:428-450; HQSliceIO, Slices.cpp:488-530):
+//
+//   index(s, c, b, y, x) = s * NC + comp_start[c] + band_start[c][b] + y * part_w[c][b] + x
+//
+// so the slice coder streams one contiguous block per slice, a DWT level stores/loads band rows as
+// runs of part_w contiguous words, and nothing is ever gathered.  The reference's in-place
+// interleaved Array2D order exists only at the Library boundary (layout kernels in dwt.cu).
 // ---------------------------------------------------------------------------------------------
 struct PlaneGeom {
   int h, w;    // unpadded picture plane
