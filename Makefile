@@ -10,7 +10,13 @@ CSRC      := $(PKG)/csrc
 LIB       := $(PKG)/libvc2b200.so
 OBJS      := $(CSRC)/dwt.o $(CSRC)/slices.o $(CSRC)/cabi.o
 
-all: $(LIB)
+ORACLE    := oracle/_build/libvc2oracle.so
+
+all: $(LIB) $(ORACLE)
+
+$(ORACLE): oracle/vc2_oracle.c
+	mkdir -p oracle/_build
+	$(CC) -O2 -std=c99 -fPIC -shared $< -o $@ -lm
 
 $(CSRC)/%.o: $(CSRC)/%.cu $(CSRC)/*.cuh include/vc2_cabi.h
 	$(NVCC) $(NVFLAGS) -c $< -o $@
