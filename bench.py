@@ -301,7 +301,7 @@ def main():
         alg = {
             "dwt_l0": 2 * S + 4 * S, "dwt_deep": 0.0,
             "pack": 4 * S + C_bytes, "unpack": C_bytes + 4 * S,
-            "idwt_deep": 0.0, "idwt_l0": 4 * S + 2 * S, "ld_dc": 0.0,
+            "idwt_deep": 0.0, "idwt_l0": 4 * S + 2 * S, "ld_dc": 0.0, "assemble": 2 * C_bytes,
         }
         deep = sum(8.0 * S / (4 ** l) for l in range(1, w["depth"]))
         alg["dwt_deep"] = deep

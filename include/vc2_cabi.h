@@ -111,7 +111,8 @@ enum vc2_stage {
   VC2_STAGE_IDWT_DEEP = 4, /* inverse lifting, coarse levels                             */
   VC2_STAGE_IDWT_L0 = 5,   /* inverse lifting, finest level (writes the picture)         */
   VC2_STAGE_LD_DC = 6,     /* LD LL-band DC prediction wavefront                         */
-  VC2_NUM_STAGES = 7
+  VC2_STAGE_ASSEMBLE = 7,  /* slice size scan + gather of the slice images into the payload */
+  VC2_NUM_STAGES = 8
 };
 int vc2_profile_enable(vc2_ctx* ctx, int on);
 int vc2_profile_read(vc2_ctx* ctx, float* ms, int* launches, int nstages);
@@ -200,7 +201,7 @@ int vc2_codec_decode_dev(vc2_codec*, int n_pictures);
 void* vc2_codec_samples_dev(vc2_codec*, int slot);       /* raw planar picture bytes: encoder input   */
 void* vc2_codec_recon_dev(vc2_codec*, int slot);         /* raw planar picture bytes: decoder output  */
 uint8_t* vc2_codec_payload_dev(vc2_codec*, int slot);    /* slice payload                                   */
-int32_t* vc2_codec_coeffs_dev(vc2_codec*, int slot, int comp); /* slice-major block: slot base + comp start  */
+int32_t* vc2_codec_coeffs_dev(vc2_codec*, int slot);     /* group-interleaved coefficient block */
 uint32_t* vc2_codec_slice_offsets_dev(vc2_codec*, int slot);   /* n_slices+1                              */
 
 /* host <-> slot transfers (pinned staging inside; asynchronous, ordered on the context stream) */

@@ -72,7 +72,7 @@ def _load():
         "vc2_codec_samples_dev": (vp, [vp, C.c_int]),
         "vc2_codec_recon_dev": (vp, [vp, C.c_int]),
         "vc2_codec_payload_dev": (vp, [vp, C.c_int]),
-        "vc2_codec_coeffs_dev": (vp, [vp, C.c_int, C.c_int]),
+        "vc2_codec_coeffs_dev": (vp, [vp, C.c_int]),
         "vc2_codec_slice_offsets_dev": (vp, [vp, C.c_int]),
         "vc2_codec_upload_picture": (C.c_int, [vp, C.c_int, vp]),
         "vc2_codec_download_picture": (C.c_int, [vp, C.c_int, vp]),

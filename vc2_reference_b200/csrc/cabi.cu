@@ -418,7 +418,6 @@ static void fill_slice_geom(SliceGeom& g, const vc2_geom& vg, const int32_t* qma
   g.prefix = vg.prefix; g.scalar = vg.scalar;
   g.plane[0] = make_plane(vg.luma_h, vg.luma_w, vg.depth);
   g.plane[1] = g.plane[2] = make_plane(vg.chroma_h, vg.chroma_w, vg.depth);
-  g.coef_pic_stride = g.plane[0].size() + 2 * g.plane[1].size();
   int cs = 0;
   for (int c = 0; c < 3; ++c) {
     g.comp_start[c] = cs;
@@ -434,15 +433,17 @@ static void fill_slice_geom(SliceGeom& g, const vc2_geom& vg, const int32_t* qma
     cs += bs;
   }
   g.comp_start[3] = cs;
+  g.coef_pic_stride = (long long)((g.slices_x * g.slices_y + 31) / 32) * 32 * cs;   // whole groups of 32 slices
   for (int b = 0; b < g.nbands; ++b) g.qmatrix[b] = qmatrix ? qmatrix[b] : 0;
 }
 
-// one plane treated as a single component made of a single slice (stand-alone transforms)
+// one plane treated as a single component cut into the smallest slices (one 2^depth x 2^depth cell each),
+// so that the groups of the interleaved layout are full (stand-alone transforms)
 static void fill_plane_geom(SliceGeom& g, int h, int w, int ph, int pw, int depth) {
   memset(&g, 0, sizeof(g));
   g.depth = depth;
   g.nbands = 3 * depth + 1;
-  g.slices_x = g.slices_y = 1;
+  g.slices_x = pw >> depth; g.slices_y = ph >> depth;
   g.scalar = 1;
   g.plane[0].h = h; g.plane[0].w = w; g.plane[0].ph = ph; g.plane[0].pw = pw; g.plane[0].depth = depth;
   g.plane[1] = g.plane[2] = g.plane[0];
@@ -450,16 +451,16 @@ static void fill_plane_geom(SliceGeom& g, int h, int w, int ph, int pw, int dept
   g.plane[2] = g.plane[1];
   int bs = 0;
   for (int b = 0; b < g.nbands; ++b) {
-    const int lev = b == 0 ? depth : depth - ((b - 1) / 3 + 1) + 1;
-    g.part_h[0][b] = ph >> lev;
-    g.part_w[0][b] = pw >> lev;
+    const int side = b == 0 ? 1 : 1 << ((b - 1) / 3);   // level L band part = 2^(L-1) square
+    g.part_h[0][b] = side;
+    g.part_w[0][b] = side;
     g.band_start[0][b] = bs;
-    bs += g.part_h[0][b] * g.part_w[0][b];
+    bs += side * side;
   }
   g.band_start[0][g.nbands] = bs;
   g.comp_start[0] = 0;
   g.comp_start[1] = g.comp_start[2] = g.comp_start[3] = bs;
-  g.coef_pic_stride = bs;
+  g.coef_pic_stride = (long long)((g.slices_x * g.slices_y + 31) / 32) * 32 * bs;
 }
 
 static bool geom_ok(const vc2_geom* g) {
@@ -513,49 +514,43 @@ static int first_error(const uint32_t* flags, int n) {
 struct PackBuffers {
   uint8_t* out; long long out_stride; long long out_capacity;
   uint32_t* slice_off; uint32_t* err_flags; int32_t* qidx;
-  unsigned long long* tile_state; unsigned* ticket;
+  uint32_t* staging; uint32_t* sizes;
   const int32_t* slice_bytes_dev; const uint32_t* fixed_off_dev;
 };
 
+// staging words per slice: every coefficient at the 32-bit VLC limit, plus header bytes and slack
+static int staging_words(const SliceGeom& g) { return (g.prefix + 4 + 4 * g.comp_start[3] + 3) / 4 + 4; }
+
 static cudaError_t run_pack(vc2_ctx* ctx, const SliceGeom& g, const int32_t* coef, int npictures, int mode, int quantise,
-                            int search, int const_q, int emit, const PackBuffers& B, int img_bytes) {
+                            int search, int const_q, int emit, const PackBuffers& B) {
   PackParams p;
   memset(&p, 0, sizeof(p));
   p.g = g;
   p.coef = coef;
   p.mode = mode; p.quantise = quantise; p.search = search; p.const_q = const_q; p.emit = emit;
-  p.qidx = B.qidx; p.slice_bytes = B.slice_bytes_dev; p.fixed_off = B.fixed_off_dev;
-  p.out = B.out; p.out_pic_stride = B.out_stride; p.out_capacity = B.out_capacity;
-  p.slice_off = B.slice_off; p.err_flags = B.err_flags; p.tile_state = B.tile_state; p.ticket = B.ticket;
-  const int nslices = g.slices_x * g.slices_y;
-  int words = 0;
-  for (int c = 0; c < 3; ++c) {
-    const int n = g.band_start[c][g.nbands];
-    p.run_len[c] = (n + 31) / 32;
-    p.run_stride[c] = p.run_len[c] | 1;
-    p.run_base[c] = words;
-    words += 32 * p.run_stride[c];
-  }
-  p.coef_words = words;
-  p.img_words = (img_bytes + 3) / 4 + 4;
-  const size_t per_warp = (size_t)(p.coef_words + p.img_words) * 4;
-  int W = 8;
-  while (W > 1 && per_warp * W > 200 * 1024) W >>= 1;
-  if (per_warp * W > 227 * 1024) return cudaErrorInvalidConfiguration;
-  p.warps_per_cta = W;
-  p.ctas_per_pic = (nslices + W - 1) / W;
-  cudaError_t e = cudaMemsetAsync(B.ticket, 0, sizeof(unsigned) * npictures, ctx->stream);
-  if (e != cudaSuccess) return e;
-  e = cudaMemsetAsync(B.tile_state, 0, sizeof(unsigned long long) * (size_t)p.ctas_per_pic * npictures, ctx->stream);
-  if (e != cudaSuccess) return e;
+  p.qidx = B.qidx; p.slice_bytes = B.slice_bytes_dev;
+  p.staging = B.staging; p.wcap = staging_words(g); p.sizes = B.sizes; p.err_flags = B.err_flags;
+  cudaError_t e;
   {
     ProfScope ps(ctx, VC2_STAGE_PACK);
-    e = pack_launch(ctx->stream, p, npictures, per_warp * W);
+    e = pack_launch(ctx->stream, p, npictures);
   }
-  if (e == cudaSuccess) ctx->launches++;
+  if (e != cudaSuccess) return e;
+  ctx->launches++;
+  if (!emit) return cudaSuccess;
+  AssembleParams a;
+  memset(&a, 0, sizeof(a));
+  a.nslices = g.slices_x * g.slices_y;
+  a.sizes = B.sizes; a.fixed_off = B.fixed_off_dev; a.slice_off = B.slice_off;
+  a.staging = B.staging; a.wcap = p.wcap;
+  a.out = B.out; a.out_pic_stride = B.out_stride; a.out_capacity = B.out_capacity; a.err_flags = B.err_flags;
+  {
+    ProfScope ps(ctx, VC2_STAGE_ASSEMBLE);
+    e = assemble_launch(ctx->stream, a, npictures);
+  }
+  if (e == cudaSuccess) ctx->launches += 2;
   return e;
 }
-static size_t pack_state_words(const SliceGeom& g) { return (size_t)g.slices_x * g.slices_y; }   // >= ctas per picture
 
 // ================================================================================================
 // Library-surface operations (host buffers)
@@ -569,14 +564,14 @@ extern "C" int vc2_dwt_forward(vc2_ctx* ctx, const int32_t* src, int h, int w, i
   B.pg = make_plane(h, w, depth);
   const size_t n_in = (size_t)h * w * 4, n_pad = (size_t)B.pg.size() * 4;
   CU(ctx->tmp[0].reserve(n_in));
-  CU(ctx->tmp[1].reserve(n_pad));
+  SliceGeom g;
+  fill_plane_geom(g, h, w, B.pg.ph, B.pg.pw, depth);
+  CU(ctx->tmp[1].reserve((size_t)g.coef_pic_stride * 4));
   CU(ctx->tmp[2].reserve(n_pad / 4));
   CU(ctx->tmp[3].reserve(n_pad / 16 + 4));
   CU(ctx->tmp[4].reserve(n_pad));
   B.pix = ctx->tmp[0].p; B.pix_pitch = w; B.pix_pic_stride = (long long)h * w;
-  SliceGeom g;
-  fill_plane_geom(g, h, w, B.pg.ph, B.pg.pw, depth);
-  B.coef = ctx->tmp[1].as<int32_t>(); B.coef_pic_stride = B.pg.size(); B.comp = 0;
+  B.coef = ctx->tmp[1].as<int32_t>(); B.coef_pic_stride = g.coef_pic_stride; B.comp = 0;
   B.scratch[0] = ctx->tmp[2].as<int32_t>(); B.scratch[1] = ctx->tmp[3].as<int32_t>();
   CU(cudaMemcpyAsync(B.pix, src, n_in, cudaMemcpyHostToDevice, ctx->stream));
   CU(run_dwt(ctx, false, kernel, depth, SAMPLE_I32, g, &B, 1, 1));
@@ -597,14 +592,14 @@ extern "C" int vc2_dwt_inverse(vc2_ctx* ctx, const int32_t* src, int ph, int pw,
   B.pg.h = h; B.pg.w = w; B.pg.ph = ph; B.pg.pw = pw; B.pg.depth = depth;
   const size_t n_out = (size_t)h * w * 4, n_pad = (size_t)ph * pw * 4;
   CU(ctx->tmp[0].reserve(n_out));
-  CU(ctx->tmp[1].reserve(n_pad));
+  SliceGeom g;
+  fill_plane_geom(g, h, w, ph, pw, depth);
+  CU(ctx->tmp[1].reserve((size_t)g.coef_pic_stride * 4));
   CU(ctx->tmp[2].reserve(n_pad / 4));
   CU(ctx->tmp[3].reserve(n_pad / 16 + 4));
   CU(ctx->tmp[4].reserve(n_pad));
   B.pix = ctx->tmp[0].p; B.pix_pitch = w; B.pix_pic_stride = (long long)h * w;
-  SliceGeom g;
-  fill_plane_geom(g, h, w, ph, pw, depth);
-  B.coef = ctx->tmp[1].as<int32_t>(); B.coef_pic_stride = B.pg.size(); B.comp = 0;
+  B.coef = ctx->tmp[1].as<int32_t>(); B.coef_pic_stride = g.coef_pic_stride; B.comp = 0;
   B.scratch[0] = ctx->tmp[2].as<int32_t>(); B.scratch[1] = ctx->tmp[3].as<int32_t>();
   CU(cudaMemcpyAsync(ctx->tmp[4].p, src, n_pad, cudaMemcpyHostToDevice, ctx->stream));
   CU(layout_launch(ctx->stream, true, ctx->tmp[4].as<int32_t>(), B.coef, g, 0));
@@ -642,8 +637,8 @@ static int quant_host(vc2_ctx* ctx, const int32_t* coef, int ph, int pw, int dep
   if (ld) {
     LdDcParams d;
     memset(&d, 0, sizeof(d));
-    d.base = p.dst; d.qidx = p.qidx; d.H = ph >> depth; d.W = pw >> depth; d.bh = d.H; d.bw = d.W;
-    d.A = 0; d.B = (long long)pw << depth; d.C = 0; d.D = 1ll << depth;
+    d.base = p.dst; d.qidx = p.qidx; d.H = ph >> depth; d.W = pw >> depth;
+    d.interleaved = 0; d.pitch = pw; d.depth = depth;
     d.slices_y = ny; d.slices_x = nx; d.qm0 = qmatrix[0];
     CU(ld_dc_launch(ctx->stream, d));
     ctx->launches++;
@@ -713,23 +708,24 @@ static int pack_host(vc2_ctx* ctx, const int32_t* Y, const int32_t* U, const int
   } else {
     total_cap = (size_t)img_bytes * nslices;
   }
-  // layout of tmp[2]: payload | slice_off | err | qidx | slice_bytes | fixed | ticket | tile_state
+  // layout of tmp[2]: payload | slice_off | err | sizes | qidx | slice_bytes | fixed ; tmp[3]: staging
   const size_t o_pay = 0, o_off = (total_cap + 259) / 256 * 256, o_err = o_off + (size_t)(nslices + 1) * 4,
-               o_q = o_err + (size_t)nslices * 4, o_sb = o_q + (size_t)nslices * 4, o_fx = o_sb + (size_t)nslices * 4,
-               o_tk = o_fx + (size_t)(nslices + 1) * 4, o_ts = (o_tk + 4 + 7) / 8 * 8, o_end = o_ts + pack_state_words(g) * 8;
+               o_sz = o_err + (size_t)nslices * 4, o_q = o_sz + (size_t)nslices * 4, o_sb = o_q + (size_t)nslices * 4,
+               o_fx = o_sb + (size_t)nslices * 4, o_end = o_fx + (size_t)(nslices + 1) * 4;
   CU(ctx->tmp[2].reserve(o_end));
+  CU(ctx->tmp[3].reserve((size_t)staging_words(g) * 4 * nslices));
   uint8_t* base = ctx->tmp[2].as<uint8_t>();
   PackBuffers B;
   B.out = base + o_pay; B.out_stride = 0; B.out_capacity = (long long)total_cap;
   B.slice_off = (uint32_t*)(base + o_off); B.err_flags = (uint32_t*)(base + o_err); B.qidx = (int32_t*)(base + o_q);
+  B.sizes = (uint32_t*)(base + o_sz); B.staging = ctx->tmp[3].as<uint32_t>();
   B.slice_bytes_dev = slice_bytes ? (const int32_t*)(base + o_sb) : nullptr;
   B.fixed_off_dev = mode == VC2_HQ_CBR ? (const uint32_t*)(base + o_fx) : nullptr;
-  B.ticket = (unsigned*)(base + o_tk); B.tile_state = (unsigned long long*)(base + o_ts);
   CU(cudaMemsetAsync(base + o_off, 0, o_q - o_off, ctx->stream));
   if (qidx_in) CU(cudaMemcpyAsync(B.qidx, qidx_in, (size_t)nslices * 4, cudaMemcpyHostToDevice, ctx->stream));
   if (slice_bytes) CU(cudaMemcpyAsync(base + o_sb, slice_bytes, (size_t)nslices * 4, cudaMemcpyHostToDevice, ctx->stream));
   if (mode == VC2_HQ_CBR) CU(cudaMemcpyAsync(base + o_fx, fixed.data(), (size_t)(nslices + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
-  CU(run_pack(ctx, g, ctx->tmp[1].as<int32_t>(), 1, mode, search ? 1 : 0, search, -1, emit, B, img_bytes));
+  CU(run_pack(ctx, g, ctx->tmp[1].as<int32_t>(), 1, mode, search ? 1 : 0, search, -1, emit, B));
   std::vector<uint32_t> flags(nslices), offs(nslices + 1);
   CU(cudaMemcpyAsync(flags.data(), B.err_flags, (size_t)nslices * 4, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaMemcpyAsync(offs.data(), B.slice_off, (size_t)(nslices + 1) * 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -825,11 +821,10 @@ struct vc2_codec {
   size_t pic_bytes = 0;          // raw planar bytes per picture
   size_t comp_bytes[3] = {0, 0, 0};
   size_t payload_cap = 0;        // per picture
-  int img_bytes = 0;
   std::vector<int32_t> slice_bytes;   // CBR / LD
   std::vector<uint32_t> fixed_off;
   // device buffers
-  DevBuf samples, recon, coef, scratch0, scratch1, payload, slice_off, err, qidx, state, ticket, sbytes, fixed, tmp_plane, tmp_q;
+  DevBuf samples, recon, coef, scratch0, scratch1, payload, slice_off, err, qidx, staging, sizes, sbytes, fixed, tmp_plane, tmp_q;
   long long scratch_stride[2] = {0, 0};
   long long scratch_off[2][3];
   std::vector<size_t> payload_len;    // host copy per slot (decode)
@@ -843,7 +838,7 @@ static void codec_free(vc2_codec* k) {
   cudaSetDevice(k->ctx->device);
   cudaStreamSynchronize(k->ctx->stream);
   DevBuf* all[] = {&k->samples, &k->recon, &k->coef, &k->scratch0, &k->scratch1, &k->payload, &k->slice_off, &k->err,
-                   &k->qidx, &k->state, &k->ticket, &k->sbytes, &k->fixed, &k->tmp_plane, &k->tmp_q};
+                   &k->qidx, &k->staging, &k->sizes, &k->sbytes, &k->fixed, &k->tmp_plane, &k->tmp_q};
   for (DevBuf* b : all) b->release();
   if (k->host_offs) cudaFreeHost(k->host_offs);
   if (k->copy_in) cudaStreamDestroy(k->copy_in);
@@ -882,8 +877,7 @@ extern "C" vc2_codec* vc2_codec_create(vc2_ctx* ctx, const vc2_codec_params* prm
       k->fixed_off[i + 1] = k->fixed_off[i] + (uint32_t)(k->slice_bytes[i] + (prm->mode == VC2_LD ? 0 : g.prefix));
     }
   }
-  k->img_bytes = max_slice_bytes(g, prm->mode, k->slice_bytes.empty() ? nullptr : k->slice_bytes.data());
-  if (prm->mode == VC2_HQ_VBR) k->payload_cap = (size_t)k->img_bytes * k->nslices;
+  if (prm->mode == VC2_HQ_VBR) k->payload_cap = (size_t)max_slice_bytes(g, prm->mode, nullptr) * k->nslices;
   else k->payload_cap = k->fixed_off[k->nslices];
   k->payload_cap = (k->payload_cap + 255) / 256 * 256 + 256;
 
@@ -905,8 +899,8 @@ extern "C" vc2_codec* vc2_codec_create(vc2_ctx* ctx, const vc2_codec_params* prm
   R(k->slice_off, (size_t)(k->nslices + 1) * 4 * B);
   R(k->err, (size_t)k->nslices * 4 * B);
   R(k->qidx, (size_t)k->nslices * 4 * B);
-  R(k->state, pack_state_words(g) * 8 * B);
-  R(k->ticket, (size_t)4 * B);
+  if (prm->mode != VC2_LD) R(k->staging, (size_t)staging_words(g) * 4 * k->nslices * B);
+  R(k->sizes, (size_t)k->nslices * 4 * B);
   R(k->sbytes, (size_t)k->nslices * 4);
   R(k->fixed, (size_t)(k->nslices + 1) * 4);
   R(k->tmp_plane, (size_t)g.plane[0].size() * 4);
@@ -966,15 +960,13 @@ static int codec_encode_range(vc2_codec* k, int first, int n) {
   B.slice_off = k->slice_off.as<uint32_t>() + (size_t)first * (k->nslices + 1);
   B.err_flags = k->err.as<uint32_t>() + (size_t)first * k->nslices;
   B.qidx = k->qidx.as<int32_t>() + (size_t)first * k->nslices;
-  B.tile_state = k->state.as<unsigned long long>() + (size_t)first * pack_state_words(k->g);
-  B.ticket = k->ticket.as<unsigned>() + first;
+  B.staging = k->staging.as<uint32_t>() + (size_t)first * k->nslices * staging_words(k->g);
+  B.sizes = k->sizes.as<uint32_t>() + (size_t)first * k->nslices;
   const bool cbr = k->prm.mode == VC2_HQ_CBR;
   B.slice_bytes_dev = cbr ? k->sbytes.as<int32_t>() : nullptr;
   B.fixed_off_dev = cbr ? k->fixed.as<uint32_t>() : nullptr;
   const int32_t* coef = k->coef.as<int32_t>() + (long long)first * k->g.coef_pic_stride;
-  // run_pack derives ctas_per_pic from the geometry; tile_state is strided by it inside the kernel,
-  // so hand it a base that is dense in ctas_per_pic (it is: we sized it with nslices per picture)
-  CU(run_pack(ctx, k->g, coef, n, k->prm.mode, 1, cbr ? 1 : 0, cbr ? -1 : k->prm.qindex, 1, B, k->img_bytes));
+  CU(run_pack(ctx, k->g, coef, n, k->prm.mode, 1, cbr ? 1 : 0, cbr ? -1 : k->prm.qindex, 1, B));
   return VC2_OK;
 }
 
@@ -1014,11 +1006,11 @@ static int codec_decode_range(vc2_codec* k, int first, int n) {
       for (int c = 0; c < 3; ++c) {
         LdDcParams d;
         memset(&d, 0, sizeof(d));
-        d.base = p.coef + (long long)i * g.coef_pic_stride + g.comp_start[c];   // band 0 starts each component
+        d.base = p.coef + (long long)i * g.coef_pic_stride;
         d.qidx = p.qidx + (size_t)i * k->nslices;
         d.H = g.plane[c].ph >> g.depth; d.W = g.plane[c].pw >> g.depth;
-        d.bh = g.part_h[c][0]; d.bw = g.part_w[c][0];
-        d.A = (long long)g.slices_x * g.comp_start[3]; d.B = d.bw; d.C = g.comp_start[3]; d.D = 1;
+        d.interleaved = 1; d.bh = g.part_h[c][0]; d.bw = g.part_w[c][0];
+        d.k0 = g.comp_start[c]; d.nc4 = g.comp_start[3] >> 2;   // band 0 starts each component
         d.slices_y = g.slices_y; d.slices_x = g.slices_x; d.qm0 = g.qmatrix[0];
         ProfScope ps(ctx, VC2_STAGE_LD_DC);
         CU(ld_dc_launch(ctx->stream, d));
@@ -1047,9 +1039,9 @@ extern "C" void* vc2_codec_recon_dev(vc2_codec* k, int slot) {
 extern "C" uint8_t* vc2_codec_payload_dev(vc2_codec* k, int slot) {
   return (k && slot >= 0 && slot < k->prm.max_pictures) ? k->payload.as<uint8_t>() + (size_t)slot * k->payload_cap : nullptr;
 }
-extern "C" int32_t* vc2_codec_coeffs_dev(vc2_codec* k, int slot, int comp) {
-  if (!k || slot < 0 || slot >= k->prm.max_pictures || comp < 0 || comp > 2) return nullptr;
-  return k->coef.as<int32_t>() + (long long)slot * k->g.coef_pic_stride + k->g.comp_start[comp];
+extern "C" int32_t* vc2_codec_coeffs_dev(vc2_codec* k, int slot) {
+  if (!k || slot < 0 || slot >= k->prm.max_pictures) return nullptr;
+  return k->coef.as<int32_t>() + (long long)slot * k->g.coef_pic_stride;
 }
 extern "C" uint32_t* vc2_codec_slice_offsets_dev(vc2_codec* k, int slot) {
   return (k && slot >= 0 && slot < k->prm.max_pictures) ? k->slice_off.as<uint32_t>() + (size_t)slot * (k->nslices + 1) : nullptr;
@@ -1134,7 +1126,7 @@ extern "C" int vc2_codec_read_transform(vc2_codec* k, int slot, int32_t* y, int3
   int32_t* dst[3] = {y, u, v};
   for (int c = 0; c < 3; ++c) {
     if (!dst[c]) continue;
-    CU(layout_launch(ctx->stream, false, vc2_codec_coeffs_dev(k, slot, 0), k->tmp_plane.as<int32_t>(), k->g, c));
+    CU(layout_launch(ctx->stream, false, vc2_codec_coeffs_dev(k, slot), k->tmp_plane.as<int32_t>(), k->g, c));
     ctx->launches++;
     CU(cudaMemcpyAsync(dst[c], k->tmp_plane.p, (size_t)k->g.plane[c].size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
@@ -1150,7 +1142,7 @@ extern "C" int vc2_codec_read_quantised(vc2_codec* k, int slot, int32_t* y, int3
   for (int c = 0; c < 3; ++c) {
     if (!dst[c]) continue;
     const PlaneGeom& pg = k->g.plane[c];
-    CU(layout_launch(ctx->stream, false, vc2_codec_coeffs_dev(k, slot, 0), k->tmp_plane.as<int32_t>(), k->g, c));
+    CU(layout_launch(ctx->stream, false, vc2_codec_coeffs_dev(k, slot), k->tmp_plane.as<int32_t>(), k->g, c));
     QuantParams p;
     memset(&p, 0, sizeof(p));
     p.src = k->tmp_plane.as<int32_t>(); p.dst = k->tmp_q.as<int32_t>();

@@ -115,15 +115,16 @@ __device__ __forceinline__ void extend_rows(int* E, int* O, int q, int rlo, int 
   for (int r = last + 2 + 2 * half; r < RH; r += 4) X[r * RP] = X[last * RP];
 }
 
-struct BandAddr {   // slice-major addressing of one lattice column / row (see vc2_common.cuh)
-  int bh, bw, lgbh, lgbw, nx, NC;
-  __device__ __forceinline__ int col(int bx) const {   // part that depends on the band column
-    const int sx = lgbw >= 0 ? (bx >> lgbw) : (bx / bw);
-    return sx * NC + (bx - sx * bw);
+struct BandAddr {   // group-interleaved addressing of one band sample (see vc2_common.cuh)
+  int bh, bw, lgbh, lgbw, nx, nc4;
+  int sx, xin;       // slice column and column inside the slice's part of the band: fixed per thread
+  __device__ __forceinline__ void set_col(int bx) {
+    sx = lgbw >= 0 ? (bx >> lgbw) : (bx / bw);
+    xin = bx - sx * bw;
   }
-  __device__ __forceinline__ int row(int by) const {   // part that depends on the band row
+  __device__ __forceinline__ long long at(int base, int by) const {
     const int sy = lgbh >= 0 ? (by >> lgbh) : (by / bh);
-    return sy * nx * NC + (by - sy * bh) * bw;
+    return coef_index(sy * nx + sx, base + (by - sy * bh) * bw + xin, nc4);
   }
 };
 
@@ -154,8 +155,8 @@ __device__ __forceinline__ void fwd_vstep(int* E, int* O, const DwtComp& C, int 
   if (j >= T::HX / 2 && j < T::HX / 2 + T::TWU / 2 && j <= phi) {
     int* X = (isO ? O : E) + j;
     const int bx = (xs >> 1) + j;
-    const BandAddr ba = {C.bh, C.bw, C.lgbh, C.lgbw, C.nx, C.NC};
-    const int coff = ba.col(bx);
+    BandAddr ba = {C.bh, C.bw, C.lgbh, C.lgbw, C.nx, C.NC >> 2, 0, 0};
+    ba.set_col(bx);
     int32_t* coef = C.coef + (long long)pic * C.coef_pic_stride;
     int t0 = tlo + ((tlo & 1) != P ? 1 : 0);
     for (int r = t0 + 2 * half; r <= thi; r += 4) {
@@ -167,7 +168,7 @@ __device__ __forceinline__ void fwd_vstep(int* E, int* O, const DwtComp& C, int 
           C.ll[(long long)pic * C.ll_pic_stride + (long long)by * C.ll_pitch + bx] = v;
         } else {
           const int base = P ? (isO ? C.base_hh : C.base_lh) : (isO ? C.base_hl : C.base_ll);
-          coef[base + ba.row(by) + coff] = v;
+          coef[ba.at(base, by)] = v;
         }
       }
     }
@@ -297,8 +298,8 @@ __global__ void __launch_bounds__(NT) dwt_inv_kernel(const DwtParams p) {
     if (j >= plo && j <= phi) {
       int* X = (isO ? O : E) + j;
       const int bx = (xs >> 1) + j;
-      const BandAddr ba = {C.bh, C.bw, C.lgbh, C.lgbw, C.nx, C.NC};
-      const int coff = ba.col(bx);
+      BandAddr ba = {C.bh, C.bw, C.lgbh, C.lgbw, C.nx, C.NC >> 2, 0, 0};
+      ba.set_col(bx);
       const int32_t* coef = C.coef + (long long)pic * C.coef_pic_stride;
       for (int r = rlo + half; r <= rhi; r += 2) {
         const int gy = ys + r, by = gy >> 1;
@@ -306,7 +307,7 @@ __global__ void __launch_bounds__(NT) dwt_inv_kernel(const DwtParams p) {
         if (!(gy & 1) && !isO && C.ll) v = C.ll[(long long)pic * C.ll_pic_stride + (long long)by * C.ll_pitch + bx];
         else {
           const int base = (gy & 1) ? (isO ? C.base_hh : C.base_lh) : (isO ? C.base_hl : C.base_ll);
-          v = coef[base + ba.row(by) + coff];
+          v = coef[ba.at(base, by)];
         }
         X[r * RP] = v;
       }
@@ -386,7 +387,7 @@ __device__ __forceinline__ long long slice_major_index(const SliceGeom& g, int c
   }
   const int bh = g.part_h[c][b], bw = g.part_w[c][b];
   const int sy = by / bh, sx = bx / bw;
-  return (long long)(sy * g.slices_x + sx) * g.comp_start[3] + g.comp_start[c] + g.band_start[c][b] + (by - sy * bh) * bw + (bx - sx * bw);
+  return coef_index(sy * g.slices_x + sx, g.comp_start[c] + g.band_start[c][b] + (by - sy * bh) * bw + (bx - sx * bw), g.comp_start[3] >> 2);
 }
 
 __global__ void layout_kernel(const int32_t* __restrict__ src, int32_t* __restrict__ dst, const SliceGeom g, int c, bool to_slice_major) {

@@ -13,7 +13,7 @@ namespace vc2 {
 
 struct SliceGeom {
   PlaneGeom plane[3];        // Y, C1, C2 padded plane geometry
-  long long coef_pic_stride; // elements between pictures = slices * comp_start[3]
+  long long coef_pic_stride; // elements between pictures = 32 * ceil(slices / 32) * comp_start[3]
   int depth, nbands;
   int slices_x, slices_y;
   int prefix, scalar;
@@ -27,7 +27,7 @@ struct SliceGeom {
 
 struct PackParams {
   SliceGeom g;
-  const int32_t* coef;          // slice-major coefficients [pic]
+  const int32_t* coef;          // group-interleaved coefficients [pic]
   int mode;                     // VC2_HQ_VBR / VC2_HQ_CBR
   int quantise;                 // 1: coefficients are unquantised, apply quant(); 0: already quantised
   int search;                   // 1: run quantIndicesCBR per slice and use (and store) its result
@@ -35,21 +35,23 @@ struct PackParams {
   int emit;                     // 0: rate control only (vc2_cbr_qindices)
   int32_t* qidx;                // [pic][slices] in (search == 0 && const_q < 0) or out
   const int32_t* slice_bytes;   // [slices] per-slice byte budget (CBR), same for every picture
-  const uint32_t* fixed_off;    // [slices + 1] slice offsets when they are known a priori (CBR) else NULL
+  uint32_t* staging;            // [pic][slices][wcap] slice images as MSB-first 32-bit words
+  int wcap;                     // staging words per slice (worst case: every code 32 bits)
+  uint32_t* sizes;              // [pic][slices] out: bytes of each coded slice
+  uint32_t* err_flags;          // [pic][slices] out (VC2_FLAG_*)
+};
+
+struct AssembleParams {         // exclusive scan of the slice sizes and the gather into the payload
+  int nslices;
+  const uint32_t* sizes;        // [pic][slices]
+  const uint32_t* fixed_off;    // [slices + 1] slice offsets known a priori (CBR) or NULL (scan the sizes)
+  uint32_t* slice_off;          // [pic][slices + 1] out
+  const uint32_t* staging;      // [pic][slices][wcap]
+  int wcap;
   uint8_t* out;                 // payload [pic]
   long long out_pic_stride;
   long long out_capacity;       // bytes available per picture
-  uint32_t* slice_off;          // [pic][slices + 1] out
-  uint32_t* err_flags;          // [pic][slices] out (VC2_FLAG_*)
-  unsigned long long* tile_state;  // [pic][ctas] decoupled look-back state, zeroed before launch
-  unsigned* ticket;             // [pic] zeroed before launch
-  int ctas_per_pic;
-  int warps_per_cta;
-  int img_words;                // shared-memory slice image capacity per warp (32-bit words)
-  int coef_words;               // shared-memory coefficient words per warp (run-major, padded)
-  int run_len[3];               // coefficients per lane run = ceil(n / 32), per component
-  int run_stride[3];            // run_len | 1 : odd stride keeps the 32 runs on distinct banks
-  int run_base[3];              // start of each component's runs inside the per-warp coefficient area
+  uint32_t* err_flags;          // [pic][slices]: VC2_FLAG_STREAM when the payload does not fit
 };
 
 struct UnpackParams {
@@ -58,7 +60,7 @@ struct UnpackParams {
   long long in_pic_stride;
   const uint32_t* slice_off;    // [pic][slices + 1]
   long long slice_off_pic_stride;  // 0 when every picture shares one table (CBR / LD)
-  int32_t* coef;                // slice-major coefficients out [pic]
+  int32_t* coef;                // group-interleaved coefficients out [pic]
   int32_t* qidx;                // [pic][slices] out
   uint32_t* err_flags;          // [pic][slices]
   int dequantise;               // 1: store scale(v, q'); 0: store the quantised value
@@ -77,17 +79,21 @@ struct QuantParams {            // stand-alone quantise / dequantise on IN-PLACE
 };
 
 struct LdDcParams {             // LD LL-band reconstruction with DC prediction (Quantisation.cpp:287-306)
-  int32_t* base;                // LL sample (y, x) lives at base + (y/bh)*A + (y%bh)*B + (x/bw)*C + (x%bw)*D
-  const int32_t* qidx;          //   in-place plane: bh = H, bw = W, B = pw << depth, D = 1 << depth
-  int H, W;                     //   slice-major   : bh, bw = LL part of a slice, A = nx*NC, B = bw, C = NC, D = 1
-  int bh, bw;
-  long long A, B, C, D;
+  int32_t* base;                // in-place plane (interleaved == 0) or one picture's group-interleaved block
+  const int32_t* qidx;
+  int H, W;                     // LL band dims of the whole picture
+  int interleaved;              // 0: LL sample (y, x) at base[(y * pitch + x) << depth]; 1: coef_index(slice, k0 + ...)
+  long long pitch;              // in-place: padded plane width
+  int depth;
+  int bh, bw;                   // interleaved: LL part of one slice
+  int k0, nc4;                  // interleaved: comp_start of the component, NC / 4
   int slices_y, slices_x;
   int qm0;
 };
 
 cudaError_t upload_quant_tables(const QuantTables& t);
-cudaError_t pack_launch(cudaStream_t s, const PackParams& p, int npictures, size_t smem_bytes);
+cudaError_t pack_launch(cudaStream_t s, const PackParams& p, int npictures);
+cudaError_t assemble_launch(cudaStream_t s, const AssembleParams& p, int npictures);
 cudaError_t unpack_launch(cudaStream_t s, const UnpackParams& p, int npictures);
 cudaError_t layout_launch(cudaStream_t s, bool to_slice_major, const int32_t* src, int32_t* dst, const SliceGeom& g, int c);
 cudaError_t quant_launch(cudaStream_t s, const QuantParams& p);

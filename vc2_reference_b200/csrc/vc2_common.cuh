@@ -10,20 +10,31 @@
 namespace vc2 {
 
 // ---------------------------------------------------------------------------------------------
-// SLICE-MAJOR coefficient layout used INSIDE the device pipeline.
+// GROUP-INTERLEAVED SLICE LAYOUT used INSIDE the device pipeline.
 //
-// One picture's coefficients (all three padded component planes) are stored slice by slice, in
-// raster slice order; inside a slice: Y, C1, C2; inside a component: subbands in coding order
-// (band 0 = LL, then VC-2 level L = 1..depth: HL, LH, HH = bands 3(L-1)+1..3), each subband's
-// part of the slice in raster order - i.e. exactly the order in which the reference codes a
-// slice (split_into_subbands, WaveletTransform.cpp:428-450; HQSliceIO, Slices.cpp:488-530):
+// One picture's coefficients (all three padded component planes) are stored slice by slice.  The
+// coefficients of ONE slice form a list of NC values in the reference's coding order: Y, C1, C2;
+// inside a component the subbands in coding order (band 0 = LL, then VC-2 level L = 1..depth:
+// HL, LH, HH = bands 3(L-1)+1..3), each subband's part of the slice in raster order
+// (split_into_subbands, WaveletTransform.cpp:428-450; HQSliceIO, Slices.cpp:488-530):
 //
-//   index(s, c, b, y, x) = s * NC + comp_start[c] + band_start[c][b] + y * part_w[c][b] + x
+//   k(c, b, y, x) = comp_start[c] + band_start[c][b] + y * part_w[c][b] + x          0 <= k < NC
 //
-// so the slice coder streams one contiguous block per slice, a DWT level stores/loads band rows as
-// runs of part_w contiguous words, and nothing is ever gathered.  The reference's in-place
-// interleaved Array2D order exists only at the Library boundary (layout kernels in dwt.cu).
+// Slices are taken in raster order, s = sy * slices_x + sx, and 32 consecutive slices form a GROUP.
+// Inside a group the 32 coefficient lists are interleaved in pieces of four coefficients (16 bytes):
+//
+//   index(s, k) = (((s / 32) * (NC / 4) + k / 4) * 32 + s % 32) * 4 + k % 4
+//
+// The slice coders run ONE THREAD PER SLICE, a warp = one group: lane r streams through list r, and
+// every 128-bit access of the warp is one contiguous 512-byte run.  The DWT kernels address the same
+// layout: four consecutive coefficients of a band row are one aligned 16-byte piece whenever
+// part_w % 4 == 0.  The reference's in-place interleaved Array2D order exists only at the Library
+// boundary (layout kernels in dwt.cu).
 // ---------------------------------------------------------------------------------------------
+__host__ __device__ inline long long coef_index(int s, int k, int nc4) {
+  return ((((long long)(s >> 5) * nc4 + (k >> 2)) * 32 + (s & 31)) << 2) + (k & 3);
+}
+
 struct PlaneGeom {
   int h, w;    // unpadded picture plane
   int ph, pw;  // padded
