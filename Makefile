@@ -8,7 +8,7 @@ NVFLAGS   := -O3 -std=c++17 -lineinfo $(ARCH) -Xcompiler -fPIC
 PKG       := vc2_reference_b200
 CSRC      := $(PKG)/csrc
 LIB       := $(PKG)/libvc2b200.so
-OBJS      := $(CSRC)/dwt.o $(CSRC)/slices.o $(CSRC)/cabi.o
+OBJS      := $(CSRC)/dwt_fwd.o $(CSRC)/dwt_inv.o $(CSRC)/slices.o $(CSRC)/cabi.o
 
 ORACLE    := oracle/_build/libvc2oracle.so
 
@@ -20,6 +20,12 @@ $(ORACLE): oracle/vc2_oracle.c
 
 $(CSRC)/%.o: $(CSRC)/%.cu $(CSRC)/*.cuh include/vc2_cabi.h
 	$(NVCC) $(NVFLAGS) -c $< -o $@
+
+# the lifting kernels are one source compiled twice (forward / inverse) so that the two halves build in parallel
+$(CSRC)/dwt_fwd.o: $(CSRC)/dwt.cu $(CSRC)/*.cuh include/vc2_cabi.h
+	$(NVCC) $(NVFLAGS) -DVC2_DWT_PART=1 -c $< -o $@
+$(CSRC)/dwt_inv.o: $(CSRC)/dwt.cu $(CSRC)/*.cuh include/vc2_cabi.h
+	$(NVCC) $(NVFLAGS) -DVC2_DWT_PART=2 -c $< -o $@
 
 $(LIB): $(OBJS)
 	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -lcudart

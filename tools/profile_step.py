@@ -28,7 +28,12 @@ def main():
     codec = vc2.Codec(ctx, g, c["mode"], qindex=c["q"], picture_bytes=c["s"], luma_depth=c["bits"], max_pictures=B)
     for i in range(B):
         codec.upload_picture(i, gen.frame_bytes(1234, i, c["w"], c["h"], c["fmt"], c["bits"]))
+    for _ in range(2):      # warm-up: lazy module loading, first-touch
+        codec.encode(B)
+        codec.decode(B)
+    ctx.synchronize()
     ctx.profile_enable(True)
+    ctx.profile_read()
     for _ in range(steps):
         codec.encode(B)
         codec.decode(B)

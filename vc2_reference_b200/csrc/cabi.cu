@@ -3,6 +3,7 @@
 // dwt.cu / slices.cu; there is deliberately no CPU path for any of it.
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -14,7 +15,8 @@
 #include "slices.cuh"
 
 namespace vc2 {
-cudaError_t dwt_level_launch(cudaStream_t s, bool inverse, int kernel, int sample_kind, const DwtParams& p, int npictures);
+cudaError_t dwt_fwd_launch(cudaStream_t s, int kernel, int sample_kind, const DwtParams& p, int npictures, int seg_rows);
+cudaError_t dwt_inv_launch(cudaStream_t s, int kernel, int sample_kind, const DwtParams& p, int npictures, int seg_rows);
 }  // namespace vc2
 
 using namespace vc2;
@@ -213,6 +215,8 @@ struct vc2_ctx {
   std::string err;
   long launches = 0;
   DevBuf tmp[8];   // scratch for the Library-surface (host pointer) calls
+  int dwt_min_warps = 148 * 48;   // streaming DWT: cut rows into segments until the grid has at least this many warps
+  int dwt_seg_rows = 0;           // > 0: forced rows per warp (tuning, VC2_DWT_SEG_ROWS)
   // optional per-kernel timing with CUDA events on the launch stream (vc2_profile_*)
   bool profiling = false;
   struct Span { int stage; cudaEvent_t a, b; };
@@ -270,6 +274,8 @@ extern "C" vc2_ctx* vc2_create(int device) {
   vc2_ctx* c = new (std::nothrow) vc2_ctx();
   if (!c) return nullptr;
   c->device = device;
+  if (const char* e = getenv("VC2_DWT_SEG_ROWS")) c->dwt_seg_rows = atoi(e) & ~1;
+  if (const char* e = getenv("VC2_DWT_MIN_WARPS")) c->dwt_min_warps = atoi(e);
   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return nullptr; }
   c->own_stream = true;
   QuantTables t;
@@ -403,7 +409,15 @@ static cudaError_t run_dwt(vc2_ctx* ctx, bool inverse, int kernel, int depth, in
       C.sshift = B.sshift; C.soffset = B.soffset; C.clip_min = B.clip_min; C.clip_max = B.clip_max;
     }
     ProfScope ps(ctx, inverse ? (l == 0 ? VC2_STAGE_IDWT_L0 : VC2_STAGE_IDWT_DEEP) : (l == 0 ? VC2_STAGE_DWT_L0 : VC2_STAGE_DWT_DEEP));
-    cudaError_t e = dwt_level_launch(ctx->stream, inverse, kernel, l == 0 ? sample_kind : SAMPLE_I32, p, npictures);
+    // rows per warp: long segments amortise the warm-up rows of the streaming kernels, short ones fill the GPU
+    long long cols = 0;
+    int maxh = 0;
+    for (int c = 0; c < ncomp; ++c) { cols += p.c[c].lat_w; maxh = std::max(maxh, p.c[c].lat_h); }
+    int seg_rows = 256;
+    while (seg_rows > 32 && (cols / 240 + ncomp) * ((maxh + seg_rows - 1) / seg_rows) * npictures < ctx->dwt_min_warps) seg_rows >>= 1;
+    if (ctx->dwt_seg_rows > 0) seg_rows = ctx->dwt_seg_rows;
+    cudaError_t e = inverse ? dwt_inv_launch(ctx->stream, kernel, l == 0 ? sample_kind : SAMPLE_I32, p, npictures, seg_rows)
+                            : dwt_fwd_launch(ctx->stream, kernel, l == 0 ? sample_kind : SAMPLE_I32, p, npictures, seg_rows);
     if (e != cudaSuccess) return e;
     ctx->launches++;
   }

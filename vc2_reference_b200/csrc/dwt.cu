@@ -1,377 +1,638 @@
-// Forward / inverse lifting level kernels and the in-place <-> slice-major layout kernels.
-// See dwt.cuh for the reference line citations and the tiling scheme.
+// Forward / inverse lifting level kernels (streaming, register resident) and the in-place <->
+// group-interleaved layout kernels.  See dwt.cuh for the reference line citations.
+//
+// One WARP owns a vertical strip of 32*V lattice columns (lane = V consecutive columns, V/2 sample
+// pairs) and walks down a segment of rows two at a time.  Nothing is staged in shared memory:
+//   * horizontal lifting of a row runs in registers, neighbouring pairs come from the adjacent
+//     lanes by warp shuffle;
+//   * vertical lifting keeps, per lane and column, two small rings of rows in registers (rows of
+//     the parity that feeds the first step, and rows of the other parity) and applies step i to
+//     the row that lags the newest loaded row by lag(i) - the earliest moment at which all of its
+//     taps have completed step i-1 AND nobody needs its own previous value any more.  Ring rows are
+//     indexed by age (compile-time registers) and age by one slot per row pair.
+// The reference's edge rule (a tap outside the array uses the nearest sample of the same parity)
+// is reproduced by an "edge" variant of each step taken only for rows near the top/bottom (the tap
+// is redirected to the first row of that parity, or to a register copy of the last one), and by
+// extending the source-parity sequence past the left/right border before each horizontal step.
 #include "dwt.cuh"
 #include "slices.cuh"
+
+#ifndef VC2_DWT_PART
+#error "compile with -DVC2_DWT_PART=1 (forward) or =2 (inverse + layout)"
+#endif
 
 namespace vc2 {
 
 namespace {
 
 constexpr unsigned FULL = 0xFFFFFFFFu;
-constexpr int TH = 64;      // useful tile rows (lattice samples)
-constexpr int RW = 128;     // region columns: one warp row segment, 4 samples per lane
-constexpr int RP = RW / 2;  // pairs per region row = shared-memory row pitch of E and O
-constexpr int NT = 256;     // threads per CTA (8 warps)
+constexpr int WARPS = 4;   // warps per CTA: four vertically adjacent row segments of one strip
 
-template <int K>
-struct Tile {
-  static constexpr int R = Wavelet<K>::R, HX = Wavelet<K>::HX;
-  static constexpr int RH = TH + 2 * R;
-  static constexpr int TWU = RW - 2 * HX;   // useful columns per tile
-  static constexpr int BYTES = 2 * RH * RP * (int)sizeof(int);
+// ---- compile-time schedule of the vertical pipeline ------------------------------------------------
+__host__ __device__ constexpr int cmax(int a, int b) { return a > b ? a : b; }
+__host__ __device__ constexpr int cgcd(int a, int b) { return b == 0 ? a : cgcd(b, a % b); }
+__host__ __device__ constexpr int pmod(int a, int m) { return ((a % m) + m) % m; }
+
+template <int K, int DIR>
+struct Sched {
+  static constexpr int n = Wavelet<K>::NSTEPS;
+  // i-th step executed: forward = declared order, inverse = reversed
+  __host__ __device__ static constexpr int sidx(int i) { return DIR > 0 ? i : n - 1 - i; }
+  __host__ __device__ static constexpr int par(int i) {
+    return sidx(i) == 0 ? Step<K, 0>::P : sidx(i) == 1 ? Step<K, 1>::P : sidx(i) == 2 ? Step<K, (n > 2 ? 2 : 0)>::P : Step<K, (n > 3 ? 3 : 0)>::P;
+  }
+  __host__ __device__ static constexpr int taps(int i) {
+    return sidx(i) == 0 ? Step<K, 0>::N : sidx(i) == 1 ? Step<K, 1>::N : sidx(i) == 2 ? Step<K, (n > 2 ? 2 : 0)>::N : Step<K, (n > 3 ? 3 : 0)>::N;
+  }
+  __host__ __device__ static constexpr int reach(int i) { return 2 * taps(i) - 1; }
+  static constexpr int PB = par(0);        // parity of the rows the first step updates ("B rows")
+  static constexpr int PA = 1 - PB;        // parity of the rows the first step reads ("A rows")
+  // step i targets row a - lag(i), a = newest A row
+  __host__ __device__ static constexpr int lag(int i) { return i == 0 ? reach(0) : lag(i - 1) + cmax(reach(i), reach(i - 1)); }
+  __host__ __device__ static constexpr int total_reach() { return reach(0) + reach(1) + (n > 2 ? reach(n > 2 ? 2 : 0) : 0) + (n > 3 ? reach(n > 3 ? 3 : 0) : 0); }
+  static constexpr bool last_targets_A = ((n - 1) % 2) == 1;
+  static constexpr int oldestA = last_targets_A ? lag(n - 1) : lag(n - 1) + reach(n - 1);   // back from a
+  static constexpr int oldestB = last_targets_A ? lag(n - 1) + reach(n - 1) : lag(n - 1);
+  static constexpr int WA = oldestA / 2 + 1;
+  static constexpr int WB = (oldestB - reach(0)) / 2 + 1;
+  static constexpr int U = WA * WB / cgcd(WA, WB);   // unroll period of the row-pair loop
+  // ring slot of the first row of each parity (row PA lives in A slot 0 by construction)
+  static constexpr int cB = (PA - reach(0) - PB) / 2;   // (r0 - PB) / 2 = tau + cB  (PA - PB - reach(0) is even)
+  static constexpr int firstB = pmod(-cB, WB);
 };
 
-// reach of one lifting step along the lifted axis, and the reach still to come after / before it
-template <int K, int S> __host__ __device__ constexpr int step_reach() { return Wavelet<K>::R == 0 ? 0 : 2 * Step<K, S>::N - 1; }
-template <int K, int S> __host__ __device__ constexpr int reach_after() {   // forward order: steps S+1 .. NSTEPS-1
-  if constexpr (S + 1 >= Wavelet<K>::NSTEPS) return 0;
-  else return step_reach<K, S + 1>() + reach_after<K, S + 1>();
-}
-template <int K, int S> __host__ __device__ constexpr int reach_before() {  // inverse order: steps S-1 .. 0
-  if constexpr (S == 0) return 0;
-  else return step_reach<K, S - 1>() + reach_before<K, S - 1>();
-}
+template <int K> struct Vec { static constexpr int V = (K == VC2_FIDELITY) ? 4 : 8; };
+
+template <int K>
+struct Geo {
+  static constexpr int V = Vec<K>::V, PPL = V / 2;
+  static constexpr int R = Wavelet<K>::R;
+  static constexpr int HX = (R + V - 1) / V * V;      // horizontal halo, whole lanes
+  static constexpr int XW = 32 * V;                   // columns per warp
+  static constexpr int XU = XW - 2 * HX;              // useful columns per warp
+};
 
 // ---- horizontal lifting step in registers ------------------------------------------------------
-// A lane holds pairs 2*lane and 2*lane+1 of a 64-pair row segment: e[a] / o[a] = even / odd sample
-// of pair 2*lane+a.  Neighbouring pairs come from other lanes by shuffle.  When the segment
-// touches the left/right edge of the lattice (hedge), the source-parity sequence is first extended
-// beyond [plo, phi] with its edge value = the reference's tap clamping.
-template <int K, int S, int DIR>
-__device__ __forceinline__ void hstep(int (&e)[2], int (&o)[2], int lane, bool hedge, int plo, int phi) {
+// A lane holds pairs PPL*lane .. PPL*lane+PPL-1 of a row segment: e[a] / o[a] = even / odd sample of
+// pair PPL*lane+a.  Neighbouring pairs come from other lanes by shuffle.  When the segment touches
+// the left/right edge of the lattice (hedge), the source-parity sequence is first extended beyond
+// [plo, phi] with its edge value = the reference's tap clamping.
+template <int PPL>
+__device__ __forceinline__ int pick(const int (&x)[PPL], int i) {
+  int v = x[0];
+#pragma unroll
+  for (int a = 1; a < PPL; ++a) v = (i == a) ? x[a] : v;
+  return v;
+}
+
+template <int K, int S, int DIR, int PPL>
+__device__ __forceinline__ void hstep(int (&e)[PPL], int (&o)[PPL], int lane, bool hedge, int plo, int phi) {
   using ST = Step<K, S>;
   constexpr int P = ST::P, N = ST::N;
-  int (&src)[2] = P ? e : o;
-  int (&tgt)[2] = P ? o : e;
+  int (&src)[PPL] = P ? e : o;
+  int (&tgt)[PPL] = P ? o : e;
   if (hedge) {
-    const int vlo = __shfl_sync(FULL, (plo & 1) ? src[1] : src[0], plo >> 1);
-    const int vhi = __shfl_sync(FULL, (phi & 1) ? src[1] : src[0], phi >> 1);
-    const int p0 = 2 * lane;
-    if (p0 < plo) src[0] = vlo; else if (p0 > phi) src[0] = vhi;
-    if (p0 + 1 < plo) src[1] = vlo; else if (p0 + 1 > phi) src[1] = vhi;
+    const int vlo = __shfl_sync(FULL, pick<PPL>(src, plo % PPL), plo / PPL);
+    const int vhi = __shfl_sync(FULL, pick<PPL>(src, phi % PPL), phi / PPL);
+#pragma unroll
+    for (int a = 0; a < PPL; ++a) {
+      const int p = PPL * lane + a;
+      if (p < plo) src[a] = vlo; else if (p > phi) src[a] = vhi;
+    }
   }
-  constexpr int QMIN = -(P ? N - 1 : N), QMAX = 1 + (P ? N : N - 1);
-  int nb[QMAX - QMIN + 1];   // source values at pair offsets QMIN..QMAX from pair 2*lane
+  constexpr int QMIN = -(P ? N - 1 : N), QMAX = PPL - 1 + (P ? N : N - 1);
+  int nb[QMAX - QMIN + 1];   // source values at pair offsets QMIN..QMAX from pair PPL*lane
 #pragma unroll
   for (int q = QMIN; q <= QMAX; ++q) {
-    const int r = q & 1, dl = (q - r) / 2;
+    const int r = pmod(q, PPL), dl = (q - r) / PPL;
     nb[q - QMIN] = dl == 0 ? src[r] : __shfl_sync(FULL, src[r], lane + dl);
   }
 #pragma unroll
-  for (int a = 0; a < 2; ++a) {
+  for (int a = 0; a < PPL; ++a) {
     unsigned sum = (unsigned)ST::ADD;
 #pragma unroll
     for (int k = 0; k < N; ++k) {
-      if (ST::cl(k) != 0) sum += (unsigned)ST::cl(k) * (unsigned)nb[a - (P ? k : k + 1) - QMIN];
-      if (ST::cr(k) != 0) sum += (unsigned)ST::cr(k) * (unsigned)nb[a + (P ? k + 1 : k) - QMIN];
+      const unsigned l = (unsigned)nb[a - (P ? k : k + 1) - QMIN], r = (unsigned)nb[a + (P ? k + 1 : k) - QMIN];
+      if (ST::cl(k) == ST::cr(k)) { if (ST::cl(k) != 0) sum += (unsigned)ST::cl(k) * (l + r); }
+      else {
+        if (ST::cl(k) != 0) sum += (unsigned)ST::cl(k) * l;
+        if (ST::cr(k) != 0) sum += (unsigned)ST::cr(k) * r;
+      }
     }
     const int delta = ((int)sum) >> ST::SH;
     tgt[a] = (ST::SIGN * DIR > 0) ? (int)((unsigned)tgt[a] + (unsigned)delta) : (int)((unsigned)tgt[a] - (unsigned)delta);
   }
 }
 
-template <int K, int DIR>
-__device__ __forceinline__ void hsteps(int (&e)[2], int (&o)[2], int lane, bool hedge, int plo, int phi) {
+template <int K, int DIR, int PPL>
+__device__ __forceinline__ void hsteps(int (&e)[PPL], int (&o)[PPL], int lane, bool hedge, int plo, int phi) {
   constexpr int N = Wavelet<K>::NSTEPS;
   if constexpr (DIR > 0) {
-    hstep<K, 0, DIR>(e, o, lane, hedge, plo, phi);
-    hstep<K, 1, DIR>(e, o, lane, hedge, plo, phi);
+    hstep<K, 0, DIR, PPL>(e, o, lane, hedge, plo, phi);
+    hstep<K, 1, DIR, PPL>(e, o, lane, hedge, plo, phi);
     if constexpr (N == 4) {
-      hstep<K, 2, DIR>(e, o, lane, hedge, plo, phi);
-      hstep<K, 3, DIR>(e, o, lane, hedge, plo, phi);
+      hstep<K, 2, DIR, PPL>(e, o, lane, hedge, plo, phi);
+      hstep<K, 3, DIR, PPL>(e, o, lane, hedge, plo, phi);
     }
   } else {
     if constexpr (N == 4) {
-      hstep<K, 3, DIR>(e, o, lane, hedge, plo, phi);
-      hstep<K, 2, DIR>(e, o, lane, hedge, plo, phi);
+      hstep<K, 3, DIR, PPL>(e, o, lane, hedge, plo, phi);
+      hstep<K, 2, DIR, PPL>(e, o, lane, hedge, plo, phi);
     }
-    hstep<K, 1, DIR>(e, o, lane, hedge, plo, phi);
-    hstep<K, 0, DIR>(e, o, lane, hedge, plo, phi);
+    hstep<K, 1, DIR, PPL>(e, o, lane, hedge, plo, phi);
+    hstep<K, 0, DIR, PPL>(e, o, lane, hedge, plo, phi);
   }
 }
 
-// ---- vertical lifting step on the shared-memory tile ---------------------------------------------
-// x points at the target sample X[r][j]; taps sit at fixed row offsets (row pitch RP)
-template <int K, int S, int DIR>
-__device__ __forceinline__ int vlift(const int* x) {
-  using ST = Step<K, S>;
-  unsigned sum = (unsigned)ST::ADD;
+// ---- the per-lane state of the vertical pipeline ---------------------------------------------------
+// Rings are indexed by AGE: A[i] = A row (a - 2i), B[i] = B row (r0 - 2i), a = newest A row of the current
+// row pair, r0 = a - reach(0).  shift() ages every row by one pair (register moves).
+template <int K, int DIR>
+struct Rings {
+  using SC = Sched<K, DIR>;
+  static constexpr int V = Vec<K>::V;
+  int A[SC::WA][V];
+  int B[SC::WB][V];
+  __device__ __forceinline__ void clear() {
 #pragma unroll
-  for (int k = 0; k < ST::N; ++k) {
-    if (ST::cl(k) != 0) sum += (unsigned)ST::cl(k) * (unsigned)x[-(2 * k + 1) * RP];
-    if (ST::cr(k) != 0) sum += (unsigned)ST::cr(k) * (unsigned)x[(2 * k + 1) * RP];
+    for (int v = 0; v < V; ++v) {
+#pragma unroll
+      for (int i = 0; i < SC::WA; ++i) A[i][v] = 0;
+#pragma unroll
+      for (int i = 0; i < SC::WB; ++i) B[i][v] = 0;
+    }
   }
-  const int delta = ((int)sum) >> ST::SH;
-  return (ST::SIGN * DIR > 0) ? (int)((unsigned)x[0] + (unsigned)delta) : (int)((unsigned)x[0] - (unsigned)delta);
-}
-
-// copy the first / last valid row of parity q into the out-of-lattice halo rows of that parity
-// (rows [0, rlo) and (rhi, RH)); only CTAs at the top / bottom edge of the lattice have any
-__device__ __forceinline__ void extend_rows(int* E, int* O, int q, int rlo, int rhi, int RH) {
-  const int col = threadIdx.x & 127, half = threadIdx.x >> 7;
-  int* X = (col < RP ? E : O) + (col & (RP - 1));
-  const int first = rlo + q, last = rhi - (1 - q);
-  for (int r = q + 2 * half; r < rlo; r += 4) X[r * RP] = X[first * RP];
-  for (int r = last + 2 + 2 * half; r < RH; r += 4) X[r * RP] = X[last * RP];
-}
-
-struct BandAddr {   // group-interleaved addressing of one band sample (see vc2_common.cuh)
-  int bh, bw, lgbh, lgbw, nx, nc4;
-  int sx, xin;       // slice column and column inside the slice's part of the band: fixed per thread
-  __device__ __forceinline__ void set_col(int bx) {
-    sx = lgbw >= 0 ? (bx >> lgbw) : (bx / bw);
-    xin = bx - sx * bw;
-  }
-  __device__ __forceinline__ long long at(int base, int by) const {
-    const int sy = lgbh >= 0 ? (by >> lgbh) : (by / bh);
-    return coef_index(sy * nx + sx, base + (by - sy * bh) * bw + xin, nc4);
+  __device__ __forceinline__ void shift() {
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+#pragma unroll
+      for (int i = SC::WA - 1; i > 0; --i) A[i][v] = A[i - 1][v];
+#pragma unroll
+      for (int i = SC::WB - 1; i > 0; --i) B[i][v] = B[i - 1][v];
+    }
   }
 };
 
-__device__ __forceinline__ int sample_u16be(unsigned w, int sshift, int soffset) {
-  return (int)((((w >> 8) | (w << 8)) & 0xFFFFu) >> sshift) - soffset;
+// ring row of a (warp uniform) run-time age: select chain, only used by the edge variant
+template <int W, int V>
+__device__ __forceinline__ int pick_row(const int (&ring)[W][V], int age, int v) {
+  int x = ring[0][v];
+#pragma unroll
+  for (int i = 1; i < W; ++i) x = (age == i) ? ring[i][v] : x;
+  return x;
 }
 
-// ------------------------------------------------------------------------------------------
-// forward level:  pix (dense plane)  ->  LL (compact plane or band 0), HL, LH, HH (slice-major)
-// ------------------------------------------------------------------------------------------
-template <int K, int S>
-__device__ __forceinline__ void fwd_vstep(int* E, int* O, const DwtComp& C, int pic, int ys, int rlo, int rhi, int xs, int phi,
-                                          bool vedge) {
-  using T = Tile<K>;
+// vertical step I of the schedule on target row r = a - lag(I).
+// EDGE: taps above row 0 / below row `last` are redirected to the first / last row of their parity
+// (its current state is still in the ring: the window of needed rows always contains it).
+template <int K, int DIR, int I, bool EDGE>
+__device__ __forceinline__ void vstep(Rings<K, DIR>& g, int a, int r, int last) {
+  using SC = Sched<K, DIR>;
+  constexpr int S = SC::sidx(I);
   using ST = Step<K, S>;
-  constexpr int R = T::R, RH = T::RH, P = ST::P, NS = Wavelet<K>::NSTEPS;
-  constexpr bool LAST = (S == NS - 1);
-  constexpr bool FINAL_FOR_PARITY = (S >= NS - 2);   // steps alternate parity: the last two finish one parity each
-  if (vedge) {
-    extend_rows(E, O, 1 - P, rlo, rhi, RH);
-    __syncthreads();
-  }
-  constexpr int RA = reach_after<K, S>();
-  const int tlo = max(R - RA, rlo), thi = min(R + TH - 1 + RA, rhi);
-  const int col = threadIdx.x & 127, half = threadIdx.x >> 7;
-  const int j = col & (RP - 1);
-  const bool isO = col >= RP;
-  if (j >= T::HX / 2 && j < T::HX / 2 + T::TWU / 2 && j <= phi) {
-    int* X = (isO ? O : E) + j;
-    const int bx = (xs >> 1) + j;
-    BandAddr ba = {C.bh, C.bw, C.lgbh, C.lgbw, C.nx, C.NC >> 2, 0, 0};
-    ba.set_col(bx);
-    int32_t* coef = C.coef + (long long)pic * C.coef_pic_stride;
-    int t0 = tlo + ((tlo & 1) != P ? 1 : 0);
-    for (int r = t0 + 2 * half; r <= thi; r += 4) {
-      const int v = vlift<K, S, +1>(X + r * RP);
-      if (!LAST) X[r * RP] = v;
-      if (FINAL_FOR_PARITY && r >= R && r < R + TH) {
-        const int by = (ys + r) >> 1;
-        if (P == 0 && !isO && C.ll) {
-          C.ll[(long long)pic * C.ll_pic_stride + (long long)by * C.ll_pitch + bx] = v;
-        } else {
-          const int base = P ? (isO ? C.base_hh : C.base_lh) : (isO ? C.base_hl : C.base_ll);
-          coef[ba.at(base, by)] = v;
+  constexpr int V = Vec<K>::V, N = ST::N;
+  constexpr bool TA = (I % 2) == 1;               // target is an A row
+  constexpr int L = SC::lag(I);
+  constexpr int tage = TA ? L / 2 : (L - SC::reach(0)) / 2;
+  // ages of the first and of the last row of the source parity
+  const int newest = TA ? a - SC::reach(0) : a, spar = TA ? SC::PB : SC::PA;
+  const int age_first = (newest - spar) >> 1, age_last = (newest - (last - 1 + spar)) >> 1;
+#pragma unroll
+  for (int v = 0; v < V; ++v) {
+    unsigned sum = (unsigned)ST::ADD;
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      int l, rr;
+      if constexpr (TA) {   // sources are B rows r -/+ (2k+1)
+        l = g.B[(L + (2 * k + 1) - SC::reach(0)) / 2][v];
+        rr = g.B[(L - (2 * k + 1) - SC::reach(0)) / 2][v];
+        if (EDGE) {
+          if (r - (2 * k + 1) < 0) l = pick_row<SC::WB, V>(g.B, age_first, v);
+          if (r + (2 * k + 1) > last) rr = pick_row<SC::WB, V>(g.B, age_last, v);
+        }
+      } else {              // sources are A rows
+        l = g.A[(L + (2 * k + 1)) / 2][v];
+        rr = g.A[(L - (2 * k + 1)) / 2][v];
+        if (EDGE) {
+          if (r - (2 * k + 1) < 0) l = pick_row<SC::WA, V>(g.A, age_first, v);
+          if (r + (2 * k + 1) > last) rr = pick_row<SC::WA, V>(g.A, age_last, v);
         }
       }
+      if (ST::cl(k) == ST::cr(k)) { if (ST::cl(k) != 0) sum += (unsigned)ST::cl(k) * ((unsigned)l + (unsigned)rr); }
+      else {
+        if (ST::cl(k) != 0) sum += (unsigned)ST::cl(k) * (unsigned)l;
+        if (ST::cr(k) != 0) sum += (unsigned)ST::cr(k) * (unsigned)rr;
+      }
+    }
+    const int delta = ((int)sum) >> ST::SH;
+    int& t = TA ? g.A[tage][v] : g.B[tage][v];
+    t = (ST::SIGN * DIR > 0) ? (int)((unsigned)t + (unsigned)delta) : (int)((unsigned)t - (unsigned)delta);
+  }
+}
+
+// run step I for the current row pair if its target row exists
+template <int K, int DIR, int I>
+__device__ __forceinline__ void vstep_guarded(Rings<K, DIR>& g, int a, int H) {
+  using SC = Sched<K, DIR>;
+  const int r = a - SC::lag(I);
+  if (r < 0 || r > H - 1) return;
+  const int last = H - 1;
+  if (r - SC::reach(I) < 0 || r + SC::reach(I) > last) vstep<K, DIR, I, true>(g, a, r, last);
+  else vstep<K, DIR, I, false>(g, a, r, last);
+}
+
+// ---- global memory access of one lane's V columns of one row -------------------------------------------
+struct BandAddr {   // group-interleaved addressing of band samples (see vc2_common.cuh)
+  int bh, bw, lgbh, lgbw, nx, nc4;
+  __device__ __forceinline__ long long at(int base, int by, int bx) const {
+    const int sy = lgbh >= 0 ? (by >> lgbh) : (by / bh);
+    const int sx = lgbw >= 0 ? (bx >> lgbw) : (bx / bw);
+    return coef_index(sy * nx + sx, base + (by - sy * bh) * bw + (bx - sx * bw), nc4);
+  }
+};
+
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+constexpr int PD = 2;   // prefetch distance in row pairs
+
+// forward: touch the cache line(s) of this lane's samples of picture row `row`
+template <int KIND, int V>
+__device__ __forceinline__ void prefetch_pix(const DwtComp& C, int pic, int row, int gx) {
+  if (row > C.pix_h - 1 || gx < 0 || gx + V - 1 >= C.pix_w) return;
+  const int esz = KIND == SAMPLE_I32 ? 4 : KIND == SAMPLE_U16BE ? 2 : 1;
+  const uint8_t* base = (const uint8_t*)C.pix + (KIND == SAMPLE_I32 ? (long long)pic * C.pix_pic_stride * 4 : (long long)pic * C.pix_pic_stride);
+  prefetch_l1(base + ((long long)row * C.pix_pitch + gx) * esz);
+}
+
+__device__ __forceinline__ int sample_u16be(unsigned w, int sshift, int soffset) {
+  return (int)(__byte_perm(w, 0, 0x4401) >> sshift) - soffset;
+}
+
+// forward: load V consecutive samples of picture row `row` starting at column gx (may be negative / past the edge)
+template <int KIND, int V>
+__device__ __forceinline__ void load_pix(const DwtComp& C, int pic, int row, int gx, int (&x)[V]) {
+  const int sy = min(row, C.pix_h - 1);                 // waveletPad: replicate the last row (WaveletTransform.cpp:88)
+  const bool inside = gx >= 0 && gx + V - 1 < C.pix_w;   // all V samples are real picture samples
+  if (KIND == SAMPLE_I32) {
+    const int* rp = (const int*)C.pix + (long long)pic * C.pix_pic_stride + (long long)sy * C.pix_pitch;
+    if (inside && ((reinterpret_cast<uintptr_t>(rp + gx) & 15) == 0)) {
+#pragma unroll
+      for (int j = 0; j < V; j += 4) {
+        const int4 q = __ldg(reinterpret_cast<const int4*>(rp + gx + j));
+        x[j] = q.x; x[j + 1] = q.y; x[j + 2] = q.z; x[j + 3] = q.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < V; ++j) x[j] = rp[min(max(gx + j, 0), C.pix_w - 1)];   // :89 replicate the last column
+    }
+  } else if (KIND == SAMPLE_U16BE) {
+    const uint16_t* rp = (const uint16_t*)((const uint8_t*)C.pix + (long long)pic * C.pix_pic_stride) + (long long)sy * C.pix_pitch;
+    if (inside && ((reinterpret_cast<uintptr_t>(rp + gx) & (2 * V - 1)) == 0)) {
+      unsigned w[V / 2];
+      if (V == 8) {
+        const uint4 q = __ldg(reinterpret_cast<const uint4*>(rp + gx));
+        w[0] = q.x; w[1] = q.y; w[V / 2 - 2] = q.z; w[V / 2 - 1] = q.w;
+      } else {
+        const uint2 q = __ldg(reinterpret_cast<const uint2*>(rp + gx));
+        w[0] = q.x; w[1] = q.y;
+      }
+#pragma unroll
+      for (int j = 0; j < V / 2; ++j) {
+        x[2 * j] = sample_u16be(w[j] & 0xFFFFu, C.sshift, C.soffset);
+        x[2 * j + 1] = (int)(__byte_perm(w[j], 0, 0x4423) >> C.sshift) - C.soffset;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < V; ++j) x[j] = sample_u16be(rp[min(max(gx + j, 0), C.pix_w - 1)], C.sshift, C.soffset);
+    }
+  } else {
+    const uint8_t* rp = (const uint8_t*)C.pix + (long long)pic * C.pix_pic_stride + (long long)sy * C.pix_pitch;
+#pragma unroll
+    for (int j = 0; j < V; ++j) x[j] = (int)((unsigned)rp[min(max(gx + j, 0), C.pix_w - 1)] >> C.sshift) - C.soffset;
+  }
+}
+
+// PPL consecutive samples of band row `by` starting at band column bx0 (multiple of PPL): vector access when
+// the run is one aligned piece of the interleaved layout, else element by element
+template <int PPL, bool STORE>
+__device__ __forceinline__ void band_access(int32_t* coef, const BandAddr& ba, int base, int by, int bx0, int bxmax, int (&x)[PPL]) {
+  if (bx0 < 0 || bx0 > bxmax) {
+    if (!STORE) {
+#pragma unroll
+      for (int j = 0; j < PPL; ++j) x[j] = 0;
+    }
+    return;
+  }
+  const bool vec = PPL == 4 && (ba.bw & 3) == 0 && (base & 3) == 0 && bx0 + 3 <= bxmax;
+  if (vec) {
+    int4* p = reinterpret_cast<int4*>(coef + ba.at(base, by, bx0));
+    if (STORE) *p = make_int4(x[0], x[1], x[PPL > 2 ? 2 : 0], x[PPL > 3 ? 3 : 0]);
+    else { const int4 q = __ldg(p); x[0] = q.x; x[1] = q.y; x[PPL > 2 ? 2 : 0] = q.z; x[PPL > 3 ? 3 : 0] = q.w; }
+  } else {
+#pragma unroll
+    for (int j = 0; j < PPL; ++j) {
+      if (bx0 + j <= bxmax) {
+        int32_t* p = coef + ba.at(base, by, bx0 + j);
+        if (STORE) *p = x[j]; else x[j] = *p;
+      } else if (!STORE) x[j] = 0;
     }
   }
-  if (!LAST) __syncthreads();
+}
+template <int PPL>
+__device__ __forceinline__ void band_prefetch(const int32_t* coef, const BandAddr& ba, int base, int by, int bx0, int bxmax) {
+  if (bx0 < 0 || bx0 > bxmax) return;
+  prefetch_l1(coef + ba.at(base, by, bx0));
+}
+// same for the compact LL plane between levels
+template <int PPL, bool STORE>
+__device__ __forceinline__ void ll_access(int32_t* ll, long long pitch, int by, int bx0, int bxmax, int (&x)[PPL]) {
+  if (bx0 < 0 || bx0 > bxmax) {
+    if (!STORE) {
+#pragma unroll
+      for (int j = 0; j < PPL; ++j) x[j] = 0;
+    }
+    return;
+  }
+  int32_t* p = ll + (long long)by * pitch + bx0;
+  if (PPL == 4 && bx0 + 3 <= bxmax && ((reinterpret_cast<uintptr_t>(p) & 15) == 0)) {
+    int4* q = reinterpret_cast<int4*>(p);
+    if (STORE) *q = make_int4(x[0], x[1], x[PPL > 2 ? 2 : 0], x[PPL > 3 ? 3 : 0]);
+    else { const int4 t = __ldg(q); x[0] = t.x; x[1] = t.y; x[PPL > 2 ? 2 : 0] = t.z; x[PPL > 3 ? 3 : 0] = t.w; }
+  } else {
+#pragma unroll
+    for (int j = 0; j < PPL; ++j) {
+      if (bx0 + j <= bxmax) { if (STORE) p[j] = x[j]; else x[j] = p[j]; }
+      else if (!STORE) x[j] = 0;
+    }
+  }
+}
+
+// per-warp constants of one strip segment
+struct StripCtx {
+  int pic, lane;
+  int xs;            // lattice column of lane 0's first sample
+  int x0;            // first useful lattice column of this strip
+  int plo, phi;      // valid pair range inside the warp segment
+  bool hedge;
+  int H;             // lattice rows
+  int y0, y1;        // rows to output: [y0, y1)
+  int bxmax;         // last band column = lat_w / 2 - 1
+  bool mine;         // this lane's columns are useful (not halo) and inside the lattice
+};
+
+// ------------------------------------------------------------------------------------------
+// forward level:  pix (dense plane)  ->  LL (compact plane or band 0), HL, LH, HH (interleaved)
+// ------------------------------------------------------------------------------------------
+template <int K, int KIND, int PPL>
+__device__ __forceinline__ void fwd_fetch_row(const DwtComp& C, const StripCtx& S, int row, int (&dst)[2 * PPL]) {
+  constexpr int V = 2 * PPL, SHIFT = Wavelet<K>::SHIFT;
+  int x[V];
+  load_pix<KIND, V>(C, S.pic, row, S.xs + V * S.lane, x);
+  int e[PPL], o[PPL];
+#pragma unroll
+  for (int a = 0; a < PPL; ++a) {
+    e[a] = (int)((unsigned)x[2 * a] << SHIFT);
+    o[a] = (int)((unsigned)x[2 * a + 1] << SHIFT);
+  }
+  hsteps<K, +1, PPL>(e, o, S.lane, S.hedge, S.plo, S.phi);
+#pragma unroll
+  for (int a = 0; a < PPL; ++a) { dst[a] = e[a]; dst[PPL + a] = o[a]; }   // columns: [even samples | odd samples]
+}
+
+template <int K, int PPL>
+__device__ __forceinline__ void fwd_emit_row(const DwtComp& C, const StripCtx& S, const BandAddr& ba, int row, const int (&src)[2 * PPL]) {
+  if (!S.mine || row < S.y0 || row >= S.y1) return;
+  int32_t* coef = C.coef + (long long)S.pic * C.coef_pic_stride;
+  const int by = row >> 1, bx0 = ((S.xs >> 1) + PPL * S.lane);
+  int lo[PPL], hi[PPL];
+#pragma unroll
+  for (int a = 0; a < PPL; ++a) { lo[a] = src[a]; hi[a] = src[PPL + a]; }
+  if (row & 1) {
+    band_access<PPL, true>(coef, ba, C.base_lh, by, bx0, S.bxmax, lo);
+    band_access<PPL, true>(coef, ba, C.base_hh, by, bx0, S.bxmax, hi);
+  } else {
+    if (C.ll) ll_access<PPL, true>(C.ll + (long long)S.pic * C.ll_pic_stride, C.ll_pitch, by, bx0, S.bxmax, lo);
+    else band_access<PPL, true>(coef, ba, C.base_ll, by, bx0, S.bxmax, lo);
+    band_access<PPL, true>(coef, ba, C.base_hl, by, bx0, S.bxmax, hi);
+  }
 }
 
 template <int K, int KIND>
-__global__ void __launch_bounds__(NT) dwt_fwd_kernel(const DwtParams p) {
-  using T = Tile<K>;
-  constexpr int R = T::R, RH = T::RH, HX = T::HX, SHIFT = Wavelet<K>::SHIFT, NS = Wavelet<K>::NSTEPS;
-  extern __shared__ int smem[];
-  int* E = smem;
-  int* O = smem + RH * RP;
-
-  const int comp = blockIdx.z % p.ncomp, pic = blockIdx.z / p.ncomp;
-  const DwtComp& C = p.c[comp];
-  const int x0 = blockIdx.x * T::TWU, y0 = blockIdx.y * TH;
-  if (x0 >= C.lat_w || y0 >= C.lat_h) return;
-  const int xs = x0 - HX, ys = y0 - R;
-  const int plo = max(0, -xs / 2), phi = min(RP - 1, (C.lat_w - 2 - xs) / 2);
-  const bool hedge = xs < 0 || xs + RW > C.lat_w;
-  const int rlo = max(0, -ys), rhi = min(RH - 1, C.lat_h - 1 - ys);
-  const bool vedge = ys < 0 || ys + RH > C.lat_h;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-
-  // ---- phase 1: load a row segment, accuracy shift, horizontal lifting in registers, park in the tile
+__device__ __forceinline__ void fwd_pair(const DwtComp& C, const StripCtx& S, const BandAddr& ba, Rings<K, +1>& g, int tau) {
+  using SC = Sched<K, +1>;
+  constexpr int V = Vec<K>::V, PPL = V / 2, n = SC::n;
+  const int H = S.H;
+  const int a = 2 * tau + SC::PA;
+  prefetch_pix<KIND, V>(C, S.pic, a + 2 * PD, S.xs + V * S.lane);
+  prefetch_pix<KIND, V>(C, S.pic, a + 2 * PD - SC::reach(0), S.xs + V * S.lane);
+  g.shift();
+  if (a <= H - 1) fwd_fetch_row<K, KIND, PPL>(C, S, a, g.A[0]);
+  const int r0 = a - SC::reach(0);
+  if (r0 >= 0 && r0 <= H - 1) fwd_fetch_row<K, KIND, PPL>(C, S, r0, g.B[0]);
+  vstep_guarded<K, +1, 0>(g, a, H);
+  vstep_guarded<K, +1, 1>(g, a, H);
+  if constexpr (n == 4) {
+    vstep_guarded<K, +1, 2>(g, a, H);
+    vstep_guarded<K, +1, 3>(g, a, H);
+  }
+  // rows that just became final: the targets of the last two steps
+  constexpr int L1 = SC::lag(n - 1), L2 = SC::lag(n - 2);
   {
-    const int gx = xs + 4 * lane;
-    const bool inside = gx >= 0 && gx + 3 < C.pix_w;   // all four samples are real picture samples
-    for (int r = rlo + warp; r <= rhi; r += NT / 32) {
-      const int sy = min(ys + r, C.pix_h - 1);          // waveletPad: replicate the last row (WaveletTransform.cpp:88)
-      int v[4];
-      if (KIND == SAMPLE_I32) {
-        const int* row = (const int*)C.pix + (long long)pic * C.pix_pic_stride + (long long)sy * C.pix_pitch;
-        if (inside && ((reinterpret_cast<uintptr_t>(row + gx) & 15) == 0)) {
-          const int4 q = *reinterpret_cast<const int4*>(row + gx);
-          v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
-        } else {
-#pragma unroll
-          for (int k = 0; k < 4; ++k) v[k] = row[min(max(gx + k, 0), C.pix_w - 1)];   // :89 replicate the last column
-        }
-      } else if (KIND == SAMPLE_U16BE) {
-        const uint16_t* row = (const uint16_t*)((const uint8_t*)C.pix + (long long)pic * C.pix_pic_stride) + (long long)sy * C.pix_pitch;
-        if (inside && ((reinterpret_cast<uintptr_t>(row + gx) & 7) == 0)) {
-          const uint2 q = *reinterpret_cast<const uint2*>(row + gx);
-          v[0] = sample_u16be(q.x & 0xFFFFu, C.sshift, C.soffset);
-          v[1] = sample_u16be(q.x >> 16, C.sshift, C.soffset);
-          v[2] = sample_u16be(q.y & 0xFFFFu, C.sshift, C.soffset);
-          v[3] = sample_u16be(q.y >> 16, C.sshift, C.soffset);
-        } else {
-#pragma unroll
-          for (int k = 0; k < 4; ++k) v[k] = sample_u16be(row[min(max(gx + k, 0), C.pix_w - 1)], C.sshift, C.soffset);
-        }
-      } else {
-        const uint8_t* row = (const uint8_t*)C.pix + (long long)pic * C.pix_pic_stride + (long long)sy * C.pix_pitch;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) v[k] = (int)((unsigned)row[min(max(gx + k, 0), C.pix_w - 1)] >> C.sshift) - C.soffset;
-      }
-      int e[2] = {(int)((unsigned)v[0] << SHIFT), (int)((unsigned)v[2] << SHIFT)};
-      int o[2] = {(int)((unsigned)v[1] << SHIFT), (int)((unsigned)v[3] << SHIFT)};
-      hsteps<K, +1>(e, o, lane, hedge, plo, phi);
-      *reinterpret_cast<int2*>(E + r * RP + 2 * lane) = make_int2(e[0], e[1]);
-      *reinterpret_cast<int2*>(O + r * RP + 2 * lane) = make_int2(o[0], o[1]);
+    const int r = a - L1;
+    if (r >= 0 && r <= H - 1) {
+      if constexpr (SC::last_targets_A) fwd_emit_row<K, PPL>(C, S, ba, r, g.A[L1 / 2]);
+      else fwd_emit_row<K, PPL>(C, S, ba, r, g.B[(L1 - SC::reach(0)) / 2]);
     }
   }
-  __syncthreads();
-
-  // ---- phase 2: vertical lifting on the tile, results straight to global memory
-  fwd_vstep<K, 0>(E, O, C, pic, ys, rlo, rhi, xs, phi, vedge);
-  fwd_vstep<K, 1>(E, O, C, pic, ys, rlo, rhi, xs, phi, vedge);
-  if constexpr (NS == 4) {
-    fwd_vstep<K, 2>(E, O, C, pic, ys, rlo, rhi, xs, phi, vedge);
-    fwd_vstep<K, 3>(E, O, C, pic, ys, rlo, rhi, xs, phi, vedge);
+  {
+    const int r = a - L2;
+    if (r >= 0 && r <= H - 1) {
+      if constexpr (!SC::last_targets_A) fwd_emit_row<K, PPL>(C, S, ba, r, g.A[L2 / 2]);
+      else fwd_emit_row<K, PPL>(C, S, ba, r, g.B[(L2 - SC::reach(0)) / 2]);
+    }
   }
+}
+
+// common strip set-up; returns false when this warp has nothing to do
+template <int K>
+__device__ __forceinline__ bool strip_setup(const DwtComp& C, int seg_rows, StripCtx& S, bool inverse) {
+  using G = Geo<K>;
+  S.lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  S.x0 = blockIdx.x * G::XU;
+  S.y0 = (blockIdx.y * WARPS + warp) * seg_rows;
+  if (S.x0 >= C.lat_w || S.y0 >= C.lat_h) return false;
+  if (inverse && (S.x0 >= C.pix_w || S.y0 >= C.pix_h)) return false;   // nothing of this strip survives the crop (WaveletTransform.cpp:340)
+  S.y1 = min(S.y0 + seg_rows, C.lat_h);
+  S.xs = S.x0 - G::HX;
+  S.H = C.lat_h;
+  S.plo = max(0, -S.xs / 2);
+  S.phi = min(G::XW / 2 - 1, (C.lat_w - 2 - S.xs) / 2);
+  S.hedge = S.xs < 0 || S.xs + G::XW > C.lat_w;
+  S.bxmax = C.lat_w / 2 - 1;
+  const int gx = S.xs + G::V * S.lane;
+  S.mine = gx >= S.x0 && gx < S.x0 + G::XU && gx < C.lat_w;
+  return true;
+}
+
+template <int K, int KIND>
+__global__ void __launch_bounds__(32 * WARPS, 4) dwt_fwd_kernel(const DwtParams p, int seg_rows) {
+  using SC = Sched<K, +1>;
+  const int comp = blockIdx.z % p.ncomp;
+  const DwtComp& C = p.c[comp];
+  StripCtx S;
+  S.pic = blockIdx.z / p.ncomp;
+  if (!strip_setup<K>(C, seg_rows, S, false)) return;
+  const BandAddr ba = {C.bh, C.bw, C.lgbh, C.lgbw, C.nx, C.NC >> 2};
+  Rings<K, +1> g;
+  g.clear();
+  // first row pair: early enough that every row of [y0, y1) has its whole dependency cone inside the walk;
+  // last pair: until the last step has reached row y1 - 1
+  const int tau0 = max((S.y0 - SC::total_reach() - SC::PA) >> 1, 0);
+  const int tau_end = (S.y1 - 1 + SC::lag(SC::n - 1) - SC::PA + 2) >> 1;
+#pragma unroll 1
+  for (int tau = tau0; tau < tau_end; ++tau) fwd_pair<K, KIND>(C, S, ba, g, tau);
 }
 
 // ------------------------------------------------------------------------------------------
 // inverse level:  LL, HL, LH, HH  ->  pix (dense plane; cropped / clipped / packed at level 0)
 // ------------------------------------------------------------------------------------------
-template <int K, int S>
-__device__ __forceinline__ void inv_vstep(int* E, int* O, int rlo, int rhi, int plo, int phi, bool vedge) {
-  using T = Tile<K>;
-  using ST = Step<K, S>;
-  constexpr int R = T::R, RH = T::RH, P = ST::P;
-  if (vedge) {
-    extend_rows(E, O, 1 - P, rlo, rhi, RH);
-    __syncthreads();
+template <int K, int PPL>
+__device__ __forceinline__ void inv_fetch_row(const DwtComp& C, const StripCtx& S, const BandAddr& ba, int row, int (&dst)[2 * PPL]) {
+  int32_t* coef = C.coef + (long long)S.pic * C.coef_pic_stride;
+  const int by = row >> 1, bx0 = ((S.xs >> 1) + PPL * S.lane);
+  int lo[PPL], hi[PPL];
+  if (row & 1) {
+    band_access<PPL, false>(coef, ba, C.base_lh, by, bx0, S.bxmax, lo);
+    band_access<PPL, false>(coef, ba, C.base_hh, by, bx0, S.bxmax, hi);
+  } else {
+    if (C.ll) ll_access<PPL, false>(C.ll + (long long)S.pic * C.ll_pic_stride, C.ll_pitch, by, bx0, S.bxmax, lo);
+    else band_access<PPL, false>(coef, ba, C.base_ll, by, bx0, S.bxmax, lo);
+    band_access<PPL, false>(coef, ba, C.base_hl, by, bx0, S.bxmax, hi);
   }
-  constexpr int RA = reach_before<K, S>();
-  const int tlo = max(R - RA, rlo), thi = min(R + TH - 1 + RA, rhi);
-  const int col = threadIdx.x & 127, half = threadIdx.x >> 7;
-  const int j = col & (RP - 1);
-  if (j >= plo && j <= phi) {
-    int* X = (col >= RP ? O : E) + j;
-    const int t0 = tlo + ((tlo & 1) != P ? 1 : 0);
-    for (int r = t0 + 2 * half; r <= thi; r += 4) X[r * RP] = vlift<K, S, -1>(X + r * RP);
+#pragma unroll
+  for (int a = 0; a < PPL; ++a) { dst[a] = lo[a]; dst[PPL + a] = hi[a]; }
+}
+
+template <int PPL>
+__device__ __forceinline__ void inv_prefetch_row(const DwtComp& C, const StripCtx& S, const BandAddr& ba, int row) {
+  if (row > S.H - 1) return;
+  const int32_t* coef = C.coef + (long long)S.pic * C.coef_pic_stride;
+  const int by = row >> 1, bx0 = ((S.xs >> 1) + PPL * S.lane);
+  if (row & 1) {
+    band_prefetch<PPL>(coef, ba, C.base_lh, by, bx0, S.bxmax);
+    band_prefetch<PPL>(coef, ba, C.base_hh, by, bx0, S.bxmax);
+  } else {
+    if (C.ll) { if (bx0 >= 0 && bx0 <= S.bxmax) prefetch_l1(C.ll + (long long)S.pic * C.ll_pic_stride + (long long)by * C.ll_pitch + bx0); }
+    else band_prefetch<PPL>(coef, ba, C.base_ll, by, bx0, S.bxmax);
+    band_prefetch<PPL>(coef, ba, C.base_hl, by, bx0, S.bxmax);
   }
-  __syncthreads();
+}
+
+template <int K, int KIND, int PPL>
+__device__ __forceinline__ void inv_emit_row(const DwtComp& C, const StripCtx& S, int row, const int (&src)[2 * PPL]) {
+  constexpr int V = 2 * PPL, SHIFT = Wavelet<K>::SHIFT;
+  if (row < S.y0 || row >= S.y1) return;   // warp uniform
+  int e[PPL], o[PPL];
+#pragma unroll
+  for (int a = 0; a < PPL; ++a) { e[a] = src[a]; o[a] = src[PPL + a]; }
+  hsteps<K, -1, PPL>(e, o, S.lane, S.hedge, S.plo, S.phi);
+  const int gx = S.xs + V * S.lane;
+  if (!S.mine || row >= C.pix_h || gx >= C.pix_w) return;
+  int v[V];
+  const int rnd = SHIFT ? (1 << (SHIFT - 1)) : 0;
+#pragma unroll
+  for (int a = 0; a < PPL; ++a) { v[2 * a] = e[a]; v[2 * a + 1] = o[a]; }
+#pragma unroll
+  for (int k = 0; k < V; ++k) {
+    if (SHIFT) v[k] = (v[k] + rnd) >> SHIFT;
+    if (KIND != SAMPLE_I32) v[k] = (int)((unsigned)(min(max(v[k], C.clip_min), C.clip_max) + C.soffset) << C.sshift);
+  }
+  const long long rowoff = (long long)row * C.pix_pitch;
+  const bool whole = gx + V - 1 < C.pix_w;
+  if (KIND == SAMPLE_I32) {
+    int* dst = (int*)C.pix + (long long)S.pic * C.pix_pic_stride + rowoff + gx;
+    if (whole && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+      for (int j = 0; j < V; j += 4) *reinterpret_cast<int4*>(dst + j) = make_int4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    } else {
+#pragma unroll
+      for (int k = 0; k < V; ++k) if (gx + k < C.pix_w) dst[k] = v[k];
+    }
+  } else if (KIND == SAMPLE_U16BE) {
+    // offset binary, MSB justified, big endian (Arrays.cpp:396-414)
+    uint16_t* dst = (uint16_t*)((uint8_t*)C.pix + (long long)S.pic * C.pix_pic_stride) + rowoff + gx;
+    unsigned w[V / 2];
+#pragma unroll
+    for (int j = 0; j < V / 2; ++j) w[j] = __byte_perm((unsigned)v[2 * j], (unsigned)v[2 * j + 1], 0x4501);
+    if (whole && ((reinterpret_cast<uintptr_t>(dst) & (2 * V - 1)) == 0)) {
+      if (V == 8) *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[V / 2 - 2], w[V / 2 - 1]);
+      else *reinterpret_cast<uint2*>(dst) = make_uint2(w[0], w[1]);
+    } else {
+#pragma unroll
+      for (int k = 0; k < V; ++k) if (gx + k < C.pix_w) dst[k] = (uint16_t)((k & 1) ? (w[k / 2] >> 16) : (w[k / 2] & 0xFFFFu));
+    }
+  } else {
+    uint8_t* dst = (uint8_t*)C.pix + (long long)S.pic * C.pix_pic_stride + rowoff + gx;
+#pragma unroll
+    for (int k = 0; k < V; ++k) if (gx + k < C.pix_w) dst[k] = (uint8_t)v[k];
+  }
 }
 
 template <int K, int KIND>
-__global__ void __launch_bounds__(NT) dwt_inv_kernel(const DwtParams p) {
-  using T = Tile<K>;
-  constexpr int R = T::R, RH = T::RH, HX = T::HX, SHIFT = Wavelet<K>::SHIFT, NS = Wavelet<K>::NSTEPS;
-  extern __shared__ int smem[];
-  int* E = smem;
-  int* O = smem + RH * RP;
-
-  const int comp = blockIdx.z % p.ncomp, pic = blockIdx.z / p.ncomp;
-  const DwtComp& C = p.c[comp];
-  const int x0 = blockIdx.x * T::TWU, y0 = blockIdx.y * TH;
-  if (x0 >= C.lat_w || y0 >= C.lat_h) return;
-  if (x0 >= C.pix_w || y0 >= C.pix_h) return;   // nothing of this tile survives the crop (WaveletTransform.cpp:340)
-  const int xs = x0 - HX, ys = y0 - R;
-  const int plo = max(0, -xs / 2), phi = min(RP - 1, (C.lat_w - 2 - xs) / 2);
-  const bool hedge = xs < 0 || xs + RW > C.lat_w;
-  const int rlo = max(0, -ys), rhi = min(RH - 1, C.lat_h - 1 - ys);
-  const bool vedge = ys < 0 || ys + RH > C.lat_h;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-
-  // ---- phase 1: gather the four subbands into the tile
+__device__ __forceinline__ void inv_pair(const DwtComp& C, const StripCtx& S, const BandAddr& ba, Rings<K, -1>& g, int tau) {
+  using SC = Sched<K, -1>;
+  constexpr int V = Vec<K>::V, PPL = V / 2, n = SC::n;
+  const int H = S.H;
+  const int a = 2 * tau + SC::PA;
+  inv_prefetch_row<PPL>(C, S, ba, a + 2 * PD);
+  inv_prefetch_row<PPL>(C, S, ba, a + 2 * PD - SC::reach(0));
+  g.shift();
+  if (a <= H - 1) inv_fetch_row<K, PPL>(C, S, ba, a, g.A[0]);
+  const int r0 = a - SC::reach(0);
+  if (r0 >= 0 && r0 <= H - 1) inv_fetch_row<K, PPL>(C, S, ba, r0, g.B[0]);
+  vstep_guarded<K, -1, 0>(g, a, H);
+  vstep_guarded<K, -1, 1>(g, a, H);
+  if constexpr (n == 4) {
+    vstep_guarded<K, -1, 2>(g, a, H);
+    vstep_guarded<K, -1, 3>(g, a, H);
+  }
+  constexpr int L1 = SC::lag(n - 1), L2 = SC::lag(n - 2);
   {
-    const int col = threadIdx.x & 127, half = threadIdx.x >> 7;
-    const int j = col & (RP - 1);
-    const bool isO = col >= RP;
-    if (j >= plo && j <= phi) {
-      int* X = (isO ? O : E) + j;
-      const int bx = (xs >> 1) + j;
-      BandAddr ba = {C.bh, C.bw, C.lgbh, C.lgbw, C.nx, C.NC >> 2, 0, 0};
-      ba.set_col(bx);
-      const int32_t* coef = C.coef + (long long)pic * C.coef_pic_stride;
-      for (int r = rlo + half; r <= rhi; r += 2) {
-        const int gy = ys + r, by = gy >> 1;
-        int v;
-        if (!(gy & 1) && !isO && C.ll) v = C.ll[(long long)pic * C.ll_pic_stride + (long long)by * C.ll_pitch + bx];
-        else {
-          const int base = (gy & 1) ? (isO ? C.base_hh : C.base_lh) : (isO ? C.base_hl : C.base_ll);
-          v = coef[ba.at(base, by)];
-        }
-        X[r * RP] = v;
-      }
+    const int r = a - L1;
+    if (r >= 0 && r <= H - 1) {
+      if constexpr (SC::last_targets_A) inv_emit_row<K, KIND, PPL>(C, S, r, g.A[L1 / 2]);
+      else inv_emit_row<K, KIND, PPL>(C, S, r, g.B[(L1 - SC::reach(0)) / 2]);
     }
   }
-  __syncthreads();
-
-  // ---- phase 2: vertical inverse lifting (steps in reverse order, sign flipped)
-  if constexpr (NS == 4) {
-    inv_vstep<K, 3>(E, O, rlo, rhi, plo, phi, vedge);
-    inv_vstep<K, 2>(E, O, rlo, rhi, plo, phi, vedge);
-  }
-  inv_vstep<K, 1>(E, O, rlo, rhi, plo, phi, vedge);
-  inv_vstep<K, 0>(E, O, rlo, rhi, plo, phi, vedge);
-
-  // ---- phase 3: horizontal inverse lifting in registers, rounding, crop, clip, pack, store
   {
-    const int gx = xs + 4 * lane;
-    const bool mine = gx >= x0 && gx < x0 + T::TWU && gx < C.pix_w;   // lane groups are wholly useful or wholly halo
-    const int rnd = SHIFT ? (1 << (SHIFT - 1)) : 0;
-    const int rend = min(R + TH - 1, min(rhi, C.pix_h - 1 - ys));
-    for (int r = R + warp; r <= rend; r += NT / 32) {
-      const int2 ev = *reinterpret_cast<const int2*>(E + r * RP + 2 * lane);
-      const int2 ov = *reinterpret_cast<const int2*>(O + r * RP + 2 * lane);
-      int e[2] = {ev.x, ev.y}, o[2] = {ov.x, ov.y};
-      hsteps<K, -1>(e, o, lane, hedge, plo, phi);
-      if (!mine) continue;
-      int v[4] = {e[0], o[0], e[1], o[1]};
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        if (SHIFT) v[k] = (v[k] + rnd) >> SHIFT;
-        if (KIND != SAMPLE_I32) v[k] = (int)((unsigned)(min(max(v[k], C.clip_min), C.clip_max) + C.soffset) << C.sshift);
-      }
-      const long long rowoff = (long long)(ys + r) * C.pix_pitch;
-      const bool whole = gx + 3 < C.pix_w;
-      if (KIND == SAMPLE_I32) {
-        int* dst = (int*)C.pix + (long long)pic * C.pix_pic_stride + rowoff + gx;
-        if (whole && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) *reinterpret_cast<int4*>(dst) = make_int4(v[0], v[1], v[2], v[3]);
-        else {
-#pragma unroll
-          for (int k = 0; k < 4; ++k) if (gx + k < C.pix_w) dst[k] = v[k];
-        }
-      } else if (KIND == SAMPLE_U16BE) {
-        // offset binary, MSB justified, big endian (Arrays.cpp:396-414)
-        uint16_t* dst = (uint16_t*)((uint8_t*)C.pix + (long long)pic * C.pix_pic_stride) + rowoff + gx;
-        unsigned h[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) h[k] = __byte_perm((unsigned)v[k], 0, 0x4401);
-        if (whole && ((reinterpret_cast<uintptr_t>(dst) & 7) == 0)) *reinterpret_cast<uint2*>(dst) = make_uint2(h[0] | (h[1] << 16), h[2] | (h[3] << 16));
-        else {
-#pragma unroll
-          for (int k = 0; k < 4; ++k) if (gx + k < C.pix_w) dst[k] = (uint16_t)h[k];
-        }
-      } else {
-        uint8_t* dst = (uint8_t*)C.pix + (long long)pic * C.pix_pic_stride + rowoff + gx;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) if (gx + k < C.pix_w) dst[k] = (uint8_t)v[k];
-      }
+    const int r = a - L2;
+    if (r >= 0 && r <= H - 1) {
+      if constexpr (!SC::last_targets_A) inv_emit_row<K, KIND, PPL>(C, S, r, g.A[L2 / 2]);
+      else inv_emit_row<K, KIND, PPL>(C, S, r, g.B[(L2 - SC::reach(0)) / 2]);
     }
   }
 }
 
+template <int K, int KIND>
+__global__ void __launch_bounds__(32 * WARPS, 4) dwt_inv_kernel(const DwtParams p, int seg_rows) {
+  using SC = Sched<K, -1>;
+  const int comp = blockIdx.z % p.ncomp;
+  const DwtComp& C = p.c[comp];
+  StripCtx S;
+  S.pic = blockIdx.z / p.ncomp;
+  if (!strip_setup<K>(C, seg_rows, S, true)) return;
+  S.y1 = min(S.y1, C.pix_h + (C.pix_h & 1));   // rows beyond the crop are never needed
+  const BandAddr ba = {C.bh, C.bw, C.lgbh, C.lgbw, C.nx, C.NC >> 2};
+  Rings<K, -1> g;
+  g.clear();
+  const int tau0 = max((S.y0 - SC::total_reach() - SC::PA) >> 1, 0);
+  const int tau_end = (S.y1 - 1 + SC::lag(SC::n - 1) - SC::PA + 2) >> 1;
+#pragma unroll 1
+  for (int tau = tau0; tau < tau_end; ++tau) inv_pair<K, KIND>(C, S, ba, g, tau);
+}
+
 // ------------------------------------------------------------------------------------------
-// layout kernels: reference in-place interleaved plane <-> slice-major coefficient block
+// layout kernels: reference in-place interleaved plane <-> group-interleaved coefficient block
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ long long slice_major_index(const SliceGeom& g, int c, int y, int x) {
   const int d = g.depth;
@@ -400,42 +661,25 @@ __global__ void layout_kernel(const int32_t* __restrict__ src, int32_t* __restri
 }
 
 template <int K, int KIND>
-cudaError_t launch_fwd(cudaStream_t s, const DwtParams& p, dim3 grid) {
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(dwt_fwd_kernel<K, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, Tile<K>::BYTES);
-    if (e != cudaSuccess) return e;
-    attr_done = true;
-  }
-  dwt_fwd_kernel<K, KIND><<<grid, NT, Tile<K>::BYTES, s>>>(p);
-  return cudaGetLastError();
-}
-template <int K, int KIND>
-cudaError_t launch_inv(cudaStream_t s, const DwtParams& p, dim3 grid) {
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(dwt_inv_kernel<K, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, Tile<K>::BYTES);
-    if (e != cudaSuccess) return e;
-    attr_done = true;
-  }
-  dwt_inv_kernel<K, KIND><<<grid, NT, Tile<K>::BYTES, s>>>(p);
-  return cudaGetLastError();
-}
-
-template <int K, int KIND>
-cudaError_t launch_level(cudaStream_t s, bool inverse, const DwtParams& p, int npictures) {
+cudaError_t launch_level(cudaStream_t s, const DwtParams& p, int npictures, int seg_rows) {
   int mw = 0, mh = 0;
   for (int c = 0; c < p.ncomp; ++c) {
     mw = p.c[c].lat_w > mw ? p.c[c].lat_w : mw;
     mh = p.c[c].lat_h > mh ? p.c[c].lat_h : mh;
   }
-  const dim3 grid((mw + Tile<K>::TWU - 1) / Tile<K>::TWU, (mh + TH - 1) / TH, npictures * p.ncomp);
-  return inverse ? launch_inv<K, KIND>(s, p, grid) : launch_fwd<K, KIND>(s, p, grid);
+  const int segs = (mh + seg_rows - 1) / seg_rows;
+  const dim3 grid((mw + Geo<K>::XU - 1) / Geo<K>::XU, (segs + WARPS - 1) / WARPS, npictures * p.ncomp);
+#if VC2_DWT_PART == 1
+  dwt_fwd_kernel<K, KIND><<<grid, 32 * WARPS, 0, s>>>(p, seg_rows);
+#else
+  dwt_inv_kernel<K, KIND><<<grid, 32 * WARPS, 0, s>>>(p, seg_rows);
+#endif
+  return cudaGetLastError();
 }
 
 template <int KIND>
-cudaError_t dispatch(cudaStream_t s, bool inverse, int kernel, const DwtParams& p, int npictures) {
-#define VC2_CASE(K) case K: return launch_level<K, KIND>(s, inverse, p, npictures);
+cudaError_t dispatch(cudaStream_t s, int kernel, const DwtParams& p, int npictures, int seg_rows) {
+#define VC2_CASE(K) case K: return launch_level<K, KIND>(s, p, npictures, seg_rows);
   switch (kernel) {
     VC2_CASE(VC2_DD97) VC2_CASE(VC2_LEGALL) VC2_CASE(VC2_DD137) VC2_CASE(VC2_HAAR0)
     VC2_CASE(VC2_HAAR1) VC2_CASE(VC2_FIDELITY) VC2_CASE(VC2_DAUB97)
@@ -446,21 +690,31 @@ cudaError_t dispatch(cudaStream_t s, bool inverse, int kernel, const DwtParams& 
 
 }  // namespace
 
-cudaError_t dwt_level_launch(cudaStream_t s, bool inverse, int kernel, int sample_kind, const DwtParams& p, int npictures) {
+// seg_rows: lattice rows per warp (even); the host picks it so that the grid fills the GPU.
+// This file is compiled twice (Makefile): VC2_DWT_PART=1 forward kernels, =2 inverse kernels + layout.
+#if VC2_DWT_PART == 1
+cudaError_t dwt_fwd_launch(cudaStream_t s, int kernel, int sample_kind, const DwtParams& p, int npictures, int seg_rows) {
+#else
+cudaError_t dwt_inv_launch(cudaStream_t s, int kernel, int sample_kind, const DwtParams& p, int npictures, int seg_rows) {
+#endif
+  if (seg_rows < 2 || (seg_rows & 1)) return cudaErrorInvalidValue;
   switch (sample_kind) {
-    case SAMPLE_I32: return dispatch<SAMPLE_I32>(s, inverse, kernel, p, npictures);
-    case SAMPLE_U16BE: return dispatch<SAMPLE_U16BE>(s, inverse, kernel, p, npictures);
-    case SAMPLE_U8: return dispatch<SAMPLE_U8>(s, inverse, kernel, p, npictures);
+    case SAMPLE_I32: return dispatch<SAMPLE_I32>(s, kernel, p, npictures, seg_rows);
+    case SAMPLE_U16BE: return dispatch<SAMPLE_U16BE>(s, kernel, p, npictures, seg_rows);
+    case SAMPLE_U8: return dispatch<SAMPLE_U8>(s, kernel, p, npictures, seg_rows);
     default: return cudaErrorInvalidValue;
   }
 }
 
-// src/dst: one in-place plane (ph x pw) and one picture's slice-major block
+#if VC2_DWT_PART == 2
+// src/dst: one in-place plane (ph x pw) and one picture's group-interleaved block
 cudaError_t layout_launch(cudaStream_t s, bool to_slice_major, const int32_t* src, int32_t* dst, const SliceGeom& g, int c) {
   const PlaneGeom& pg = g.plane[c];
   const dim3 block(32, 8), grid((pg.pw + 31) / 32, (pg.ph + 7) / 8);
   layout_kernel<<<grid, block, 0, s>>>(src, dst, g, c, to_slice_major);
   return cudaGetLastError();
 }
+
+#endif
 
 }  // namespace vc2
