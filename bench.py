@@ -267,21 +267,68 @@ def main():
     for dst, src in zip(h_pics, frames):
         dst[:] = src
 
-    def e2e_step():
-        lens = codec.encode_host(h_pics, h_pay)
-        codec.decode_host(h_pay, lens, h_out)
-        return lens
-    for _ in range(3):
-        lens = e2e_step()
+    # A two-stage host pipeline, as a transcoding application would run it: batch k+1 is encoded (thread A,
+    # its own context, streams and codec) while batch k is decoded (thread B), so the H2D-heavy encode and the
+    # D2H-heavy decode share the full-duplex PCIe link.  Every batch still makes the whole round trip
+    # host pictures -> host payloads -> host pictures; the payload buffers are double buffered.
+    import threading
+    import queue
+    ctx2 = vc2.Context(local_rank)
+    dec_codec = vc2.Codec(ctx2, g, "HQ_ConstQ", qindex=w["q"], luma_depth=w["bits"], max_pictures=B)
+    h_pay2 = [h_pay, [pin(cap) for _ in range(B)]]
+
+    def e2e_run(nsteps):
+        q = queue.Queue(maxsize=1)
+        free = queue.Queue()
+        free.put(0)
+        free.put(1)
+        out = {}
+
+        def producer():
+            for _ in range(nsteps):
+                b = free.get()
+                q.put((b, codec.encode_host(h_pics, h_pay2[b])))
+            q.put(None)
+
+        def consumer():
+            while True:
+                item = q.get()
+                if item is None:
+                    return
+                b, ln = item
+                dec_codec.decode_host(h_pay2[b], ln, h_out)
+                out["lens"], out["buf"] = ln, b
+                free.put(b)
+        ta, tb = threading.Thread(target=producer), threading.Thread(target=consumer)
+        ta.start(); tb.start(); ta.join(); tb.join()
+        return out["lens"], out["buf"]
+
+    e2e_run(3)
     e2e_steps = max(3, min(args.steps, 10))
     barrier()
-    ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ea.record()
-    for _ in range(e2e_steps):
-        lens = e2e_step()
-    eb.record()
+    t0 = time.perf_counter()
+    lens, lastbuf = e2e_run(e2e_steps)
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) * 1000.0
     barrier()
-    e2e_ms = ea.elapsed_time(eb)
+    h_pay = h_pay2[lastbuf]
+    assert h_out[0].tobytes() == codec.download_picture(0), "host round trip and device round trip disagree"
+
+    # what the PCIe link gives a plain pinned copy, for scale (not part of any reported throughput)
+    def copy_gbs(dst, src, nbytes):
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(4):
+            dst.copy_(src, non_blocking=True)
+        b.record()
+        torch.cuda.synchronize()
+        return 4 * nbytes / (a.elapsed_time(b) / 1000.0) / 1e9
+    nb = 256 << 20
+    hbuf = torch.empty(nb, dtype=torch.uint8, pin_memory=True)
+    dbuf = torch.empty(nb, dtype=torch.uint8, device="cuda")
+    pcie = {"h2d_gbs": copy_gbs(dbuf, hbuf, nb), "d2h_gbs": copy_gbs(hbuf, dbuf, nb)}
+    del hbuf, dbuf
     n_slices = g.slices_x * g.slices_y
     h2d = B * codec.picture_bytes + sum(lens) + B * 4 * (n_slices + 1)
     d2h = sum(lens) + B * codec.picture_bytes + 2 * B * 4 * n_slices + 4 * B
@@ -330,7 +377,9 @@ def main():
                        "compressed_bytes_per_frame": C_bytes},
             "gpixel_per_s": fps * w["w"] * w["h"] / 1e9,
             "encode_fps": world * B / (enc_ms / 1000.0), "decode_fps": world * B / (dec_ms / 1000.0),
-            "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e2e_steps},
+            "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
+                    "how": "vc2_codec_encode_host + vc2_codec_decode_host on pinned host buffers; batch k+1 encodes while batch k decodes (two host threads)",
+                    "pcie_pinned_copy": pcie},
             "gpu_launches": launches,
             "clocks": clk,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
@@ -357,6 +406,8 @@ def main():
             else:
                 line["cpu_baseline"] = {"value": None, "unit": "frames/s", "cores": 0, "kind": "reference", "sample": "oracle/_ref missing"}
         print(json.dumps(line))
+    dec_codec.close()
+    ctx2.close()
     codec.close()
     ctx.close()
     if world > 1:

@@ -5,10 +5,12 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #include <algorithm>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "dwt.cuh"
@@ -844,7 +846,10 @@ struct vc2_codec {
   std::vector<size_t> payload_len;    // host copy per slot (decode)
   uint32_t* host_offs = nullptr;      // pinned staging for slice offset tables
   cudaStream_t copy_in = nullptr, copy_out = nullptr;
-  cudaEvent_t ev_in[2], ev_done[2], ev_out[2];
+  // software pipeline of the host-buffer entry points: one event triple per slot
+  std::vector<cudaEvent_t> ev_in, ev_done, ev_out;
+  uint32_t* host_flags = nullptr;     // pinned: per-slot error flags [B][nslices]
+  uint32_t* host_len = nullptr;       // pinned: per-slot payload length [B]
 };
 
 static void codec_free(vc2_codec* k) {
@@ -855,6 +860,11 @@ static void codec_free(vc2_codec* k) {
                    &k->qidx, &k->staging, &k->sizes, &k->sbytes, &k->fixed, &k->tmp_plane, &k->tmp_q};
   for (DevBuf* b : all) b->release();
   if (k->host_offs) cudaFreeHost(k->host_offs);
+  if (k->host_flags) cudaFreeHost(k->host_flags);
+  if (k->host_len) cudaFreeHost(k->host_len);
+  for (auto e : k->ev_in) cudaEventDestroy(e);
+  for (auto e : k->ev_done) cudaEventDestroy(e);
+  for (auto e : k->ev_out) cudaEventDestroy(e);
   if (k->copy_in) cudaStreamDestroy(k->copy_in);
   if (k->copy_out) cudaStreamDestroy(k->copy_out);
   delete k;
@@ -919,7 +929,18 @@ extern "C" vc2_codec* vc2_codec_create(vc2_ctx* ctx, const vc2_codec_params* prm
   R(k->fixed, (size_t)(k->nslices + 1) * 4);
   R(k->tmp_plane, (size_t)g.plane[0].size() * 4);
   R(k->tmp_q, (size_t)g.plane[0].size() * 4);
-  if (ok && cudaMallocHost((void**)&k->host_offs, (size_t)(k->nslices + 1) * 4 * B) != cudaSuccess) ok = false;
+  if (ok && cudaMallocHost((void**)&k->host_offs, (size_t)(k->nslices + 1) * 4 * 2 * B) != cudaSuccess) ok = false;   // two table sets: one in flight, one being built
+  if (ok && cudaMallocHost((void**)&k->host_flags, (size_t)k->nslices * 4 * 2 * B) != cudaSuccess) ok = false;
+  if (ok && cudaMallocHost((void**)&k->host_len, (size_t)4 * B) != cudaSuccess) ok = false;
+  for (int i = 0; ok && i < B; ++i) {
+    cudaEvent_t e[3];
+    for (int j = 0; j < 3; ++j) if (cudaEventCreateWithFlags(&e[j], cudaEventDisableTiming) != cudaSuccess) ok = false;
+    if (ok) { k->ev_in.push_back(e[0]); k->ev_done.push_back(e[1]); k->ev_out.push_back(e[2]); }
+  }
+  for (int i = 0; ok && i < B; ++i) {   // decode_host keeps two chunks in flight: a second set of "picture has left" events
+    cudaEvent_t e;
+    if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) ok = false; else k->ev_out.push_back(e);
+  }
   if (ok && cudaStreamCreateWithFlags(&k->copy_in, cudaStreamNonBlocking) != cudaSuccess) ok = false;
   if (ok && cudaStreamCreateWithFlags(&k->copy_out, cudaStreamNonBlocking) != cudaSuccess) ok = false;
   if (ok && !k->slice_bytes.empty()) {
@@ -1180,35 +1201,101 @@ extern "C" int vc2_codec_read_indices(vc2_codec* k, int slot, int32_t* qidx) {
   return VC2_OK;
 }
 
-// ---- end to end with host buffers: batches of max_pictures, H2D -> kernels -> D2H -----------------
+// ---- end to end with host buffers -------------------------------------------------------------------
+// Software pipeline over the B = max_pictures slots, one picture per stage: the H2D copy of picture i+1
+// (copy_in stream), the kernels of picture i (context stream) and the D2H copy of picture i-1 (copy_out
+// stream) overlap; streams are ordered with events, the host only blocks to learn a payload length
+// (encode) or to reuse a pinned staging table (decode).
+// pictures per pipeline stage: kernels on a single picture leave most of the GPU idle, so once the batch has
+// room for it a stage carries two pictures (the copy of a stage still overlaps the kernels of the previous one)
+static int stage_pictures(int B) { return (B >= 4 && B % 2 == 0) ? 2 : 1; }
+
 extern "C" int vc2_codec_encode_host(vc2_codec* k, int n, const void* const* pictures, uint8_t* const* payloads, size_t cap,
                                      size_t* payload_len) {
   KARG(k && pictures && payloads && payload_len && n >= 1);
   vc2_ctx* ctx = k->ctx;
   CU(cudaSetDevice(ctx->device));
-  const int B = k->prm.max_pictures;
-  std::vector<uint32_t> flags;
-  for (int base = 0; base < n; base += B) {
-    const int m = std::min(B, n - base);
-    for (int i = 0; i < m; ++i)
-      CU(cudaMemcpyAsync(vc2_codec_samples_dev(k, i), pictures[base + i], k->pic_bytes, cudaMemcpyHostToDevice, ctx->stream));
-    const int st = codec_encode_range(k, 0, m);
-    if (st) return st;
-    // payload lengths = last entry of each slice offset table
-    CU(cudaMemcpy2DAsync(k->host_offs, 4, k->slice_off.as<uint32_t>() + k->nslices, (size_t)(k->nslices + 1) * 4, 4, m,
-                         cudaMemcpyDeviceToHost, ctx->stream));
-    flags.resize((size_t)m * k->nslices);
-    CU(cudaMemcpyAsync(flags.data(), k->err.p, flags.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
-    for (int i = 0; i < m; ++i) {
-      const int e = first_error(flags.data() + (size_t)i * k->nslices, k->nslices);
-      if (e) return fail(ctx, e);
-      payload_len[base + i] = k->host_offs[i];
-      if (payload_len[base + i] > cap) return fail(ctx, VC2_ERR_CAPACITY);
-      CU(cudaMemcpyAsync(payloads[base + i], vc2_codec_payload_dev(k, i), payload_len[base + i], cudaMemcpyDeviceToHost, ctx->stream));
+  const int B = k->prm.max_pictures, ns = k->nslices;
+  const int sub = stage_pictures(B), nstage_slots = B / sub;
+  const int lag = std::min(2, nstage_slots - 1);   // stages in flight behind the newest upload
+  const int nstages = (n + sub - 1) / sub;
+  int status = VC2_OK;
+  auto drain = [&](int st) -> int {     // stage st: wait for its kernels, then send its payloads home
+    const int slot0 = (st % nstage_slots) * sub, first = st * sub, m = std::min(sub, n - first);
+    cudaError_t e = cudaEventSynchronize(k->ev_done[slot0]);
+    if (e != cudaSuccess) return cuda_fail(ctx, e);
+    for (int j = 0; j < m; ++j) {
+      const int er = first_error(k->host_flags + (size_t)(slot0 + j) * ns, ns);
+      if (er) return fail(ctx, er);
+      payload_len[first + j] = k->host_len[slot0 + j];
+      if (payload_len[first + j] > cap) return fail(ctx, VC2_ERR_CAPACITY);
+      e = cudaMemcpyAsync(payloads[first + j], vc2_codec_payload_dev(k, slot0 + j), payload_len[first + j], cudaMemcpyDeviceToHost, k->copy_out);
+      if (e != cudaSuccess) return cuda_fail(ctx, e);
     }
-    CU(cudaStreamSynchronize(ctx->stream));
+    e = cudaEventRecord(k->ev_out[slot0], k->copy_out);
+    return e == cudaSuccess ? VC2_OK : cuda_fail(ctx, e);
+  };
+  CU(cudaStreamSynchronize(ctx->stream));   // earlier work of the caller on the slots
+  for (int st = 0; st < nstages && status == VC2_OK; ++st) {
+    const int slot0 = (st % nstage_slots) * sub, first = st * sub, m = std::min(sub, n - first);
+    if (st >= nstage_slots) CU(cudaStreamWaitEvent(k->copy_in, k->ev_done[slot0], 0));   // the samples in these slots have been consumed
+    for (int j = 0; j < m; ++j)
+      CU(cudaMemcpyAsync(vc2_codec_samples_dev(k, slot0 + j), pictures[first + j], k->pic_bytes, cudaMemcpyHostToDevice, k->copy_in));
+    CU(cudaEventRecord(k->ev_in[slot0], k->copy_in));
+    CU(cudaStreamWaitEvent(ctx->stream, k->ev_in[slot0], 0));
+    if (st >= nstage_slots) CU(cudaStreamWaitEvent(ctx->stream, k->ev_out[slot0], 0));   // the payloads have left these slots
+    status = codec_encode_range(k, slot0, m);
+    if (status) break;
+    CU(cudaMemcpy2DAsync(k->host_len + slot0, 4, vc2_codec_slice_offsets_dev(k, slot0) + ns, (size_t)(ns + 1) * 4, 4, m,
+                         cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(k->host_flags + (size_t)slot0 * ns, k->err.as<uint32_t>() + (size_t)slot0 * ns, (size_t)ns * 4 * m,
+                       cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaEventRecord(k->ev_done[slot0], ctx->stream));
+    if (st >= lag) status = drain(st - lag);
   }
+  for (int st = std::max(0, nstages - lag); st < nstages && status == VC2_OK; ++st) status = drain(st);
+  cudaStreamSynchronize(k->copy_out);
+  cudaStreamSynchronize(ctx->stream);
+  return status;
+}
+
+// Slice offsets of m HQ payloads.  Walking the length bytes of ONE payload is a chain of dependent loads
+// (Slices.cpp:544-605: every length is where the previous component ended), one cache miss each.  Several
+// payloads are therefore walked in lock step - their chains are independent, so the misses overlap - and
+// the pictures are dealt to a few host threads.
+static int index_many(const vc2_codec* k, int m, const uint8_t* const* payloads, const size_t* lens, uint32_t* tables) {
+  const int ns = k->nslices, prefix = k->g.prefix, scalar = k->g.scalar;
+  const int T = std::max(1, std::min({m / 2, 4, (int)std::thread::hardware_concurrency()}));
+  std::vector<int> status(T, VC2_OK);
+  auto work = [&](int t) {
+    enum { W = 8 };
+    for (int j0 = t * W; j0 < m; j0 += T * W) {
+      const int w = std::min((int)W, m - j0);
+      size_t pos[W] = {0};
+      for (int s = 0; s < ns; ++s)
+        for (int j = 0; j < w; ++j) {
+          const uint8_t* p = payloads[j0 + j];
+          const size_t len = lens[j0 + j];
+          tables[(size_t)(j0 + j) * (ns + 1) + s] = (uint32_t)pos[j];
+          size_t q = pos[j] + prefix + 1;
+          for (int c = 0; c < 3; ++c) {
+            if (q >= len) { status[t] = VC2_ERR_STREAM; return; }
+            q += 1 + (size_t)p[q] * scalar;
+          }
+          if (q > len) { status[t] = VC2_ERR_STREAM; return; }
+          pos[j] = q;
+        }
+      for (int j = 0; j < w; ++j) tables[(size_t)(j0 + j) * (ns + 1) + ns] = (uint32_t)pos[j];
+    }
+  };
+  if (T == 1) work(0);
+  else {
+    std::vector<std::thread> th;
+    for (int t = 1; t < T; ++t) th.emplace_back(work, t);
+    work(0);
+    for (auto& x : th) x.join();
+  }
+  for (int t = 0; t < T; ++t) if (status[t]) return status[t];
   return VC2_OK;
 }
 
@@ -1217,29 +1304,69 @@ extern "C" int vc2_codec_decode_host(vc2_codec* k, int n, const uint8_t* const* 
   KARG(k && pictures && payloads && payload_len && n >= 1);
   vc2_ctx* ctx = k->ctx;
   CU(cudaSetDevice(ctx->device));
-  const int B = k->prm.max_pictures;
-  std::vector<uint32_t> flags;
-  for (int base = 0; base < n; base += B) {
-    const int m = std::min(B, n - base);
+  const int B = k->prm.max_pictures, ns = k->nslices;
+  const bool hq = k->prm.mode != VC2_LD;
+  for (int i = 0; i < n; ++i) {
+    if (payload_len[i] > k->payload_cap) return fail(ctx, VC2_ERR_CAPACITY);
+    if (!hq && payload_len[i] < k->fixed_off[ns]) return fail(ctx, VC2_ERR_STREAM);
+  }
+  CU(cudaStreamSynchronize(ctx->stream));
+  auto tables = [&](int set) { return k->host_offs + (size_t)set * B * (ns + 1); };
+  auto flags = [&](int set) { return k->host_flags + (size_t)set * B * ns; };
+  auto check = [&](int c) -> int {   // wait for chunk c and look at its error flags
+    const int m = std::min(B, n - c * B);
+    const int sub = stage_pictures(B);
+    cudaError_t e = cudaEventSynchronize(k->ev_out[(c & 1) * B + (m - 1) / sub * sub]);
+    if (e != cudaSuccess) return cuda_fail(ctx, e);
     for (int i = 0; i < m; ++i) {
-      if (payload_len[base + i] > k->payload_cap) return fail(ctx, VC2_ERR_CAPACITY);
-      const int st = codec_index_payload(k, i, payloads[base + i], payload_len[base + i]);
-      if (st) return fail(ctx, st);
-      CU(cudaMemcpyAsync(vc2_codec_payload_dev(k, i), payloads[base + i], payload_len[base + i], cudaMemcpyHostToDevice, ctx->stream));
+      const int st = first_error(flags(c & 1) + (size_t)i * ns, ns);
+      if (st && st != VC2_ERR_VLC_RANGE) return fail(ctx, st);
     }
-    if (k->prm.mode != VC2_LD)
-      CU(cudaMemcpyAsync(k->slice_off.p, k->host_offs, (size_t)(k->nslices + 1) * 4 * m, cudaMemcpyHostToDevice, ctx->stream));
-    const int st = codec_decode_range(k, 0, m);
-    if (st) return st;
-    for (int i = 0; i < m; ++i)
-      CU(cudaMemcpyAsync(pictures[base + i], vc2_codec_recon_dev(k, i), k->pic_bytes, cudaMemcpyDeviceToHost, ctx->stream));
-    flags.resize((size_t)m * k->nslices);
-    CU(cudaMemcpyAsync(flags.data(), k->err.p, flags.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
-    for (int i = 0; i < m; ++i) {
-      const int e = first_error(flags.data() + (size_t)i * k->nslices, k->nslices);
-      if (e && e != VC2_ERR_VLC_RANGE) return fail(ctx, e);
+    return VC2_OK;
+  };
+  const int chunks = (n + B - 1) / B;
+  int status = VC2_OK, last_stage_slot = 0;
+  (void)last_stage_slot;
+  if (hq) status = index_many(k, std::min(B, n), payloads, payload_len, tables(0));
+  if (status) return fail(ctx, status);
+  for (int c = 0; c < chunks && status == VC2_OK; ++c) {
+    const int base = c * B, m = std::min(B, n - base);
+    const int sub = stage_pictures(B);
+    for (int i = 0; i < m; i += sub) {   // slots i .. i+mm-1; every wait below is stream side, the host does not block
+      const int mm = std::min(sub, m - i);
+      if (c > 0) CU(cudaStreamWaitEvent(k->copy_in, k->ev_done[i], 0));      // the previous payloads in these slots have been parsed
+      for (int j = i; j < i + mm; ++j) {
+        CU(cudaMemcpyAsync(vc2_codec_payload_dev(k, j), payloads[base + j], payload_len[base + j], cudaMemcpyHostToDevice, k->copy_in));
+        if (hq)
+          CU(cudaMemcpyAsync(vc2_codec_slice_offsets_dev(k, j), tables(c & 1) + (size_t)j * (ns + 1), (size_t)(ns + 1) * 4,
+                             cudaMemcpyHostToDevice, k->copy_in));
+      }
+      CU(cudaEventRecord(k->ev_in[i], k->copy_in));
+      CU(cudaStreamWaitEvent(ctx->stream, k->ev_in[i], 0));
+      if (c > 0) CU(cudaStreamWaitEvent(ctx->stream, k->ev_out[((c - 1) & 1) * B + i], 0));   // the previous pictures have left these slots
+      status = codec_decode_range(k, i, mm);
+      if (status) break;
+      CU(cudaEventRecord(k->ev_done[i], ctx->stream));
+      CU(cudaStreamWaitEvent(k->copy_out, k->ev_done[i], 0));
+      for (int j = i; j < i + mm; ++j)
+        CU(cudaMemcpyAsync(pictures[base + j], vc2_codec_recon_dev(k, j), k->pic_bytes, cudaMemcpyDeviceToHost, k->copy_out));
+      CU(cudaMemcpyAsync(flags(c & 1) + (size_t)i * ns, k->err.as<uint32_t>() + (size_t)i * ns, (size_t)ns * 4 * mm, cudaMemcpyDeviceToHost,
+                         k->copy_out));
+      CU(cudaEventRecord(k->ev_out[(c & 1) * B + i], k->copy_out));
+      last_stage_slot = i;
+    }
+    if (status) break;
+    if (c + 1 < chunks) {
+      // build the next chunk's tables while this chunk is in flight; their set was last read by chunk c-1
+      if (c >= 1) status = check(c - 1);
+      if (!status && hq)
+        status = index_many(k, std::min(B, n - (c + 1) * B), payloads + (c + 1) * B, payload_len + (c + 1) * B, tables((c + 1) & 1));
+      if (status && status > -100) fail(ctx, status);
     }
   }
-  return VC2_OK;
+  if (status == VC2_OK && chunks >= 2) status = check(chunks - 2);
+  if (status == VC2_OK) status = check(chunks - 1);
+  cudaStreamSynchronize(k->copy_out);
+  cudaStreamSynchronize(ctx->stream);
+  return status;
 }
