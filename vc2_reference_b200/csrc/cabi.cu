@@ -218,6 +218,7 @@ struct vc2_ctx {
   long launches = 0;
   DevBuf tmp[8];   // scratch for the Library-surface (host pointer) calls
   int dwt_min_warps = 148 * 48;   // streaming DWT: cut rows into segments until the grid has at least this many warps
+  int dwt_pd = 2;                 // prefetch distance in row pairs (VC2_DWT_PD)
   int dwt_seg_rows = 0;           // > 0: forced rows per warp (tuning, VC2_DWT_SEG_ROWS)
   // optional per-kernel timing with CUDA events on the launch stream (vc2_profile_*)
   bool profiling = false;
@@ -278,6 +279,7 @@ extern "C" vc2_ctx* vc2_create(int device) {
   c->device = device;
   if (const char* e = getenv("VC2_DWT_SEG_ROWS")) c->dwt_seg_rows = atoi(e) & ~1;
   if (const char* e = getenv("VC2_DWT_MIN_WARPS")) c->dwt_min_warps = atoi(e);
+  if (const char* e = getenv("VC2_DWT_PD")) c->dwt_pd = atoi(e);
   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return nullptr; }
   c->own_stream = true;
   QuantTables t;
@@ -382,6 +384,7 @@ static cudaError_t run_dwt(vc2_ctx* ctx, bool inverse, int kernel, int depth, in
     DwtParams p;
     memset(&p, 0, sizeof(p));
     p.ncomp = ncomp;
+    p.pd = ctx->dwt_pd;
     for (int c = 0; c < ncomp; ++c) {
       const CompBuf& B = cb[c];
       DwtComp& C = p.c[c];

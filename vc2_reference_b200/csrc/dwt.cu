@@ -252,7 +252,7 @@ struct BandAddr {   // group-interleaved addressing of band samples (see vc2_com
 };
 
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
-constexpr int PD = 2;   // prefetch distance in row pairs
+// prefetch distance in row pairs: StripCtx::pd (DwtParams::pd, host tuned)
 
 // forward: touch the cache line(s) of this lane's samples of picture row `row`
 template <int KIND, int V>
@@ -377,6 +377,7 @@ struct StripCtx {
   int y0, y1;        // rows to output: [y0, y1)
   int bxmax;         // last band column = lat_w / 2 - 1
   bool mine;         // this lane's columns are useful (not halo) and inside the lattice
+  int pd;            // prefetch distance in row pairs
 };
 
 // ------------------------------------------------------------------------------------------
@@ -422,8 +423,8 @@ __device__ __forceinline__ void fwd_pair(const DwtComp& C, const StripCtx& S, co
   constexpr int V = Vec<K>::V, PPL = V / 2, n = SC::n;
   const int H = S.H;
   const int a = 2 * tau + SC::PA;
-  prefetch_pix<KIND, V>(C, S.pic, a + 2 * PD, S.xs + V * S.lane);
-  prefetch_pix<KIND, V>(C, S.pic, a + 2 * PD - SC::reach(0), S.xs + V * S.lane);
+  prefetch_pix<KIND, V>(C, S.pic, a + 2 * S.pd, S.xs + V * S.lane);
+  prefetch_pix<KIND, V>(C, S.pic, a + 2 * S.pd - SC::reach(0), S.xs + V * S.lane);
   g.shift();
   if (a <= H - 1) fwd_fetch_row<K, KIND, PPL>(C, S, a, g.A[0]);
   const int r0 = a - SC::reach(0);
@@ -481,6 +482,7 @@ __global__ void __launch_bounds__(32 * WARPS, 4) dwt_fwd_kernel(const DwtParams 
   const DwtComp& C = p.c[comp];
   StripCtx S;
   S.pic = blockIdx.z / p.ncomp;
+  S.pd = p.pd;
   if (!strip_setup<K>(C, seg_rows, S, false)) return;
   const BandAddr ba = {C.bh, C.bw, C.lgbh, C.lgbw, C.nx, C.NC >> 2};
   Rings<K, +1> g;
@@ -584,8 +586,8 @@ __device__ __forceinline__ void inv_pair(const DwtComp& C, const StripCtx& S, co
   constexpr int V = Vec<K>::V, PPL = V / 2, n = SC::n;
   const int H = S.H;
   const int a = 2 * tau + SC::PA;
-  inv_prefetch_row<PPL>(C, S, ba, a + 2 * PD);
-  inv_prefetch_row<PPL>(C, S, ba, a + 2 * PD - SC::reach(0));
+  inv_prefetch_row<PPL>(C, S, ba, a + 2 * S.pd);
+  inv_prefetch_row<PPL>(C, S, ba, a + 2 * S.pd - SC::reach(0));
   g.shift();
   if (a <= H - 1) inv_fetch_row<K, PPL>(C, S, ba, a, g.A[0]);
   const int r0 = a - SC::reach(0);
@@ -620,6 +622,7 @@ __global__ void __launch_bounds__(32 * WARPS, 4) dwt_inv_kernel(const DwtParams 
   const DwtComp& C = p.c[comp];
   StripCtx S;
   S.pic = blockIdx.z / p.ncomp;
+  S.pd = p.pd;
   if (!strip_setup<K>(C, seg_rows, S, true)) return;
   S.y1 = min(S.y1, C.pix_h + (C.pix_h & 1));   // rows beyond the crop are never needed
   const BandAddr ba = {C.bh, C.bw, C.lgbh, C.lgbw, C.nx, C.NC >> 2};

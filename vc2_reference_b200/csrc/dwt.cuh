@@ -96,6 +96,7 @@ struct DwtComp {
 struct DwtParams {
   DwtComp c[3];
   int ncomp;
+  int pd;   // prefetch distance of the streaming kernels, in row pairs
 };
 
 }  // namespace vc2
