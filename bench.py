@@ -229,8 +229,6 @@ def main():
     assert len(codec.download_picture(0)) == codec.picture_bytes
 
     ctx.kernel_launches(reset=True)
-    ctx.profile_enable(True)
-    ctx.profile_read()
     clocks = ClockSampler(local_rank)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -242,6 +240,14 @@ def main():
     ms = ev0.elapsed_time(ev1)
     clk = clocks.stop()
     launches = ctx.kernel_launches(reset=True)
+
+    # per-kernel CUDA-event times: the same steps again with the context's stage profiler on.  The profiler
+    # serialises the sub-batch streams (overlapped kernels cannot be timed one by one), so the stage times
+    # add up to slightly more than ms_per_step of the timed region above.
+    ctx.profile_enable(True)
+    ctx.profile_read()
+    for _ in range(args.steps):
+        step()
     prof = ctx.profile_read()
     ctx.profile_enable(False)
 
@@ -328,7 +334,21 @@ def main():
     hbuf = torch.empty(nb, dtype=torch.uint8, pin_memory=True)
     dbuf = torch.empty(nb, dtype=torch.uint8, device="cuda")
     pcie = {"h2d_gbs": copy_gbs(dbuf, hbuf, nb), "d2h_gbs": copy_gbs(hbuf, dbuf, nb)}
-    del hbuf, dbuf
+    # both directions at once (two streams): the ceiling of the concurrent encode + decode pipeline, which moves
+    # h2d_bytes_per_step one way and d2h_bytes_per_step the other way every step
+    hbuf2 = torch.empty(nb, dtype=torch.uint8, pin_memory=True)
+    dbuf2 = torch.empty(nb, dtype=torch.uint8, device="cuda")
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(4):
+        with torch.cuda.stream(s1):
+            dbuf.copy_(hbuf, non_blocking=True)
+        with torch.cuda.stream(s2):
+            hbuf2.copy_(dbuf2, non_blocking=True)
+    torch.cuda.synchronize()
+    pcie["bidir_total_gbs"] = 2 * 4 * nb / (time.perf_counter() - t0) / 1e9
+    del hbuf, dbuf, hbuf2, dbuf2
     n_slices = g.slices_x * g.slices_y
     h2d = B * codec.picture_bytes + sum(lens) + B * 4 * (n_slices + 1)
     d2h = sum(lens) + B * codec.picture_bytes + 2 * B * 4 * n_slices + 4 * B
@@ -373,13 +393,15 @@ def main():
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int32", "data": "synthetic",
             "config": {"workload": w["name"], "frames_per_step_per_gpu": B, "parallelism": "frame-sharded x%d, no collective" % world,
+                       "streams": "batch split into %s sub-batches on forked streams; stage times from a serialised pass" % os.environ.get("VC2_CODEC_SUBBATCH", "4"),
                        "cache": "inputs larger than L2 (%.0f MB of samples + %.0f MB of coefficients per step)" % (B * codec.picture_bytes / 1e6, B * 4 * S / 1e6),
                        "compressed_bytes_per_frame": C_bytes},
             "gpixel_per_s": fps * w["w"] * w["h"] / 1e9,
             "encode_fps": world * B / (enc_ms / 1000.0), "decode_fps": world * B / (dec_ms / 1000.0),
             "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
                     "how": "vc2_codec_encode_host + vc2_codec_decode_host on pinned host buffers; batch k+1 encodes while batch k decodes (two host threads)",
-                    "pcie_pinned_copy": pcie},
+                    "pcie_pinned_copy": pcie,
+                    "pcie_bound_fps": world * B * pcie["bidir_total_gbs"] * 1e9 / float(h2d + d2h)},
             "gpu_launches": launches,
             "clocks": clk,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "peak_source": peak_src, "unit": "GB/s",

@@ -129,3 +129,48 @@ def test_batch_slots_are_independent(ctx):
     many.upload_payload(0, singles[0])
     many.decode(1)
     assert outs[0].tobytes() == many.download_picture(0)
+
+
+@pytest.mark.parametrize("name", ["S01_LeGall_d3_422", "S05_Fidelity_d2_422", "S11_DD97_d4_422", "C1"])
+def test_host_entry_points_vs_golden(ctx, name):
+    """vc2_codec_encode_host / _decode_host (device-side slice index, several chunks per call) reproduce the
+    reference's payload and decoded bytes; prefix / scalar variants included"""
+    c = GOLD[name]["params"]
+    taps = GOLD[name]["taps"]
+    g = vc2.make_geom(c["h"], c["w"], c["fmt"], c["kernel"], c["wdepth"], c["u"], c["a"], c["P"], c["S"])
+    reps = 3                                   # 2 golden frames x 3 -> 6 pictures through a 4-slot codec: two chunks
+    frames = [np.frombuffer(gen.frame_bytes(c["seed"], f % c["frames"], c["w"], c["h"], c["fmt"], c["bits"]), np.uint8).copy()
+              for f in range(c["frames"] * reps)]
+    k = vc2.Codec(ctx, g, "HQ_ConstQ", qindex=c["q"], luma_depth=c["bits"], max_pictures=4)
+    bufs = [np.zeros(k.payload_capacity, np.uint8) for _ in frames]
+    lens = k.encode_host(frames, bufs)
+    for r in range(reps):
+        md = hashlib.md5()
+        for f in range(c["frames"]):
+            i = r * c["frames"] + f
+            md.update(bufs[i][:lens[i]].tobytes())
+        assert md.hexdigest() == taps["enc_Packaged"]["md5"], (name, "Packaged", r)
+    outs = [np.zeros(k.picture_bytes, np.uint8) for _ in frames]
+    k.decode_host(bufs, lens, outs)
+    for r in range(reps):
+        md = hashlib.md5()
+        for f in range(c["frames"]):
+            md.update(outs[r * c["frames"] + f].tobytes())
+        assert md.hexdigest() == taps["dec_Decoded"]["md5"], (name, "Decoded", r)
+    k.close()
+
+
+def test_decode_host_reports_truncated_payload(ctx):
+    """a payload that ends inside a slice is a stream error (the reference's reader would run off the end)"""
+    c = GOLD["S08_DD137_d4_422"]["params"]
+    g = vc2.make_geom(c["h"], c["w"], c["fmt"], c["kernel"], c["wdepth"], c["u"], c["a"], c["P"], c["S"])
+    k = vc2.Codec(ctx, g, "HQ_ConstQ", qindex=c["q"], luma_depth=c["bits"], max_pictures=2)
+    frames = [np.frombuffer(gen.frame_bytes(c["seed"], f, c["w"], c["h"], c["fmt"], c["bits"]), np.uint8).copy() for f in range(2)]
+    bufs = [np.zeros(k.payload_capacity, np.uint8) for _ in frames]
+    lens = k.encode_host(frames, bufs)
+    outs = [np.zeros(k.picture_bytes, np.uint8) for _ in frames]
+    with pytest.raises(vc2.Vc2Error) as e:
+        k.decode_host(bufs, [lens[0], lens[1] // 2], outs)
+    assert e.value.status == -9       # VC2_ERR_STREAM
+    k.decode_host(bufs, lens, outs)      # the codec is still usable afterwards
+    k.close()

@@ -849,8 +849,19 @@ struct vc2_codec {
   std::vector<size_t> payload_len;    // host copy per slot (decode)
   uint32_t* host_offs = nullptr;      // pinned staging for slice offset tables
   cudaStream_t copy_in = nullptr, copy_out = nullptr;
+  // device-resident entry points: the batch is cut into sub-batches that run on their own streams, so the
+  // small-grid kernels of one sub-batch (deep DWT levels, the slice scan) overlap the wide kernels of another
+  static constexpr int MAX_SUB = 4;
+  int nsub = 4;                        // VC2_CODEC_SUBBATCH
+  cudaStream_t sub_stream[MAX_SUB] = {nullptr, nullptr, nullptr, nullptr};   // [0] unused (= context stream)
+  cudaEvent_t sub_fork = nullptr, sub_join[MAX_SUB] = {nullptr, nullptr, nullptr, nullptr};
   // software pipeline of the host-buffer entry points: one event triple per slot
   std::vector<cudaEvent_t> ev_in, ev_done, ev_out;
+  // decode_host: the slice index of every payload is built on the device (hq_index_kernel, one CTA walking one
+  // picture for about a millisecond) on a per-slot stream, between the payload upload and the parse kernel, so
+  // the walks of all pictures in flight overlap each other and the other stages
+  std::vector<cudaStream_t> index_stream;
+  std::vector<cudaEvent_t> ev_idx;
   uint32_t* host_flags = nullptr;     // pinned: per-slot error flags [B][nslices]
   uint32_t* host_len = nullptr;       // pinned: per-slot payload length [B]
 };
@@ -868,8 +879,15 @@ static void codec_free(vc2_codec* k) {
   for (auto e : k->ev_in) cudaEventDestroy(e);
   for (auto e : k->ev_done) cudaEventDestroy(e);
   for (auto e : k->ev_out) cudaEventDestroy(e);
+  for (auto e : k->ev_idx) cudaEventDestroy(e);
+  for (auto st : k->index_stream) cudaStreamDestroy(st);
   if (k->copy_in) cudaStreamDestroy(k->copy_in);
   if (k->copy_out) cudaStreamDestroy(k->copy_out);
+  for (int i = 1; i < vc2_codec::MAX_SUB; ++i) {
+    if (k->sub_stream[i]) cudaStreamDestroy(k->sub_stream[i]);
+    if (k->sub_join[i]) cudaEventDestroy(k->sub_join[i]);
+  }
+  if (k->sub_fork) cudaEventDestroy(k->sub_fork);
   delete k;
 }
 
@@ -944,8 +962,22 @@ extern "C" vc2_codec* vc2_codec_create(vc2_ctx* ctx, const vc2_codec_params* prm
     cudaEvent_t e;
     if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) ok = false; else k->ev_out.push_back(e);
   }
+  for (int i = 0; ok && i < B; ++i) {
+    cudaEvent_t e;
+    if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) ok = false; else k->ev_idx.push_back(e);
+  }
+  for (int i = 0; ok && i < std::min(B, 8); ++i) {
+    cudaStream_t st;
+    if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) ok = false; else k->index_stream.push_back(st);
+  }
   if (ok && cudaStreamCreateWithFlags(&k->copy_in, cudaStreamNonBlocking) != cudaSuccess) ok = false;
   if (ok && cudaStreamCreateWithFlags(&k->copy_out, cudaStreamNonBlocking) != cudaSuccess) ok = false;
+  if (const char* e = getenv("VC2_CODEC_SUBBATCH")) k->nsub = std::min(std::max(atoi(e), 1), (int)vc2_codec::MAX_SUB);
+  if (ok && cudaEventCreateWithFlags(&k->sub_fork, cudaEventDisableTiming) != cudaSuccess) ok = false;
+  for (int i = 1; ok && i < k->nsub; ++i) {
+    if (cudaStreamCreateWithFlags(&k->sub_stream[i], cudaStreamNonBlocking) != cudaSuccess) ok = false;
+    if (ok && cudaEventCreateWithFlags(&k->sub_join[i], cudaEventDisableTiming) != cudaSuccess) ok = false;
+  }
   if (ok && !k->slice_bytes.empty()) {
     ok = cudaMemcpy(k->sbytes.p, k->slice_bytes.data(), (size_t)k->nslices * 4, cudaMemcpyHostToDevice) == cudaSuccess &&
          cudaMemcpy(k->fixed.p, k->fixed_off.data(), (size_t)(k->nslices + 1) * 4, cudaMemcpyHostToDevice) == cudaSuccess;
@@ -1008,11 +1040,41 @@ static int codec_encode_range(vc2_codec* k, int first, int n) {
   return VC2_OK;
 }
 
+// run fn(first, count) over the batch: whole on the context stream, or - when the batch is big enough and the
+// per-kernel profiler is off (its event pairs would time overlapped kernels) - as sub-batches on forked streams
+// that are joined back into the context stream
+template <class Fn>
+static int codec_run_split(vc2_codec* k, int n, Fn fn) {
+  vc2_ctx* ctx = k->ctx;
+  const int parts = ctx->profiling ? 1 : std::min(k->nsub, n / 2);
+  if (parts <= 1) return fn(0, n);
+  cudaStream_t main_stream = ctx->stream;
+  CU(cudaEventRecord(k->sub_fork, main_stream));
+  int st = VC2_OK;
+  for (int p = 0, first = 0; p < parts && st == VC2_OK; ++p) {
+    const int cnt = n / parts + (p < n % parts ? 1 : 0);
+    if (p > 0) {
+      if (cudaStreamWaitEvent(k->sub_stream[p], k->sub_fork, 0) != cudaSuccess) { st = VC2_ERR_CUDA; break; }
+      ctx->stream = k->sub_stream[p];
+    }
+    st = fn(first, cnt);
+    ctx->stream = main_stream;
+    if (p > 0) {
+      // always join, also after a failure, so the context stream never runs ahead of a sub-batch
+      if (cudaEventRecord(k->sub_join[p], k->sub_stream[p]) != cudaSuccess ||
+          cudaStreamWaitEvent(main_stream, k->sub_join[p], 0) != cudaSuccess) st = st == VC2_OK ? VC2_ERR_CUDA : st;
+    }
+    first += cnt;
+  }
+  if (st == VC2_ERR_CUDA) return fail(ctx, VC2_ERR_CUDA, "sub-batch stream");
+  return st;
+}
+
 extern "C" int vc2_codec_encode_dev(vc2_codec* k, int n) {
   if (!k || n < 1 || n > k->prm.max_pictures) return fail(k ? k->ctx : nullptr, VC2_ERR_ARG);
   vc2_ctx* ctx = k->ctx;
   CU(cudaSetDevice(ctx->device));
-  return codec_encode_range(k, 0, n);
+  return codec_run_split(k, n, [&](int first, int cnt) { return codec_encode_range(k, first, cnt); });
 }
 
 static int codec_decode_range(vc2_codec* k, int first, int n) {
@@ -1065,7 +1127,7 @@ extern "C" int vc2_codec_decode_dev(vc2_codec* k, int n) {
   if (!k || n < 1 || n > k->prm.max_pictures) return fail(k ? k->ctx : nullptr, VC2_ERR_ARG);
   vc2_ctx* ctx = k->ctx;
   CU(cudaSetDevice(ctx->device));
-  return codec_decode_range(k, 0, n);
+  return codec_run_split(k, n, [&](int first, int cnt) { return codec_decode_range(k, first, cnt); });
 }
 
 extern "C" void* vc2_codec_samples_dev(vc2_codec* k, int slot) {
@@ -1262,46 +1324,6 @@ extern "C" int vc2_codec_encode_host(vc2_codec* k, int n, const void* const* pic
   return status;
 }
 
-// Slice offsets of m HQ payloads.  Walking the length bytes of ONE payload is a chain of dependent loads
-// (Slices.cpp:544-605: every length is where the previous component ended), one cache miss each.  Several
-// payloads are therefore walked in lock step - their chains are independent, so the misses overlap - and
-// the pictures are dealt to a few host threads.
-static int index_many(const vc2_codec* k, int m, const uint8_t* const* payloads, const size_t* lens, uint32_t* tables) {
-  const int ns = k->nslices, prefix = k->g.prefix, scalar = k->g.scalar;
-  const int T = std::max(1, std::min({m / 2, 4, (int)std::thread::hardware_concurrency()}));
-  std::vector<int> status(T, VC2_OK);
-  auto work = [&](int t) {
-    enum { W = 8 };
-    for (int j0 = t * W; j0 < m; j0 += T * W) {
-      const int w = std::min((int)W, m - j0);
-      size_t pos[W] = {0};
-      for (int s = 0; s < ns; ++s)
-        for (int j = 0; j < w; ++j) {
-          const uint8_t* p = payloads[j0 + j];
-          const size_t len = lens[j0 + j];
-          tables[(size_t)(j0 + j) * (ns + 1) + s] = (uint32_t)pos[j];
-          size_t q = pos[j] + prefix + 1;
-          for (int c = 0; c < 3; ++c) {
-            if (q >= len) { status[t] = VC2_ERR_STREAM; return; }
-            q += 1 + (size_t)p[q] * scalar;
-          }
-          if (q > len) { status[t] = VC2_ERR_STREAM; return; }
-          pos[j] = q;
-        }
-      for (int j = 0; j < w; ++j) tables[(size_t)(j0 + j) * (ns + 1) + ns] = (uint32_t)pos[j];
-    }
-  };
-  if (T == 1) work(0);
-  else {
-    std::vector<std::thread> th;
-    for (int t = 1; t < T; ++t) th.emplace_back(work, t);
-    work(0);
-    for (auto& x : th) x.join();
-  }
-  for (int t = 0; t < T; ++t) if (status[t]) return status[t];
-  return VC2_OK;
-}
-
 extern "C" int vc2_codec_decode_host(vc2_codec* k, int n, const uint8_t* const* payloads, const size_t* payload_len,
                                      void* const* pictures) {
   KARG(k && pictures && payloads && payload_len && n >= 1);
@@ -1314,7 +1336,6 @@ extern "C" int vc2_codec_decode_host(vc2_codec* k, int n, const uint8_t* const* 
     if (!hq && payload_len[i] < k->fixed_off[ns]) return fail(ctx, VC2_ERR_STREAM);
   }
   CU(cudaStreamSynchronize(ctx->stream));
-  auto tables = [&](int set) { return k->host_offs + (size_t)set * B * (ns + 1); };
   auto flags = [&](int set) { return k->host_flags + (size_t)set * B * ns; };
   auto check = [&](int c) -> int {   // wait for chunk c and look at its error flags
     const int m = std::min(B, n - c * B);
@@ -1330,8 +1351,6 @@ extern "C" int vc2_codec_decode_host(vc2_codec* k, int n, const uint8_t* const* 
   const int chunks = (n + B - 1) / B;
   int status = VC2_OK, last_stage_slot = 0;
   (void)last_stage_slot;
-  if (hq) status = index_many(k, std::min(B, n), payloads, payload_len, tables(0));
-  if (status) return fail(ctx, status);
   for (int c = 0; c < chunks && status == VC2_OK; ++c) {
     const int base = c * B, m = std::min(B, n - base);
     const int sub = stage_pictures(B);
@@ -1340,9 +1359,21 @@ extern "C" int vc2_codec_decode_host(vc2_codec* k, int n, const uint8_t* const* 
       if (c > 0) CU(cudaStreamWaitEvent(k->copy_in, k->ev_done[i], 0));      // the previous payloads in these slots have been parsed
       for (int j = i; j < i + mm; ++j) {
         CU(cudaMemcpyAsync(vc2_codec_payload_dev(k, j), payloads[base + j], payload_len[base + j], cudaMemcpyHostToDevice, k->copy_in));
-        if (hq)
-          CU(cudaMemcpyAsync(vc2_codec_slice_offsets_dev(k, j), tables(c & 1) + (size_t)j * (ns + 1), (size_t)(ns + 1) * 4,
-                             cudaMemcpyHostToDevice, k->copy_in));
+        if (!hq) continue;
+        // slice offsets of this payload: walked on the device as soon as its bytes have landed
+        cudaStream_t is = k->index_stream[j % (int)k->index_stream.size()];
+        CU(cudaEventRecord(k->ev_idx[j], k->copy_in));
+        CU(cudaStreamWaitEvent(is, k->ev_idx[j], 0));
+        IndexParams ip;
+        memset(&ip, 0, sizeof(ip));
+        ip.in = vc2_codec_payload_dev(k, j); ip.in_pic_stride = (long long)k->payload_cap;
+        ip.len[0] = (uint32_t)payload_len[base + j];
+        ip.slice_off = vc2_codec_slice_offsets_dev(k, j);
+        ip.nslices = ns; ip.prefix = k->g.prefix; ip.scalar = k->g.scalar;
+        CU(index_launch(is, ip, 1));
+        ctx->launches++;
+        CU(cudaEventRecord(k->ev_idx[j], is));
+        CU(cudaStreamWaitEvent(ctx->stream, k->ev_idx[j], 0));
       }
       CU(cudaEventRecord(k->ev_in[i], k->copy_in));
       CU(cudaStreamWaitEvent(ctx->stream, k->ev_in[i], 0));
@@ -1359,13 +1390,7 @@ extern "C" int vc2_codec_decode_host(vc2_codec* k, int n, const uint8_t* const* 
       last_stage_slot = i;
     }
     if (status) break;
-    if (c + 1 < chunks) {
-      // build the next chunk's tables while this chunk is in flight; their set was last read by chunk c-1
-      if (c >= 1) status = check(c - 1);
-      if (!status && hq)
-        status = index_many(k, std::min(B, n - (c + 1) * B), payloads + (c + 1) * B, payload_len + (c + 1) * B, tables((c + 1) & 1));
-      if (status && status > -100) fail(ctx, status);
-    }
+    if (c + 1 < chunks && c >= 1) status = check(c - 1);   // the flag set of chunk c+1 was last used by chunk c-1
   }
   if (status == VC2_OK && chunks >= 2) status = check(chunks - 2);
   if (status == VC2_OK) status = check(chunks - 1);

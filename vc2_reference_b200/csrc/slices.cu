@@ -580,6 +580,91 @@ __global__ void __launch_bounds__(128) slice_unpack_kernel(const UnpackParams p)
 }
 
 // ------------------------------------------------------------------------------------------
+// Slice index of an HQ payload: slice s+1 starts where the three length-prefixed components of slice s
+// end (Slices.cpp:544-605), a chain of dependent byte loads.  One CTA per picture: warps 1..7 stream the
+// payload through a shared-memory ring while thread 0 walks the chain inside it (three dependent
+// shared-memory loads per slice instead of three DRAM round trips).
+// A payload that runs off its end leaves the remaining slices empty; the parser flags those.
+// ------------------------------------------------------------------------------------------
+constexpr int INDEX_SEG = 32 * 1024;                 // bytes per ring segment
+constexpr int INDEX_RING = 4 * INDEX_SEG;             // four segments: two being walked, one being filled, one spare
+constexpr unsigned INDEX_MASK = INDEX_RING - 1;
+
+__global__ void __launch_bounds__(256) hq_index_kernel(const IndexParams p) {
+  extern __shared__ uint4 s_ring[];
+  __shared__ int s_stop[2];
+  const int pic = blockIdx.x, ns = p.nslices;
+  const uint8_t* in = p.in + (long long)pic * p.in_pic_stride;
+  const unsigned len = p.len[pic];
+  uint32_t* off = p.slice_off + (long long)pic * (ns + 1);
+  const unsigned maxslice = (unsigned)(p.prefix + 4 + 3 * 255 * p.scalar);
+  const long long readable = p.in_pic_stride & ~15ll;   // the picture's buffer, whole 16-byte pieces
+  auto load_seg = [&](unsigned k, int first, int nthreads) {   // segment k of the payload -> ring slot k % 4
+    const long long b0 = (long long)k * INDEX_SEG;
+    if (b0 >= readable) return;
+    const int n16 = (int)(min((long long)INDEX_SEG, readable - b0) >> 4);
+    const uint4* src = reinterpret_cast<const uint4*>(in + b0);
+    uint4* dst = s_ring + (size_t)(k & 3) * (INDEX_SEG / 16);
+    for (int i = first; i < n16; i += nthreads) dst[i] = __ldg(src + i);
+  };
+  if (maxslice > (unsigned)INDEX_SEG) {
+    // slices may be longer than a ring segment (huge scalar): plain walk in global memory
+    if (threadIdx.x == 0) {
+      unsigned pos = 0;
+      int s = 0;
+      for (; s < ns; ++s) {
+        unsigned q = pos + p.prefix + 1;
+        bool bad = false;
+        for (int c = 0; c < 3 && !bad; ++c) {
+          if (q >= len) bad = true; else q += 1u + (unsigned)in[q] * (unsigned)p.scalar;
+        }
+        if (bad || q > len) break;
+        off[s] = pos;
+        pos = q;
+      }
+      for (int t = s; t <= ns; ++t) off[t] = pos;
+    }
+    return;
+  }
+  load_seg(0, threadIdx.x, blockDim.x);
+  load_seg(1, threadIdx.x, blockDim.x);
+  __syncthreads();
+  unsigned pos = 0;   // walker state (thread 0)
+  int s = 0;
+  for (unsigned k = 0;; ++k) {
+    if (threadIdx.x >= 32) {
+      load_seg(k + 2, threadIdx.x - 32, blockDim.x - 32);     // warps 1..7 fill the ring ahead of the walker
+    } else if (threadIdx.x == 0) {
+      // every slice that STARTS in segment k; its bytes end before segment k + 2 (maxslice <= INDEX_SEG)
+      const uint8_t* w = reinterpret_cast<const uint8_t*>(s_ring);
+      const unsigned seg_end = (k + 1) * INDEX_SEG;
+      const unsigned hdr = p.prefix + 1, sc = p.scalar;
+      bool bad = false;
+      while (s < ns && pos < seg_end) {
+        unsigned q = pos + hdr;
+        q += 1u + w[q & INDEX_MASK] * sc;
+        q += 1u + w[q & INDEX_MASK] * sc;
+        q += 1u + w[q & INDEX_MASK] * sc;
+        if (q > len) { bad = true; break; }   // also catches a length byte at or beyond len: q only grows
+        off[s] = pos;
+        pos = q;
+        ++s;
+      }
+      if (bad) {
+        for (int t = s; t <= ns; ++t) off[t] = pos;   // empty slices: the parser raises VC2_FLAG_STREAM
+        s = ns + 1;
+      } else if (s == ns) {
+        off[ns] = pos;
+        s = ns + 1;
+      }
+      s_stop[k & 1] = s > ns;
+    }
+    __syncthreads();
+    if (s_stop[k & 1]) break;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // stand-alone quantise / dequantise of an in-place ordered plane (Library surface)
 // ------------------------------------------------------------------------------------------
 __global__ void quant_kernel(const QuantParams p) {
@@ -656,6 +741,14 @@ cudaError_t unpack_launch(cudaStream_t s, const UnpackParams& p, int npictures) 
   const dim3 grid((nslices + 127) / 128, npictures);
   if (p.ld) slice_unpack_kernel<true><<<grid, 128, 0, s>>>(p);
   else slice_unpack_kernel<false><<<grid, 128, 0, s>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t index_launch(cudaStream_t s, const IndexParams& p, int npictures) {
+  cudaError_t e = cudaFuncSetAttribute(hq_index_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, INDEX_RING);   // per device
+  if (e != cudaSuccess) return e;
+  if (npictures < 1 || npictures > VC2_INDEX_MAX_PICTURES) return cudaErrorInvalidValue;
+  hq_index_kernel<<<npictures, 256, INDEX_RING, s>>>(p);
   return cudaGetLastError();
 }
 

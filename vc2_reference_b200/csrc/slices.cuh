@@ -67,6 +67,16 @@ struct UnpackParams {
   int ld;                       // 1: LD slice syntax (Slices.cpp:246-303); LL band left quantised
 };
 
+// slice index of HQ payloads on the device (the reader's walk over the length bytes, Slices.cpp:544-605)
+#define VC2_INDEX_MAX_PICTURES 8
+struct IndexParams {
+  const uint8_t* in;            // payload [pic]
+  long long in_pic_stride;      // bytes; also the readable size of one picture's buffer
+  uint32_t len[VC2_INDEX_MAX_PICTURES];   // payload bytes per picture
+  uint32_t* slice_off;          // [pic][slices + 1] out
+  int nslices, prefix, scalar;
+};
+
 struct QuantParams {            // stand-alone quantise / dequantise on IN-PLACE ordered planes
   const int32_t* src;
   int32_t* dst;
@@ -95,6 +105,7 @@ cudaError_t upload_quant_tables(const QuantTables& t);
 cudaError_t pack_launch(cudaStream_t s, const PackParams& p, int npictures);
 cudaError_t assemble_launch(cudaStream_t s, const AssembleParams& p, int npictures);
 cudaError_t unpack_launch(cudaStream_t s, const UnpackParams& p, int npictures);
+cudaError_t index_launch(cudaStream_t s, const IndexParams& p, int npictures);
 cudaError_t layout_launch(cudaStream_t s, bool to_slice_major, const int32_t* src, int32_t* dst, const SliceGeom& g, int c);
 cudaError_t quant_launch(cudaStream_t s, const QuantParams& p);
 cudaError_t ld_dc_launch(cudaStream_t s, const LdDcParams& p);
