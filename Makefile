@@ -12,7 +12,18 @@ OBJS      := $(CSRC)/dwt_fwd.o $(CSRC)/dwt_inv.o $(CSRC)/slices.o $(CSRC)/cabi.o
 
 ORACLE    := oracle/_build/libvc2oracle.so
 
-all: $(LIB) $(ORACLE)
+HOSTLIB   := $(PKG)/libvc2host.so
+BIN       := $(PKG)/bin
+CXXFLAGS  := -O2 -std=c++14 -fPIC -Wall -Wno-comment -Iinclude -Ihost
+
+all: $(LIB) $(ORACLE) $(HOSTLIB) $(BIN)/EncodeStream $(BIN)/DecodeStream
+
+# C++ host layer: the Library mirror (include/vc2/*.h) and the drop-in command lines, over the C-ABI
+$(HOSTLIB): host/vc2_library.cpp host/vc2_stream.cpp include/vc2/*.h include/vc2_cabi.h include/vc2_host.h $(LIB)
+	$(CXX) $(CXXFLAGS) -shared host/vc2_library.cpp host/vc2_stream.cpp -o $@ -L$(PKG) -lvc2b200 -Wl,-rpath,'$$ORIGIN'
+$(BIN)/%: host/%.cpp host/cmdline.h include/vc2/*.h include/vc2_cabi.h $(HOSTLIB)
+	mkdir -p $(BIN)
+	$(CXX) $(CXXFLAGS) $< -o $@ -L$(PKG) -lvc2host -lvc2b200 -lpthread -Wl,-rpath,'$$ORIGIN/..'
 
 $(ORACLE): oracle/vc2_oracle.c
 	mkdir -p oracle/_build
@@ -31,5 +42,5 @@ $(LIB): $(OBJS)
 	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -lcudart
 
 clean:
-	rm -f $(OBJS) $(LIB)
+	rm -f $(OBJS) $(LIB) $(HOSTLIB) $(BIN)/EncodeStream $(BIN)/DecodeStream
 .PHONY: all clean

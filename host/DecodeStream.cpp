@@ -1,0 +1,294 @@
+// DecodeStream - drop-in for the reference command line (src/DecodeStream/DecodeStream.cpp, DecodeParams.cpp)
+// on the B200 hot path: same flags, same output bytes.  The stream is split into data units on the host
+// (parse-info chain), HQ / LD pictures are decoded in batches by the fused CUDA codec
+// (vc2_codec_decode_host); with --gpus N consecutive batches go to different GPUs and the pictures are
+// written in stream order.
+//
+// Not built here (SURVEY.md 8f "next" rows): fragments, interlaced streams.
+#include <cstdio>
+#include <cstdlib>
+#include <fstream>
+#include <iostream>
+#include <iterator>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "cmdline.h"
+#include "vc2/Codec.h"
+#include "vc2/DataUnit.h"
+#include "vc2/Quantisation.h"
+#include "vc2/Slices.h"
+#include "vc2/WaveletTransform.h"
+
+using namespace vc2;
+using std::clog;
+using std::endl;
+
+namespace {
+
+enum Output { TRANSFORM, QUANTISED, INDICES, DECODED };
+
+struct PictureUnit {
+  const uint8_t* data;
+  size_t len;
+};
+
+struct Config {   // everything the codec geometry depends on
+  bool ld = false;
+  int height = 0, width = 0, bits = 0;
+  ColourFormat cf = CF_UNSET;
+  PicturePreamble pre;
+  int compressedBytes = 0;
+  bool same(const Config& o) const {
+    return ld == o.ld && height == o.height && width == o.width && bits == o.bits && cf == o.cf &&
+           pre.wavelet_kernel == o.pre.wavelet_kernel && pre.depth == o.pre.depth && pre.slices_x == o.pre.slices_x &&
+           pre.slices_y == o.pre.slices_y && pre.slice_prefix == o.pre.slice_prefix && pre.slice_size_scalar == o.pre.slice_size_scalar &&
+           compressedBytes == o.compressedBytes;
+  }
+};
+
+void write_be32_plane(std::ostream& out, const int* v, size_t n) {
+  std::string buf(n * 4, '\0');
+  for (size_t i = 0; i < n; ++i) {
+    const uint32_t w = (uint32_t)v[i];
+    buf[4 * i] = (char)(w >> 24); buf[4 * i + 1] = (char)(w >> 16); buf[4 * i + 2] = (char)(w >> 8); buf[4 * i + 3] = (char)w;
+  }
+  out.write(buf.data(), (std::streamsize)buf.size());
+}
+
+// end of an HQ picture's slice data when the parse info carries no next offset: walk the length bytes
+size_t hq_payload_length(const uint8_t* p, size_t avail, int nslices, int prefix, int scalar) {
+  std::vector<uint32_t> off(nslices + 1);
+  if (vc2_hq_index_slices(p, avail, nslices, prefix, scalar, off.data()) != VC2_OK) throw std::logic_error("Stream Error: HQ picture runs past the end of the stream");
+  return off[nslices];
+}
+
+class Decoder {
+ public:
+  Decoder(std::ostream& out, Output output, int gpus, int batch, bool verbose)
+      : out_(out), output_(output), G_(gpus), B_(batch), verbose_(verbose), frames_(0) {}
+
+  void add(const Config& c, const PictureUnit& u) {
+    if (!pending_.empty() && !cfg_.same(c)) flush();
+    if (pending_.empty() && (codecs_.empty() || !cfg_.same(c))) open(c);
+    pending_.push_back(u);
+    if ((int)pending_.size() == G_ * B_) flush();
+  }
+
+  void flush() {
+    if (pending_.empty()) return;
+    if (output_ != DECODED) { taps(); pending_.clear(); return; }
+    const int n = (int)pending_.size();
+    std::vector<std::string> errors(G_);
+    std::vector<std::thread> th;
+    for (int g = 0; g < G_; ++g) {
+      const int first = g * B_, cnt = std::min(B_, n - first);
+      if (cnt <= 0) break;
+      th.emplace_back([&, g, first, cnt]() {
+        try {
+          std::vector<const uint8_t*> pay(cnt);
+          std::vector<size_t> len(cnt);
+          std::vector<void*> pics(cnt);
+          for (int i = 0; i < cnt; ++i) { pay[i] = pending_[first + i].data; len[i] = pending_[first + i].len; pics[i] = recon_[first + i].data(); }
+          codecs_[g]->decode(cnt, pay.data(), len.data(), pics.data());
+        } catch (const std::exception& e) { errors[g] = e.what(); }
+      });
+    }
+    for (auto& t : th) t.join();
+    for (int g = 0; g < G_; ++g) if (!errors[g].empty()) throw std::logic_error(errors[g]);
+    for (int i = 0; i < n; ++i, ++frames_) {
+      if (verbose_) clog << "Decoded frame number " << frames_ << endl;
+      out_.write(reinterpret_cast<const char*>(recon_[i].data()), (std::streamsize)recon_[i].size());
+    }
+    if (!out_) throw std::runtime_error("Failed to write output file");
+    pending_.clear();
+  }
+
+  long frames() const { return frames_; }
+
+ private:
+  void open(const Config& c) {
+    cfg_ = c;
+    codecs_.clear();
+    vc2_codec_params cp;
+    const int depth = c.pre.depth, cell = 1 << depth;
+    const PictureFormat f(c.height, c.width, c.cf);
+    // slice sizes in units of 2^depth from the slice counts (the inverse of sliceSizeIsValid)
+    const int ph = paddedSize(f.lumaHeight(), depth), pw = paddedSize(f.lumaWidth(), depth);
+    if (c.pre.slices_y < 1 || c.pre.slices_x < 1 || ph % (c.pre.slices_y * cell) || pw % (c.pre.slices_x * cell))
+      throw std::logic_error("Stream Error: slice counts do not divide the padded picture");
+    if (vc2_make_geom(c.height, c.width, (int)c.cf, (int)c.pre.wavelet_kernel, depth, ph / c.pre.slices_y / cell, pw / c.pre.slices_x / cell,
+                      c.ld ? 0 : c.pre.slice_prefix, c.ld ? 1 : c.pre.slice_size_scalar, &cp.geom) != VC2_OK)
+      throw std::logic_error("Stream Error: unsupported picture / slice geometry");
+    cp.fmt.bytes_per_sample = c.bits == 8 ? 1 : 2;            // DecodeStream.cpp:268-271
+    cp.fmt.luma_depth = c.bits; cp.fmt.chroma_depth = c.bits;   // :265-266: the luma depth serves both
+    cp.mode = c.ld ? VC2_LD : VC2_HQ_VBR;
+    cp.qindex = 0; cp.picture_bytes = c.compressedBytes; cp.max_pictures = B_;
+    geom_ = cp.geom;
+    if (output_ == DECODED) {
+      const int G = std::min(G_, std::max(1, vc2_device_count()));
+      G_ = G;
+      for (int g = 0; g < G; ++g) codecs_.emplace_back(new Codec(g, cp));
+      recon_.assign((size_t)G * B_, std::vector<uint8_t>(codecs_[0]->pictureBytes()));
+    }
+  }
+
+  // -o Quantised / Transform / Indices: the Library-surface calls (DecodeStream.cpp:512-575)
+  void taps() {
+    const int depth = cfg_.pre.depth;
+    const PictureFormat f(cfg_.height, cfg_.width, cfg_.cf);
+    const PictureFormat tf(paddedSize(f.lumaHeight(), depth), paddedSize(f.lumaWidth(), depth), cfg_.cf);
+    const Array1D qm = quantMatrix(cfg_.pre.wavelet_kernel, depth);
+    for (size_t i = 0; i < pending_.size(); ++i, ++frames_) {
+      const PictureUnit& u = pending_[i];
+      Slices s = cfg_.ld ? readSlicesLD(u.data, u.len, tf, cfg_.pre.wavelet_kernel, depth, cfg_.pre.slices_y, cfg_.pre.slices_x,
+                                        slice_bytes(cfg_.pre.slices_y, cfg_.pre.slices_x, cfg_.compressedBytes, 1))
+                         : readSlicesHQ(u.data, u.len, tf, cfg_.pre.wavelet_kernel, depth, cfg_.pre.slices_y, cfg_.pre.slices_x,
+                                        cfg_.pre.slice_prefix, cfg_.pre.slice_size_scalar);
+      if (output_ == INDICES) {
+        std::string b(s.qIndices.num_elements(), '\0');
+        for (size_t j = 0; j < b.size(); ++j) b[j] = (char)s.qIndices.data()[j];
+        out_.write(b.data(), (std::streamsize)b.size());
+        continue;
+      }
+      Picture p = s.yuvCoeffs;
+      if (output_ == TRANSFORM)
+        p = cfg_.ld ? inverse_quantise_transform(s.yuvCoeffs, s.qIndices, qm) : inverse_quantise_transform_np(s.yuvCoeffs, s.qIndices, qm);
+      write_be32_plane(out_, p.y().data(), p.y().num_elements());
+      write_be32_plane(out_, p.c1().data(), p.c1().num_elements());
+      write_be32_plane(out_, p.c2().data(), p.c2().num_elements());
+    }
+  }
+
+  std::ostream& out_;
+  Output output_;
+  int G_, B_;
+  bool verbose_;
+  long frames_;
+  Config cfg_;
+  vc2_geom geom_;
+  std::vector<std::unique_ptr<Codec>> codecs_;
+  std::vector<std::vector<uint8_t>> recon_;
+  std::vector<PictureUnit> pending_;
+};
+
+}  // namespace
+
+int main(int argc, char** argv) {
+  if (argc < 2) {
+    clog << "DecodeStream (B200 hot path): decodes a VC-2 HQ / LD stream to planar raw video\n\nFor more details and useage use -h or --help" << endl;
+    return EXIT_SUCCESS;
+  }
+  try {
+    vc2cli::CmdLine c;
+    c.add("v", "verbose", true);
+    c.add("o", "output", false);
+    c.add("G", "gpus", false);
+    c.add("B", "batch", false);
+    std::string inName, outName;
+    Output output = DECODED;
+    bool verbose = false;
+    int gpus = 1, batch = 8;
+    try {
+      c.parse(argc, argv);
+      if (c.positional().size() != 2) throw std::invalid_argument("Command line error: Required argument missing: inFile / outFile");
+      inName = c.positional()[0]; outName = c.positional()[1];
+      verbose = c.isSet("v");
+      const std::string o = c.str("o", "Decoded");
+      if (o == "Transform") output = TRANSFORM; else if (o == "Quantised") output = QUANTISED; else if (o == "Indices") output = INDICES;
+      else if (o == "Decoded") output = DECODED;
+      else throw std::invalid_argument("Command line error: Couldn't read argument value from string '" + o + "' for arg -o");
+      gpus = std::max(1, c.integer("G", getenv("VC2_GPUS") ? atoi(getenv("VC2_GPUS")) : 1));
+      batch = std::max(1, c.integer("B", getenv("VC2_BATCH") ? atoi(getenv("VC2_BATCH")) : 8));
+    } catch (const std::exception& e) {
+      std::cerr << "Error: " << e.what() << endl;
+      return EXIT_FAILURE;
+    }
+    std::vector<uint8_t> stream;
+    if (inName == "-") stream.assign(std::istreambuf_iterator<char>(std::cin), std::istreambuf_iterator<char>());
+    else {
+      std::ifstream f(inName.c_str(), std::ios::in | std::ios::binary);
+      if (!f) { perror(("Failed to open input file \"" + inName + "\"").c_str()); return EXIT_FAILURE; }
+      stream.assign(std::istreambuf_iterator<char>(f), std::istreambuf_iterator<char>());
+    }
+    stream.resize(stream.size() + 64, 0);   // slack behind the last payload for the parser's word reads
+    const size_t streamLen = stream.size() - 64;
+    std::ofstream outF;
+    std::ostream* out = &std::cout;
+    if (outName != "-") {
+      outF.open(outName.c_str(), std::ios::out | std::ios::binary);
+      if (!outF) { perror(("Failed to open output file \"" + outName + "\"").c_str()); return EXIT_FAILURE; }
+      out = &outF;
+    }
+
+    Decoder dec(*out, output, gpus, batch, verbose);
+    StreamReader rd(stream.data(), streamLen);
+    rd.synchronise();   // DecodeStream.cpp:177-178
+    bool haveSeq = false;
+    SequenceHeader seq;
+    while (!rd.atEnd()) {
+      const DataUnit du = rd.readDataUnit();
+      if (verbose) clog << endl << "Have read data unit of type: " << (int)du.type << endl;
+      const size_t unitEnd = du.next_parse_offset ? du.offset + du.next_parse_offset : 0;
+      switch (du.type) {
+        case SEQUENCE_HEADER:
+          seq = rd.readSequenceHeader();
+          haveSeq = true;
+          if (verbose) {
+            clog << "height        = " << seq.height << endl << "width         = " << seq.width << endl;
+            clog << "interlaced    = " << std::boolalpha << seq.interlace << endl;
+          }
+          if (seq.interlace) throw std::logic_error("interlaced streams are not available in this build");
+          break;
+        case END_OF_SEQUENCE:
+          if (verbose) clog << "End of Sequence after " << dec.frames() << " frames" << endl;
+          break;
+        case AUXILIARY_DATA:
+        case PADDING_DATA:
+          if ((long)du.next_parse_offset - 13 < 0) throw std::logic_error("Auxilliary data length is less than zero.");
+          rd.seek(unitEnd);
+          break;
+        case HQ_PICTURE:
+        case LD_PICTURE: {
+          const bool ld = du.type == LD_PICTURE;
+          unsigned long picnum = 0;
+          const PicturePreamble pre = rd.readPictureHeader(ld, picnum);
+          if (verbose) clog << "Picture number      : " << picnum << endl;
+          if (!haveSeq) { clog << "Cannot decode frame, no previous sequence header!" << endl; if (unitEnd) rd.seek(unitEnd); break; }
+          Config cfg;
+          cfg.ld = ld; cfg.height = seq.height; cfg.width = seq.width; cfg.bits = seq.bitdepth; cfg.cf = seq.chromaFormat; cfg.pre = pre;
+          PictureUnit u;
+          u.data = stream.data() + rd.pos();
+          if (ld) {
+            // DecodeStream.cpp:312: bytes of the whole picture from the slice-bytes ratio
+            cfg.compressedBytes = (int)((long long)pre.slice_bytes.numerator * pre.slices_y * pre.slices_x / pre.slice_bytes.denominator);
+            u.len = (size_t)cfg.compressedBytes;
+            if (rd.pos() + u.len > streamLen) throw std::logic_error("Stream Error: LD picture runs past the end of the stream");
+          } else {
+            u.len = unitEnd ? unitEnd - rd.pos()
+                            : hq_payload_length(u.data, streamLen - rd.pos(), pre.slices_x * pre.slices_y, pre.slice_prefix, pre.slice_size_scalar);
+            if (rd.pos() + u.len > streamLen) throw std::logic_error("Stream Error: HQ picture runs past the end of the stream");
+          }
+          dec.add(cfg, u);
+          rd.seek(rd.pos() + u.len);
+          break;
+        }
+        case HQ_FRAGMENT:
+        case LD_FRAGMENT:
+          throw std::logic_error("fragmented pictures are not available in this build");
+        default:
+          throw std::logic_error("Stream Error: Unknown data unit type.");
+      }
+    }
+    dec.flush();
+    out->flush();
+    clog << "End of data stream reached successfully, exiting." << endl;
+  } catch (const std::exception& ex) {   // DecodeStream.cpp:985-988
+    std::cout << "Error: " << ex.what() << endl;
+    return EXIT_FAILURE;
+  }
+  return EXIT_SUCCESS;
+}

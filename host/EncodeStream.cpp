@@ -1,0 +1,322 @@
+// EncodeStream - drop-in for the reference command line (src/EncodeStream/EncodeStream.cpp, EncodeParams.cpp)
+// on the B200 hot path: same flags, same stream bytes.  Pictures are encoded in batches by the fused CUDA
+// codec (vc2_codec_encode_host); with --gpus N consecutive batches go to different GPUs (the codec is
+// intra-only) and this thread reassembles the data units in picture order.
+//
+// Not built here (SURVEY.md 8f "next" rows): LD encoding, interlaced coding, fragments, -o PSNR.
+#include <cstdio>
+#include <cstdlib>
+#include <fstream>
+#include <iostream>
+#include <memory>
+#include <sstream>
+#include <stdexcept>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "cmdline.h"
+#include "vc2/Codec.h"
+#include "vc2/DataUnit.h"
+#include "vc2/Quantisation.h"
+#include "vc2/Slices.h"
+#include "vc2/WaveletTransform.h"
+
+using namespace vc2;
+using std::clog;
+using std::endl;
+
+namespace {
+
+enum Output { TRANSFORM, QUANTISED, INDICES, PACKAGED, STREAM, DECODED };
+enum Mode { HQ_CBR, HQ_ConstQ, LD };
+
+struct Params {
+  std::string inFile, outFile;
+  bool verbose = false;
+  int height = 0, width = 0, bytes = 2, lumaDepth = 0, chromaDepth = 0;
+  ColourFormat cf = CF_UNSET;
+  bool interlaced = false, topFieldFirst = true;
+  WaveletKernel kernel = NullKernel;
+  int depth = 0, ySize = 0, xSize = 0;
+  Output output = STREAM;
+  Mode mode = HQ_ConstQ;
+  int frameRate = 3, scalar = 1, prefix = 0, fragment = 0, compressedBytes = 0, qIndex = 0;
+  int gpus = 1, batch = 8;
+};
+
+// EncodeParams.cpp:52-250: the same flags, checks and messages
+Params parse(int argc, char** argv) {
+  vc2cli::CmdLine c;
+  const char* value_flags[][2] = {{"m", "mode"}, {"o", "output"}, {"a", "hSlice"}, {"u", "vSlice"}, {"d", "waveletDepth"}, {"k", "kernel"},
+                                  {"c", "chromaDepth"}, {"l", "lumaDepth"}, {"z", "bitDepth"}, {"n", "bytes"}, {"f", "format"},
+                                  {"x", "width"}, {"y", "height"}, {"r", "framerate"}, {"S", "scalar"}, {"P", "prefix"},
+                                  {"F", "fragmentLength"}, {"s", "compressedBytes"}, {"q", "quantIndex"}, {"G", "gpus"}, {"B", "batch"}};
+  for (auto& f : value_flags) c.add(f[0], f[1], false);
+  const char* switches[][2] = {{"v", "verbose"}, {"b", "bottomFieldFirst"}, {"t", "topFieldFirst"}, {"i", "interlace"}, {"p", "progressive"}};
+  for (auto& f : switches) c.add(f[0], f[1], true);
+  c.parse(argc, argv);
+  if (c.positional().size() != 2) throw std::invalid_argument("Command line error: Required argument missing: inFile / outFile");
+  for (const char* req : {"m", "a", "u", "d", "k", "f", "x", "y"})
+    if (!c.isSet(req)) throw std::invalid_argument(std::string("Command line error: Required argument missing: ") + req);
+  Params p;
+  p.inFile = c.positional()[0]; p.outFile = c.positional()[1];
+  p.verbose = c.isSet("v");
+  p.height = c.integer("y", 0); p.width = c.integer("x", 0);
+  const std::string f = c.str("f");
+  if (f == "4:4:4") p.cf = CF444; else if (f == "4:2:2") p.cf = CF422; else if (f == "4:2:0") p.cf = CF420;
+  else throw std::invalid_argument("invalid colour format");
+  p.bytes = c.integer("n", 2);
+  int bitDepth = c.integer("z", 0);
+  p.lumaDepth = c.integer("l", 0); p.chromaDepth = c.integer("c", 0);
+  p.interlaced = c.isSet("i");
+  p.topFieldFirst = !c.isSet("b");
+  { std::istringstream ss(c.str("k")); ss >> p.kernel; }
+  p.depth = c.integer("d", 0); p.ySize = c.integer("u", 0); p.xSize = c.integer("a", 0);
+  const std::string o = c.str("o", "Stream");
+  if (o == "Transform") p.output = TRANSFORM; else if (o == "Quantised") p.output = QUANTISED; else if (o == "Indices") p.output = INDICES;
+  else if (o == "Packaged") p.output = PACKAGED; else if (o == "Stream") p.output = STREAM; else if (o == "Decoded") p.output = DECODED;
+  else if (o == "PSNR") throw std::invalid_argument("output PSNR is not available in this build");
+  else throw std::invalid_argument("Command line error: Couldn't read argument value from string '" + o + "' for arg -o");
+  const std::string m = c.str("m");
+  if (m == "HQ_ConstQ") p.mode = HQ_ConstQ; else if (m == "HQ_CBR") p.mode = HQ_CBR; else if (m == "LD") p.mode = LD;
+  else throw std::invalid_argument("Command line error: Couldn't read argument value from string '" + m + "' for arg -m");
+  p.frameRate = c.integer("r", 3);
+  p.scalar = c.integer("S", 1); p.prefix = c.integer("P", 0); p.fragment = c.integer("F", 0);
+  p.compressedBytes = c.integer("s", 0); p.qIndex = c.integer("q", 0);
+  p.gpus = c.integer("G", getenv("VC2_GPUS") ? atoi(getenv("VC2_GPUS")) : 1);
+  p.batch = c.integer("B", getenv("VC2_BATCH") ? atoi(getenv("VC2_BATCH")) : 8);
+
+  if (c.isSet("z") && (c.isSet("l") || c.isSet("c")))
+    throw std::invalid_argument("bitDepth is incompatible with luma depth (and/or chroma depth): use one or the other");
+  if (c.isSet("p") && c.isSet("i")) throw std::invalid_argument("image can't be both interlaced and progressive: specify one or the other");
+  if (c.isSet("p") && (c.isSet("t") || c.isSet("b"))) throw std::invalid_argument("field parity is incompatible with progressive image");
+  if (c.isSet("t") && c.isSet("b"))
+    throw std::invalid_argument("image can't be both top field first and bottom field first: specify one or the other");
+  if (!c.isSet("z")) bitDepth = 8 * p.bytes;
+  if (!c.isSet("l")) p.lumaDepth = bitDepth;
+  if (!c.isSet("c")) p.chromaDepth = p.lumaDepth;
+  if (p.height < 1) throw std::invalid_argument("picture height must be > 0");
+  if (p.width < 1) throw std::invalid_argument("picture width must be > 0");
+  if (p.bytes < 1 || p.bytes > 4) throw std::invalid_argument("bytes must be in range 1 to 4");
+  if (c.isSet("z")) {
+    if (bitDepth < 1 || bitDepth > 8 * p.bytes) throw std::invalid_argument("bit depth must be in range 1 to 8*(bytes per sample)");
+  } else {
+    if (p.lumaDepth < 1 || p.lumaDepth > 8 * p.bytes) throw std::invalid_argument("luma bit depth must be in range 1 to 8*(bytes per sample)");
+    if (p.chromaDepth < 1 || p.chromaDepth > 8 * p.bytes)
+      throw std::invalid_argument("chroma bit depth must be in range 1 to 8*(bytes per sample)");
+  }
+  if (p.kernel == NullKernel) throw std::invalid_argument("invalid wavelet kernel");
+  if (p.depth < 1) throw std::invalid_argument("wavelet depth must be 1 or more");
+  const bool hq = p.mode == HQ_CBR || p.mode == HQ_ConstQ;
+  if (!hq && c.isSet("S")) throw std::invalid_argument("Slice Scalar is only used in HQ_CBR and HQ_ConstQ modes");
+  if (!hq && c.isSet("P")) throw std::invalid_argument("Slice Prefix is only used in HQ_CBR and HQ_ConstQ modes");
+  if (p.mode == HQ_ConstQ && c.isSet("F")) throw std::invalid_argument("Fragment length is only used in HQ_CBR and LD modes");
+  if (p.mode == HQ_ConstQ && c.isSet("s")) throw std::invalid_argument("Compressed bytes is only used in HQ_CBR and LD modes");
+  if (p.mode != HQ_ConstQ && c.isSet("q")) throw std::invalid_argument("Quantisation index is only used in HQ_ConstQ mode");
+  if (p.mode != HQ_ConstQ && !c.isSet("s")) throw std::invalid_argument("Compressed bytes must be set in HQ_CBR and LD modes");
+  if (p.mode == HQ_ConstQ && !c.isSet("q")) throw std::invalid_argument("Quantisation index must be set in HQ_ConstQ mode");
+  if (hq && p.scalar < 1) throw std::invalid_argument("slice scalar must be >=1");
+  if (hq && p.prefix < 0) throw std::invalid_argument("slice prefix must be >=0");
+  if (p.mode != HQ_ConstQ && p.compressedBytes < 1) throw std::invalid_argument("number of compressed bytes must be >0");
+  if (p.mode == HQ_ConstQ && (p.qIndex < 0 || p.qIndex > 119)) throw std::invalid_argument("quantisation index must be in the range 0 to 119");
+  if (p.frameRate < 0 || p.frameRate > 16) throw std::invalid_argument("Invalid Frame Rate: ");
+  // scope of this build
+  if (p.mode == LD) throw std::invalid_argument("LD encoding is not available in this build (LD streams are decode-only)");
+  if (p.interlaced) throw std::invalid_argument("interlaced coding is not available in this build");
+  if (p.fragment > 0) throw std::invalid_argument("fragmented pictures are not available in this build");
+  if (p.bytes > 2) throw std::invalid_argument("this build reads 1 or 2 bytes per sample");
+  if (p.gpus < 1) p.gpus = 1;
+  if (p.batch < 1) p.batch = 1;
+  return p;
+}
+
+void write_be32_plane(std::ostream& out, const int32_t* v, size_t n) {   // pictureio::wordWidth(4) << signed_binary
+  std::string buf(n * 4, '\0');
+  for (size_t i = 0; i < n; ++i) {
+    const uint32_t w = (uint32_t)v[i];
+    buf[4 * i] = (char)(w >> 24); buf[4 * i + 1] = (char)(w >> 16); buf[4 * i + 2] = (char)(w >> 8); buf[4 * i + 3] = (char)w;
+  }
+  out.write(buf.data(), (std::streamsize)buf.size());
+}
+
+struct Worker {
+  std::unique_ptr<Codec> codec;
+  std::vector<std::vector<uint8_t>> payload;   // per slot
+  std::vector<size_t> len;
+  std::string error;
+};
+
+}  // namespace
+
+int main(int argc, char** argv) {
+  if (argc < 2) {
+    clog << "EncodeStream (B200 hot path): encodes planar raw video into a VC-2 HQ stream\n\nFor more details and useage use -h or --help" << endl;
+    return EXIT_SUCCESS;
+  }
+  try {
+    Params p;
+    try { p = parse(argc, argv); }
+    catch (const std::exception& e) {   // EncodeStream.cpp:250-256
+      std::cerr << "Error: " << e.what() << endl;
+      return EXIT_FAILURE;
+    }
+    std::ifstream inF;
+    std::istream* in = &std::cin;
+    if (p.inFile != "-") {
+      inF.open(p.inFile.c_str(), std::ios::in | std::ios::binary);
+      if (!inF) { perror(("Failed to open input file \"" + p.inFile + "\"").c_str()); return EXIT_FAILURE; }
+      in = &inF;
+    }
+    std::ofstream outF;
+    std::ostream* out = &std::cout;
+    if (p.outFile != "-") {
+      outF.open(p.outFile.c_str(), std::ios::out | std::ios::binary);
+      if (!outF) { perror(("Failed to open output file \"" + p.outFile + "\"").c_str()); return EXIT_FAILURE; }
+      out = &outF;
+    }
+    const PictureFormat format(p.height, p.width, p.cf);
+    const int ySlices = sliceSizeIsValid(p.depth, format.lumaHeight(), format.chromaHeight(), p.ySize);
+    const int xSlices = sliceSizeIsValid(p.depth, format.lumaWidth(), format.chromaWidth(), p.xSize);
+    if (ySlices == 0 || xSlices == 0) {   // EncodeStream.cpp:379-405
+      if (waveletTransformIsPossible(p.depth, format.lumaWidth(), format.chromaWidth()) &&
+          waveletTransformIsPossible(p.depth, format.lumaHeight(), format.chromaHeight())) {
+        clog << "Consider setting --hSlice (-a) to " << suggestSliceSize(p.depth, format.lumaWidth(), format.chromaWidth(), p.xSize)
+             << " and --vSlice (-u) to " << suggestSliceSize(p.depth, format.lumaHeight(), format.chromaHeight(), p.ySize) << "." << endl;
+      } else {
+        const int d = suggestWaveletDepth(format.lumaWidth(), format.lumaHeight(), format.chromaWidth(), format.chromaHeight(), p.depth);
+        clog << "It is not possible to encode this input with a wavelet depth of " << p.depth << "." << endl;
+        clog << "Consider setting --waveletDepth (-d) to " << d << " and --hSlice (-a) to "
+             << suggestSliceSize(d, format.lumaWidth(), format.chromaWidth(), p.xSize) << " and --vSlice (-u) to "
+             << suggestSliceSize(d, format.lumaHeight(), format.chromaHeight(), p.ySize) << "." << endl;
+      }
+      throw std::logic_error("The given waveletDepth, hSlice, and vSlice parameters cannot encode this input. See above for suggested parameters.");
+    }
+    const Array1D qMatrix = quantMatrix(p.kernel, p.depth);
+    if (p.verbose) {
+      clog << "Vertical slices per picture          = " << ySlices << endl;
+      clog << "Horizontal slices per picture        = " << xSlices << endl;
+      clog << "Quantisation matrix = " << qMatrix[0];
+      for (size_t i = 1; i < qMatrix.size(); ++i) clog << ", " << qMatrix[i];
+      clog << endl;
+    }
+
+    vc2_codec_params cp;
+    if (vc2_make_geom(p.height, p.width, (int)p.cf, (int)p.kernel, p.depth, p.ySize, p.xSize, p.prefix, p.scalar, &cp.geom) != VC2_OK)
+      throw std::logic_error("The given waveletDepth, hSlice, and vSlice parameters cannot encode this input. See above for suggested parameters.");
+    cp.fmt.bytes_per_sample = p.bytes; cp.fmt.luma_depth = p.lumaDepth; cp.fmt.chroma_depth = p.chromaDepth;
+    cp.mode = p.mode == HQ_CBR ? VC2_HQ_CBR : VC2_HQ_VBR;
+    cp.qindex = p.qIndex; cp.picture_bytes = p.compressedBytes;
+    const bool taps = p.output == TRANSFORM || p.output == QUANTISED || p.output == INDICES;
+    const int G = taps ? 1 : std::min(p.gpus, std::max(1, vc2_device_count()));
+    const int B = p.batch;
+    cp.max_pictures = B;
+    std::vector<Worker> workers(G);
+    for (int g = 0; g < G; ++g) {
+      workers[g].codec.reset(new Codec(g, cp));
+      workers[g].payload.assign(B, std::vector<uint8_t>(workers[g].codec->payloadCapacity()));
+      workers[g].len.assign(B, 0);
+    }
+    const size_t picBytes = workers[0].codec->pictureBytes();
+    const size_t cap = workers[0].codec->payloadCapacity();
+
+    StreamWriter writer;
+    std::string unit;
+    if (p.output == STREAM) {
+      if (p.verbose) clog << endl << "Writing Sequence Header" << endl << endl;
+      writer.startSequence(unit, SequenceHeader(PROFILE_HQ, format.lumaHeight(), format.lumaWidth(), format.chromaFormat(), false,
+                                                (FrameRate)p.frameRate, p.topFieldFirst, p.lumaDepth));
+      out->write(unit.data(), (std::streamsize)unit.size());
+    }
+    PicturePreamble pre;
+    pre.wavelet_kernel = p.kernel; pre.depth = p.depth; pre.slices_x = xSlices; pre.slices_y = ySlices;
+    pre.slice_prefix = p.prefix; pre.slice_size_scalar = p.scalar; pre.slice_bytes = rationalise(0, 1);
+
+    // one round = up to G batches of B pictures; frames[g][i] is picture number frame0 + g*B + i
+    std::vector<std::vector<std::vector<uint8_t>>> frames(G, std::vector<std::vector<uint8_t>>(B, std::vector<uint8_t>(picBytes)));
+    std::vector<std::vector<uint8_t>> recon;
+    if (p.output == DECODED) recon.assign(B, std::vector<uint8_t>(picBytes));
+    unsigned long long frame = 0;
+    bool eof = false;
+    while (!eof) {
+      std::vector<int> count(G, 0);
+      for (int g = 0; g < G && !eof; ++g)
+        for (int i = 0; i < B; ++i) {
+          in->read(reinterpret_cast<char*>(frames[g][i].data()), (std::streamsize)picBytes);
+          if ((size_t)in->gcount() != picBytes) {
+            if (frame == 0 && g == 0 && i == 0) { std::cerr << "\rFailed to read input frame number 0" << endl; return EXIT_FAILURE; }
+            eof = true;
+            break;
+          }
+          ++count[g];
+        }
+      // encode: one host thread per GPU
+      std::vector<std::thread> th;
+      for (int g = 0; g < G; ++g) {
+        if (!count[g]) continue;
+        th.emplace_back([&, g]() {
+          Worker& w = workers[g];
+          try {
+            std::vector<const void*> pics(count[g]);
+            std::vector<uint8_t*> pay(count[g]);
+            for (int i = 0; i < count[g]; ++i) { pics[i] = frames[g][i].data(); pay[i] = w.payload[i].data(); }
+            w.codec->encode(count[g], pics.data(), pay.data(), cap, w.len.data());
+          } catch (const std::exception& e) { w.error = e.what(); }
+        });
+      }
+      for (auto& t : th) t.join();
+      // ordered reassembly
+      for (int g = 0; g < G; ++g) {
+        Worker& w = workers[g];
+        if (!count[g]) continue;
+        if (!w.error.empty()) throw std::logic_error(w.error);
+        for (int i = 0; i < count[g]; ++i, ++frame) {
+          if (p.verbose) clog << "Encoded frame number " << frame << " (" << w.len[i] << " bytes)" << endl;
+          if (p.output == STREAM) {
+            unit.clear();
+            writer.hqPicture(unit, (unsigned long)(frame & 0xFFFFFFFFull), pre, w.payload[i].data(), w.len[i]);
+            out->write(unit.data(), (std::streamsize)unit.size());
+          } else if (p.output == PACKAGED) {
+            out->write(reinterpret_cast<const char*>(w.payload[i].data()), (std::streamsize)w.len[i]);
+          } else if (taps) {
+            // the slots still hold this batch: read the requested intermediate back (EncodeStream -o Transform / Quantised / Indices)
+            const size_t ny = (size_t)cp.geom.slices_y * cp.geom.slices_x;
+            const size_t nY = (size_t)paddedSize(format.lumaHeight(), p.depth) * paddedSize(format.lumaWidth(), p.depth);
+            const size_t nC = (size_t)paddedSize(format.chromaHeight(), p.depth) * paddedSize(format.chromaWidth(), p.depth);
+            if (p.output == INDICES) {
+              std::vector<int32_t> q(ny);
+              w.codec->check(vc2_codec_read_indices(w.codec->handle(), i, q.data()));
+              std::string b(ny, '\0');
+              for (size_t j = 0; j < ny; ++j) b[j] = (char)q[j];
+              out->write(b.data(), (std::streamsize)b.size());
+            } else {
+              std::vector<int32_t> Y(nY), U(nC), V(nC);
+              w.codec->check(p.output == TRANSFORM ? vc2_codec_read_transform(w.codec->handle(), i, Y.data(), U.data(), V.data())
+                                                   : vc2_codec_read_quantised(w.codec->handle(), i, Y.data(), U.data(), V.data()));
+              write_be32_plane(*out, Y.data(), nY); write_be32_plane(*out, U.data(), nC); write_be32_plane(*out, V.data(), nC);
+            }
+          }
+        }
+        if (p.output == DECODED) {   // local decode of the batch just written (EncodeStream.cpp:649-690)
+          std::vector<const uint8_t*> pay(count[g]);
+          std::vector<void*> pics(count[g]);
+          for (int i = 0; i < count[g]; ++i) { pay[i] = w.payload[i].data(); pics[i] = recon[i].data(); }
+          w.codec->decode(count[g], pay.data(), w.len.data(), pics.data());
+          for (int i = 0; i < count[g]; ++i) out->write(reinterpret_cast<const char*>(recon[i].data()), (std::streamsize)picBytes);
+        }
+        if (!*out) { std::cerr << "Failed to write output file \"" << p.outFile << "\"" << endl; return EXIT_FAILURE; }
+      }
+    }
+    if (p.verbose) clog << "\rEnd of input reached after " << frame << " frames" << endl;
+    if (p.output == STREAM) {
+      unit.clear();
+      writer.endSequence(unit);
+      out->write(unit.data(), (std::streamsize)unit.size());
+    }
+    out->flush();
+  } catch (const std::exception& ex) {   // EncodeStream.cpp:782-785: message on standard OUTPUT, failure status
+    std::cout << "Error: " << ex.what() << endl;
+    return EXIT_FAILURE;
+  }
+  return EXIT_SUCCESS;
+}

@@ -1,6 +1,7 @@
 // vc2_stream.cpp - VC-2 stream framing (host only): parse info chain, sequence header, picture headers.
 // Behaviour follows /root/reference/src/Library/src/DataUnit.cpp (line numbers cited per function); the
 // implementation is table driven and works on byte strings instead of iostream state.
+#include <cstring>
 #include <stdexcept>
 #include <string>
 
@@ -356,3 +357,83 @@ PicturePreamble StreamReader::readPictureHeader(bool ld, unsigned long& pictureN
 }
 
 }  // namespace vc2
+
+// ---- C-ABI (include/vc2_host.h) ----------------------------------------------------------------------
+#include "vc2_host.h"
+
+namespace {
+vc2::ColourFormat cf_of(int c) { return c == 0 ? vc2::CF444 : c == 1 ? vc2::CF422 : vc2::CF420; }
+}
+
+extern "C" int vc2host_sequence_header(int profile_hq, int height, int width, int cf, int interlace, int frame_rate, int tff, int bitdepth,
+                                       uint8_t* out, int cap) {
+  try {
+    vc2::StreamWriter w;
+    std::string s;
+    w.startSequence(s, vc2::SequenceHeader(profile_hq ? vc2::PROFILE_HQ : vc2::PROFILE_LD, height, width, cf_of(cf), interlace != 0,
+                                           (vc2::FrameRate)frame_rate, tff != 0, bitdepth));
+    if ((int)s.size() > cap) return -2;
+    memcpy(out, s.data(), s.size());
+    return (int)s.size();
+  } catch (const std::exception&) { return -1; }
+}
+
+extern "C" long long vc2host_wrap_hq_stream(int height, int width, int cf, int frame_rate, int tff, int bitdepth, int kernel, int depth,
+                                            int slices_x, int slices_y, int prefix, int scalar, int n, const uint8_t* const* payloads,
+                                            const size_t* payload_len, uint8_t* out, size_t cap) {
+  try {
+    vc2::StreamWriter w;
+    std::string s;
+    w.startSequence(s, vc2::SequenceHeader(vc2::PROFILE_HQ, height, width, cf_of(cf), false, (vc2::FrameRate)frame_rate, tff != 0, bitdepth));
+    vc2::PicturePreamble p;
+    p.wavelet_kernel = (vc2::WaveletKernel)kernel; p.depth = depth; p.slices_x = slices_x; p.slices_y = slices_y;
+    p.slice_prefix = prefix; p.slice_size_scalar = scalar; p.slice_bytes = vc2::rationalise(0, 1);
+    for (int i = 0; i < n; ++i) w.hqPicture(s, (unsigned long)i, p, payloads[i], payload_len[i]);
+    w.endSequence(s);
+    if (s.size() > cap) return -2;
+    memcpy(out, s.data(), s.size());
+    return (long long)s.size();
+  } catch (const std::exception&) { return -1; }
+}
+
+extern "C" int vc2host_parse_units(const uint8_t* data, size_t len, int max_units, int64_t* units) {
+  try {
+    vc2::StreamReader r(data, len);
+    int n = 0;
+    if (!r.synchronise()) return 0;
+    while (!r.atEnd() && n < max_units) {
+      const vc2::DataUnit du = r.readDataUnit();
+      units[4 * n] = data[du.offset + 4]; units[4 * n + 1] = (int64_t)du.offset;
+      units[4 * n + 2] = du.next_parse_offset; units[4 * n + 3] = du.prev_parse_offset;
+      ++n;
+      if (du.next_parse_offset == 0) break;   // end of sequence (or an unterminated unit): nothing to chain to
+      r.seek(du.offset + du.next_parse_offset);
+    }
+    return n;
+  } catch (const std::exception&) { return -1; }
+}
+
+extern "C" int vc2host_read_sequence_header(const uint8_t* data, size_t len, size_t offset, int32_t* f) {
+  try {
+    vc2::StreamReader r(data, len);
+    r.seek(offset);
+    const vc2::SequenceHeader h = r.readSequenceHeader();
+    f[0] = h.major_version; f[1] = h.profile == vc2::PROFILE_HQ ? 3 : 0; f[2] = h.height; f[3] = h.width; f[4] = (int)h.chromaFormat;
+    f[5] = h.interlace; f[6] = (int)h.frameRate; f[7] = h.topFieldFirst; f[8] = h.bitdepth; f[9] = (int)(r.pos() - offset);
+    return 0;
+  } catch (const std::exception&) { return -1; }
+}
+
+extern "C" int vc2host_read_picture_header(const uint8_t* data, size_t len, size_t offset, int ld, int major_version, int64_t* f) {
+  try {
+    vc2::StreamReader r(data, len);
+    r.setMajorVersion(major_version);
+    r.seek(offset);
+    unsigned long picnum = 0;
+    const vc2::PicturePreamble p = r.readPictureHeader(ld != 0, picnum);
+    f[0] = (int64_t)picnum; f[1] = (int)p.wavelet_kernel; f[2] = p.depth; f[3] = p.slices_x; f[4] = p.slices_y;
+    f[5] = ld ? p.slice_bytes.numerator : p.slice_prefix; f[6] = ld ? p.slice_bytes.denominator : p.slice_size_scalar;
+    f[7] = (int64_t)(r.pos() - offset); f[8] = 0;
+    return 0;
+  } catch (const std::exception&) { return -1; }
+}

@@ -83,6 +83,7 @@ class StreamReader {
   // picture number + PicturePreamble (:1314-1410); ld selects the LD parameter set
   PicturePreamble readPictureHeader(bool ld, unsigned long& pictureNumber);
   size_t pos() const { return pos_; }
+  void setMajorVersion(int m) { major_ = m; }   // normally taken from the sequence header just read
   void seek(size_t p) { pos_ = p; }
   const uint8_t* data() const { return d_; }
   size_t size() const { return n_; }

@@ -5,9 +5,9 @@
  * reference exception text can be fetched with vc2_last_error().
  *
  * bbc/vc2-reference has no FFI: its boundary is the set of free functions in
- * src/Library/*.h called by EncodeStream.cpp / DecodeStream.cpp.  Each entry
+ * the src/Library headers called by EncodeStream.cpp / DecodeStream.cpp.  Each entry
  * point below names the reference function(s) it replaces (paths relative to
- * /root/reference).  The C++ mirror of the Library headers (include/vc2/*.h)
+ * /root/reference).  The C++ mirror of the Library headers (the include/vc2/ headers)
  * is a thin layer over these calls; INTEGRATION.md shows the binding.
  *
  * Layout contract (same as the reference's Array2D, src/Library/Arrays.h:28-31):

@@ -1,0 +1,102 @@
+"""GPU: the drop-in command lines (vc2_reference_b200/bin/EncodeStream, DecodeStream; host/*.cpp) run with the
+reference's own flags and must produce the reference's bytes: stream, intermediate taps, decoded pictures
+(golden digests in tests/golden/md5.json were made by the unmodified reference with the same flags)."""
+import hashlib
+import json
+import os
+import subprocess
+
+import pytest
+
+import gen
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+BIN = os.path.join(ROOT, "vc2_reference_b200", "bin")
+REF = os.path.join(ROOT, "oracle", "_ref")
+GOLD = json.load(open(os.path.join(HERE, "golden", "md5.json")))
+FMT = {"444": "4:4:4", "422": "4:2:2", "420": "4:2:0"}
+
+
+def enc_args(c):
+    a = ["-m", c["mode"], "-x", str(c["w"]), "-y", str(c["h"]), "-f", FMT[c["fmt"]], "-z", str(c["bits"]),
+         "-k", c["kernel"], "-d", str(c["wdepth"]), "-u", str(c["u"]), "-a", str(c["a"]), "-r", str(c["r"])]
+    a += ["-q", str(c["q"])] if c["mode"] == "HQ_ConstQ" else ["-s", str(c["s"])]
+    if c["mode"] != "LD":
+        a += ["-S", str(c["S"]), "-P", str(c["P"])]
+    return a
+
+
+def md5(path):
+    return hashlib.md5(open(path, "rb").read()).hexdigest()
+
+
+def write_input(c, path):
+    with open(path, "wb") as f:
+        for i in range(c["frames"]):
+            f.write(gen.frame_bytes(c["seed"], i, c["w"], c["h"], c["fmt"], c["bits"], c["smooth"]))
+
+
+def run(cmd):
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert r.returncode == 0, (cmd, r.stdout.decode(errors="replace")[-400:], r.stderr.decode(errors="replace")[-400:])
+    return r
+
+
+@pytest.mark.parametrize("name", ["S01_LeGall_d3_422", "S04_Haar1_d4_420", "S05_Fidelity_d2_422", "S08_DD137_d4_422",
+                                  "B00_DD97_d2_420", "B06_Daub97_d3_444", "C1", "C2"])
+def test_command_lines_vs_golden(tmp_path, name):
+    c, taps = GOLD[name]["params"], GOLD[name]["taps"]
+    src = str(tmp_path / "in.yuv")
+    write_input(c, src)
+    # a batch smaller than the clip and (when there are several GPUs) two devices: chunking and reassembly
+    extra = ["-B", "1", "-G", "2"] if name.startswith("S") else []
+    for tap in ["Stream", "Packaged", "Transform", "Quantised"] + (["Indices"] if c["mode"] != "HQ_ConstQ" else []):
+        dst = str(tmp_path / ("enc_" + tap))
+        run([os.path.join(BIN, "EncodeStream")] + enc_args(c) + extra + ["-o", tap, src, dst])
+        assert md5(dst) == taps["enc_" + tap]["md5"], (name, tap)
+    stream = str(tmp_path / "enc_Stream")
+    for tap in ["Decoded", "Transform", "Quantised", "Indices"]:
+        dst = str(tmp_path / ("dec_" + tap))
+        run([os.path.join(BIN, "DecodeStream")] + extra + ["-o", tap, stream, dst])
+        assert md5(dst) == taps["dec_" + tap]["md5"], (name, tap)
+    # EncodeStream -o Decoded = the decoder's picture (local decode loop, EncodeStream.cpp:649-767)
+    dst = str(tmp_path / "enc_Decoded")
+    run([os.path.join(BIN, "EncodeStream")] + enc_args(c) + ["-o", "Decoded", src, dst])
+    if c["bits"] != 8:     # the stand-alone decoder writes 8-bit streams as one byte per sample, the encoder keeps -n
+        assert md5(dst) == taps["dec_Decoded"]["md5"]
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(REF, "EncodeStream")), reason="oracle/_ref not built")
+def test_decode_ld_stream_from_reference_encoder(tmp_path):
+    """LD is decode-only here: the stream comes from the reference's encoder, both decoders must agree"""
+    c = dict(w=352, h=288, fmt="420", bits=8, frames=3, seed=77, smooth=False)
+    src = str(tmp_path / "in.yuv")
+    write_input(c, src)
+    stream = str(tmp_path / "ld.vc2")
+    run([os.path.join(REF, "EncodeStream"), "-m", "LD", "-x", "352", "-y", "288", "-f", "4:2:0", "-z", "8", "-k", "LeGall", "-d", "3",
+         "-u", "2", "-a", "2", "-r", "3", "-s", "40000", src, stream])
+    for tap in ["Decoded", "Transform", "Quantised", "Indices"]:
+        a, b = str(tmp_path / ("ref_" + tap)), str(tmp_path / ("our_" + tap))
+        run([os.path.join(REF, "DecodeStream"), "-o", tap, stream, a])
+        run([os.path.join(BIN, "DecodeStream"), "-o", tap, stream, b])
+        assert md5(a) == md5(b), tap
+
+
+def test_error_reporting_matches_reference(tmp_path):
+    """bad parameters: 'Error: <reference text>' and a failure status (EncodeStream.cpp:250-256, 782-785)"""
+    src = str(tmp_path / "in.yuv")
+    open(src, "wb").write(b"\0" * 64)
+    r = subprocess.run([os.path.join(BIN, "EncodeStream"), "-m", "HQ_ConstQ", "-x", "64", "-y", "32", "-f", "4:2:2", "-k", "LeGall", "-d", "2",
+                        "-u", "1", "-a", "1", src, str(tmp_path / "o")], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert r.returncode != 0 and b"Quantisation index must be set in HQ_ConstQ mode" in r.stderr
+    # a slice scalar that is too small for the content is the reference's logic_error, on standard output
+    c = GOLD["C3"]["params"]
+    one = dict(c, frames=1)
+    big = str(tmp_path / "c3.yuv")
+    write_input(one, big)
+    a = enc_args(one)
+    a[a.index("-S") + 1] = "1"
+    r = subprocess.run([os.path.join(BIN, "EncodeStream")] + a + [big, str(tmp_path / "o2")], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert r.returncode != 0 and b"Error: Slice scalar is too small" in r.stdout, r.stdout[-300:]
