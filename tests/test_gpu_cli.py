@@ -52,16 +52,19 @@ def test_command_lines_vs_golden(tmp_path, name):
     write_input(c, src)
     # a batch smaller than the clip and (when there are several GPUs) two devices: chunking and reassembly
     extra = ["-B", "1", "-G", "2"] if name.startswith("S") else []
-    for tap in ["Stream", "Packaged", "Transform", "Quantised"] + (["Indices"] if c["mode"] != "HQ_ConstQ" else []):
+    small = not name.startswith("C")       # the 1080p configs: stream and pictures only (each run pays a CUDA start-up)
+    for tap in ["Stream"] + (["Packaged", "Transform", "Quantised"] if small else []) + (["Indices"] if c["mode"] != "HQ_ConstQ" else []):
         dst = str(tmp_path / ("enc_" + tap))
         run([os.path.join(BIN, "EncodeStream")] + enc_args(c) + extra + ["-o", tap, src, dst])
         assert md5(dst) == taps["enc_" + tap]["md5"], (name, tap)
     stream = str(tmp_path / "enc_Stream")
-    for tap in ["Decoded", "Transform", "Quantised", "Indices"]:
+    for tap in ["Decoded"] + (["Transform", "Quantised", "Indices"] if small else []):
         dst = str(tmp_path / ("dec_" + tap))
         run([os.path.join(BIN, "DecodeStream")] + extra + ["-o", tap, stream, dst])
         assert md5(dst) == taps["dec_" + tap]["md5"], (name, tap)
     # EncodeStream -o Decoded = the decoder's picture (local decode loop, EncodeStream.cpp:649-767)
+    if not small:
+        return
     dst = str(tmp_path / "enc_Decoded")
     run([os.path.join(BIN, "EncodeStream")] + enc_args(c) + ["-o", "Decoded", src, dst])
     if c["bits"] != 8:     # the stand-alone decoder writes 8-bit streams as one byte per sample, the encoder keeps -n
