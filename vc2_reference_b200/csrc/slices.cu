@@ -5,7 +5,60 @@ namespace vc2 {
 
 __constant__ QuantTables c_qt;
 
-cudaError_t upload_quant_tables(const QuantTables& t) { return cudaMemcpyToSymbol(c_qt, &t, sizeof(t)); }
+
+// ---- SignedVLC code tables (VLC.cpp:21-52, 78-85, 283-317), built on the host, staged into shared memory by
+// the slice coders: the arithmetic pipe is the bottleneck of both coders, a table look-up runs on the LSU.
+//   d_enc_lut[2 * |v| + (v < 0)] = (code << 5) | bits                 for |v| < ENC_LUT_MAG
+//   d_dec_lut[top DEC_LUT_BITS bits of the window] = value * 16 + bits, or 0 when the code is longer than that
+constexpr int ENC_LUT_MAG = 256;
+constexpr int DEC_LUT_BITS = 12;
+__device__ uint32_t d_enc_lut[2 * ENC_LUT_MAG];
+__device__ int16_t d_dec_lut[1 << DEC_LUT_BITS];
+
+cudaError_t upload_quant_tables(const QuantTables& t) {
+  cudaError_t e = cudaMemcpyToSymbol(c_qt, &t, sizeof(t));
+  if (e != cudaSuccess) return e;
+  static uint32_t enc[2 * ENC_LUT_MAG];
+  static int16_t dec[1 << DEC_LUT_BITS];
+  for (int mag = 0; mag < ENC_LUT_MAG; ++mag)
+    for (int neg = 0; neg < 2; ++neg) {
+      uint32_t code = 1, nb = 1;
+      if (mag) {
+        const uint32_t m = (uint32_t)mag + 1u;
+        int k = 0;
+        while ((m >> (k + 1)) != 0) ++k;
+        code = 0;
+        for (int i = k - 1; i >= 0; --i) code = (code << 2) | ((m >> i) & 1u);   // 0 b(k-1) 0 b(k-2) ... 0 b0
+        code = (code << 2) | 2u | (uint32_t)neg;                                 // 1 s
+        nb = 2 * k + 2;
+      }
+      enc[2 * mag + neg] = (code << 5) | nb;
+    }
+  for (int i = 0; i < (1 << DEC_LUT_BITS); ++i) {
+    int pos = DEC_LUT_BITS - 1, m = 1, entry = 0;
+    for (int k = 0; pos >= 0; ++k) {
+      const int follow = (i >> pos) & 1;
+      --pos;
+      if (follow) {   // stop bit: magnitude complete, a sign bit follows when it is not zero
+        int v = m - 1, len = 2 * k + 1;
+        if (v) {
+          if (pos < 0) break;
+          if ((i >> pos) & 1) v = -v;
+          ++len;
+        }
+        entry = v * 16 + len;
+        break;
+      }
+      if (pos < 0) break;
+      m = (m << 1) | ((i >> pos) & 1);
+      --pos;
+    }
+    dec[i] = (int16_t)entry;
+  }
+  e = cudaMemcpyToSymbol(d_enc_lut, enc, sizeof(enc));
+  if (e != cudaSuccess) return e;
+  return cudaMemcpyToSymbol(d_dec_lut, dec, sizeof(dec));
+}
 
 namespace {
 
@@ -133,16 +186,30 @@ __device__ __forceinline__ void walk_component(const int4* __restrict__ src, con
   }
 }
 
-// SignedVLC of a (quantised) value: m = |v| + 1 clamped to the 32-bit code domain (VLC.h:27-28)
-__device__ __forceinline__ void vlc_of(int qv, unsigned& bigor, uint32_t& code, int& nb, bool& nonzero) {
-  uint32_t m = (uint32_t)abs(qv) + 1u;
-  bigor |= m;
-  m = min(m, 65535u);
-  nonzero = m > 1u;
-  const int k = 31 - __clz(m);
-  nb = 2 * k + 1 + (nonzero ? 1 : 0);
-  const uint32_t low = m ^ (1u << k);
-  code = (spread16(low) << 2) | (nonzero ? (2u | (qv < 0 ? 1u : 0u)) : 1u);
+// SignedVLC of a value of magnitude mag (sign neg): table look-up for |v| < ENC_LUT_MAG, else computed with
+// m = |v| + 1 clamped to the 32-bit code domain (VLC.h:27-28; bigor collects the m that leave it)
+__device__ __forceinline__ void vlc_of(const uint32_t* __restrict__ lut, uint32_t mag, bool neg, unsigned& bigor, uint32_t& code, int& nb) {
+  if (mag < (uint32_t)ENC_LUT_MAG) {
+    const uint32_t e = lut[2u * mag + (neg ? 1u : 0u)];
+    nb = (int)(e & 31u);
+    code = e >> 5;
+  } else {
+    uint32_t m = mag + 1u;
+    bigor |= m;
+    m = min(m, 65535u);
+    const int k = 31 - __clz(m);
+    nb = 2 * k + 2;
+    code = (spread16(m ^ (1u << k)) << 2) | 2u | (neg ? 1u : 0u);
+  }
+}
+__device__ __forceinline__ uint32_t quant_mag(int v, const BandP& bp) {   // |quant(v, q)|
+  const uint32_t a = (uint32_t)abs(v) << 2;
+  const uint32_t t = __umulhi(bp.qm, a);
+  return (t + ((a - t) >> 1)) >> bp.ql;
+}
+// stage a table of n 32-bit words from global into shared memory (whole CTA; caller synchronises)
+__device__ __forceinline__ void stage_table(uint32_t* dst, const uint32_t* src, int n) {
+  for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
 }
 
 // MSB-first bit writer into this slice's staging words (one thread owns the whole slice)
@@ -188,14 +255,18 @@ struct BitWriter {
 };
 
 struct CountOp {      // component_slice_bytes' bit count of quantise(v) (rate-control probe)
+  const uint32_t* lut;
   int bits, last;
   unsigned bigor;
   __device__ __forceinline__ void operator()(int v, const BandP& bp) {
-    const uint32_t m = (uint32_t)abs(quant_band(v, bp)) + 1u;
-    bigor |= m;
-    const int k = 31 - __clz(min(m, 65535u));
-    bits += 2 * k + 1 + (m > 1u ? 1 : 0);
-    if (m > 1u) last = bits;
+    const uint32_t mag = quant_mag(v, bp);
+    if (mag < (uint32_t)ENC_LUT_MAG) bits += (int)(lut[2u * mag] & 31u);
+    else {
+      const uint32_t m = mag + 1u;
+      bigor |= m;
+      bits += 2 * (31 - __clz(min(m, 65535u))) + 2;
+    }
+    if (mag) last = bits;
   }
 };
 struct SseOp {        // yss_for_slice (Quantisation.cpp:627-642): product in int, sum in long long
@@ -207,17 +278,17 @@ struct SseOp {        // yss_for_slice (Quantisation.cpp:627-642): product in in
 };
 template <bool QUANT>
 struct EmitOp {
+  const uint32_t* lut;
   BitWriter* W;
   int last;
   unsigned bigor;
   __device__ __forceinline__ void operator()(int v, const BandP& bp) {
-    const int qv = QUANT ? quant_band(v, bp) : v;
+    const uint32_t mag = QUANT ? quant_mag(v, bp) : (uint32_t)abs(v);
     uint32_t code;
     int nb;
-    bool nz;
-    vlc_of(qv, bigor, code, nb, nz);
+    vlc_of(lut, mag, v < 0, bigor, code, nb);
     W->put(code, nb);
-    if (nz) last = W->pos();
+    if (mag) last = W->pos();
   }
 };
 
@@ -236,6 +307,9 @@ __device__ __forceinline__ int scaled_bytes(int count, int scalar, bool& too_big
 // The slice sizes are scanned and the images gathered into the payload by assemble_kernel.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) hq_pack_kernel(const PackParams p) {
+  __shared__ uint32_t s_enc[2 * ENC_LUT_MAG];
+  stage_table(s_enc, d_enc_lut, 2 * ENC_LUT_MAG);
+  __syncthreads();
   const SliceGeom& g = p.g;
   const int nslices = g.slices_x * g.slices_y;
   const int pic = blockIdx.y;
@@ -257,7 +331,7 @@ __global__ void __launch_bounds__(128) hq_pack_kernel(const PackParams p) {
       int need = 0;
       bool too_big = false, badq = false;
       for (int c = 0; c < 3; ++c) {
-        CountOp op = {0, 0, 0u};
+        CountOp op = {s_enc, 0, 0, 0u};
         walk_component(src + (size_t)(g.comp_start[c] >> 2) * 32, g, c, trialQ, badq, op);
         need += scaled_bytes(op.last, g.scalar, too_big);
       }
@@ -310,11 +384,11 @@ __global__ void __launch_bounds__(128) hq_pack_kernel(const PackParams p) {
         const int4* csrc = src + (size_t)(g.comp_start[c] >> 2) * 32;
         int last;
         if (p.quantise) {
-          EmitOp<true> op = {&W, data_start, 0u};
+          EmitOp<true> op = {s_enc, &W, data_start, 0u};
           walk_component(csrc, g, c, qi, badq, op);
           last = op.last; bigor |= op.bigor;
         } else {
-          EmitOp<false> op = {&W, data_start, 0u};
+          EmitOp<false> op = {s_enc, &W, data_start, 0u};
           walk_component(csrc, g, c, qi, badq, op);
           last = op.last; bigor |= op.bigor;
         }
@@ -414,54 +488,76 @@ __global__ void __launch_bounds__(256) assemble_kernel(const AssembleParams p) {
 
 // ------------------------------------------------------------------------------------------
 // MSB-first bit reader over global memory, one thread per slice: 64-bit window (hi:lo), refilled
-// 32 bits at a time from aligned words with one word of prefetch.
+// 32 bits at a time from aligned words with one word of prefetch.  The reader is BOUNDED
+// (vlc::bounded, VLC.cpp:182-185): bits at and beyond `bound` read as ones; they are forced to one
+// when a word enters the window, so the per-code path carries no bound arithmetic.
 // ------------------------------------------------------------------------------------------
 struct BitReader {
   const uint32_t* p;   // next aligned word to prefetch
   uint32_t hi, lo, ahead;
   int nb;              // valid bits in hi:lo (top aligned)
+  int left;            // real stream bits that have not entered the window yet (<= 0: only ones follow)
   __device__ __forceinline__ static uint32_t be(uint32_t x) { return __byte_perm(x, 0, 0x0123); }
-  // start reading at byte address a (any alignment); the buffers have slack behind the data
-  __device__ __forceinline__ void init(const uint8_t* a) {
+  // start reading at byte address a (any alignment); the first `bound` bits are real.  The buffers have slack
+  // behind the data.
+  __device__ __forceinline__ void init(const uint8_t* a, int bound) {
     const uintptr_t u = reinterpret_cast<uintptr_t>(a);
     p = reinterpret_cast<const uint32_t*>(u & ~(uintptr_t)3);
+    const int lead = 8 * (int)(u & 3);
     hi = be(__ldg(p)); lo = be(__ldg(p + 1)); ahead = __ldg(p + 2);
     p += 3;
+    const int real = lead + bound;   // real bits among the 64 just loaded
+    if (real < 64) {
+      const unsigned long long ones = real <= 0 ? ~0ull : (~0ull >> real);
+      hi |= (uint32_t)(ones >> 32);
+      lo |= (uint32_t)ones;
+    }
+    left = real - 64;
     nb = 64;
-    skip(8 * (int)(u & 3));
+    skip(lead);
   }
   __device__ __forceinline__ void skip(int n) {   // n in 0..32, n <= nb
     hi = __funnelshift_lc(lo, hi, n);
     lo = n >= 32 ? 0u : lo << n;
     nb -= n;
-    if (nb <= 32) {   // lo is empty: append the next word behind the nb valid bits of hi
-      const uint32_t nw = be(ahead);
-      ahead = __ldg(p++);
-      hi |= __funnelshift_rc(nw, 0u, nb);
-      lo = __funnelshift_lc(0u, nw, 32 - nb);
-      nb += 32;
-    }
+    if (nb <= 32) refill();
   }
-  // one signed interleaved exp-Golomb value (VLC.cpp:283-317) from a window whose bits at and beyond
-  // `rem` read as ones (vlc::bounded, VLC.cpp:182-185); rem is decremented by the code length
-  __device__ __forceinline__ int get_vlc(int& rem, bool& range_err) {
-    uint32_t w = hi;
-    if (rem < 32) w |= rem <= 0 ? 0xFFFFFFFFu : (0xFFFFFFFFu >> rem);
+  __device__ __forceinline__ void skip_short(int n) {   // n in 0..31
+    hi = __funnelshift_l(lo, hi, n);
+    lo <<= n;
+    nb -= n;
+    if (nb <= 32) refill();
+  }
+  __device__ __forceinline__ void refill() {   // lo is empty: append the next word behind the nb valid bits of hi
+    uint32_t nw = be(ahead);
+    ahead = __ldg(p++);
+    nw |= __funnelshift_rc(0xFFFFFFFFu, 0u, max(left, 0));   // ones from bit `left` on (nothing when left >= 32)
+    left -= 32;
+    hi |= __funnelshift_rc(nw, 0u, nb);
+    lo = __funnelshift_lc(0u, nw, 32 - nb);
+    nb += 32;
+  }
+  // one signed interleaved exp-Golomb value (VLC.cpp:283-317): table look-up on the leading DEC_LUT_BITS bits,
+  // computed for longer codes
+  __device__ __forceinline__ int get_vlc(const int16_t* __restrict__ lut, bool& range_err) {
+    const int e = lut[hi >> (32 - DEC_LUT_BITS)];
+    if (e != 0) {
+      skip_short(e & 15);
+      return e >> 4;
+    }
+    const uint32_t w = hi;
     const uint32_t f = w & 0xAAAAAAAAu;
     if (f == 0) {   // more than 16 magnitude bits: outside the reference's 32-bit VLC domain
       range_err = true;
       skip(32);
-      rem -= 32;
       return 0;
     }
-    const int k = __clz(f) >> 1;
-    const uint32_t t = __funnelshift_rc(w, 0u, 32 - 2 * k);   // the 2k leading bits, right aligned (0 when k == 0)
+    const int k = __clz(f) >> 1;   // k >= 1 here (k == 0 is in the table)
+    const uint32_t t = w >> (32 - 2 * k);   // the 2k leading bits, right aligned
     const uint32_t mag = ((1u << k) | compress16(t)) - 1u;
     const uint32_t neg = (w >> (30 - 2 * k)) & 1u;
-    const int len = k ? 2 * k + 2 : 1;
-    skip(len);
-    rem -= len;
-    return (k && neg) ? -(int)mag : (int)mag;
+    skip(2 * k + 2);
+    return neg ? -(int)mag : (int)mag;
   }
   __device__ __forceinline__ uint32_t get_bits(int n) {   // n in 1..32
     const uint32_t w = n == 32 ? hi : (hi >> (32 - n));
@@ -475,8 +571,11 @@ struct BitReader {
 // Every lane walks its own slice bytes; the decoded (and inverse quantised) coefficients of the
 // warp leave as contiguous 512-byte runs of the group-interleaved layout.
 // ------------------------------------------------------------------------------------------
-template <bool LD>
+template <bool LD, bool DEQ>
 __global__ void __launch_bounds__(128) slice_unpack_kernel(const UnpackParams p) {
+  __shared__ int16_t s_dec[1 << DEC_LUT_BITS];
+  stage_table(reinterpret_cast<uint32_t*>(s_dec), reinterpret_cast<const uint32_t*>(d_dec_lut), (1 << DEC_LUT_BITS) / 2);
+  __syncthreads();
   const SliceGeom& g = p.g;
   const int nslices = g.slices_x * g.slices_y;
   const int pic = blockIdx.y;
@@ -506,24 +605,32 @@ __global__ void __launch_bounds__(128) slice_unpack_kernel(const UnpackParams p)
       }
       const int start = pos + 1;
       pos = start + len;
-      br.init(bytes + (bad ? 0 : start));
-      int rem = 8 * len;
+      br.init(bytes + (bad ? 0 : start), 8 * len);
       int k = 0, b = 0, bend = g.band_start[c][1];
       BandP bp = band_params(qi, g.qmatrix[0], badq);
       int4* cdst = dst + (size_t)(g.comp_start[c] >> 2) * 32;
       const int n = g.band_start[c][g.nbands];
       for (int piece = 0; piece < (n >> 2); ++piece) {
         int v[4];
+        if (bend - k >= 4) {   // warp uniform: the four coefficients belong to the current band
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          while (k == bend) {
-            ++b;
-            bend = g.band_start[c][b + 1];
-            bp = band_params(qi, g.qmatrix[b], badq);
+          for (int e = 0; e < 4; ++e) {
+            const int x = br.get_vlc(s_dec, range_err);
+            v[e] = DEQ ? scale_band(x, bp) : x;
           }
-          const int x = br.get_vlc(rem, range_err);
-          v[e] = p.dequantise ? scale_band(x, bp) : x;
-          ++k;
+          k += 4;
+        } else {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            while (k == bend) {
+              ++b;
+              bend = g.band_start[c][b + 1];
+              bp = band_params(qi, g.qmatrix[b], badq);
+            }
+            const int x = br.get_vlc(s_dec, range_err);
+            v[e] = DEQ ? scale_band(x, bp) : x;
+            ++k;
+          }
         }
         cdst[(size_t)piece * 32] = make_int4(v[0], v[1], v[2], v[3]);
       }
@@ -531,7 +638,7 @@ __global__ void __launch_bounds__(128) slice_unpack_kernel(const UnpackParams p)
     if (bad) flags |= VC2_FLAG_STREAM;
   } else {
     // qindex (7 bits) | luma length | luma (bounded) | U/V interleaved (bounded)   (Slices.cpp:253-296)
-    br.init(bytes);
+    br.init(bytes, 8 * size);
     qi = (int)br.get_bits(7);
     int lb = 0;   // utils::intlog2(8*bytes-7)
     { const int v = 8 * size - 7; while ((1 << lb) < v) ++lb; }
@@ -541,8 +648,8 @@ __global__ void __launch_bounds__(128) slice_unpack_kernel(const UnpackParams p)
     for (int blk = 0; blk < 2; ++blk) {
       // the two blocks start and end on arbitrary bits: restart the reader at the byte holding the first bit
       const int bstart = blk == 0 ? 7 + lb : 7 + lb + ybits;
-      int rem = blk == 0 ? ybits : max(uvbits, 0);
-      br.init(bytes + min(bstart >> 3, size));
+      const int rem = blk == 0 ? ybits : max(uvbits, 0);
+      br.init(bytes + min(bstart >> 3, size), (bstart & 7) + rem);
       br.skip(bstart & 7);
       const int c = blk;   // band geometry: Y, or chroma (U and V are alike)
       int k = 0, b = 0, bend = g.band_start[c][1];
@@ -559,11 +666,11 @@ __global__ void __launch_bounds__(128) slice_unpack_kernel(const UnpackParams p)
             bend = g.band_start[c][b + 1];
             bp = band_params(qi, g.qmatrix[b], badq);
           }
-          const bool deq = p.dequantise && b != 0;   // the LL band is reconstructed by the DC prediction kernel
-          const int x = br.get_vlc(rem, range_err);
+          const bool deq = DEQ && b != 0;   // the LL band is reconstructed by the DC prediction kernel
+          const int x = br.get_vlc(s_dec, range_err);
           v[e] = deq ? scale_band(x, bp) : x;
           if (blk == 1) {   // u0 v0 u1 v1 ... (Slices.cpp:287-294)
-            const int y = br.get_vlc(rem, range_err);
+            const int y = br.get_vlc(s_dec, range_err);
             w[e] = deq ? scale_band(y, bp) : y;
           }
           ++k;
@@ -574,7 +681,7 @@ __global__ void __launch_bounds__(128) slice_unpack_kernel(const UnpackParams p)
     }
   }
   p.qidx[sidx] = qi;
-  if (badq && p.dequantise) flags |= VC2_FLAG_QUANT_INDEX;
+  if (badq && DEQ) flags |= VC2_FLAG_QUANT_INDEX;
   if (range_err) flags |= VC2_FLAG_VLC_RANGE;
   if (flags) atomicOr(&p.err_flags[sidx], flags);
 }
@@ -739,8 +846,13 @@ cudaError_t assemble_launch(cudaStream_t s, const AssembleParams& p, int npictur
 cudaError_t unpack_launch(cudaStream_t s, const UnpackParams& p, int npictures) {
   const int nslices = p.g.slices_x * p.g.slices_y;
   const dim3 grid((nslices + 127) / 128, npictures);
-  if (p.ld) slice_unpack_kernel<true><<<grid, 128, 0, s>>>(p);
-  else slice_unpack_kernel<false><<<grid, 128, 0, s>>>(p);
+  if (p.ld) {
+    if (p.dequantise) slice_unpack_kernel<true, true><<<grid, 128, 0, s>>>(p);
+    else slice_unpack_kernel<true, false><<<grid, 128, 0, s>>>(p);
+  } else {
+    if (p.dequantise) slice_unpack_kernel<false, true><<<grid, 128, 0, s>>>(p);
+    else slice_unpack_kernel<false, false><<<grid, 128, 0, s>>>(p);
+  }
   return cudaGetLastError();
 }
 
