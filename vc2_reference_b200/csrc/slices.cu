@@ -145,8 +145,8 @@ __device__ __forceinline__ int quant_band(int v, const BandP& bp) {
   return v < 0 ? -q : q;
 }
 __device__ __forceinline__ int scale_band(int v, const BandP& bp) {   // bp.qo already holds quant_offset + 2
-  if (v == 0) return 0;
-  const uint32_t m = ((uint32_t)abs(v) * bp.qf + bp.qo) >> 2;
+  const uint32_t a = (uint32_t)abs(v);
+  const uint32_t m = (a * bp.qf + (a ? bp.qo : 0u)) >> 2;   // 0 -> 0 without a branch (lanes differ)
   return v < 0 ? -(int)m : (int)m;
 }
 
@@ -214,18 +214,25 @@ __device__ __forceinline__ void stage_table(uint32_t* dst, const uint32_t* src, 
 
 // MSB-first bit writer into this slice's staging words (one thread owns the whole slice)
 struct BitWriter {
-  uint32_t* w;
+  uint32_t* w;    // first word of the slice image
+  uint32_t* wp;   // next word to write
   unsigned long long acc;   // the low nacc bits are pending
-  int nacc, wc;
-  __device__ __forceinline__ void init(uint32_t* words) { w = words; acc = 0; nacc = 0; wc = 0; }
-  __device__ __forceinline__ int pos() const { return 32 * wc + nacc; }
+  int nacc;
+  __device__ __forceinline__ void init(uint32_t* words) { w = wp = words; acc = 0; nacc = 0; }
+  __device__ __forceinline__ int wc() const { return (int)(wp - w); }
+  __device__ __forceinline__ int pos() const { return 32 * wc() + nacc; }
+  // cheap monotonic cursor (one multiply-add): pos() + 8 * (low address bits of w); compare / subtract only
+  __device__ __forceinline__ unsigned mark() const { return 8u * (unsigned)reinterpret_cast<uintptr_t>(wp) + (unsigned)nacc; }
+  __device__ __forceinline__ int unmark(unsigned m) const { return (int)(m - 8u * (unsigned)reinterpret_cast<uintptr_t>(w)); }
   __device__ __forceinline__ void put(uint32_t code, int nb) {   // nb in 0..32
     acc = (acc << nb) | code;
     nacc += nb;
-    if (nacc >= 32) {
-      w[wc++] = (uint32_t)(acc >> (nacc - 32));
-      nacc -= 32;
-    }
+    // branch-free flush: the lanes of a warp (one slice each) reach 32 pending bits at different coefficients
+    const bool full = nacc >= 32;
+    const uint32_t out = (uint32_t)(acc >> ((nacc - 32) & 31));
+    if (full) *wp = out;
+    wp += full ? 1 : 0;
+    nacc -= full ? 32 : 0;
   }
   // move the cursor to absolute bit position target: pad with zeros, or drop what was written beyond it
   // (only the '1' codes of trailing zero coefficients can be dropped, VLC.cpp:151-155)
@@ -238,19 +245,19 @@ struct BitWriter {
     }
     if (target < cur) {
       const int twc = target >> 5, tb = target & 31;
-      if (twc == wc) acc >>= (nacc - tb);
-      else { acc = (unsigned long long)w[twc] >> (32 - tb); wc = twc; }
+      if (twc == wc()) acc >>= (nacc - tb);
+      else { acc = (unsigned long long)w[twc] >> (32 - tb); wp = w + twc; }
       nacc = tb;
     }
   }
   // overwrite the (zero) byte at byte-aligned bit position bitpos < pos()
   __device__ __forceinline__ void patch_byte(int bitpos, uint32_t value) {
     const int idx = bitpos >> 5;
-    if (idx < wc) w[idx] |= value << (24 - (bitpos & 31));
-    else acc |= (unsigned long long)value << (nacc - (bitpos - 32 * wc) - 8);
+    if (idx < wc()) w[idx] |= value << (24 - (bitpos & 31));
+    else acc |= (unsigned long long)value << (nacc - (bitpos - 32 * wc()) - 8);
   }
   __device__ __forceinline__ void finish() {
-    if (nacc > 0) { w[wc++] = (uint32_t)(acc << (32 - nacc)); nacc = 0; }
+    if (nacc > 0) { *wp++ = (uint32_t)(acc << (32 - nacc)); nacc = 0; }
   }
 };
 
@@ -280,7 +287,7 @@ template <bool QUANT>
 struct EmitOp {
   const uint32_t* lut;
   BitWriter* W;
-  int last;
+  unsigned last;   // BitWriter::mark() behind the last non-zero coefficient
   unsigned bigor;
   __device__ __forceinline__ void operator()(int v, const BandP& bp) {
     const uint32_t mag = QUANT ? quant_mag(v, bp) : (uint32_t)abs(v);
@@ -288,7 +295,7 @@ struct EmitOp {
     int nb;
     vlc_of(lut, mag, v < 0, bigor, code, nb);
     W->put(code, nb);
-    if (mag) last = W->pos();
+    last = mag ? W->mark() : last;
   }
 };
 
@@ -384,13 +391,13 @@ __global__ void __launch_bounds__(128) hq_pack_kernel(const PackParams p) {
         const int4* csrc = src + (size_t)(g.comp_start[c] >> 2) * 32;
         int last;
         if (p.quantise) {
-          EmitOp<true> op = {s_enc, &W, data_start, 0u};
+          EmitOp<true> op = {s_enc, &W, W.mark(), 0u};
           walk_component(csrc, g, c, qi, badq, op);
-          last = op.last; bigor |= op.bigor;
+          last = W.unmark(op.last); bigor |= op.bigor;
         } else {
-          EmitOp<false> op = {s_enc, &W, data_start, 0u};
+          EmitOp<false> op = {s_enc, &W, W.mark(), 0u};
           walk_component(csrc, g, c, qi, badq, op);
-          last = op.last; bigor |= op.bigor;
+          last = W.unmark(op.last); bigor |= op.bigor;
         }
         int L = scaled_bytes(last - data_start, g.scalar, too_big);
         if (c == 2 && p.mode == VC2_HQ_CBR) {
@@ -493,19 +500,25 @@ __global__ void __launch_bounds__(256) assemble_kernel(const AssembleParams p) {
 // when a word enters the window, so the per-code path carries no bound arithmetic.
 // ------------------------------------------------------------------------------------------
 struct BitReader {
-  const uint32_t* p;   // next aligned word to prefetch
-  uint32_t hi, lo, ahead;
-  int nb;              // valid bits in hi:lo (top aligned)
-  int left;            // real stream bits that have not entered the window yet (<= 0: only ones follow)
+  const uint32_t* p;   // next aligned word to fetch
+  uint32_t hi, lo;     // the window, top aligned; bits below the nb valid ones are zero
+  uint32_t nxt;        // the word that follows the window: byte swapped, bits beyond the bound forced to one
+  int nb;              // valid bits in hi:lo
+  int left;            // real stream bits behind nxt (<= 0: only ones follow)
   __device__ __forceinline__ static uint32_t be(uint32_t x) { return __byte_perm(x, 0, 0x0123); }
+  __device__ __forceinline__ void fetch() {
+    const uint32_t raw = __ldg(p++);
+    nxt = be(raw) | __funnelshift_rc(0xFFFFFFFFu, 0u, max(left, 0));   // ones from bit `left` on (none when left >= 32)
+    left -= 32;
+  }
   // start reading at byte address a (any alignment); the first `bound` bits are real.  The buffers have slack
-  // behind the data.
+  // behind the data.  Leaves nb >= 33.
   __device__ __forceinline__ void init(const uint8_t* a, int bound) {
     const uintptr_t u = reinterpret_cast<uintptr_t>(a);
     p = reinterpret_cast<const uint32_t*>(u & ~(uintptr_t)3);
     const int lead = 8 * (int)(u & 3);
-    hi = be(__ldg(p)); lo = be(__ldg(p + 1)); ahead = __ldg(p + 2);
-    p += 3;
+    hi = be(__ldg(p)); lo = be(__ldg(p + 1));
+    p += 2;
     const int real = lead + bound;   // real bits among the 64 just loaded
     if (real < 64) {
       const unsigned long long ones = real <= 0 ? ~0ull : (~0ull >> real);
@@ -513,51 +526,71 @@ struct BitReader {
       lo |= (uint32_t)ones;
     }
     left = real - 64;
-    nb = 64;
-    skip(lead);
+    fetch();
+    hi = __funnelshift_l(lo, hi, lead);
+    lo <<= lead;
+    nb = 64 - lead;
   }
-  __device__ __forceinline__ void skip(int n) {   // n in 0..32, n <= nb
-    hi = __funnelshift_lc(lo, hi, n);
-    lo = n >= 32 ? 0u : lo << n;
-    nb -= n;
-    if (nb <= 32) refill();
+  // nb >= 33 afterwards.  Straight-line code: the lanes of a warp (one slice each) run dry at different codes.
+  __device__ __forceinline__ void ensure() {
+    if (nb <= 32) {   // lo is empty: append nxt behind the nb valid bits of hi
+      hi |= __funnelshift_rc(nxt, 0u, nb);
+      lo = __funnelshift_lc(0u, nxt, 32 - nb);
+      nb += 32;
+      fetch();
+    }
   }
-  __device__ __forceinline__ void skip_short(int n) {   // n in 0..31
+  __device__ __forceinline__ void consume(int n) {   // n in 0..31, n <= nb
     hi = __funnelshift_l(lo, hi, n);
     lo <<= n;
     nb -= n;
-    if (nb <= 32) refill();
   }
-  __device__ __forceinline__ void refill() {   // lo is empty: append the next word behind the nb valid bits of hi
-    uint32_t nw = be(ahead);
-    ahead = __ldg(p++);
-    nw |= __funnelshift_rc(0xFFFFFFFFu, 0u, max(left, 0));   // ones from bit `left` on (nothing when left >= 32)
-    left -= 32;
-    hi |= __funnelshift_rc(nw, 0u, nb);
-    lo = __funnelshift_lc(0u, nw, 32 - nb);
-    nb += 32;
+  __device__ __forceinline__ void consume32(int n) {   // n in 0..32, n <= nb
+    hi = __funnelshift_lc(lo, hi, n);
+    lo = n >= 32 ? 0u : lo << n;
+    nb -= n;
   }
-  // one signed interleaved exp-Golomb value (VLC.cpp:283-317): table look-up on the leading DEC_LUT_BITS bits,
-  // computed for longer codes
-  __device__ __forceinline__ int get_vlc(const int16_t* __restrict__ lut, bool& range_err) {
-    const int e = lut[hi >> (32 - DEC_LUT_BITS)];
-    if (e != 0) {
-      skip_short(e & 15);
-      return e >> 4;
-    }
+  __device__ __forceinline__ void skip(int n) { consume32(n); ensure(); }   // needs nb >= 33, keeps it
+  __device__ __forceinline__ static int lookup(const int16_t* lut, uint32_t window) {
+    int e;
+    const unsigned addr = (unsigned)__cvta_generic_to_shared(lut) + ((window >> (31 - DEC_LUT_BITS)) & ((2u << DEC_LUT_BITS) - 2u));
+    asm("ld.shared.s16 %0, [%1];" : "=r"(e) : "r"(addr));
+    return e;
+  }
+  // a code longer than the table index, computed (VLC.cpp:283-317); needs nb >= 33
+  __device__ __forceinline__ int long_vlc(bool& range_err) {
     const uint32_t w = hi;
     const uint32_t f = w & 0xAAAAAAAAu;
     if (f == 0) {   // more than 16 magnitude bits: outside the reference's 32-bit VLC domain
       range_err = true;
-      skip(32);
+      consume32(32);
       return 0;
     }
-    const int k = __clz(f) >> 1;   // k >= 1 here (k == 0 is in the table)
+    const int k = __clz(f) >> 1;            // k >= 1 (k == 0 is in the table)
     const uint32_t t = w >> (32 - 2 * k);   // the 2k leading bits, right aligned
     const uint32_t mag = ((1u << k) | compress16(t)) - 1u;
     const uint32_t neg = (w >> (30 - 2 * k)) & 1u;
-    skip(2 * k + 2);
+    consume32(2 * k + 2);
     return neg ? -(int)mag : (int)mag;
+  }
+  // one signed interleaved exp-Golomb value; needs nb >= 33 and keeps it
+  __device__ __forceinline__ int get_vlc(const int16_t* lut, bool& range_err) {
+    const int e = lookup(lut, hi);
+    int v;
+    if (e != 0) { consume(e & 15); v = e >> 4; }
+    else v = long_vlc(range_err);
+    ensure();
+    return v;
+  }
+  // two values with one refill: table codes are at most DEC_LUT_BITS = 12 bits, 33 - 2 * 12 >= 1
+  __device__ __forceinline__ void get_vlc2(const int16_t* lut, bool& range_err, int& v0, int& v1) {
+    const int e0 = lookup(lut, hi);
+    if (e0 != 0) { consume(e0 & 15); v0 = e0 >> 4; }
+    else { v0 = long_vlc(range_err); ensure(); }
+    const int e1 = lookup(lut, hi);
+    if (e1 != 0) { consume(e1 & 15); v1 = e1 >> 4; }
+    else { ensure(); v1 = long_vlc(range_err); }
+    ensure();
   }
   __device__ __forceinline__ uint32_t get_bits(int n) {   // n in 1..32
     const uint32_t w = n == 32 ? hi : (hi >> (32 - n));
@@ -613,10 +646,11 @@ __global__ void __launch_bounds__(128) slice_unpack_kernel(const UnpackParams p)
       for (int piece = 0; piece < (n >> 2); ++piece) {
         int v[4];
         if (bend - k >= 4) {   // warp uniform: the four coefficients belong to the current band
+          br.get_vlc2(s_dec, range_err, v[0], v[1]);
+          br.get_vlc2(s_dec, range_err, v[2], v[3]);
+          if (DEQ) {
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int x = br.get_vlc(s_dec, range_err);
-            v[e] = DEQ ? scale_band(x, bp) : x;
+            for (int e = 0; e < 4; ++e) v[e] = scale_band(v[e], bp);
           }
           k += 4;
         } else {
