@@ -112,7 +112,8 @@ enum vc2_stage {
   VC2_STAGE_IDWT_L0 = 5,   /* inverse lifting, finest level (writes the picture)         */
   VC2_STAGE_LD_DC = 6,     /* LD LL-band DC prediction wavefront                         */
   VC2_STAGE_ASSEMBLE = 7,  /* slice size scan + gather of the slice images into the payload */
-  VC2_NUM_STAGES = 8
+  VC2_STAGE_INDEX = 8,     /* HQ slice index: the walk over the slice length bytes of a payload */
+  VC2_NUM_STAGES = 9
 };
 int vc2_profile_enable(vc2_ctx* ctx, int on);
 int vc2_profile_read(vc2_ctx* ctx, float* ms, int* launches, int nstages);
@@ -192,10 +193,19 @@ size_t vc2_codec_payload_capacity(const vc2_codec*);     /* worst-case slice pay
 /* device-resident stages (asynchronous on the context stream).  Slot = picture index in the batch.
  *   encode: raw samples (device) -> DWT -> [CBR search] -> quantise + slice pack -> payload (device)
  *     replaces EncodeStream.cpp:456-565 + Slices.cpp:645-660 for n pictures
- *   decode: payload + slice offsets (device) -> parse + dequantise -> IDWT -> clip -> raw samples
- *     replaces DecodeStream.cpp:512-605 for n pictures */
+ *   decode: payload + payload length (device) -> slice index from the length bytes (HQ, Slices.cpp:544-605)
+ *     -> parse + dequantise -> IDWT -> clip -> raw samples
+ *     replaces DecodeStream.cpp:512-605 for n pictures.  The slice offsets are always rebuilt from the payload;
+ *     the table the encoder left behind is overwritten, not used. */
 int vc2_codec_encode_dev(vc2_codec*, int n_pictures);
 int vc2_codec_decode_dev(vc2_codec*, int n_pictures);
+/* pipelined mode (default off): consecutive encode_dev / decode_dev calls with the same n_pictures are ordered per
+ * sub-batch (same slots, same internal stream) instead of call by call, so the serial slice-index walk of one
+ * sub-batch overlaps the kernels of the others.  The context stream still waits for every sub-batch of every call,
+ * and the codec's own upload / host-buffer calls re-synchronise the sub-batches.  Work the CALLER puts on the
+ * context stream between two calls (e.g. its own kernels writing vc2_codec_samples_dev) is only ordered before the
+ * next call when pipelined mode is off. */
+int vc2_codec_set_pipelined(vc2_codec*, int on);
 
 /* device buffers owned by the codec (for device-resident use and for tests) */
 void* vc2_codec_samples_dev(vc2_codec*, int slot);       /* raw planar picture bytes: encoder input   */

@@ -174,3 +174,62 @@ def test_decode_host_reports_truncated_payload(ctx):
     assert e.value.status == -9       # VC2_ERR_STREAM
     k.decode_host(bufs, lens, outs)      # the codec is still usable afterwards
     k.close()
+
+
+def test_device_decode_indexes_the_payload_itself(ctx):
+    """decode_dev rebuilds the slice offsets from the length bytes of the payload (Slices.cpp:544-605): a second codec
+    that only ever receives payload bytes + length decodes to the same picture, and a cut payload is a stream error"""
+    c = GOLD["S08_DD137_d4_422"]["params"]
+    g = vc2.make_geom(c["h"], c["w"], c["fmt"], c["kernel"], c["wdepth"], c["u"], c["a"], c["P"], c["S"])
+    n = 3
+    frames = [gen.frame_bytes(c["seed"], f, c["w"], c["h"], c["fmt"], c["bits"]) for f in range(n)]
+    k = vc2.Codec(ctx, g, "HQ_ConstQ", qindex=c["q"], luma_depth=c["bits"], max_pictures=n)
+    for i, f in enumerate(frames):
+        k.upload_picture(i, f)
+    k.encode(n)
+    k.decode(n)      # payload and payload length come straight from the encoder, on the device
+    pays = [k.download_payload(i) for i in range(n)]
+    pics = [k.download_picture(i) for i in range(n)]
+    d = vc2.Codec(ctx, g, "HQ_ConstQ", qindex=0, luma_depth=c["bits"], max_pictures=n)
+    for i in range(n):
+        d.upload_payload(i, pays[i][0])
+    d.decode(n)
+    for i in range(n):
+        d.slot_status(i)
+        assert d.download_picture(i) == pics[i]
+        assert np.array_equal(d.download_payload(i)[2], pays[i][2])     # the rebuilt offset table = the encoder's
+    d.upload_payload(1, pays[1][0][: len(pays[1][0]) // 2])
+    d.decode(n)
+    d.slot_status(0)
+    with pytest.raises(vc2.Vc2Error) as e:
+        d.slot_status(1)
+    assert e.value.status == -9       # VC2_ERR_STREAM
+    d.close()
+    k.close()
+
+
+def test_pipelined_mode_is_bit_identical(ctx):
+    """vc2_codec_set_pipelined only changes the ordering between sub-batches of consecutive calls, never the bytes"""
+    c = GOLD["S08_DD137_d4_422"]["params"]
+    g = vc2.make_geom(c["h"], c["w"], c["fmt"], c["kernel"], c["wdepth"], c["u"], c["a"], c["P"], c["S"])
+    n = 8
+    frames = [gen.frame_bytes(7, f, c["w"], c["h"], c["fmt"], c["bits"]) for f in range(2 * n)]
+    k = vc2.Codec(ctx, g, "HQ_ConstQ", qindex=c["q"], luma_depth=c["bits"], max_pictures=n)
+    want = []
+    for base in (0, n):
+        for i in range(n):
+            k.upload_picture(i, frames[base + i])
+        k.encode(n)
+        k.decode(n)
+        want.append([(k.download_payload(i)[0], k.download_picture(i)) for i in range(n)])
+    k.set_pipelined(True)
+    for rep in range(2):
+        for half, base in enumerate((0, n)):
+            for i in range(n):
+                k.upload_picture(i, frames[base + i])
+            for _ in range(3):          # back-to-back calls without a host sync in between
+                k.encode(n)
+                k.decode(n)
+            got = [(k.download_payload(i)[0], k.download_picture(i)) for i in range(n)]
+            assert got == want[half]
+    k.close()

@@ -69,6 +69,7 @@ def _load():
         "vc2_codec_payload_capacity": (C.c_size_t, [vp]),
         "vc2_codec_encode_dev": (C.c_int, [vp, C.c_int]),
         "vc2_codec_decode_dev": (C.c_int, [vp, C.c_int]),
+        "vc2_codec_set_pipelined": (C.c_int, [vp, C.c_int]),
         "vc2_codec_samples_dev": (vp, [vp, C.c_int]),
         "vc2_codec_recon_dev": (vp, [vp, C.c_int]),
         "vc2_codec_payload_dev": (vp, [vp, C.c_int]),

@@ -90,7 +90,7 @@ class Context:
     def kernel_launches(self, reset=False):
         return lib.vc2_kernel_launches(self.h, 1 if reset else 0)
 
-    STAGES = ["dwt_l0", "dwt_deep", "pack", "unpack", "idwt_deep", "idwt_l0", "ld_dc", "assemble"]
+    STAGES = ["dwt_l0", "dwt_deep", "pack", "unpack", "idwt_deep", "idwt_l0", "ld_dc", "assemble", "index"]
 
     def profile_enable(self, on=True):
         _check(lib.vc2_profile_enable(self.h, 1 if on else 0), self.h)
@@ -228,6 +228,9 @@ class Codec:
 
     def decode(self, n):
         _check(lib.vc2_codec_decode_dev(self.h, n), self.ctx.h)
+
+    def set_pipelined(self, on):
+        _check(lib.vc2_codec_set_pipelined(self.h, 1 if on else 0), self.ctx.h)
 
     def slot_status(self, slot):
         _check(lib.vc2_codec_slot_status(self.h, slot), self.ctx.h)

@@ -535,6 +535,7 @@ struct PackBuffers {
   uint32_t* slice_off; uint32_t* err_flags; int32_t* qidx;
   uint32_t* staging; uint32_t* sizes;
   const int32_t* slice_bytes_dev; const uint32_t* fixed_off_dev;
+  uint32_t* total_len = nullptr;   // [pic] payload bytes, device memory (optional)
 };
 
 // staging words per slice: every coefficient at the 32-bit VLC limit, plus header bytes and slack
@@ -560,7 +561,7 @@ static cudaError_t run_pack(vc2_ctx* ctx, const SliceGeom& g, const int32_t* coe
   AssembleParams a;
   memset(&a, 0, sizeof(a));
   a.nslices = g.slices_x * g.slices_y;
-  a.sizes = B.sizes; a.fixed_off = B.fixed_off_dev; a.slice_off = B.slice_off;
+  a.sizes = B.sizes; a.fixed_off = B.fixed_off_dev; a.slice_off = B.slice_off; a.total_len = B.total_len;
   a.staging = B.staging; a.wcap = p.wcap;
   a.out = B.out; a.out_pic_stride = B.out_stride; a.out_capacity = B.out_capacity; a.err_flags = B.err_flags;
   {
@@ -844,17 +845,26 @@ struct vc2_codec {
   std::vector<uint32_t> fixed_off;
   // device buffers
   DevBuf samples, recon, coef, scratch0, scratch1, payload, slice_off, err, qidx, staging, sizes, sbytes, fixed, tmp_plane, tmp_q;
+  DevBuf dev_len;                     // [B] payload bytes of each slot: written by the encoder's scan or by upload_payload
+  std::vector<uint32_t> len32;        // host copy the uploads are staged from
   long long scratch_stride[2] = {0, 0};
   long long scratch_off[2][3];
   std::vector<size_t> payload_len;    // host copy per slot (decode)
-  uint32_t* host_offs = nullptr;      // pinned staging for slice offset tables
   cudaStream_t copy_in = nullptr, copy_out = nullptr;
   // device-resident entry points: the batch is cut into sub-batches that run on their own streams, so the
   // small-grid kernels of one sub-batch (deep DWT levels, the slice scan) overlap the wide kernels of another
-  static constexpr int MAX_SUB = 4;
+  static constexpr int MAX_SUB = 8;
   int nsub = 4;                        // VC2_CODEC_SUBBATCH
-  cudaStream_t sub_stream[MAX_SUB] = {nullptr, nullptr, nullptr, nullptr};   // [0] unused (= context stream)
-  cudaEvent_t sub_fork = nullptr, sub_join[MAX_SUB] = {nullptr, nullptr, nullptr, nullptr};
+  cudaStream_t sub_stream[MAX_SUB] = {};   // [0] is only used in pipelined mode (else part 0 runs on the context stream)
+  cudaEvent_t sub_fork = nullptr, sub_join[MAX_SUB] = {};
+  cudaEvent_t sub_stagger[MAX_SUB] = {};
+  // pipelined mode (vc2_codec_set_pipelined): consecutive device-resident calls are ordered per sub-batch only -
+  // sub-batch p of a call waits for sub-batch p of the previous call (same stream, same slots), not for the whole
+  // previous call - so the slice index walk of one sub-batch (a millisecond of one SM per picture) hides behind the
+  // kernels of the others.  The context stream still joins every sub-batch of every call.
+  bool pipelined = false;
+  bool main_dirty = true;              // the context stream carries work the sub-batch streams have not waited for
+  int last_split_n = -1;
   // software pipeline of the host-buffer entry points: one event triple per slot
   std::vector<cudaEvent_t> ev_in, ev_done, ev_out;
   // decode_host: the slice index of every payload is built on the device (hq_index_kernel, one CTA walking one
@@ -871,9 +881,8 @@ static void codec_free(vc2_codec* k) {
   cudaSetDevice(k->ctx->device);
   cudaStreamSynchronize(k->ctx->stream);
   DevBuf* all[] = {&k->samples, &k->recon, &k->coef, &k->scratch0, &k->scratch1, &k->payload, &k->slice_off, &k->err,
-                   &k->qidx, &k->staging, &k->sizes, &k->sbytes, &k->fixed, &k->tmp_plane, &k->tmp_q};
+                   &k->qidx, &k->staging, &k->sizes, &k->sbytes, &k->fixed, &k->tmp_plane, &k->tmp_q, &k->dev_len};
   for (DevBuf* b : all) b->release();
-  if (k->host_offs) cudaFreeHost(k->host_offs);
   if (k->host_flags) cudaFreeHost(k->host_flags);
   if (k->host_len) cudaFreeHost(k->host_len);
   for (auto e : k->ev_in) cudaEventDestroy(e);
@@ -883,9 +892,10 @@ static void codec_free(vc2_codec* k) {
   for (auto st : k->index_stream) cudaStreamDestroy(st);
   if (k->copy_in) cudaStreamDestroy(k->copy_in);
   if (k->copy_out) cudaStreamDestroy(k->copy_out);
-  for (int i = 1; i < vc2_codec::MAX_SUB; ++i) {
+  for (int i = 0; i < vc2_codec::MAX_SUB; ++i) {
     if (k->sub_stream[i]) cudaStreamDestroy(k->sub_stream[i]);
     if (k->sub_join[i]) cudaEventDestroy(k->sub_join[i]);
+    if (k->sub_stagger[i]) cudaEventDestroy(k->sub_stagger[i]);
   }
   if (k->sub_fork) cudaEventDestroy(k->sub_fork);
   delete k;
@@ -950,7 +960,8 @@ extern "C" vc2_codec* vc2_codec_create(vc2_ctx* ctx, const vc2_codec_params* prm
   R(k->fixed, (size_t)(k->nslices + 1) * 4);
   R(k->tmp_plane, (size_t)g.plane[0].size() * 4);
   R(k->tmp_q, (size_t)g.plane[0].size() * 4);
-  if (ok && cudaMallocHost((void**)&k->host_offs, (size_t)(k->nslices + 1) * 4 * 2 * B) != cudaSuccess) ok = false;   // two table sets: one in flight, one being built
+  R(k->dev_len, (size_t)B * 4);
+  k->len32.assign(B, 0);
   if (ok && cudaMallocHost((void**)&k->host_flags, (size_t)k->nslices * 4 * 2 * B) != cudaSuccess) ok = false;
   if (ok && cudaMallocHost((void**)&k->host_len, (size_t)4 * B) != cudaSuccess) ok = false;
   for (int i = 0; ok && i < B; ++i) {
@@ -974,15 +985,17 @@ extern "C" vc2_codec* vc2_codec_create(vc2_ctx* ctx, const vc2_codec_params* prm
   if (ok && cudaStreamCreateWithFlags(&k->copy_out, cudaStreamNonBlocking) != cudaSuccess) ok = false;
   if (const char* e = getenv("VC2_CODEC_SUBBATCH")) k->nsub = std::min(std::max(atoi(e), 1), (int)vc2_codec::MAX_SUB);
   if (ok && cudaEventCreateWithFlags(&k->sub_fork, cudaEventDisableTiming) != cudaSuccess) ok = false;
-  for (int i = 1; ok && i < k->nsub; ++i) {
+  for (int i = 0; ok && i < k->nsub; ++i) {
     if (cudaStreamCreateWithFlags(&k->sub_stream[i], cudaStreamNonBlocking) != cudaSuccess) ok = false;
     if (ok && cudaEventCreateWithFlags(&k->sub_join[i], cudaEventDisableTiming) != cudaSuccess) ok = false;
+    if (ok && cudaEventCreateWithFlags(&k->sub_stagger[i], cudaEventDisableTiming) != cudaSuccess) ok = false;
   }
   if (ok && !k->slice_bytes.empty()) {
     ok = cudaMemcpy(k->sbytes.p, k->slice_bytes.data(), (size_t)k->nslices * 4, cudaMemcpyHostToDevice) == cudaSuccess &&
          cudaMemcpy(k->fixed.p, k->fixed_off.data(), (size_t)(k->nslices + 1) * 4, cudaMemcpyHostToDevice) == cudaSuccess;
   }
   if (ok) ok = cudaMemset(k->err.p, 0, (size_t)k->nslices * 4 * B) == cudaSuccess;
+  if (ok) ok = cudaMemset(k->dev_len.p, 0, (size_t)B * 4) == cudaSuccess;
   if (!ok) { fail(ctx, VC2_ERR_CUDA, "codec allocation failed"); codec_free(k); return nullptr; }
   k->payload_len.assign(B, 0);
   return k;
@@ -1035,6 +1048,7 @@ static int codec_encode_range(vc2_codec* k, int first, int n) {
   const bool cbr = k->prm.mode == VC2_HQ_CBR;
   B.slice_bytes_dev = cbr ? k->sbytes.as<int32_t>() : nullptr;
   B.fixed_off_dev = cbr ? k->fixed.as<uint32_t>() : nullptr;
+  B.total_len = k->dev_len.as<uint32_t>() + first;
   const int32_t* coef = k->coef.as<int32_t>() + (long long)first * k->g.coef_pic_stride;
   CU(run_pack(ctx, k->g, coef, n, k->prm.mode, 1, cbr ? 1 : 0, cbr ? -1 : k->prm.qindex, 1, B));
   return VC2_OK;
@@ -1046,28 +1060,46 @@ static int codec_encode_range(vc2_codec* k, int first, int n) {
 template <class Fn>
 static int codec_run_split(vc2_codec* k, int n, Fn fn) {
   vc2_ctx* ctx = k->ctx;
-  const int parts = ctx->profiling ? 1 : std::min(k->nsub, n / 2);
-  if (parts <= 1) return fn(0, n);
+  const bool pipe = k->pipelined && !ctx->profiling;
+  const int parts = ctx->profiling ? 1 : std::max(1, std::min(k->nsub, n / 2));
+  if (parts <= 1 && !pipe) { k->main_dirty = true; k->last_split_n = -1; return fn(0, n); }
   cudaStream_t main_stream = ctx->stream;
-  CU(cudaEventRecord(k->sub_fork, main_stream));
+  // the fork: sub-batch streams wait for what the context stream carries.  In pipelined mode that is only needed
+  // when something other than the previous split call (same n, same slot -> stream map) went onto it
+  const bool fork = !pipe || k->main_dirty || k->last_split_n != n;
+  if (fork) CU(cudaEventRecord(k->sub_fork, main_stream));
   int st = VC2_OK;
   for (int p = 0, first = 0; p < parts && st == VC2_OK; ++p) {
     const int cnt = n / parts + (p < n % parts ? 1 : 0);
-    if (p > 0) {
-      if (cudaStreamWaitEvent(k->sub_stream[p], k->sub_fork, 0) != cudaSuccess) { st = VC2_ERR_CUDA; break; }
-      ctx->stream = k->sub_stream[p];
+    cudaStream_t s = (p > 0 || pipe) ? k->sub_stream[p] : main_stream;
+    if (s != main_stream) {
+      if (fork && cudaStreamWaitEvent(s, k->sub_fork, 0) != cudaSuccess) { st = VC2_ERR_CUDA; break; }
+      // pipelined mode, first call after a fork: run the sub-batches one after the other.  The later, unforked
+      // calls then keep that phase shift, so the streams are never all inside their index walk at the same time
+      if (pipe && fork && p > 0 && cudaStreamWaitEvent(s, k->sub_stagger[p - 1], 0) != cudaSuccess) { st = VC2_ERR_CUDA; break; }
+      ctx->stream = s;
     }
     st = fn(first, cnt);
     ctx->stream = main_stream;
-    if (p > 0) {
+    if (pipe && fork && cudaEventRecord(k->sub_stagger[p], s) != cudaSuccess) st = st == VC2_OK ? VC2_ERR_CUDA : st;
+    if (s != main_stream) {
       // always join, also after a failure, so the context stream never runs ahead of a sub-batch
-      if (cudaEventRecord(k->sub_join[p], k->sub_stream[p]) != cudaSuccess ||
+      if (cudaEventRecord(k->sub_join[p], s) != cudaSuccess ||
           cudaStreamWaitEvent(main_stream, k->sub_join[p], 0) != cudaSuccess) st = st == VC2_OK ? VC2_ERR_CUDA : st;
     }
     first += cnt;
   }
+  k->main_dirty = !pipe;
+  k->last_split_n = pipe ? n : -1;
   if (st == VC2_ERR_CUDA) return fail(ctx, VC2_ERR_CUDA, "sub-batch stream");
   return st;
+}
+
+extern "C" int vc2_codec_set_pipelined(vc2_codec* k, int on) {
+  if (!k) return VC2_ERR_ARG;
+  k->pipelined = on != 0;
+  k->main_dirty = true;
+  return VC2_OK;
 }
 
 extern "C" int vc2_codec_encode_dev(vc2_codec* k, int n) {
@@ -1077,7 +1109,7 @@ extern "C" int vc2_codec_encode_dev(vc2_codec* k, int n) {
   return codec_run_split(k, n, [&](int first, int cnt) { return codec_encode_range(k, first, cnt); });
 }
 
-static int codec_decode_range(vc2_codec* k, int first, int n) {
+static int codec_decode_range(vc2_codec* k, int first, int n, bool index_here) {
   vc2_ctx* ctx = k->ctx;
   const SliceGeom& g = k->g;
   const bool ld = k->prm.mode == VC2_LD;
@@ -1095,6 +1127,19 @@ static int codec_decode_range(vc2_codec* k, int first, int n) {
   p.err_flags = k->err.as<uint32_t>() + (size_t)first * k->nslices;
   p.dequantise = 1;
   p.ld = ld ? 1 : 0;
+  if (index_here && !ld) {
+    // the reader's walk over the length bytes of every slice (Slices.cpp:544-605): the slice offsets are always
+    // derived from the payload itself, never taken from the encoder
+    IndexParams ip;
+    memset(&ip, 0, sizeof(ip));
+    ip.in = p.in; ip.in_pic_stride = p.in_pic_stride;
+    ip.len_dev = k->dev_len.as<uint32_t>() + first;
+    ip.slice_off = k->slice_off.as<uint32_t>() + (size_t)first * (k->nslices + 1);
+    ip.nslices = k->nslices; ip.prefix = g.prefix; ip.scalar = g.scalar;
+    ProfScope ps(ctx, VC2_STAGE_INDEX);
+    CU(index_launch(ctx->stream, ip, n));
+    ctx->launches++;
+  }
   {
     ProfScope ps(ctx, VC2_STAGE_UNPACK);
     CU(unpack_launch(ctx->stream, p, n));
@@ -1127,7 +1172,7 @@ extern "C" int vc2_codec_decode_dev(vc2_codec* k, int n) {
   if (!k || n < 1 || n > k->prm.max_pictures) return fail(k ? k->ctx : nullptr, VC2_ERR_ARG);
   vc2_ctx* ctx = k->ctx;
   CU(cudaSetDevice(ctx->device));
-  return codec_run_split(k, n, [&](int first, int cnt) { return codec_decode_range(k, first, cnt); });
+  return codec_run_split(k, n, [&](int first, int cnt) { return codec_decode_range(k, first, cnt, true); });
 }
 
 extern "C" void* vc2_codec_samples_dev(vc2_codec* k, int slot) {
@@ -1157,6 +1202,7 @@ extern "C" int vc2_codec_upload_picture(vc2_codec* k, int slot, const void* raw)
   vc2_ctx* ctx = k->ctx;
   CU(cudaSetDevice(ctx->device));
   CU(cudaMemcpyAsync(vc2_codec_samples_dev(k, slot), raw, k->pic_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  k->main_dirty = true;
   return VC2_OK;
 }
 extern "C" int vc2_codec_download_picture(vc2_codec* k, int slot, void* raw) {
@@ -1168,25 +1214,18 @@ extern "C" int vc2_codec_download_picture(vc2_codec* k, int slot, void* raw) {
   return VC2_OK;
 }
 
-// host-side slice index of one payload into the pinned staging table of `slot`
-static int codec_index_payload(vc2_codec* k, int slot, const uint8_t* payload, size_t len) {
-  if (k->prm.mode == VC2_LD) return len >= k->fixed_off[k->nslices] ? VC2_OK : VC2_ERR_STREAM;
-  return vc2_hq_index_slices(payload, len, k->nslices, k->g.prefix, k->g.scalar, k->host_offs + (size_t)slot * (k->nslices + 1));
-}
-
 extern "C" int vc2_codec_upload_payload(vc2_codec* k, int slot, const uint8_t* payload, size_t len) {
   KARG(k && payload && slot >= 0 && slot < k->prm.max_pictures);
   vc2_ctx* ctx = k->ctx;
   if (len > k->payload_cap) return fail(ctx, VC2_ERR_CAPACITY);
+  if (k->prm.mode == VC2_LD && len < k->fixed_off[k->nslices]) return fail(ctx, VC2_ERR_STREAM);
   CU(cudaSetDevice(ctx->device));
-  CU(cudaStreamSynchronize(ctx->stream));   // the pinned offset table of this slot may still be in flight
-  const int st = codec_index_payload(k, slot, payload, len);
-  if (st) return fail(ctx, st);
+  // bytes and length only: decode_dev walks the slice length bytes on the device (hq_index_kernel)
   CU(cudaMemcpyAsync(vc2_codec_payload_dev(k, slot), payload, len, cudaMemcpyHostToDevice, ctx->stream));
-  if (k->prm.mode != VC2_LD)
-    CU(cudaMemcpyAsync(vc2_codec_slice_offsets_dev(k, slot), k->host_offs + (size_t)slot * (k->nslices + 1),
-                       (size_t)(k->nslices + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
   k->payload_len[slot] = len;
+  k->len32[slot] = (uint32_t)len;
+  CU(cudaMemcpyAsync(k->dev_len.as<uint32_t>() + slot, &k->len32[slot], 4, cudaMemcpyHostToDevice, ctx->stream));
+  k->main_dirty = true;
   return VC2_OK;
 }
 
@@ -1280,6 +1319,7 @@ extern "C" int vc2_codec_encode_host(vc2_codec* k, int n, const void* const* pic
   KARG(k && pictures && payloads && payload_len && n >= 1);
   vc2_ctx* ctx = k->ctx;
   CU(cudaSetDevice(ctx->device));
+  k->main_dirty = true;
   const int B = k->prm.max_pictures, ns = k->nslices;
   const int sub = stage_pictures(B), nstage_slots = B / sub;
   const int lag = std::min(2, nstage_slots - 1);   // stages in flight behind the newest upload
@@ -1329,6 +1369,7 @@ extern "C" int vc2_codec_decode_host(vc2_codec* k, int n, const uint8_t* const* 
   KARG(k && pictures && payloads && payload_len && n >= 1);
   vc2_ctx* ctx = k->ctx;
   CU(cudaSetDevice(ctx->device));
+  k->main_dirty = true;
   const int B = k->prm.max_pictures, ns = k->nslices;
   const bool hq = k->prm.mode != VC2_LD;
   for (int i = 0; i < n; ++i) {
@@ -1378,7 +1419,7 @@ extern "C" int vc2_codec_decode_host(vc2_codec* k, int n, const uint8_t* const* 
       CU(cudaEventRecord(k->ev_in[i], k->copy_in));
       CU(cudaStreamWaitEvent(ctx->stream, k->ev_in[i], 0));
       if (c > 0) CU(cudaStreamWaitEvent(ctx->stream, k->ev_out[((c - 1) & 1) * B + i], 0));   // the previous pictures have left these slots
-      status = codec_decode_range(k, i, mm);
+      status = codec_decode_range(k, i, mm, false);
       if (status) break;
       CU(cudaEventRecord(k->ev_done[i], ctx->stream));
       CU(cudaStreamWaitEvent(k->copy_out, k->ev_done[i], 0));

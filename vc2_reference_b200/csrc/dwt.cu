@@ -27,6 +27,9 @@ namespace {
 
 constexpr unsigned FULL = 0xFFFFFFFFu;
 constexpr int WARPS = 4;   // warps per CTA: four vertically adjacent row segments of one strip
+#ifndef VC2_DWT_MINB
+#define VC2_DWT_MINB 4     // resident CTAs per SM the register allocation is held to (4 -> 128 registers per thread)
+#endif
 
 // ---- compile-time schedule of the vertical pipeline ------------------------------------------------
 __host__ __device__ constexpr int cmax(int a, int b) { return a > b ? a : b; }
@@ -476,7 +479,7 @@ __device__ __forceinline__ bool strip_setup(const DwtComp& C, int seg_rows, Stri
 }
 
 template <int K, int KIND>
-__global__ void __launch_bounds__(32 * WARPS, 4) dwt_fwd_kernel(const DwtParams p, int seg_rows) {
+__global__ void __launch_bounds__(32 * WARPS, VC2_DWT_MINB) dwt_fwd_kernel(const DwtParams p, int seg_rows) {
   using SC = Sched<K, +1>;
   const int comp = blockIdx.z % p.ncomp;
   const DwtComp& C = p.c[comp];
@@ -616,7 +619,7 @@ __device__ __forceinline__ void inv_pair(const DwtComp& C, const StripCtx& S, co
 }
 
 template <int K, int KIND>
-__global__ void __launch_bounds__(32 * WARPS, 4) dwt_inv_kernel(const DwtParams p, int seg_rows) {
+__global__ void __launch_bounds__(32 * WARPS, VC2_DWT_MINB) dwt_inv_kernel(const DwtParams p, int seg_rows) {
   using SC = Sched<K, -1>;
   const int comp = blockIdx.z % p.ncomp;
   const DwtComp& C = p.c[comp];

@@ -433,6 +433,7 @@ __global__ void __launch_bounds__(1024) slice_scan_kernel(const AssembleParams p
   uint32_t* so = p.slice_off + (long long)pic * (n + 1);
   if (p.fixed_off) {
     for (int i = t; i <= n; i += blockDim.x) so[i] = p.fixed_off[i];
+    if (t == 0 && p.total_len) p.total_len[pic] = p.fixed_off[n];
     return;
   }
   const uint32_t* sz = p.sizes + (long long)pic * n;
@@ -450,7 +451,10 @@ __global__ void __launch_bounds__(1024) slice_scan_kernel(const AssembleParams p
   }
   unsigned run = s_part[t] - sum;
   for (int i = i0; i < i1; ++i) { so[i] = run; run += sz[i]; }
-  if (t == (int)blockDim.x - 1) so[n] = s_part[t];
+  if (t == (int)blockDim.x - 1) {
+    so[n] = s_part[t];
+    if (p.total_len) p.total_len[pic] = s_part[t];
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -732,11 +736,12 @@ constexpr int INDEX_RING = 4 * INDEX_SEG;             // four segments: two bein
 constexpr unsigned INDEX_MASK = INDEX_RING - 1;
 
 __global__ void __launch_bounds__(256) hq_index_kernel(const IndexParams p) {
-  extern __shared__ uint4 s_ring[];
-  __shared__ int s_stop[2];
+  extern __shared__ uint4 s_ring[];   // the ring, then two stop flags
+  int* s_stop = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(s_ring) + INDEX_RING);
+  const bool ring_at_zero = (unsigned)__cvta_generic_to_shared(s_ring) == 0u;
   const int pic = blockIdx.x, ns = p.nslices;
   const uint8_t* in = p.in + (long long)pic * p.in_pic_stride;
-  const unsigned len = p.len[pic];
+  const unsigned len = p.len_dev ? min(p.len_dev[pic], (unsigned)min(p.in_pic_stride, 0xFFFFFFFFll)) : p.len[pic];
   uint32_t* off = p.slice_off + (long long)pic * (ns + 1);
   const unsigned maxslice = (unsigned)(p.prefix + 4 + 3 * 255 * p.scalar);
   const long long readable = p.in_pic_stride & ~15ll;   // the picture's buffer, whole 16-byte pieces
@@ -781,6 +786,33 @@ __global__ void __launch_bounds__(256) hq_index_kernel(const IndexParams p) {
       const unsigned seg_end = (k + 1) * INDEX_SEG;
       const unsigned hdr = p.prefix + 1, sc = p.scalar;
       bool bad = false;
+      // fast path: four slices per loop-carried branch.  The walk is one chain of dependent shared-memory loads
+      // (three per slice); a branch per slice would add its resolution to every link, and so would any address
+      // arithmetic: with the ring at shared-memory address 0 a link is  load -> multiply-add -> mask -> load.
+      // a = stream position of the next length byte.  The positions may run past the two valid ring segments -
+      // the reads are masked into the ring and a group is only committed when its fourth slice starts inside
+      // segment k, in which case every byte it looked at was valid.
+      if (ring_at_zero) {
+        auto hop = [&](unsigned a, unsigned add) {
+          unsigned b;
+          asm volatile("ld.shared.u8 %0, [%1];" : "=r"(b) : "r"(a & INDEX_MASK));
+          unsigned r;   // a + add is ready before the byte arrives: keep it out of the chain
+          asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(b), "r"(sc), "r"(a + add));
+          return r;
+        };
+        unsigned a = pos + hdr;
+        while (s + 4 <= ns) {
+          const unsigned a1 = hop(hop(hop(a, 1u), 1u), 1u + hdr);    // first length byte of slice s + 1
+          const unsigned a2 = hop(hop(hop(a1, 1u), 1u), 1u + hdr);
+          const unsigned a3 = hop(hop(hop(a2, 1u), 1u), 1u + hdr);
+          const unsigned a4 = hop(hop(hop(a3, 1u), 1u), 1u + hdr);
+          if (a3 - hdr >= seg_end || a4 - hdr > len) break;
+          off[s] = a - hdr; off[s + 1] = a1 - hdr; off[s + 2] = a2 - hdr; off[s + 3] = a3 - hdr;
+          a = a4;
+          s += 4;
+        }
+        pos = a - hdr;
+      }
       while (s < ns && pos < seg_end) {
         unsigned q = pos + hdr;
         q += 1u + w[q & INDEX_MASK] * sc;
@@ -891,10 +923,10 @@ cudaError_t unpack_launch(cudaStream_t s, const UnpackParams& p, int npictures) 
 }
 
 cudaError_t index_launch(cudaStream_t s, const IndexParams& p, int npictures) {
-  cudaError_t e = cudaFuncSetAttribute(hq_index_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, INDEX_RING);   // per device
+  cudaError_t e = cudaFuncSetAttribute(hq_index_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, INDEX_RING + 16);   // per device
   if (e != cudaSuccess) return e;
-  if (npictures < 1 || npictures > VC2_INDEX_MAX_PICTURES) return cudaErrorInvalidValue;
-  hq_index_kernel<<<npictures, 256, INDEX_RING, s>>>(p);
+  if (npictures < 1 || (!p.len_dev && npictures > VC2_INDEX_MAX_PICTURES)) return cudaErrorInvalidValue;
+  hq_index_kernel<<<npictures, 256, INDEX_RING + 16, s>>>(p);
   return cudaGetLastError();
 }
 

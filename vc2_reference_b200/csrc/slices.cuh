@@ -46,6 +46,7 @@ struct AssembleParams {         // exclusive scan of the slice sizes and the gat
   const uint32_t* sizes;        // [pic][slices]
   const uint32_t* fixed_off;    // [slices + 1] slice offsets known a priori (CBR) or NULL (scan the sizes)
   uint32_t* slice_off;          // [pic][slices + 1] out
+  uint32_t* total_len;          // [pic] out: payload bytes of each picture (NULL: not wanted)
   const uint32_t* staging;      // [pic][slices][wcap]
   int wcap;
   uint8_t* out;                 // payload [pic]
@@ -72,7 +73,8 @@ struct UnpackParams {
 struct IndexParams {
   const uint8_t* in;            // payload [pic]
   long long in_pic_stride;      // bytes; also the readable size of one picture's buffer
-  uint32_t len[VC2_INDEX_MAX_PICTURES];   // payload bytes per picture
+  uint32_t len[VC2_INDEX_MAX_PICTURES];   // payload bytes per picture (len_dev == NULL)
+  const uint32_t* len_dev;      // [pic] payload bytes per picture in device memory; lifts the picture limit
   uint32_t* slice_off;          // [pic][slices + 1] out
   int nslices, prefix, scalar;
 };
