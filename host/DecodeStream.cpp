@@ -4,12 +4,17 @@
 // (vc2_codec_decode_host); with --gpus N consecutive batches go to different GPUs and the pictures are
 // written in stream order.
 //
-// Not built here (SURVEY.md 8f "next" rows): fragments, interlaced streams.
+// Fragmented pictures (DecodeStream.cpp:614-977) are reassembled on the host: the slices of the fragments of a
+// picture, in slice order, are exactly the slice payload of the unfragmented picture.  Interlaced streams decode as
+// field pictures of half the height; two consecutive pictures are woven into one output frame (Frame.cpp:62-110).
 #include <cstdio>
 #include <cstdlib>
 #include <fstream>
 #include <iostream>
+#include <cstring>
+#include <deque>
 #include <iterator>
+#include <map>
 #include <memory>
 #include <stdexcept>
 #include <string>
@@ -42,8 +47,9 @@ struct Config {   // everything the codec geometry depends on
   ColourFormat cf = CF_UNSET;
   PicturePreamble pre;
   int compressedBytes = 0;
+  bool interlace = false, tff = true;   // height is the PICTURE height (a field when interlaced)
   bool same(const Config& o) const {
-    return ld == o.ld && height == o.height && width == o.width && bits == o.bits && cf == o.cf &&
+    return interlace == o.interlace && tff == o.tff && ld == o.ld && height == o.height && width == o.width && bits == o.bits && cf == o.cf &&
            pre.wavelet_kernel == o.pre.wavelet_kernel && pre.depth == o.pre.depth && pre.slices_x == o.pre.slices_x &&
            pre.slices_y == o.pre.slices_y && pre.slice_prefix == o.pre.slice_prefix && pre.slice_size_scalar == o.pre.slice_size_scalar &&
            compressedBytes == o.compressedBytes;
@@ -71,6 +77,12 @@ class Decoder {
   Decoder(std::ostream& out, Output output, int gpus, int batch, bool verbose)
       : out_(out), output_(output), G_(gpus), B_(batch), verbose_(verbose), frames_(0) {}
 
+  // a payload this object keeps alive until it has been decoded (reassembled fragments)
+  const uint8_t* keep(std::vector<uint8_t>&& bytes) {
+    owned_.emplace_back(std::move(bytes));
+    return owned_.back().data();
+  }
+
   void add(const Config& c, const PictureUnit& u) {
     if (!pending_.empty() && !cfg_.same(c)) flush();
     if (pending_.empty() && (codecs_.empty() || !cfg_.same(c))) open(c);
@@ -80,7 +92,7 @@ class Decoder {
 
   void flush() {
     if (pending_.empty()) return;
-    if (output_ != DECODED) { taps(); pending_.clear(); return; }
+    if (output_ != DECODED) { taps(); pending_.clear(); owned_.clear(); return; }
     const int n = (int)pending_.size();
     std::vector<std::string> errors(G_);
     std::vector<std::thread> th;
@@ -99,18 +111,46 @@ class Decoder {
     }
     for (auto& t : th) t.join();
     for (int g = 0; g < G_; ++g) if (!errors[g].empty()) throw std::logic_error(errors[g]);
-    for (int i = 0; i < n; ++i, ++frames_) {
+    for (int i = 0; i < n; ++i) {
+      if (cfg_.interlace) {
+        // DecodeStream.cpp:566-583: the first picture of a pair is the first field, the second completes the frame
+        if (field_.empty()) { field_ = recon_[i]; continue; }
+        weave(field_, recon_[i]);
+        field_.clear();
+        out_.write(reinterpret_cast<const char*>(frame_.data()), (std::streamsize)frame_.size());
+      } else {
+        out_.write(reinterpret_cast<const char*>(recon_[i].data()), (std::streamsize)recon_[i].size());
+      }
       if (verbose_) clog << "Decoded frame number " << frames_ << endl;
-      out_.write(reinterpret_cast<const char*>(recon_[i].data()), (std::streamsize)recon_[i].size());
+      ++frames_;
     }
     if (!out_) throw std::runtime_error("Failed to write output file");
     pending_.clear();
+    owned_.clear();
   }
 
   long frames() const { return frames_; }
 
  private:
+  // two field pictures -> the rows of one frame (Frame::firstField / secondField, Frame.cpp:40-110)
+  void weave(const std::vector<uint8_t>& first, const std::vector<uint8_t>& second) {
+    const PictureFormat ff(cfg_.height, cfg_.width, cfg_.cf);
+    const int bytes = cfg_.bits == 8 ? 1 : 2;
+    const int h[3] = {ff.lumaHeight(), ff.chromaHeight(), ff.chromaHeight()};
+    const size_t w[3] = {(size_t)ff.lumaWidth() * bytes, (size_t)ff.chromaWidth() * bytes, (size_t)ff.chromaWidth() * bytes};
+    frame_.resize(first.size() + second.size());
+    const uint8_t* top = cfg_.tff ? first.data() : second.data();
+    const uint8_t* bot = cfg_.tff ? second.data() : first.data();
+    uint8_t* dst = frame_.data();
+    for (int c = 0; c < 3; ++c)
+      for (int y = 0; y < h[c]; ++y) {
+        memcpy(dst, top, w[c]); top += w[c]; dst += w[c];
+        memcpy(dst, bot, w[c]); bot += w[c]; dst += w[c];
+      }
+  }
+
   void open(const Config& c) {
+    if (!cfg_.same(c)) field_.clear();
     cfg_ = c;
     codecs_.clear();
     vc2_codec_params cp;
@@ -173,6 +213,15 @@ class Decoder {
   std::vector<std::unique_ptr<Codec>> codecs_;
   std::vector<std::vector<uint8_t>> recon_;
   std::vector<PictureUnit> pending_;
+  std::deque<std::vector<uint8_t>> owned_;
+  std::vector<uint8_t> field_, frame_;   // interlaced output: the first field waiting for its partner, the woven frame
+};
+
+// the fragments of one picture (FragmentedPictureData, DecodeStream.cpp:203): slice data keyed by first slice index
+struct FragmentedPicture {
+  Config cfg;
+  int needed = 0, have = 0;
+  std::map<int, std::pair<const uint8_t*, size_t>> parts;
 };
 
 }  // namespace
@@ -229,6 +278,7 @@ int main(int argc, char** argv) {
     rd.synchronise();   // DecodeStream.cpp:177-178
     bool haveSeq = false;
     SequenceHeader seq;
+    std::map<unsigned long, FragmentedPicture> fragments;
     while (!rd.atEnd()) {
       const DataUnit du = rd.readDataUnit();
       if (verbose) clog << endl << "Have read data unit of type: " << (int)du.type << endl;
@@ -241,7 +291,6 @@ int main(int argc, char** argv) {
             clog << "height        = " << seq.height << endl << "width         = " << seq.width << endl;
             clog << "interlaced    = " << std::boolalpha << seq.interlace << endl;
           }
-          if (seq.interlace) throw std::logic_error("interlaced streams are not available in this build");
           break;
         case END_OF_SEQUENCE:
           if (verbose) clog << "End of Sequence after " << dec.frames() << " frames" << endl;
@@ -259,7 +308,8 @@ int main(int argc, char** argv) {
           if (verbose) clog << "Picture number      : " << picnum << endl;
           if (!haveSeq) { clog << "Cannot decode frame, no previous sequence header!" << endl; if (unitEnd) rd.seek(unitEnd); break; }
           Config cfg;
-          cfg.ld = ld; cfg.height = seq.height; cfg.width = seq.width; cfg.bits = seq.bitdepth; cfg.cf = seq.chromaFormat; cfg.pre = pre;
+          cfg.ld = ld; cfg.height = seq.interlace ? seq.height / 2 : seq.height; cfg.width = seq.width; cfg.bits = seq.bitdepth;
+          cfg.cf = seq.chromaFormat; cfg.pre = pre; cfg.interlace = seq.interlace; cfg.tff = seq.topFieldFirst;
           PictureUnit u;
           u.data = stream.data() + rd.pos();
           if (ld) {
@@ -277,8 +327,49 @@ int main(int argc, char** argv) {
           break;
         }
         case HQ_FRAGMENT:
-        case LD_FRAGMENT:
-          throw std::logic_error("fragmented pictures are not available in this build");
+        case LD_FRAGMENT: {   // DecodeStream.cpp:614-977
+          const bool ld = du.type == LD_FRAGMENT;
+          const FragmentHeader fh = rd.readFragmentHeader();
+          if (fh.n_slices == 0) {
+            const PicturePreamble pre = rd.readTransformParameters(ld);
+            if (verbose) clog << "Picture number      : " << fh.picture_number << endl;
+            if (!haveSeq) { clog << "Cannot decode frame, no previous sequence header!" << endl; if (unitEnd) rd.seek(unitEnd); break; }
+            FragmentedPicture fp;
+            fp.cfg.ld = ld; fp.cfg.height = seq.interlace ? seq.height / 2 : seq.height; fp.cfg.width = seq.width; fp.cfg.bits = seq.bitdepth;
+            fp.cfg.cf = seq.chromaFormat; fp.cfg.pre = pre; fp.cfg.interlace = seq.interlace; fp.cfg.tff = seq.topFieldFirst;
+            if (ld) fp.cfg.compressedBytes = (int)((long long)pre.slice_bytes.numerator * pre.slices_y * pre.slices_x / pre.slice_bytes.denominator);
+            fp.needed = pre.slices_x * pre.slices_y;
+            fragments[fh.picture_number] = fp;
+            if (unitEnd) rd.seek(unitEnd);
+            break;
+          }
+          if (rd.pos() + (size_t)fh.fragment_length > streamLen) throw std::logic_error("Stream Error: fragment runs past the end of the stream");
+          auto it = fragments.find(fh.picture_number);
+          if (it == fragments.end()) {
+            clog << "Cannot decode slices as no picture header yet read for picture number " << fh.picture_number << endl;
+          } else {
+            FragmentedPicture& fp = it->second;
+            if (verbose) clog << "Picture " << fh.picture_number << ": Reading " << fh.n_slices << " slices, starting from (" << fh.slice_offset_x
+                              << ", " << fh.slice_offset_y << ")" << endl;
+            fp.parts[fh.slice_offset_y * fp.cfg.pre.slices_x + fh.slice_offset_x] = std::make_pair(stream.data() + rd.pos(), (size_t)fh.fragment_length);
+            fp.have += fh.n_slices;
+            if (fp.have >= fp.needed) {
+              std::vector<uint8_t> payload;
+              for (auto& part : fp.parts) payload.insert(payload.end(), part.second.first, part.second.first + part.second.second);
+              const size_t len = payload.size();
+              if (ld && len < (size_t)fp.cfg.compressedBytes) throw std::logic_error("Stream Error: LD picture fragments are incomplete");
+              payload.resize(len + 64, 0);   // slack for the parser's word reads
+              PictureUnit u;
+              const Config cfg = fp.cfg;
+              fragments.erase(it);
+              u.len = ld ? (size_t)cfg.compressedBytes : len;
+              u.data = dec.keep(std::move(payload));
+              dec.add(cfg, u);
+            }
+          }
+          rd.seek(rd.pos() + (size_t)fh.fragment_length);
+          break;
+        }
         default:
           throw std::logic_error("Stream Error: Unknown data unit type.");
       }

@@ -3,9 +3,12 @@
 // codec (vc2_codec_encode_host); with --gpus N consecutive batches go to different GPUs (the codec is
 // intra-only) and this thread reassembles the data units in picture order.
 //
-// Not built here (SURVEY.md 8f "next" rows): LD encoding, interlaced coding, fragments, -o PSNR.
+// Interlaced input (-i, Frame.cpp:40-110) is coded as two field pictures per frame, each a batch slot of its own;
+// fragmented pictures (-F, DataUnit.cpp:267-342) are a host-side re-chunking of the packed slices.
+// Not built here (SURVEY.md 8f "next" rows): LD encoding, -o PSNR.
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <fstream>
 #include <iostream>
 #include <memory>
@@ -123,8 +126,6 @@ Params parse(int argc, char** argv) {
   if (p.frameRate < 0 || p.frameRate > 16) throw std::invalid_argument("Invalid Frame Rate: ");
   // scope of this build
   if (p.mode == LD) throw std::invalid_argument("LD encoding is not available in this build (LD streams are decode-only)");
-  if (p.interlaced) throw std::invalid_argument("interlaced coding is not available in this build");
-  if (p.fragment > 0) throw std::invalid_argument("fragmented pictures are not available in this build");
   if (p.bytes > 2) throw std::invalid_argument("this build reads 1 or 2 bytes per sample");
   if (p.gpus < 1) p.gpus = 1;
   if (p.batch < 1) p.batch = 1;
@@ -138,6 +139,30 @@ void write_be32_plane(std::ostream& out, const int32_t* v, size_t n) {   // pict
     buf[4 * i] = (char)(w >> 24); buf[4 * i + 1] = (char)(w >> 16); buf[4 * i + 2] = (char)(w >> 8); buf[4 * i + 3] = (char)w;
   }
   out.write(buf.data(), (std::streamsize)buf.size());
+}
+
+// rows of one parity of a planar frame -> a field picture and back (Frame::topField / bottomField, Frame.cpp:40-96)
+void split_fields(const uint8_t* frame, uint8_t* first, uint8_t* second, const PictureFormat& ff, int bytes, bool tff) {
+  const int h[3] = {ff.lumaHeight(), ff.chromaHeight(), ff.chromaHeight()};
+  const size_t w[3] = {(size_t)ff.lumaWidth() * bytes, (size_t)ff.chromaWidth() * bytes, (size_t)ff.chromaWidth() * bytes};
+  uint8_t* top = tff ? first : second;
+  uint8_t* bot = tff ? second : first;
+  for (int c = 0; c < 3; ++c)
+    for (int y = 0; y < h[c]; ++y) {   // h = field height; frame rows 2y (top field) and 2y + 1 (bottom field)
+      memcpy(top, frame, w[c]); top += w[c]; frame += w[c];
+      memcpy(bot, frame, w[c]); bot += w[c]; frame += w[c];
+    }
+}
+void merge_fields(uint8_t* frame, const uint8_t* first, const uint8_t* second, const PictureFormat& ff, int bytes, bool tff) {
+  const int h[3] = {ff.lumaHeight(), ff.chromaHeight(), ff.chromaHeight()};
+  const size_t w[3] = {(size_t)ff.lumaWidth() * bytes, (size_t)ff.chromaWidth() * bytes, (size_t)ff.chromaWidth() * bytes};
+  const uint8_t* top = tff ? first : second;
+  const uint8_t* bot = tff ? second : first;
+  for (int c = 0; c < 3; ++c)
+    for (int y = 0; y < h[c]; ++y) {
+      memcpy(frame, top, w[c]); top += w[c]; frame += w[c];
+      memcpy(frame, bot, w[c]); bot += w[c]; frame += w[c];
+    }
 }
 
 struct Worker {
@@ -175,7 +200,11 @@ int main(int argc, char** argv) {
       if (!outF) { perror(("Failed to open output file \"" + p.outFile + "\"").c_str()); return EXIT_FAILURE; }
       out = &outF;
     }
-    const PictureFormat format(p.height, p.width, p.cf);
+    const PictureFormat frameFormat(p.height, p.width, p.cf);
+    // interlaced: every picture is a field of half the height (EncodeStream.cpp:368-377)
+    const PictureFormat format(p.interlaced ? p.height / 2 : p.height, p.width, p.cf);
+    const int pictureBytes = p.interlaced ? p.compressedBytes / 2 : p.compressedBytes;
+    const int framePics = p.interlaced ? 2 : 1;
     const int ySlices = sliceSizeIsValid(p.depth, format.lumaHeight(), format.chromaHeight(), p.ySize);
     const int xSlices = sliceSizeIsValid(p.depth, format.lumaWidth(), format.chromaWidth(), p.xSize);
     if (ySlices == 0 || xSlices == 0) {   // EncodeStream.cpp:379-405
@@ -202,14 +231,14 @@ int main(int argc, char** argv) {
     }
 
     vc2_codec_params cp;
-    if (vc2_make_geom(p.height, p.width, (int)p.cf, (int)p.kernel, p.depth, p.ySize, p.xSize, p.prefix, p.scalar, &cp.geom) != VC2_OK)
+    if (vc2_make_geom(format.lumaHeight(), p.width, (int)p.cf, (int)p.kernel, p.depth, p.ySize, p.xSize, p.prefix, p.scalar, &cp.geom) != VC2_OK)
       throw std::logic_error("The given waveletDepth, hSlice, and vSlice parameters cannot encode this input. See above for suggested parameters.");
     cp.fmt.bytes_per_sample = p.bytes; cp.fmt.luma_depth = p.lumaDepth; cp.fmt.chroma_depth = p.chromaDepth;
     cp.mode = p.mode == HQ_CBR ? VC2_HQ_CBR : VC2_HQ_VBR;
-    cp.qindex = p.qIndex; cp.picture_bytes = p.compressedBytes;
+    cp.qindex = p.qIndex; cp.picture_bytes = pictureBytes;
     const bool taps = p.output == TRANSFORM || p.output == QUANTISED || p.output == INDICES;
     const int G = taps ? 1 : std::min(p.gpus, std::max(1, vc2_device_count()));
-    const int B = p.batch;
+    const int B = p.interlaced ? (p.batch + 1) / 2 * 2 : p.batch;   // both fields of a frame in one batch
     cp.max_pictures = B;
     std::vector<Worker> workers(G);
     for (int g = 0; g < G; ++g) {
@@ -224,31 +253,42 @@ int main(int argc, char** argv) {
     std::string unit;
     if (p.output == STREAM) {
       if (p.verbose) clog << endl << "Writing Sequence Header" << endl << endl;
-      writer.startSequence(unit, SequenceHeader(PROFILE_HQ, format.lumaHeight(), format.lumaWidth(), format.chromaFormat(), false,
-                                                (FrameRate)p.frameRate, p.topFieldFirst, p.lumaDepth));
+      // fragmentedPictures raises the stream to major version 3 (DataUnit.cpp:1062-1067, 1412-1421)
+      writer.startSequence(unit, SequenceHeader(PROFILE_HQ, frameFormat.lumaHeight(), frameFormat.lumaWidth(), frameFormat.chromaFormat(),
+                                                p.interlaced, (FrameRate)p.frameRate, p.topFieldFirst, p.lumaDepth, p.fragment > 0));
       out->write(unit.data(), (std::streamsize)unit.size());
     }
     PicturePreamble pre;
     pre.wavelet_kernel = p.kernel; pre.depth = p.depth; pre.slices_x = xSlices; pre.slices_y = ySlices;
     pre.slice_prefix = p.prefix; pre.slice_size_scalar = p.scalar; pre.slice_bytes = rationalise(0, 1);
+    // fragments (HQ_CBR only, EncodeParams.cpp:181): the slice sizes are known a priori (slice_bytes, Slices.cpp:28-49)
+    std::vector<uint32_t> sliceOff;
+    if (p.fragment > 0) {
+      const Array2D sb = slice_bytes(ySlices, xSlices, pictureBytes, p.scalar);
+      sliceOff.assign((size_t)ySlices * xSlices + 1, 0);
+      for (int i = 0; i < ySlices * xSlices; ++i) sliceOff[i + 1] = sliceOff[i] + (uint32_t)(sb.data()[i] + p.prefix);
+    }
 
     // one round = up to G batches of B pictures; frames[g][i] is picture number frame0 + g*B + i
     std::vector<std::vector<std::vector<uint8_t>>> frames(G, std::vector<std::vector<uint8_t>>(B, std::vector<uint8_t>(picBytes)));
     std::vector<std::vector<uint8_t>> recon;
     if (p.output == DECODED) recon.assign(B, std::vector<uint8_t>(picBytes));
+    std::vector<uint8_t> frameBuf(p.interlaced ? 2 * picBytes : 0);
     unsigned long long frame = 0;
     bool eof = false;
     while (!eof) {
       std::vector<int> count(G, 0);
       for (int g = 0; g < G && !eof; ++g)
-        for (int i = 0; i < B; ++i) {
-          in->read(reinterpret_cast<char*>(frames[g][i].data()), (std::streamsize)picBytes);
-          if ((size_t)in->gcount() != picBytes) {
+        for (int i = 0; i < B; i += framePics) {
+          uint8_t* dst = p.interlaced ? frameBuf.data() : frames[g][i].data();
+          in->read(reinterpret_cast<char*>(dst), (std::streamsize)(picBytes * framePics));
+          if ((size_t)in->gcount() != picBytes * framePics) {
             if (frame == 0 && g == 0 && i == 0) { std::cerr << "\rFailed to read input frame number 0" << endl; return EXIT_FAILURE; }
             eof = true;
             break;
           }
-          ++count[g];
+          if (p.interlaced) split_fields(frameBuf.data(), frames[g][i].data(), frames[g][i + 1].data(), format, p.bytes, p.topFieldFirst);
+          count[g] += framePics;
         }
       // encode: one host thread per GPU
       std::vector<std::thread> th;
@@ -274,7 +314,13 @@ int main(int argc, char** argv) {
           if (p.verbose) clog << "Encoded frame number " << frame << " (" << w.len[i] << " bytes)" << endl;
           if (p.output == STREAM) {
             unit.clear();
-            writer.hqPicture(unit, (unsigned long)(frame & 0xFFFFFFFFull), pre, w.payload[i].data(), w.len[i]);
+            // picture number = field + frame * fields per frame, wrapping at 2^32 (Utils.cpp:52-63)
+            if (p.fragment > 0) {
+              if (w.len[i] != sliceOff.back()) throw std::logic_error("fragment writer: payload length does not match the slice table");
+              writer.hqFragmentedPicture(unit, (unsigned long)(frame & 0xFFFFFFFFull), pre, w.payload[i].data(), sliceOff.data(), p.fragment);
+            } else {
+              writer.hqPicture(unit, (unsigned long)(frame & 0xFFFFFFFFull), pre, w.payload[i].data(), w.len[i]);
+            }
             out->write(unit.data(), (std::streamsize)unit.size());
           } else if (p.output == PACKAGED) {
             out->write(reinterpret_cast<const char*>(w.payload[i].data()), (std::streamsize)w.len[i]);
@@ -302,7 +348,14 @@ int main(int argc, char** argv) {
           std::vector<void*> pics(count[g]);
           for (int i = 0; i < count[g]; ++i) { pay[i] = w.payload[i].data(); pics[i] = recon[i].data(); }
           w.codec->decode(count[g], pay.data(), w.len.data(), pics.data());
-          for (int i = 0; i < count[g]; ++i) out->write(reinterpret_cast<const char*>(recon[i].data()), (std::streamsize)picBytes);
+          for (int i = 0; i < count[g]; i += framePics) {
+            if (p.interlaced) {
+              merge_fields(frameBuf.data(), recon[i].data(), recon[i + 1].data(), format, p.bytes, p.topFieldFirst);
+              out->write(reinterpret_cast<const char*>(frameBuf.data()), (std::streamsize)frameBuf.size());
+            } else {
+              out->write(reinterpret_cast<const char*>(recon[i].data()), (std::streamsize)picBytes);
+            }
+          }
         }
         if (!*out) { std::cerr << "Failed to write output file \"" << p.outFile << "\"" << endl; return EXIT_FAILURE; }
       }

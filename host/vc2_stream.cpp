@@ -238,6 +238,42 @@ void StreamWriter::hqPicture(std::string& out, unsigned long pictureNumber, cons
   out.append(reinterpret_cast<const char*>(slices), len);
 }
 
+void StreamWriter::hqFragmentedPicture(std::string& out, unsigned long pictureNumber, const PicturePreamble& p, const uint8_t* slices,
+                                       const uint32_t* slice_off, int fragmentLength) {
+  {   // the parameter fragment (:268-293): slice count 0
+    std::string prm;
+    BitSink b(prm);
+    b.uvlc((unsigned)p.wavelet_kernel); b.uvlc(p.depth);
+    b.bit(false); b.bit(false);                        // asym_transform_index_flag, asym_transform_flag: always present here
+    b.uvlc(p.slices_x); b.uvlc(p.slices_y); b.uvlc(p.slice_prefix); b.uvlc(p.slice_size_scalar);
+    b.bit(false);
+    b.align();
+    parseInfo(out, 0xEC, (unsigned)prm.size() + 8 + 13);
+    be(out, (unsigned)pictureNumber, 4);
+    be(out, (unsigned)prm.size(), 2);
+    be(out, 0, 2);
+    out += prm;
+  }
+  auto emit = [&](int first, int count) {                // :306-313, :331-338
+    const unsigned bytes = slice_off[first + count] - slice_off[first];
+    parseInfo(out, 0xEC, bytes + 12 + 13);
+    be(out, (unsigned)pictureNumber, 4);
+    be(out, bytes, 2);
+    be(out, (unsigned)count, 2);
+    be(out, (unsigned)(first % p.slices_x), 2);
+    be(out, (unsigned)(first / p.slices_x), 2);
+    out.append(reinterpret_cast<const char*>(slices + slice_off[first]), bytes);
+  };
+  const int n = p.slices_x * p.slices_y;
+  int first = 0, count = 0;
+  for (int s = 0; s < n; ++s) {
+    const unsigned have = slice_off[s] - slice_off[first], sz = slice_off[s + 1] - slice_off[s];
+    if (count > 0 && (int)(have + sz) > fragmentLength) { emit(first, count); first = s; count = 0; }
+    ++count;
+  }
+  emit(first, count);
+}
+
 void StreamWriter::endSequence(std::string& out) {   // :364-368
   parseInfo(out, 0x10, 0);
   prev_ = 0;
@@ -327,10 +363,33 @@ SequenceHeader StreamReader::readSequenceHeader() {
   return h;
 }
 
+FragmentHeader StreamReader::readFragmentHeader() {
+  if (pos_ + 8 > n_) throw std::logic_error("Stream Error: truncated fragment header");
+  const uint8_t* q = d_ + pos_;
+  FragmentHeader f;
+  f.picture_number = (unsigned long)q[0] << 24 | (unsigned long)q[1] << 16 | (unsigned long)q[2] << 8 | q[3];
+  f.fragment_length = q[4] << 8 | q[5];
+  f.n_slices = q[6] << 8 | q[7];
+  f.slice_offset_x = f.slice_offset_y = 0;
+  pos_ += 8;
+  if (f.n_slices != 0) {
+    if (pos_ + 4 > n_) throw std::logic_error("Stream Error: truncated fragment header");
+    f.slice_offset_x = q[8] << 8 | q[9];
+    f.slice_offset_y = q[10] << 8 | q[11];
+    pos_ += 4;
+  }
+  return f;
+}
+
 PicturePreamble StreamReader::readPictureHeader(bool ld, unsigned long& pictureNumber) {
   if (pos_ + 4 > n_) throw std::logic_error("Stream Error: truncated picture header");
   pictureNumber = (unsigned long)d_[pos_] << 24 | (unsigned long)d_[pos_ + 1] << 16 | (unsigned long)d_[pos_ + 2] << 8 | d_[pos_ + 3];
-  BitSource b(d_, n_, pos_ + 4);
+  pos_ += 4;
+  return readTransformParameters(ld);
+}
+
+PicturePreamble StreamReader::readTransformParameters(bool ld) {
+  BitSource b(d_, n_, pos_);
   PicturePreamble p;
   const unsigned wi = b.uvlc();
   p.wavelet_kernel = wi <= 6 ? (WaveletKernel)wi : NullKernel;

@@ -56,6 +56,12 @@ class StreamWriter {
   void startSequence(std::string& out, const SequenceHeader& hdr);
   // HQWrappedPictureIO (DataUnit.cpp:236-266): parse info + picture number + transform parameters + slice bytes
   void hqPicture(std::string& out, unsigned long pictureNumber, const PicturePreamble& p, const uint8_t* slices, size_t len);
+  // the fragmented form of HQWrappedPictureIO (DataUnit.cpp:267-342, parse code 0xEC): one fragment that carries
+  // the transform parameters, then fragments of whole slices - a slice is appended to the current fragment unless
+  // that would take it over fragmentLength bytes.  slice_off[n_slices + 1] are the byte offsets of the slices
+  // inside `slices`.  The sequence header must have been written with major version 3 (fragmentedPictures, :1412-1421).
+  void hqFragmentedPicture(std::string& out, unsigned long pictureNumber, const PicturePreamble& p, const uint8_t* slices,
+                           const uint32_t* slice_off, int fragmentLength);
   // dataunitio::end_sequence (:364-368)
   void endSequence(std::string& out);
  private:
@@ -65,6 +71,14 @@ class StreamWriter {
 };
 
 // ---- reading ---------------------------------------------------------------------------------------
+// picture number + fragment header of an HQ / LD fragment data unit (operator>>(Fragment), DataUnit.cpp:1146-1163)
+struct FragmentHeader {
+  unsigned long picture_number;
+  int fragment_length;       // bytes of fragment data that follow the header
+  int n_slices;              // 0: the fragment carries the transform parameters
+  int slice_offset_x, slice_offset_y;
+};
+
 struct DataUnit {
   DataUnitType type;
   size_t offset;             // of the parse info header in the stream
@@ -82,6 +96,8 @@ class StreamReader {
   SequenceHeader readSequenceHeader();                       // :883-1041, 1203-1312
   // picture number + PicturePreamble (:1314-1410); ld selects the LD parameter set
   PicturePreamble readPictureHeader(bool ld, unsigned long& pictureNumber);
+  PicturePreamble readTransformParameters(bool ld);          // the PicturePreamble alone (:1327-1410)
+  FragmentHeader readFragmentHeader();                       // :1146-1163 (after the parse info)
   size_t pos() const { return pos_; }
   void setMajorVersion(int m) { major_ = m; }   // normally taken from the sequence header just read
   void seek(size_t p) { pos_ = p; }

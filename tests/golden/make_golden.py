@@ -30,7 +30,7 @@ FMT = {"444": "4:4:4", "422": "4:2:2", "420": "4:2:0"}
 
 def case(name, w, h, fmt, depth_bits, frames, mode, kernel, wdepth, u, a, **kw):
     d = dict(name=name, w=w, h=h, fmt=fmt, bits=depth_bits, frames=frames, mode=mode, kernel=kernel,
-             wdepth=wdepth, u=u, a=a, q=None, s=None, S=1, P=0, r=3, seed=1234, smooth=False)
+             wdepth=wdepth, u=u, a=a, q=None, s=None, S=1, P=0, r=3, seed=1234, smooth=False, extra=[])
     d.update(kw)
     return d
 
@@ -60,6 +60,17 @@ for i, (k, d, f, w, h, b) in enumerate(_small):
                           s=(w * h + 2 * ch * cw) * b // 8 // 3, S=1 + (i % 2), seed=200 + i))
 
 
+# interlaced coding (-i, field order -t / -b) and fragmented pictures (-F, HQ_CBR only); command-line tests only
+CASES += [
+    case("I00_LeGall_d3_422_tff", 188, 116, "422", 10, 3, "HQ_ConstQ", "LeGall", 3, 1, 2, q=10, S=2, P=1, seed=300, extra=["-i"]),
+    case("I01_DD137_d2_420_bff", 176, 144, "420", 8, 2, "HQ_CBR", "DD137", 2, 2, 2, s=20000, seed=301, extra=["-i", "-b"]),
+    case("I02_Haar1_d3_444_tff", 128, 96, "444", 12, 2, "HQ_CBR", "Haar1", 3, 1, 1, s=30000, S=2, seed=302, extra=["-i", "-t"]),
+    case("F00_DD97_d3_422", 352, 240, "422", 10, 2, "HQ_CBR", "DD97", 3, 1, 2, s=60000, seed=310, extra=["-F", "1400"]),
+    case("F01_LeGall_d2_420_small", 176, 144, "420", 8, 2, "HQ_CBR", "LeGall", 2, 2, 2, s=12000, P=2, seed=311, extra=["-F", "50"]),
+    case("F02_Fidelity_d2_422_il", 144, 88, "422", 12, 3, "HQ_CBR", "Fidelity", 2, 1, 2, s=16000, S=2, seed=312, extra=["-F", "700", "-i"]),
+]
+
+
 def md5_file(path):
     h = hashlib.md5()
     n = 0
@@ -82,7 +93,7 @@ def enc_args(c):
         a += ["-s", str(c["s"])]
     if c["mode"] != "LD":
         a += ["-S", str(c["S"]), "-P", str(c["P"])]
-    return a
+    return a + list(c.get("extra", []))
 
 
 def run_case(c):

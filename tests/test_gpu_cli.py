@@ -25,7 +25,7 @@ def enc_args(c):
     a += ["-q", str(c["q"])] if c["mode"] == "HQ_ConstQ" else ["-s", str(c["s"])]
     if c["mode"] != "LD":
         a += ["-S", str(c["S"]), "-P", str(c["P"])]
-    return a
+    return a + list(c.get("extra", []))
 
 
 def md5(path):
@@ -45,13 +45,16 @@ def run(cmd):
 
 
 @pytest.mark.parametrize("name", ["S01_LeGall_d3_422", "S04_Haar1_d4_420", "S05_Fidelity_d2_422", "S08_DD137_d4_422",
-                                  "B00_DD97_d2_420", "B06_Daub97_d3_444", "C1", "C2"])
+                                  "B00_DD97_d2_420", "B06_Daub97_d3_444", "C1", "C2",
+                                  # interlaced coding (two field pictures per frame) and fragmented pictures
+                                  "I00_LeGall_d3_422_tff", "I01_DD137_d2_420_bff", "I02_Haar1_d3_444_tff",
+                                  "F00_DD97_d3_422", "F01_LeGall_d2_420_small", "F02_Fidelity_d2_422_il"])
 def test_command_lines_vs_golden(tmp_path, name):
     c, taps = GOLD[name]["params"], GOLD[name]["taps"]
     src = str(tmp_path / "in.yuv")
     write_input(c, src)
     # a batch smaller than the clip and (when there are several GPUs) two devices: chunking and reassembly
-    extra = ["-B", "1", "-G", "2"] if name.startswith("S") else []
+    extra = ["-B", "1", "-G", "2"] if name[0] in "SI" else ["-B", "3"] if name[0] == "F" else []
     small = not name.startswith("C")       # the 1080p configs: stream and pictures only (each run pays a CUDA start-up)
     for tap in ["Stream"] + (["Packaged", "Transform", "Quantised"] if small else []) + (["Indices"] if c["mode"] != "HQ_ConstQ" else []):
         dst = str(tmp_path / ("enc_" + tap))

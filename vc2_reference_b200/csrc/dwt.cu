@@ -28,7 +28,7 @@ namespace {
 constexpr unsigned FULL = 0xFFFFFFFFu;
 constexpr int WARPS = 4;   // warps per CTA: four vertically adjacent row segments of one strip
 #ifndef VC2_DWT_MINB
-#define VC2_DWT_MINB 4     // resident CTAs per SM the register allocation is held to (4 -> 128 registers per thread)
+#define VC2_DWT_MINB 5     // resident CTAs per SM the register allocation is held to (5 -> 102 registers per thread; measured best of 4, 5, 6)
 #endif
 
 // ---- compile-time schedule of the vertical pipeline ------------------------------------------------

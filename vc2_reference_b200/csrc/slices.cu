@@ -731,14 +731,19 @@ __global__ void __launch_bounds__(128) slice_unpack_kernel(const UnpackParams p)
 // shared-memory loads per slice instead of three DRAM round trips).
 // A payload that runs off its end leaves the remaining slices empty; the parser flags those.
 // ------------------------------------------------------------------------------------------
-constexpr int INDEX_SEG = 32 * 1024;                 // bytes per ring segment
+constexpr int INDEX_SEG = 16 * 1024;                 // bytes per ring segment
 constexpr int INDEX_RING = 4 * INDEX_SEG;             // four segments: two being walked, one being filled, one spare
 constexpr unsigned INDEX_MASK = INDEX_RING - 1;
 
 __global__ void __launch_bounds__(256) hq_index_kernel(const IndexParams p) {
-  extern __shared__ uint4 s_ring[];   // the ring, then two stop flags
+  // The ring sits at a shared-memory address that is a multiple of its size (the allocation is twice as large, the
+  // window starts behind the system's reserved bytes), so that ring address = ring_base | (position & mask) is ONE
+  // logic instruction on the walker's dependent chain.  Two stop flags follow the ring.
+  extern __shared__ uint4 s_raw[];
+  const unsigned raw_base = (unsigned)__cvta_generic_to_shared(s_raw);
+  const unsigned ring_base = (raw_base + INDEX_MASK) & ~INDEX_MASK;
+  uint4* s_ring = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(s_raw) + (ring_base - raw_base));
   int* s_stop = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(s_ring) + INDEX_RING);
-  const bool ring_at_zero = (unsigned)__cvta_generic_to_shared(s_ring) == 0u;
   const int pic = blockIdx.x, ns = p.nslices;
   const uint8_t* in = p.in + (long long)pic * p.in_pic_stride;
   const unsigned len = p.len_dev ? min(p.len_dev[pic], (unsigned)min(p.in_pic_stride, 0xFFFFFFFFll)) : p.len[pic];
@@ -788,14 +793,14 @@ __global__ void __launch_bounds__(256) hq_index_kernel(const IndexParams p) {
       bool bad = false;
       // fast path: four slices per loop-carried branch.  The walk is one chain of dependent shared-memory loads
       // (three per slice); a branch per slice would add its resolution to every link, and so would any address
-      // arithmetic: with the ring at shared-memory address 0 a link is  load -> multiply-add -> mask -> load.
+      // arithmetic: with the ring aligned to its size a link is  load -> multiply-add -> mask|base -> load.
       // a = stream position of the next length byte.  The positions may run past the two valid ring segments -
       // the reads are masked into the ring and a group is only committed when its fourth slice starts inside
       // segment k, in which case every byte it looked at was valid.
-      if (ring_at_zero) {
+      {
         auto hop = [&](unsigned a, unsigned add) {
           unsigned b;
-          asm volatile("ld.shared.u8 %0, [%1];" : "=r"(b) : "r"(a & INDEX_MASK));
+          asm volatile("ld.shared.u8 %0, [%1];" : "=r"(b) : "r"((a & INDEX_MASK) | ring_base));
           unsigned r;   // a + add is ready before the byte arrives: keep it out of the chain
           asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(b), "r"(sc), "r"(a + add));
           return r;
@@ -923,10 +928,10 @@ cudaError_t unpack_launch(cudaStream_t s, const UnpackParams& p, int npictures) 
 }
 
 cudaError_t index_launch(cudaStream_t s, const IndexParams& p, int npictures) {
-  cudaError_t e = cudaFuncSetAttribute(hq_index_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, INDEX_RING + 16);   // per device
+  cudaError_t e = cudaFuncSetAttribute(hq_index_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * INDEX_RING + 16);   // per device
   if (e != cudaSuccess) return e;
   if (npictures < 1 || (!p.len_dev && npictures > VC2_INDEX_MAX_PICTURES)) return cudaErrorInvalidValue;
-  hq_index_kernel<<<npictures, 256, INDEX_RING + 16, s>>>(p);
+  hq_index_kernel<<<npictures, 256, 2 * INDEX_RING + 16, s>>>(p);
   return cudaGetLastError();
 }
 
