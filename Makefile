@@ -16,7 +16,7 @@ HOSTLIB   := $(PKG)/libvc2host.so
 BIN       := $(PKG)/bin
 CXXFLAGS  := -O2 -std=c++14 -fPIC -Wall -Wno-comment -Iinclude -Ihost
 
-all: $(LIB) $(ORACLE) $(HOSTLIB) $(BIN)/EncodeStream $(BIN)/DecodeStream
+all: $(LIB) $(ORACLE) $(HOSTLIB) $(BIN)/EncodeStream $(BIN)/DecodeStream $(BIN)/DecodeFrame
 
 # C++ host layer: the Library mirror (include/vc2/*.h) and the drop-in command lines, over the C-ABI
 $(HOSTLIB): host/vc2_library.cpp host/vc2_stream.cpp include/vc2/*.h include/vc2_cabi.h include/vc2_host.h $(LIB)
@@ -42,5 +42,5 @@ $(LIB): $(OBJS)
 	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -lcudart
 
 clean:
-	rm -f $(OBJS) $(LIB) $(HOSTLIB) $(BIN)/EncodeStream $(BIN)/DecodeStream
+	rm -f $(OBJS) $(LIB) $(HOSTLIB) $(BIN)/EncodeStream $(BIN)/DecodeStream $(BIN)/DecodeFrame
 .PHONY: all clean

@@ -5,11 +5,15 @@
 //
 // Interlaced input (-i, Frame.cpp:40-110) is coded as two field pictures per frame, each a batch slot of its own;
 // fragmented pictures (-F, DataUnit.cpp:267-342) are a host-side re-chunking of the packed slices.
-// Not built here (SURVEY.md 8f "next" rows): LD encoding, -o PSNR.
+// -o PSNR (EncodeStream.cpp:676-767) reports, per frame, the mean / standard deviation of the slice quantiser indices
+// and the PSNR of the local decode, with the reference's float arithmetic.
+// Not built here (SURVEY.md 8f "next" rows): LD encoding.
 #include <cstdio>
 #include <cstdlib>
+#include <cmath>
 #include <cstring>
 #include <fstream>
+#include <iomanip>
 #include <iostream>
 #include <memory>
 #include <sstream>
@@ -31,7 +35,7 @@ using std::endl;
 
 namespace {
 
-enum Output { TRANSFORM, QUANTISED, INDICES, PACKAGED, STREAM, DECODED };
+enum Output { TRANSFORM, QUANTISED, INDICES, PACKAGED, STREAM, DECODED, PSNR };
 enum Mode { HQ_CBR, HQ_ConstQ, LD };
 
 struct Params {
@@ -79,7 +83,7 @@ Params parse(int argc, char** argv) {
   const std::string o = c.str("o", "Stream");
   if (o == "Transform") p.output = TRANSFORM; else if (o == "Quantised") p.output = QUANTISED; else if (o == "Indices") p.output = INDICES;
   else if (o == "Packaged") p.output = PACKAGED; else if (o == "Stream") p.output = STREAM; else if (o == "Decoded") p.output = DECODED;
-  else if (o == "PSNR") throw std::invalid_argument("output PSNR is not available in this build");
+  else if (o == "PSNR") p.output = PSNR;
   else throw std::invalid_argument("Command line error: Couldn't read argument value from string '" + o + "' for arg -o");
   const std::string m = c.str("m");
   if (m == "HQ_ConstQ") p.mode = HQ_ConstQ; else if (m == "HQ_CBR") p.mode = HQ_CBR; else if (m == "LD") p.mode = LD;
@@ -272,9 +276,9 @@ int main(int argc, char** argv) {
     // one round = up to G batches of B pictures; frames[g][i] is picture number frame0 + g*B + i
     std::vector<std::vector<std::vector<uint8_t>>> frames(G, std::vector<std::vector<uint8_t>>(B, std::vector<uint8_t>(picBytes)));
     std::vector<std::vector<uint8_t>> recon;
-    if (p.output == DECODED) recon.assign(B, std::vector<uint8_t>(picBytes));
+    if (p.output == DECODED || p.output == PSNR) recon.assign(B, std::vector<uint8_t>(picBytes));
     std::vector<uint8_t> frameBuf(p.interlaced ? 2 * picBytes : 0);
-    unsigned long long frame = 0;
+    unsigned long long frame = 0, psnrFrame = 0;
     bool eof = false;
     while (!eof) {
       std::vector<int> count(G, 0);
@@ -341,6 +345,57 @@ int main(int argc, char** argv) {
                                                    : vc2_codec_read_quantised(w.codec->handle(), i, Y.data(), U.data(), V.data()));
               write_be32_plane(*out, Y.data(), nY); write_be32_plane(*out, U.data(), nC); write_be32_plane(*out, V.data(), nC);
             }
+          }
+        }
+        if (p.output == PSNR) {   // EncodeStream.cpp:676-767
+          std::vector<const uint8_t*> pay(count[g]);
+          std::vector<void*> pics(count[g]);
+          for (int i = 0; i < count[g]; ++i) { pay[i] = w.payload[i].data(); pics[i] = recon[i].data(); }
+          w.codec->decode(count[g], pay.data(), w.len.data(), pics.data());
+          const size_t ns = (size_t)cp.geom.slices_y * cp.geom.slices_x;
+          std::vector<int32_t> q(ns);
+          const size_t nY = (size_t)format.lumaHeight() * format.lumaWidth(), nC = (size_t)format.chromaHeight() * format.chromaWidth();
+          for (int i = 0; i < count[g]; i += framePics) {
+            int stats[128] = {0};
+            long long ss[3] = {0, 0, 0};
+            for (int f = 0; f < framePics; ++f) {
+              // the encode_host call has long finished: the slots still hold this batch's indices
+              w.codec->check(vc2_codec_read_indices(w.codec->handle(), i + f, q.data()));
+              for (size_t j = 0; j < ns; ++j) ++stats[q[j] & 127];
+              const uint8_t* a = frames[g][i + f].data();
+              const uint8_t* b = recon[i + f].data();
+              size_t off = 0;
+              for (int c = 0; c < 3; ++c) {
+                const size_t n = c == 0 ? nY : nC;
+                const int shift = 8 * p.bytes - (c == 0 ? p.lumaDepth : p.chromaDepth);
+                for (size_t j = 0; j < n; ++j, off += p.bytes) {
+                  const int va = p.bytes == 2 ? ((a[off] << 8 | a[off + 1]) >> shift) : (a[off] >> shift);
+                  const int vb = p.bytes == 2 ? ((b[off] << 8 | b[off + 1]) >> shift) : (b[off] >> shift);
+                  const int d = va - vb;
+                  ss[c] += d * d;
+                }
+              }
+            }
+            const int totalSlices = framePics * (int)ns;
+            int topIndex = -1;
+            for (int z = 0; z < 128; ++z) if (stats[z] > 0) topIndex = z;
+            float mean = 0.0, meanSquare = 0.0;
+            for (int z = 0; z <= topIndex; ++z) { mean += (z * stats[z]); meanSquare += (z * z * stats[z]); }
+            mean /= totalSlices;
+            meanSquare /= totalSlices;
+            // the reference's unqualified sqrt / log10 resolve to the C double functions; results are narrowed to float
+            const float stdDev = (float)::sqrt((double)(meanSquare - (mean * mean)));
+            const int yPixels = p.width * p.height, uvPixels = frameFormat.chromaWidth() * frameFormat.chromaHeight();
+            const float YRMS = (float)(::sqrt((double)(float(ss[0]) / float(yPixels))) / (1 << p.lumaDepth));
+            const float URMS = (float)(::sqrt((double)(float(ss[1]) / float(uvPixels))) / (1 << p.chromaDepth));
+            const float VRMS = (float)(::sqrt((double)(float(ss[2]) / float(uvPixels))) / (1 << p.chromaDepth));
+            const float YPSNR = (float)(-20 * ::log10((double)YRMS)), UPSNR = (float)(-20 * ::log10((double)URMS)),
+                        VPSNR = (float)(-20 * ::log10((double)VRMS));
+            *out << "Frame " << psnrFrame++ << endl;
+            *out << std::fixed << std::setprecision(2);
+            *out << mean << " " << stdDev << endl;
+            *out << std::fixed << std::setprecision(4);
+            *out << YPSNR << " " << UPSNR << " " << VPSNR << endl;
           }
         }
         if (p.output == DECODED) {   // local decode of the batch just written (EncodeStream.cpp:649-690)

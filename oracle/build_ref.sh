@@ -5,7 +5,7 @@
 # never part of the product path.  Needs the Boost stand-in in oracle/boost_shim
 # because system Boost is absent from this image.
 #
-#   oracle/_ref/EncodeStream, DecodeStream  - the reference command lines
+#   oracle/_ref/EncodeStream, DecodeStream, DecodeFrame  - the reference command lines
 #   oracle/_ref/libvc2ref.so                - reference Library + extern "C" taps (oracle/ref_taps.cpp)
 set -euo pipefail
 HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
@@ -28,6 +28,7 @@ for p in "${pids[@]}"; do wait "$p"; done
 OBJS=$(ls "$OUT"/obj/{Arrays,DataUnit,Frame,Picture,Quantisation,Slices,Utils,VLC,WaveletTransform}.o)
 g++ $F "$R/EncodeStream/EncodeStream.cpp" "$R/EncodeStream/EncodeParams.cpp" $OBJS -o "$OUT/EncodeStream" &
 g++ $F "$R/DecodeStream/DecodeStream.cpp" "$R/DecodeStream/DecodeParams.cpp" $OBJS -o "$OUT/DecodeStream" &
+g++ $F "$R/DecodeFrame/DecodeFrame.cpp" "$R/DecodeFrame/DecodeParams.cpp" $OBJS -o "$OUT/DecodeFrame" &
 # libvc2ref.so also carries the CLI-level rate control (quantIndicesCBR lives in EncodeStream.cpp)
 ( g++ $F -Dmain=vc2ref_encodestream_main -c "$R/EncodeStream/EncodeStream.cpp" -o "$OUT/obj/EncodeStream_lib.o" &&
   g++ $F -c "$R/EncodeStream/EncodeParams.cpp" -o "$OUT/obj/EncodeParams_lib.o" &&

@@ -65,6 +65,11 @@ def test_command_lines_vs_golden(tmp_path, name):
         dst = str(tmp_path / ("dec_" + tap))
         run([os.path.join(BIN, "DecodeStream")] + extra + ["-o", tap, stream, dst])
         assert md5(dst) == taps["dec_" + tap]["md5"], (name, tap)
+    # EncodeStream -o PSNR: the reference's per-frame text report (quantiser statistics + PSNR of the local decode)
+    if "enc_PSNR" in taps:
+        dst = str(tmp_path / "enc_PSNR")
+        run([os.path.join(BIN, "EncodeStream")] + enc_args(c) + extra + ["-o", "PSNR", src, dst])
+        assert open(dst).read() == taps["enc_PSNR"]["text"], (name, "PSNR")
     # EncodeStream -o Decoded = the decoder's picture (local decode loop, EncodeStream.cpp:649-767)
     if not small:
         return
@@ -106,3 +111,28 @@ def test_error_reporting_matches_reference(tmp_path):
     a[a.index("-S") + 1] = "1"
     r = subprocess.run([os.path.join(BIN, "EncodeStream")] + a + [big, str(tmp_path / "o2")], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
     assert r.returncode != 0 and b"Error: Slice scalar is too small" in r.stdout, r.stdout[-300:]
+
+
+def frame_args(c):
+    a = ["-x", str(c["w"]), "-y", str(c["h"]), "-f", FMT[c["fmt"]], "-z", str(c["bits"]), "-k", c["kernel"], "-d", str(c["wdepth"]),
+         "-u", str(c["u"]), "-a", str(c["a"]), "-m", "HQ", "-S", str(c["S"]), "-P", str(c["P"])]
+    return a + [e for e in c.get("extra", []) if e in ("-i", "-b", "-t")]
+
+
+@pytest.mark.parametrize("name", ["S01_LeGall_d3_422", "S05_Fidelity_d2_422", "B00_DD97_d2_420", "I00_LeGall_d3_422_tff", "I01_DD137_d2_420_bff"])
+def test_decode_frame_vs_golden(tmp_path, name):
+    """DecodeFrame (bare slice data, parameters on the command line; src/DecodeFrame) against digests made by the reference tool,
+    including its habit of writing a zero frame behind every frame of -o Transform / Quantised / Indices output"""
+    c, taps = GOLD[name]["params"], GOLD[name]["taps"]
+    src, pk = str(tmp_path / "in.yuv"), str(tmp_path / "pk")
+    write_input(c, src)
+    run([os.path.join(BIN, "EncodeStream")] + enc_args(c) + ["-o", "Packaged", src, pk])
+    assert md5(pk) == taps["enc_Packaged"]["md5"]
+    for tap in ["Decoded", "Transform", "Quantised", "Indices"]:
+        dst = str(tmp_path / ("f_" + tap))
+        run([os.path.join(BIN, "DecodeFrame")] + frame_args(c) + ["-B", "3", "-o", tap, pk, dst])
+        assert md5(dst) == taps["frame_" + tap]["md5"], (name, tap)
+    # LD input: the reference tool fails on the first picture, and so does this one
+    r = subprocess.run([os.path.join(BIN, "DecodeFrame"), "-m", "LD", "-s", "1000"] + frame_args(c)[:-6] + [pk, str(tmp_path / "x")],
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert r.returncode != 0 and b"Failed to read the first compressed frame" in r.stderr

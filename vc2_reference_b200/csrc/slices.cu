@@ -758,6 +758,19 @@ __global__ void __launch_bounds__(256) hq_index_kernel(const IndexParams p) {
     uint4* dst = s_ring + (size_t)(k & 3) * (INDEX_SEG / 16);
     for (int i = first; i < n16; i += nthreads) dst[i] = __ldg(src + i);
   };
+  // the same as an asynchronous copy (LDGSTS): issued one segment earlier than it is needed, so that the barrier
+  // that ends an iteration never waits for a DRAM round trip that has only just started
+  auto load_seg_async = [&](unsigned k, int first, int nthreads) {
+    const long long b0 = (long long)k * INDEX_SEG;
+    if (b0 < readable) {
+      const int n16 = (int)(min((long long)INDEX_SEG, readable - b0) >> 4);
+      const uint4* src = reinterpret_cast<const uint4*>(in + b0);
+      const unsigned dst = ring_base + (k & 3u) * INDEX_SEG;
+      for (int i = first; i < n16; i += nthreads)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16u * i), "l"(src + i) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");   // one group per segment and thread, also when it is empty
+  };
   if (maxslice > (unsigned)INDEX_SEG) {
     // slices may be longer than a ring segment (huge scalar): plain walk in global memory
     if (threadIdx.x == 0) {
@@ -777,14 +790,17 @@ __global__ void __launch_bounds__(256) hq_index_kernel(const IndexParams p) {
     }
     return;
   }
+  // ring slots while segment k is walked: k, k + 1 valid | k + 2 landing | k + 3 being issued (the slot of k - 1)
   load_seg(0, threadIdx.x, blockDim.x);
   load_seg(1, threadIdx.x, blockDim.x);
+  if (threadIdx.x >= 32) load_seg_async(2, threadIdx.x - 32, blockDim.x - 32);   // only the threads that later wait for it
   __syncthreads();
   unsigned pos = 0;   // walker state (thread 0)
   int s = 0;
   for (unsigned k = 0;; ++k) {
     if (threadIdx.x >= 32) {
-      load_seg(k + 2, threadIdx.x - 32, blockDim.x - 32);     // warps 1..7 fill the ring ahead of the walker
+      load_seg_async(k + 3, threadIdx.x - 32, blockDim.x - 32);     // warps 1..7 fill the ring ahead of the walker
+      asm volatile("cp.async.wait_group 1;" ::: "memory");          // segment k + 2 has landed
     } else if (threadIdx.x == 0) {
       // every slice that STARTS in segment k; its bytes end before segment k + 2 (maxslice <= INDEX_SEG)
       const uint8_t* w = reinterpret_cast<const uint8_t*>(s_ring);
