@@ -3,7 +3,8 @@
 // line.  HQ pictures go through the fused batched CUDA codec; the -o Transform / Quantised / Indices taps go through
 // the Library-surface calls.  Two behaviours of the reference tool are kept as they are: after the tap output of every
 // frame it still writes its (never assigned, all-zero) output frame (the `continue` at DecodeFrame.cpp:263-299 only
-// leaves the field loop, :313-333 then runs), and LD input fails on the first picture (probed: the reference reports
+// leaves the field loop, :313-333 then runs) - and because that frame write leaves pictureio::bitDepth set on the
+// stream, every later tap word is left justified to it (Arrays.cpp:170-172, 391-397) - and LD input fails on the first picture (probed: the reference reports
 // "Failed to read the first compressed frame" for streams its own LD encoder wrote).
 #include <cstdio>
 #include <cstdlib>
@@ -31,10 +32,10 @@ namespace {
 
 enum Output { TRANSFORM, QUANTISED, INDICES, DECODED };
 
-void write_be32_plane(std::ostream& out, const int* v, size_t n) {
+void write_be32_plane(std::ostream& out, const int* v, size_t n, int shift) {
   std::string buf(n * 4, '\0');
   for (size_t i = 0; i < n; ++i) {
-    const uint32_t w = (uint32_t)v[i];
+    const uint32_t w = (uint32_t)v[i] << shift;
     buf[4 * i] = (char)(w >> 24); buf[4 * i + 1] = (char)(w >> 16); buf[4 * i + 2] = (char)(w >> 8); buf[4 * i + 3] = (char)w;
   }
   out.write(buf.data(), (std::streamsize)buf.size());
@@ -221,6 +222,7 @@ int main(int argc, char** argv) {
     }
     std::string first, frameBuf;
     long frame = 0;
+    bool sticky = false;   // a frame has been written: the stream now carries pictureio::bitDepth
     const size_t whole = pictures.size() / framePics * framePics;   // a dangling first field is never written (:236-248)
     for (size_t base = 0; base < (output == DECODED ? whole : pictures.size()); base += B) {
       const int n = (int)std::min((size_t)B, (output == DECODED ? whole : pictures.size()) - base);
@@ -242,19 +244,21 @@ int main(int argc, char** argv) {
           if (output == INDICES) {
             clog << "Writing quantisation indices to output file" << endl;
             std::string b(s.qIndices.num_elements(), '\0');
-            for (size_t j = 0; j < b.size(); ++j) b[j] = (char)s.qIndices.data()[j];
+            // one-byte words: the sticky shift 8 - chromaDepth may be negative; x86 takes the shift count modulo 32
+            const int sh = sticky ? ((8 - chromaDepth) & 31) : 0;
+            for (size_t j = 0; j < b.size(); ++j) b[j] = (char)((uint32_t)s.qIndices.data()[j] << sh);
             out->write(b.data(), (std::streamsize)b.size());
-            if ((base + i) % framePics == (size_t)framePics - 1) out->write(zeroFrame.data(), (std::streamsize)zeroFrame.size());
+            if ((base + i) % framePics == (size_t)framePics - 1) { out->write(zeroFrame.data(), (std::streamsize)zeroFrame.size()); sticky = true; }
             continue;
           }
           Picture q = s.yuvCoeffs;
           if (output != QUANTISED) q = inverse_quantise_transform_np(s.yuvCoeffs, s.qIndices, qMatrix);   // DecodeFrame.cpp:290, both modes
           if (output == QUANTISED || output == TRANSFORM) {
             clog << (output == QUANTISED ? "Writing quantised transform coefficients to output file" : "Writing transform coefficients to output file") << endl;
-            write_be32_plane(*out, q.y().data(), q.y().num_elements());
-            write_be32_plane(*out, q.c1().data(), q.c1().num_elements());
-            write_be32_plane(*out, q.c2().data(), q.c2().num_elements());
-            if ((base + i) % framePics == (size_t)framePics - 1) out->write(zeroFrame.data(), (std::streamsize)zeroFrame.size());
+            write_be32_plane(*out, q.y().data(), q.y().num_elements(), sticky ? 32 - lumaDepth : 0);
+            write_be32_plane(*out, q.c1().data(), q.c1().num_elements(), sticky ? 32 - chromaDepth : 0);
+            write_be32_plane(*out, q.c2().data(), q.c2().num_elements(), sticky ? 32 - chromaDepth : 0);
+            if ((base + i) % framePics == (size_t)framePics - 1) { out->write(zeroFrame.data(), (std::streamsize)zeroFrame.size()); sticky = true; }
             continue;
           }
           Picture pic = inverseWaveletTransform(q, kernel, depth, picFormat);
