@@ -64,6 +64,7 @@ enum vc2_status {
 #define VC2_FLAG_CBR_COMP_LENGTH    0x08u
 #define VC2_FLAG_VLC_RANGE          0x10u
 #define VC2_FLAG_STREAM             0x20u
+#define VC2_FLAG_LD_TOO_MANY_BYTES  0x40u
 #define VC2_FLAG_SEARCH_PHASE       0x80u  /* raised inside quantIndicesCBR (before any slice is written) */
 
 /* ---- PODs ----------------------------------------------------------------- */

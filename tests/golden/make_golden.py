@@ -71,6 +71,18 @@ CASES += [
 ]
 
 
+# the LD encoder (rate control with DC prediction, LD slice writer, LD picture / fragment data units)
+CASES += [
+    case("L00_LeGall_d3_420", 352, 288, "420", 8, 2, "LD", "LeGall", 3, 2, 2, s=40000, seed=400),
+    case("L01_DD97_d3_422_pad", 188, 116, "422", 10, 2, "LD", "DD97", 3, 1, 2, s=30000, seed=401),
+    case("L02_Haar1_d3_444", 128, 96, "444", 12, 2, "LD", "Haar1", 3, 1, 1, s=20000, seed=402),
+    case("L03_DD137_d2_422_lowrate", 176, 144, "422", 10, 2, "LD", "DD137", 2, 1, 2, s=6000, seed=403),
+    case("L05_LeGall_d2_420_il", 176, 144, "420", 8, 2, "LD", "LeGall", 2, 2, 2, s=24000, seed=405, extra=["-i", "-b"]),
+    case("L06_DD97_d3_422_frag", 352, 240, "422", 10, 2, "LD", "DD97", 3, 1, 2, s=60000, seed=406, extra=["-F", "1400"]),
+    case("L04_Fidelity_d2_422_il_frag", 144, 88, "422", 12, 3, "LD", "Fidelity", 2, 1, 2, s=16000, seed=404, extra=["-F", "700", "-i"]),
+]
+
+
 def md5_file(path):
     h = hashlib.md5()
     n = 0

@@ -48,13 +48,17 @@ def run(cmd):
                                   "B00_DD97_d2_420", "B06_Daub97_d3_444", "C1", "C2",
                                   # interlaced coding (two field pictures per frame) and fragmented pictures
                                   "I00_LeGall_d3_422_tff", "I01_DD137_d2_420_bff", "I02_Haar1_d3_444_tff",
-                                  "F00_DD97_d3_422", "F01_LeGall_d2_420_small", "F02_Fidelity_d2_422_il"])
+                                  "F00_DD97_d3_422", "F01_LeGall_d2_420_small", "F02_Fidelity_d2_422_il",
+                                  # the LD encoder; the reference's own decoder rejects its interlaced LD streams,
+                                  # so those cases pin the encoder side only
+                                  "L00_LeGall_d3_420", "L02_Haar1_d3_444", "L04_Fidelity_d2_422_il_frag", "L05_LeGall_d2_420_il",
+                                  "L06_DD97_d3_422_frag"])
 def test_command_lines_vs_golden(tmp_path, name):
     c, taps = GOLD[name]["params"], GOLD[name]["taps"]
     src = str(tmp_path / "in.yuv")
     write_input(c, src)
     # a batch smaller than the clip and (when there are several GPUs) two devices: chunking and reassembly
-    extra = ["-B", "1", "-G", "2"] if name[0] in "SI" else ["-B", "3"] if name[0] == "F" else []
+    extra = ["-B", "1", "-G", "2"] if name[0] in "SI" else ["-B", "3"] if name[0] in "FL" else []
     small = not name.startswith("C")       # the 1080p configs: stream and pictures only (each run pays a CUDA start-up)
     for tap in ["Stream"] + (["Packaged", "Transform", "Quantised"] if small else []) + (["Indices"] if c["mode"] != "HQ_ConstQ" else []):
         dst = str(tmp_path / ("enc_" + tap))
@@ -62,6 +66,8 @@ def test_command_lines_vs_golden(tmp_path, name):
         assert md5(dst) == taps["enc_" + tap]["md5"], (name, tap)
     stream = str(tmp_path / "enc_Stream")
     for tap in ["Decoded"] + (["Transform", "Quantised", "Indices"] if small else []):
+        if "md5" not in taps["dec_" + tap]:
+            continue          # the reference decoder fails on this stream (interlaced LD): nothing to compare with
         dst = str(tmp_path / ("dec_" + tap))
         run([os.path.join(BIN, "DecodeStream")] + extra + ["-o", tap, stream, dst])
         assert md5(dst) == taps["dec_" + tap]["md5"], (name, tap)
@@ -71,7 +77,7 @@ def test_command_lines_vs_golden(tmp_path, name):
         run([os.path.join(BIN, "EncodeStream")] + enc_args(c) + extra + ["-o", "PSNR", src, dst])
         assert open(dst).read() == taps["enc_PSNR"]["text"], (name, "PSNR")
     # EncodeStream -o Decoded = the decoder's picture (local decode loop, EncodeStream.cpp:649-767)
-    if not small:
+    if not small or "md5" not in taps["dec_Decoded"]:
         return
     dst = str(tmp_path / "enc_Decoded")
     run([os.path.join(BIN, "EncodeStream")] + enc_args(c) + ["-o", "Decoded", src, dst])

@@ -517,6 +517,7 @@ static int flags_to_status(unsigned f) {
   if (f & VC2_FLAG_SCALAR_TOO_SMALL) return VC2_ERR_SCALAR_TOO_SMALL;
   if (f & VC2_FLAG_CBR_TOO_MANY_BYTES) return VC2_ERR_CBR_TOO_MANY_BYTES;
   if (f & VC2_FLAG_CBR_COMP_LENGTH) return VC2_ERR_CBR_COMPONENT_LENGTH;
+  if (f & VC2_FLAG_LD_TOO_MANY_BYTES) return VC2_ERR_LD_TOO_MANY_BYTES;
   if (f & VC2_FLAG_VLC_RANGE) return VC2_ERR_VLC_RANGE;
   if (f & VC2_FLAG_STREAM) return VC2_ERR_STREAM;
   return VC2_OK;
@@ -846,6 +847,9 @@ struct vc2_codec {
   // device buffers
   DevBuf samples, recon, coef, scratch0, scratch1, payload, slice_off, err, qidx, staging, sizes, sbytes, fixed, tmp_plane, tmp_q;
   DevBuf dev_len;                     // [B] payload bytes of each slot: written by the encoder's scan or by upload_payload
+  DevBuf ld_qcoef, ld_acbits, ld_restored;   // LD encoder only, allocated at its first use
+  long long ld_ll_stride = 0;
+  int ld_ll_off[3] = {0, 0, 0}, ld_ll_w[3] = {0, 0, 0};
   std::vector<uint32_t> len32;        // host copy the uploads are staged from
   long long scratch_stride[2] = {0, 0};
   long long scratch_off[2][3];
@@ -881,7 +885,8 @@ static void codec_free(vc2_codec* k) {
   cudaSetDevice(k->ctx->device);
   cudaStreamSynchronize(k->ctx->stream);
   DevBuf* all[] = {&k->samples, &k->recon, &k->coef, &k->scratch0, &k->scratch1, &k->payload, &k->slice_off, &k->err,
-                   &k->qidx, &k->staging, &k->sizes, &k->sbytes, &k->fixed, &k->tmp_plane, &k->tmp_q, &k->dev_len};
+                   &k->qidx, &k->staging, &k->sizes, &k->sbytes, &k->fixed, &k->tmp_plane, &k->tmp_q, &k->dev_len,
+                   &k->ld_qcoef, &k->ld_acbits, &k->ld_restored};
   for (DevBuf* b : all) b->release();
   if (k->host_flags) cudaFreeHost(k->host_flags);
   if (k->host_len) cudaFreeHost(k->host_len);
@@ -1031,12 +1036,71 @@ static void codec_compbufs(vc2_codec* k, CompBuf cb[3], int first_slot, bool rec
   }
 }
 
+// LD encoder buffers: quantised coefficients, the per-slice bit tables of every index, the locally decoded LL bands
+static int codec_ld_buffers(vc2_codec* k) {
+  vc2_ctx* ctx = k->ctx;
+  if (k->ld_qcoef.p) return VC2_OK;
+  const SliceGeom& g = k->g;
+  const int B = k->prm.max_pictures;
+  long long off = 0;
+  for (int c = 0; c < 3; ++c) {
+    k->ld_ll_off[c] = (int)off;
+    k->ld_ll_w[c] = g.plane[c].pw >> g.depth;
+    off += (long long)(g.plane[c].ph >> g.depth) * (g.plane[c].pw >> g.depth);
+  }
+  k->ld_ll_stride = off;
+  CU(k->ld_qcoef.reserve((size_t)g.coef_pic_stride * 4 * B));
+  CU(k->ld_acbits.reserve((size_t)k->nslices * 256 * 4 * B));
+  CU(k->ld_restored.reserve((size_t)off * 4 * B));
+  CU(k->staging.reserve((size_t)staging_words(g) * 4 * k->nslices * B));
+  return VC2_OK;
+}
+
 static int codec_encode_range(vc2_codec* k, int first, int n) {
   vc2_ctx* ctx = k->ctx;
-  if (k->prm.mode == VC2_LD) return fail(ctx, VC2_ERR_ARG, "LD is decode-only");
   CompBuf cb[3];
   codec_compbufs(k, cb, first, false);
   CU(run_dwt(ctx, false, k->prm.geom.kernel, k->prm.geom.depth, k->sample_kind, k->g, cb, 3, n));
+  if (k->prm.mode == VC2_LD) {
+    // EncodeStream.cpp:141-245 (rate control), Quantisation.cpp:213-282 (predictive quantiser), Slices.cpp:195-244 (writer)
+    const int st = codec_ld_buffers(k);
+    if (st) return st;
+    LdEncParams p;
+    memset(&p, 0, sizeof(p));
+    p.g = k->g;
+    p.coef = k->coef.as<int32_t>() + (long long)first * k->g.coef_pic_stride;
+    p.qcoef = k->ld_qcoef.as<int32_t>() + (long long)first * k->g.coef_pic_stride;
+    p.acbits = k->ld_acbits.as<uint32_t>() + (size_t)first * k->nslices * 256;
+    p.qidx = k->qidx.as<int32_t>() + (size_t)first * k->nslices;
+    p.restored = k->ld_restored.as<int32_t>() + (long long)first * k->ld_ll_stride;
+    p.ll_stride = k->ld_ll_stride;
+    for (int c = 0; c < 3; ++c) { p.ll_off[c] = k->ld_ll_off[c]; p.ll_w[c] = k->ld_ll_w[c]; }
+    p.slice_bytes = k->sbytes.as<int32_t>();
+    p.staging = k->staging.as<uint32_t>() + (size_t)first * k->nslices * staging_words(k->g);
+    p.wcap = staging_words(k->g);
+    p.sizes = k->sizes.as<uint32_t>() + (size_t)first * k->nslices;
+    p.err_flags = k->err.as<uint32_t>() + (size_t)first * k->nslices;
+    {
+      ProfScope ps(ctx, VC2_STAGE_PACK);
+      CU(ld_encode_launch(ctx->stream, p, n));
+    }
+    ctx->launches += 3;
+    AssembleParams a;
+    memset(&a, 0, sizeof(a));
+    a.nslices = k->nslices;
+    a.sizes = p.sizes; a.fixed_off = k->fixed.as<uint32_t>();
+    a.slice_off = k->slice_off.as<uint32_t>() + (size_t)first * (k->nslices + 1);
+    a.total_len = k->dev_len.as<uint32_t>() + first;
+    a.staging = p.staging; a.wcap = p.wcap;
+    a.out = k->payload.as<uint8_t>() + (size_t)first * k->payload_cap;
+    a.out_pic_stride = (long long)k->payload_cap; a.out_capacity = (long long)k->payload_cap; a.err_flags = p.err_flags;
+    {
+      ProfScope ps(ctx, VC2_STAGE_ASSEMBLE);
+      CU(assemble_launch(ctx->stream, a, n));
+    }
+    ctx->launches += 2;
+    return VC2_OK;
+  }
   PackBuffers B;
   B.out = k->payload.as<uint8_t>() + (size_t)first * k->payload_cap;
   B.out_stride = (long long)k->payload_cap; B.out_capacity = (long long)k->payload_cap;
@@ -1281,6 +1345,15 @@ extern "C" int vc2_codec_read_quantised(vc2_codec* k, int slot, int32_t* y, int3
   for (int c = 0; c < 3; ++c) {
     if (!dst[c]) continue;
     const PlaneGeom& pg = k->g.plane[c];
+    if (k->prm.mode == VC2_LD) {
+      // the LD encoder keeps its quantised coefficients (LL band: prediction residuals, Quantisation.cpp:213-231)
+      if (!k->ld_qcoef.p) return fail(ctx, VC2_ERR_ARG, "no LD picture has been encoded");
+      CU(layout_launch(ctx->stream, false, k->ld_qcoef.as<int32_t>() + (long long)slot * k->g.coef_pic_stride, k->tmp_plane.as<int32_t>(), k->g, c));
+      ctx->launches++;
+      CU(cudaMemcpyAsync(dst[c], k->tmp_plane.p, (size_t)pg.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
+      CU(cudaStreamSynchronize(ctx->stream));
+      continue;
+    }
     CU(layout_launch(ctx->stream, false, vc2_codec_coeffs_dev(k, slot), k->tmp_plane.as<int32_t>(), k->g, c));
     QuantParams p;
     memset(&p, 0, sizeof(p));

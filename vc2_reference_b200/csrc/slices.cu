@@ -424,6 +424,269 @@ __global__ void __launch_bounds__(128) hq_pack_kernel(const PackParams p) {
 }
 
 // ------------------------------------------------------------------------------------------
+// LD encoder.  The reference picks the slice quantisers in raster order (quantIndicesLD,
+// EncodeStream.cpp:193-245): seven probes of a binary search per slice, each probe quantising the whole
+// slice - with the LL band predicted from its already decoded neighbours, which is what chains the slices
+// together.  Only the few LL samples of a slice take part in that chain, so the work is split in three:
+//   1. ld_ac_bits_kernel   every slice x every index 0..127, in parallel: bits up to the last non-zero
+//                          coefficient of the bands other than LL (luma list; U/V interleaved list)
+//   2. ld_rate_kernel      one CTA per picture walks the slice anti-diagonals (a slice needs its W, N and NW
+//                          neighbours): the reference's search with the LL samples quantised for real and the
+//                          rest looked up; leaves the chosen index, the locally decoded LL band and the
+//                          quantised LL residuals
+//   3. ld_pack_kernel      one thread per slice: quantise + the LD slice syntax (Slices.cpp:195-244)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int ld_intlog2(int v) {   // utils::intlog2 (Utils.cpp:40-48)
+  int lg = 0;
+  --v;
+  while (v > 0) { v >>= 1; ++lg; }
+  return lg;
+}
+__device__ __forceinline__ int lut_bits(const uint32_t* lut, uint32_t mag) {   // SignedVLC(v).numOfBits(), v of magnitude mag
+  if (mag < (uint32_t)ENC_LUT_MAG) return (int)(lut[2u * mag] & 31u);
+  return 2 * (31 - __clz(min(mag + 1u, 65535u))) + 2;
+}
+
+__global__ void __launch_bounds__(128) ld_ac_bits_kernel(const LdEncParams p) {
+  __shared__ uint32_t s_enc[2 * ENC_LUT_MAG];
+  stage_table(s_enc, d_enc_lut, 2 * ENC_LUT_MAG);
+  __syncthreads();
+  const SliceGeom& g = p.g;
+  const int nslices = g.slices_x * g.slices_y;
+  const int pic = blockIdx.z, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int s = blockIdx.x * 32 + lane;        // the four warps of a CTA share one group of 32 slices
+  if (s >= nslices) return;
+  const int nc4 = g.comp_start[3] >> 2;
+  const int4* src = reinterpret_cast<const int4*>(p.coef + (long long)pic * g.coef_pic_stride) + (size_t)(s >> 5) * nc4 * 32 + (s & 31);
+  uint32_t* tab = p.acbits + ((long long)pic * nslices + s) * 256;
+  // q is warp uniform: blockIdx.y * 32 .. + 31, eight per warp
+  for (int qi = 0; qi < 8; ++qi) {
+    const int q = blockIdx.y * 32 + warp * 8 + qi;
+    bool badq = false;
+    unsigned res[2];
+    for (int cls = 0; cls < 2; ++cls) {          // luma list, then the U/V interleaved list
+      const int c = cls;                           // band geometry of Y, or of the chroma planes
+      const int n = g.band_start[c][g.nbands], nll = g.band_start[c][1];
+      const int4* a = src + (size_t)(g.comp_start[cls == 0 ? 0 : 1] >> 2) * 32;
+      const int4* bsrc = src + (size_t)(g.comp_start[2] >> 2) * 32;
+      int gross = 0, last = 0, k = 0, b = 0, bend = g.band_start[c][1];
+      BandP bp = band_params(q, g.qmatrix[0], badq);
+      for (int piece = 0; piece < (n >> 2); ++piece) {
+        const int4 u4 = __ldg(a + (size_t)piece * 32);
+        int4 v4 = u4;
+        if (cls) v4 = __ldg(bsrc + (size_t)piece * 32);
+        const int u[4] = {u4.x, u4.y, u4.z, u4.w}, v[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e, ++k) {
+          while (k == bend) { ++b; bend = g.band_start[c][b + 1]; bp = band_params(q, g.qmatrix[b], badq); }
+          if (k < nll) continue;                   // the LL band belongs to the rate kernel
+          uint32_t mag = quant_mag(u[e], bp);
+          gross += lut_bits(s_enc, mag);
+          if (mag) last = gross;
+          if (cls) {
+            mag = quant_mag(v[e], bp);
+            gross += lut_bits(s_enc, mag);
+            if (mag) last = gross;
+          }
+        }
+      }
+      res[cls] = (unsigned)last;
+    }
+    tab[2 * q] = badq ? 0xFFFFFFFFu : res[0];
+    tab[2 * q + 1] = badq ? 0xFFFFFFFFu : res[1];
+  }
+}
+
+// the LL samples of one slice for trial index q: quantise against the prediction, restore, count bits.
+// Returns false when the index is outside the quantiser table (Quantisation.cpp:60-63).
+struct LdLL {
+  const LdEncParams* p;
+  int32_t* rest;               // this picture's restored LL planes
+  const int32_t* coefpic;      // this picture's coefficient block
+  int32_t* qpic;               // this picture's quantised block (LL residuals are stored here)
+  int nc4;
+  __device__ __forceinline__ int predict(const int32_t* r, int w, int y, int x) const {   // predictDC (Quantisation.cpp:191-208)
+    if (y > 0 && x > 0) {
+      const int sum = r[(y - 1) * w + x - 1] + r[(y - 1) * w + x] + r[y * w + x - 1];
+      return sum >= 0 ? (sum + 1) / 3 : (sum - 1) / 3;
+    }
+    if (y > 0) return r[(y - 1) * w + x];
+    if (x > 0) return r[y * w + x - 1];
+    return 0;
+  }
+  // class 0: luma LL samples; class 1: U and V LL samples interleaved.  gross / last as in luma_slice_bits / chroma_slice_bits
+  __device__ __forceinline__ void run(const uint32_t* lut, int s, int sy, int sx, int q, int cls, bool store, int& gross, int& last) const {
+    const SliceGeom& g = p->g;
+    const int aq = max(q - g.qmatrix[0], 0);
+    const QParam qp = qparam(aq);
+    const int c0 = cls == 0 ? 0 : 1, ncomp = cls == 0 ? 1 : 2;
+    const int bh = g.part_h[c0][0], bw = g.part_w[c0][0];
+    gross = 0; last = 0;
+    for (int ly = 0; ly < bh; ++ly)
+      for (int lx = 0; lx < bw; ++lx)
+        for (int j = 0; j < ncomp; ++j) {
+          const int c = c0 + j;
+          int32_t* r = rest + p->ll_off[c];
+          const int w = p->ll_w[c], y = sy * bh + ly, x = sx * bw + lx;
+          const long long idx = coef_index(s, g.comp_start[c] + ly * bw + lx, nc4);
+          const int pred = predict(r, w, y, x);
+          const int qv = quant_one(coefpic[idx] - pred, qp.qm, qp.ql);
+          r[y * w + x] = scale_one(qv, qp.qf, qp.qo) + pred;
+          if (store) qpic[idx] = qv;
+          gross += lut_bits(lut, (uint32_t)abs(qv));
+          if (qv) last = gross;
+        }
+  }
+};
+
+__global__ void __launch_bounds__(256) ld_rate_kernel(const LdEncParams p) {
+  __shared__ uint32_t s_enc[2 * ENC_LUT_MAG];
+  stage_table(s_enc, d_enc_lut, 2 * ENC_LUT_MAG);
+  __syncthreads();
+  const SliceGeom& g = p.g;
+  const int nslices = g.slices_x * g.slices_y, pic = blockIdx.x;
+  LdLL ll;
+  ll.p = &p;
+  ll.rest = p.restored + (long long)pic * p.ll_stride;
+  ll.coefpic = p.coef + (long long)pic * g.coef_pic_stride;
+  ll.qpic = p.qcoef + (long long)pic * g.coef_pic_stride;
+  ll.nc4 = g.comp_start[3] >> 2;
+  for (int diag = 0; diag < g.slices_y + g.slices_x - 1; ++diag) {
+    const int vlo = max(0, diag - (g.slices_x - 1)), vhi = min(g.slices_y - 1, diag);
+    for (int v = vlo + (int)threadIdx.x; v <= vhi; v += blockDim.x) {
+      const int h = diag - v, s = v * g.slices_x + h;
+      const long long sidx = (long long)pic * nslices + s;
+      const uint32_t* tab = p.acbits + sidx * 256;
+      const int bytes = p.slice_bytes[s];
+      const int avail = 8 * bytes - 7 - ld_intlog2(8 * bytes - 7);
+      unsigned flags = 0;
+      auto probe = [&](int q, bool store, int& bits) -> bool {   // bits the slice needs at index q
+        const unsigned acy = tab[2 * q], acuv = tab[2 * q + 1];
+        if (acy == 0xFFFFFFFFu || max(q - g.qmatrix[0], 0) > 119) return false;
+        int gy, ly, guv, luv;
+        ll.run(s_enc, s, v, h, q, 0, store, gy, ly);
+        ll.run(s_enc, s, v, h, q, 1, store, guv, luv);
+        bits = (acy ? gy + (int)acy : ly) + (acuv ? guv + (int)acuv : luv);
+        return true;
+      };
+      int trialQ = 63, q = 127, delta = 64, bits = 0;
+      bool dead = false;
+      while (delta > 0) {
+        delta >>= 1;
+        if (!probe(trialQ, false, bits)) { dead = true; break; }
+        if (bits <= avail) { if (trialQ < q) q = trialQ; trialQ -= delta; }
+        else trialQ += delta;
+      }
+      // the slice is quantised again with the chosen index: the neighbours predict from that state (:232-236)
+      if (!dead && !probe(q, true, bits)) dead = true;
+      if (dead) { flags |= VC2_FLAG_QUANT_INDEX | VC2_FLAG_SEARCH_PHASE; q = 0; }
+      p.qidx[sidx] = q;
+      p.err_flags[sidx] = flags;
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(128) ld_pack_kernel(const LdEncParams p) {
+  __shared__ uint32_t s_enc[2 * ENC_LUT_MAG];
+  stage_table(s_enc, d_enc_lut, 2 * ENC_LUT_MAG);
+  __syncthreads();
+  const SliceGeom& g = p.g;
+  const int nslices = g.slices_x * g.slices_y;
+  const int pic = blockIdx.y;
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= nslices) return;
+  const int nc4 = g.comp_start[3] >> 2;
+  const size_t lane_off = (size_t)(s >> 5) * nc4 * 32 + (s & 31);
+  const int4* src = reinterpret_cast<const int4*>(p.coef + (long long)pic * g.coef_pic_stride) + lane_off;
+  int4* qdst = reinterpret_cast<int4*>(p.qcoef + (long long)pic * g.coef_pic_stride) + lane_off;
+  const long long sidx = (long long)pic * nslices + s;
+  unsigned flags = p.err_flags[sidx];
+  const int qi = p.qidx[sidx];
+  const int size = p.slice_bytes[s];
+  if (flags) { p.sizes[sidx] = 0; return; }
+  bool badq = false;
+  // pass 1: quantise (the LL residuals are already in qcoef), keep the quantised values, count the bits
+  int ybits = 0, uvbits_needed = 0;
+  unsigned bigor = 0;
+  for (int cls = 0; cls < 2; ++cls) {
+    const int c = cls;
+    const int n = g.band_start[c][g.nbands], nll = g.band_start[c][1];
+    const size_t o0 = (size_t)(g.comp_start[cls == 0 ? 0 : 1] >> 2) * 32, o1 = (size_t)(g.comp_start[2] >> 2) * 32;
+    int gross = 0, last = 0, k = 0, b = 0, bend = g.band_start[c][1];
+    BandP bp = band_params(qi, g.qmatrix[0], badq);
+    for (int piece = 0; piece < (n >> 2); ++piece) {
+      const int4 u4 = __ldg(src + o0 + (size_t)piece * 32);
+      const int4 uq4 = qdst[o0 + (size_t)piece * 32];
+      int4 v4 = u4, vq4 = uq4;
+      if (cls) { v4 = __ldg(src + o1 + (size_t)piece * 32); vq4 = qdst[o1 + (size_t)piece * 32]; }
+      const int u[4] = {u4.x, u4.y, u4.z, u4.w}, v[4] = {v4.x, v4.y, v4.z, v4.w};
+      int uq[4] = {uq4.x, uq4.y, uq4.z, uq4.w}, vq[4] = {vq4.x, vq4.y, vq4.z, vq4.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e, ++k) {
+        while (k == bend) { ++b; bend = g.band_start[c][b + 1]; bp = band_params(qi, g.qmatrix[b], badq); }
+        if (k >= nll) uq[e] = quant_band(u[e], bp);
+        uint32_t mag = (uint32_t)abs(uq[e]);
+        if (mag >= (uint32_t)ENC_LUT_MAG) bigor |= mag + 1u;
+        gross += lut_bits(s_enc, mag);
+        if (mag) last = gross;
+        if (cls) {
+          if (k >= nll) vq[e] = quant_band(v[e], bp);
+          mag = (uint32_t)abs(vq[e]);
+          if (mag >= (uint32_t)ENC_LUT_MAG) bigor |= mag + 1u;
+          gross += lut_bits(s_enc, mag);
+          if (mag) last = gross;
+        }
+      }
+      qdst[o0 + (size_t)piece * 32] = make_int4(uq[0], uq[1], uq[2], uq[3]);
+      if (cls) qdst[o1 + (size_t)piece * 32] = make_int4(vq[0], vq[1], vq[2], vq[3]);
+    }
+    if (cls == 0) ybits = last; else uvbits_needed = last;
+  }
+  // Slices.cpp:203-213
+  const int split = ld_intlog2(8 * size - 7);
+  const int uvbits = 8 * size - 7 - split - ybits;
+  if (uvbits < uvbits_needed) flags |= VC2_FLAG_LD_TOO_MANY_BYTES;
+  if (badq) flags |= VC2_FLAG_QUANT_INDEX;
+  if (bigor >> 16) flags |= VC2_FLAG_VLC_RANGE;
+  if (flags & ~VC2_FLAG_VLC_RANGE) { p.err_flags[sidx] = flags; p.sizes[sidx] = 0; return; }
+  // pass 2: qindex (7 bits) | luma length | luma, bounded to its exact length | U/V interleaved, bounded to the rest
+  BitWriter W;
+  W.init(p.staging + sidx * p.wcap);
+  W.put((uint32_t)qi & 0x7Fu, 7);
+  W.put((uint32_t)ybits, split);
+  for (int cls = 0; cls < 2; ++cls) {
+    const int c = cls;
+    const int n = g.band_start[c][g.nbands];
+    const size_t o0 = (size_t)(g.comp_start[cls == 0 ? 0 : 1] >> 2) * 32, o1 = (size_t)(g.comp_start[2] >> 2) * 32;
+    const int start = W.pos();
+    for (int piece = 0; piece < (n >> 2); ++piece) {
+      const int4 uq4 = qdst[o0 + (size_t)piece * 32];
+      int4 vq4 = uq4;
+      if (cls) vq4 = qdst[o1 + (size_t)piece * 32];
+      const int uq[4] = {uq4.x, uq4.y, uq4.z, uq4.w}, vq[4] = {vq4.x, vq4.y, vq4.z, vq4.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        uint32_t code;
+        int nb;
+        unsigned dummy = 0;
+        vlc_of(s_enc, (uint32_t)abs(uq[e]), uq[e] < 0, dummy, code, nb);
+        W.put(code, nb);
+        if (cls) {
+          vlc_of(s_enc, (uint32_t)abs(vq[e]), vq[e] < 0, dummy, code, nb);
+          W.put(code, nb);
+        }
+      }
+    }
+    // vlc::bounded + flush (VLC.cpp:151-185): ones beyond the bound are dropped, zeros fill up to it
+    W.seek(start + (cls == 0 ? ybits : uvbits));
+  }
+  W.finish();
+  p.err_flags[sidx] = flags;
+  p.sizes[sidx] = (uint32_t)size;
+}
+
+// ------------------------------------------------------------------------------------------
 // Slice offsets = exclusive scan of the slice sizes in raster order (one CTA per picture), or the
 // a-priori table in CBR mode.
 // ------------------------------------------------------------------------------------------
@@ -919,6 +1182,18 @@ __global__ void __launch_bounds__(1024) ld_dc_kernel(const LdDcParams p) {
 cudaError_t pack_launch(cudaStream_t s, const PackParams& p, int npictures) {
   const int nslices = p.g.slices_x * p.g.slices_y;
   hq_pack_kernel<<<dim3((nslices + 127) / 128, npictures), 128, 0, s>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t ld_encode_launch(cudaStream_t s, const LdEncParams& p, int npictures) {
+  const int nslices = p.g.slices_x * p.g.slices_y;
+  ld_ac_bits_kernel<<<dim3((nslices + 31) / 32, 4, npictures), 128, 0, s>>>(p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  ld_rate_kernel<<<npictures, 256, 0, s>>>(p);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  ld_pack_kernel<<<dim3((nslices + 127) / 128, npictures), 128, 0, s>>>(p);
   return cudaGetLastError();
 }
 

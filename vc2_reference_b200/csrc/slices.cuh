@@ -103,6 +103,25 @@ struct LdDcParams {             // LD LL-band reconstruction with DC prediction 
   int qm0;
 };
 
+// LD encoder (EncodeStream.cpp:139-245 quantIndicesLD, Quantisation.cpp:213-282 predictive quantiser,
+// Slices.cpp:51-96 slice bit counts, :195-244 LD slice writer)
+struct LdEncParams {
+  SliceGeom g;
+  const int32_t* coef;          // [pic] group-interleaved transform coefficients
+  int32_t* qcoef;               // [pic] same layout, out: quantised coefficients (LL band: quantised prediction residual)
+  uint32_t* acbits;             // [pic][slice][128][2]: bits up to the last non-zero AC coefficient, luma | chroma pair
+  int32_t* qidx;                // [pic][slices] out
+  int32_t* restored;            // [pic][3][LL band] scratch: locally decoded LL band
+  long long ll_stride;          // elements per picture of `restored` (3 planes)
+  int ll_off[3], ll_w[3];       // start and width of each component's LL band inside a picture's block
+  const int32_t* slice_bytes;   // [slices]
+  uint32_t* staging;            // [pic][slices][wcap]
+  int wcap;
+  uint32_t* sizes;              // [pic][slices] out
+  uint32_t* err_flags;          // [pic][slices] out
+};
+cudaError_t ld_encode_launch(cudaStream_t s, const LdEncParams& p, int npictures);
+
 cudaError_t upload_quant_tables(const QuantTables& t);
 cudaError_t pack_launch(cudaStream_t s, const PackParams& p, int npictures);
 cudaError_t assemble_launch(cudaStream_t s, const AssembleParams& p, int npictures);
