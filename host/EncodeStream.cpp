@@ -7,7 +7,7 @@
 // fragmented pictures (-F, DataUnit.cpp:267-342) are a host-side re-chunking of the packed slices.
 // -o PSNR (EncodeStream.cpp:676-767) reports, per frame, the mean / standard deviation of the slice quantiser indices
 // and the PSNR of the local decode, with the reference's float arithmetic.
-// Not built here (SURVEY.md 8f "next" rows): LD encoding.
+// LD mode (-m LD; quantIndicesLD EncodeStream.cpp:139-245, LD slice and data unit syntax) runs on the same codec.
 #include <cstdio>
 #include <cstdlib>
 #include <cmath>
@@ -129,7 +129,6 @@ Params parse(int argc, char** argv) {
   if (p.mode == HQ_ConstQ && (p.qIndex < 0 || p.qIndex > 119)) throw std::invalid_argument("quantisation index must be in the range 0 to 119");
   if (p.frameRate < 0 || p.frameRate > 16) throw std::invalid_argument("Invalid Frame Rate: ");
   // scope of this build
-  if (p.mode == LD) throw std::invalid_argument("LD encoding is not available in this build (LD streams are decode-only)");
   if (p.bytes > 2) throw std::invalid_argument("this build reads 1 or 2 bytes per sample");
   if (p.gpus < 1) p.gpus = 1;
   if (p.batch < 1) p.batch = 1;
@@ -235,10 +234,12 @@ int main(int argc, char** argv) {
     }
 
     vc2_codec_params cp;
-    if (vc2_make_geom(format.lumaHeight(), p.width, (int)p.cf, (int)p.kernel, p.depth, p.ySize, p.xSize, p.prefix, p.scalar, &cp.geom) != VC2_OK)
+    const bool ld = p.mode == LD;
+    if (vc2_make_geom(format.lumaHeight(), p.width, (int)p.cf, (int)p.kernel, p.depth, p.ySize, p.xSize, ld ? 0 : p.prefix, ld ? 1 : p.scalar,
+                      &cp.geom) != VC2_OK)
       throw std::logic_error("The given waveletDepth, hSlice, and vSlice parameters cannot encode this input. See above for suggested parameters.");
     cp.fmt.bytes_per_sample = p.bytes; cp.fmt.luma_depth = p.lumaDepth; cp.fmt.chroma_depth = p.chromaDepth;
-    cp.mode = p.mode == HQ_CBR ? VC2_HQ_CBR : VC2_HQ_VBR;
+    cp.mode = ld ? VC2_LD : p.mode == HQ_CBR ? VC2_HQ_CBR : VC2_HQ_VBR;
     cp.qindex = p.qIndex; cp.picture_bytes = pictureBytes;
     const bool taps = p.output == TRANSFORM || p.output == QUANTISED || p.output == INDICES;
     const int G = taps ? 1 : std::min(p.gpus, std::max(1, vc2_device_count()));
@@ -258,19 +259,20 @@ int main(int argc, char** argv) {
     if (p.output == STREAM) {
       if (p.verbose) clog << endl << "Writing Sequence Header" << endl << endl;
       // fragmentedPictures raises the stream to major version 3 (DataUnit.cpp:1062-1067, 1412-1421)
-      writer.startSequence(unit, SequenceHeader(PROFILE_HQ, frameFormat.lumaHeight(), frameFormat.lumaWidth(), frameFormat.chromaFormat(),
+      writer.startSequence(unit, SequenceHeader(ld ? PROFILE_LD : PROFILE_HQ, frameFormat.lumaHeight(), frameFormat.lumaWidth(), frameFormat.chromaFormat(),
                                                 p.interlaced, (FrameRate)p.frameRate, p.topFieldFirst, p.lumaDepth, p.fragment > 0));
       out->write(unit.data(), (std::streamsize)unit.size());
     }
     PicturePreamble pre;
     pre.wavelet_kernel = p.kernel; pre.depth = p.depth; pre.slices_x = xSlices; pre.slices_y = ySlices;
-    pre.slice_prefix = p.prefix; pre.slice_size_scalar = p.scalar; pre.slice_bytes = rationalise(0, 1);
+    pre.slice_prefix = p.prefix; pre.slice_size_scalar = p.scalar;
+    pre.slice_bytes = ld ? rationalise(pictureBytes, ySlices * xSlices) : rationalise(0, 1);   // EncodeStream.cpp:628-635
     // fragments (HQ_CBR only, EncodeParams.cpp:181): the slice sizes are known a priori (slice_bytes, Slices.cpp:28-49)
     std::vector<uint32_t> sliceOff;
     if (p.fragment > 0) {
-      const Array2D sb = slice_bytes(ySlices, xSlices, pictureBytes, p.scalar);
+      const Array2D sb = slice_bytes(ySlices, xSlices, pictureBytes, ld ? 1 : p.scalar);
       sliceOff.assign((size_t)ySlices * xSlices + 1, 0);
-      for (int i = 0; i < ySlices * xSlices; ++i) sliceOff[i + 1] = sliceOff[i] + (uint32_t)(sb.data()[i] + p.prefix);
+      for (int i = 0; i < ySlices * xSlices; ++i) sliceOff[i + 1] = sliceOff[i] + (uint32_t)(sb.data()[i] + (ld ? 0 : p.prefix));
     }
 
     // one round = up to G batches of B pictures; frames[g][i] is picture number frame0 + g*B + i
@@ -321,7 +323,10 @@ int main(int argc, char** argv) {
             // picture number = field + frame * fields per frame, wrapping at 2^32 (Utils.cpp:52-63)
             if (p.fragment > 0) {
               if (w.len[i] != sliceOff.back()) throw std::logic_error("fragment writer: payload length does not match the slice table");
-              writer.hqFragmentedPicture(unit, (unsigned long)(frame & 0xFFFFFFFFull), pre, w.payload[i].data(), sliceOff.data(), p.fragment);
+              if (ld) writer.ldFragmentedPicture(unit, (unsigned long)(frame & 0xFFFFFFFFull), pre, w.payload[i].data(), sliceOff.data(), p.fragment);
+              else writer.hqFragmentedPicture(unit, (unsigned long)(frame & 0xFFFFFFFFull), pre, w.payload[i].data(), sliceOff.data(), p.fragment);
+            } else if (ld) {
+              writer.ldPicture(unit, (unsigned long)(frame & 0xFFFFFFFFull), pre, w.payload[i].data(), w.len[i]);
             } else {
               writer.hqPicture(unit, (unsigned long)(frame & 0xFFFFFFFFull), pre, w.payload[i].data(), w.len[i]);
             }

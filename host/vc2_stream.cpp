@@ -224,39 +224,49 @@ void StreamWriter::startSequence(std::string& out, const SequenceHeader& hdr) {
   out += body;
 }
 
+void StreamWriter::transformParameters(std::string& out, const PicturePreamble& p, bool ld, bool asymFlags) {
+  BitSink b(out);
+  b.uvlc((unsigned)p.wavelet_kernel); b.uvlc(p.depth);
+  if (asymFlags) { b.bit(false); b.bit(false); }   // asym_transform_index_flag, asym_transform_flag
+  b.uvlc(p.slices_x); b.uvlc(p.slices_y);
+  if (ld) { b.uvlc(p.slice_bytes.numerator); b.uvlc(p.slice_bytes.denominator); }
+  else { b.uvlc(p.slice_prefix); b.uvlc(p.slice_size_scalar); }
+  b.bit(false);                                      // no custom quantisation matrix
+  b.align();
+}
+
 void StreamWriter::hqPicture(std::string& out, unsigned long pictureNumber, const PicturePreamble& p, const uint8_t* slices, size_t len) {
   std::string hdr;
   be(hdr, (unsigned)pictureNumber, 4);
-  BitSink b(hdr);
-  b.uvlc((unsigned)p.wavelet_kernel); b.uvlc(p.depth);
-  if (major_ >= 3) { b.bit(false); b.bit(false); }   // asym_transform_index_flag, asym_transform_flag (:249-252)
-  b.uvlc(p.slices_x); b.uvlc(p.slices_y); b.uvlc(p.slice_prefix); b.uvlc(p.slice_size_scalar);
-  b.bit(false);                                      // no custom quantisation matrix
-  b.align();
+  transformParameters(hdr, p, false, major_ >= 3);   // :249-252
   parseInfo(out, 0xE8, (unsigned)(hdr.size() + len) + 13);
   out += hdr;
   out.append(reinterpret_cast<const char*>(slices), len);
 }
 
-void StreamWriter::hqFragmentedPicture(std::string& out, unsigned long pictureNumber, const PicturePreamble& p, const uint8_t* slices,
-                                       const uint32_t* slice_off, int fragmentLength) {
-  {   // the parameter fragment (:268-293): slice count 0
+void StreamWriter::ldPicture(std::string& out, unsigned long pictureNumber, const PicturePreamble& p, const uint8_t* slices, size_t len) {
+  std::string hdr;
+  be(hdr, (unsigned)pictureNumber, 4);
+  transformParameters(hdr, p, true, major_ >= 3);    // :138-141
+  parseInfo(out, 0xC8, (unsigned)(hdr.size() + len) + 13);
+  out += hdr;
+  out.append(reinterpret_cast<const char*>(slices), len);
+}
+
+void StreamWriter::fragmented(std::string& out, unsigned char code, bool ld, unsigned long pictureNumber, const PicturePreamble& p,
+                              const uint8_t* slices, const uint32_t* slice_off, int fragmentLength) {
+  {   // the parameter fragment (:155-178, :268-293): slice count 0; the asymmetric transform flags are always present here
     std::string prm;
-    BitSink b(prm);
-    b.uvlc((unsigned)p.wavelet_kernel); b.uvlc(p.depth);
-    b.bit(false); b.bit(false);                        // asym_transform_index_flag, asym_transform_flag: always present here
-    b.uvlc(p.slices_x); b.uvlc(p.slices_y); b.uvlc(p.slice_prefix); b.uvlc(p.slice_size_scalar);
-    b.bit(false);
-    b.align();
-    parseInfo(out, 0xEC, (unsigned)prm.size() + 8 + 13);
+    transformParameters(prm, p, ld, true);
+    parseInfo(out, code, (unsigned)prm.size() + 8 + 13);
     be(out, (unsigned)pictureNumber, 4);
     be(out, (unsigned)prm.size(), 2);
     be(out, 0, 2);
     out += prm;
   }
-  auto emit = [&](int first, int count) {                // :306-313, :331-338
+  auto emit = [&](int first, int count) {                // :198-205, :224-231, :306-313, :331-338
     const unsigned bytes = slice_off[first + count] - slice_off[first];
-    parseInfo(out, 0xEC, bytes + 12 + 13);
+    parseInfo(out, code, bytes + 12 + 13);
     be(out, (unsigned)pictureNumber, 4);
     be(out, bytes, 2);
     be(out, (unsigned)count, 2);
@@ -272,6 +282,16 @@ void StreamWriter::hqFragmentedPicture(std::string& out, unsigned long pictureNu
     ++count;
   }
   emit(first, count);
+}
+
+void StreamWriter::hqFragmentedPicture(std::string& out, unsigned long pictureNumber, const PicturePreamble& p, const uint8_t* slices,
+                                       const uint32_t* slice_off, int fragmentLength) {
+  fragmented(out, 0xEC, false, pictureNumber, p, slices, slice_off, fragmentLength);
+}
+
+void StreamWriter::ldFragmentedPicture(std::string& out, unsigned long pictureNumber, const PicturePreamble& p, const uint8_t* slices,
+                                       const uint32_t* slice_off, int fragmentLength) {
+  fragmented(out, 0xCC, true, pictureNumber, p, slices, slice_off, fragmentLength);
 }
 
 void StreamWriter::endSequence(std::string& out) {   // :364-368

@@ -62,10 +62,18 @@ class StreamWriter {
   // inside `slices`.  The sequence header must have been written with major version 3 (fragmentedPictures, :1412-1421).
   void hqFragmentedPicture(std::string& out, unsigned long pictureNumber, const PicturePreamble& p, const uint8_t* slices,
                            const uint32_t* slice_off, int fragmentLength);
+  // LDWrappedPictureIO (DataUnit.cpp:125-234, parse codes 0xC8 / 0xCC): as above with the LD transform parameters
+  // (slice bytes numerator / denominator from PicturePreamble::slice_bytes)
+  void ldPicture(std::string& out, unsigned long pictureNumber, const PicturePreamble& p, const uint8_t* slices, size_t len);
+  void ldFragmentedPicture(std::string& out, unsigned long pictureNumber, const PicturePreamble& p, const uint8_t* slices,
+                           const uint32_t* slice_off, int fragmentLength);
   // dataunitio::end_sequence (:364-368)
   void endSequence(std::string& out);
  private:
   void parseInfo(std::string& out, unsigned char code, unsigned next);
+  void transformParameters(std::string& out, const PicturePreamble& p, bool ld, bool asymFlags);
+  void fragmented(std::string& out, unsigned char code, bool ld, unsigned long pictureNumber, const PicturePreamble& p,
+                  const uint8_t* slices, const uint32_t* slice_off, int fragmentLength);
   unsigned prev_;
   int major_;
 };
