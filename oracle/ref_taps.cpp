@@ -25,6 +25,7 @@ const int quant_offset(int q);
 // defined in the reference's EncodeStream.cpp (compiled with -Dmain=... below)
 const Array2D quantIndicesCBR(const Picture& coefficients, const Array1D& qMatrix,
                               const Array2D& sliceBytes, const int scalar);
+const Array2D quantIndicesLD(const Picture& coefficients, const Array1D& qMatrix, const Array2D& sliceBytes);
 
 namespace {
 std::string g_err;
@@ -167,6 +168,14 @@ int ref_cbr_qindices(const int* y, const int* u, const int* v, int lh, int lw, i
   TAP_TRY
   from_array(quantIndicesCBR(to_picture(y, u, v, lh, lw, ch, cw), to_array1(qmatrix, nbands),
                              to_array(slice_bytes_, ny, nx), scalar), out);
+  TAP_CATCH
+}
+
+// EncodeStream.cpp:193-245
+int ref_ld_qindices(const int* y, const int* u, const int* v, int lh, int lw, int ch, int cw,
+                    const int* qmatrix, int nbands, const int* slice_bytes_, int ny, int nx, int* out) {
+  TAP_TRY
+  from_array(quantIndicesLD(to_picture(y, u, v, lh, lw, ch, cw), to_array1(qmatrix, nbands), to_array(slice_bytes_, ny, nx)), out);
   TAP_CATCH
 }
 

@@ -33,6 +33,7 @@
 #define ORC_ERR_CBR_COMP_LENGTH (-6)  /* Slices.cpp:359-366 */
 #define ORC_ERR_CAPACITY (-7)
 #define ORC_ERR_STREAM (-9)
+#define ORC_ERR_LD_TOO_MANY_BYTES (-10) /* Slices.cpp:209-211 */
 
 enum { K_DD97 = 0, K_LEGALL, K_DD137, K_HAAR0, K_HAAR1, K_FIDELITY, K_DAUB97 };
 #define MAX_DEPTH 6
@@ -586,6 +587,179 @@ int orc_cbr_qindices(const int32_t* y, const int32_t* u, const int32_t* v, int l
     }
   free(idx);
   free(tmp);
+  return rc;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * LD encoder: predictive quantiser (Quantisation.cpp:213-282, 357-367), quantIndicesLD with SliceQuantiserRef
+ * (EncodeStream.cpp:139-245), LD slice writer (Slices.cpp:51-96, 195-244)
+ * ---------------------------------------------------------------------------------------------- */
+static int predict_dc(const int32_t* ll, int w, int y, int x) { /* predictDC, Quantisation.cpp:191-208 */
+  if (y > 0 && x > 0) {
+    const int s = ll[(y - 1) * w + x - 1] + ll[(y - 1) * w + x] + ll[y * w + x - 1];
+    return s >= 0 ? (s + 1) / 3 : (s - 1) / 3;
+  }
+  if (y > 0) return ll[(y - 1) * w + x];
+  if (x > 0) return ll[y * w + x - 1];
+  return 0;
+}
+
+/* quantise_transform: every band with quant(), the LL band against the prediction from the restored LL band */
+int orc_quantise_ld(const int32_t* c, int ph, int pw, const int32_t* qidx, int ny, int nx, const int32_t* qm, int nbands, int32_t* out) {
+  const int depth = (nbands - 1) / 3;
+  int rc = quant_plane(c, ph, pw, qidx, ny, nx, qm, nbands, out, 0, 0);
+  if (rc) return rc;
+  const int H = ph >> depth, W = pw >> depth;
+  const long sy = (long)pw << depth, sx = 1L << depth;
+  int32_t* restored = (int32_t*)calloc((size_t)H * W, sizeof(int32_t));
+  for (int y = 0; y < H && !rc; ++y)
+    for (int x = 0; x < W; ++x) {
+      const int yb = ((y + 1) * ny - 1) / H, xb = ((x + 1) * nx - 1) / W;
+      int q = qidx[yb * nx + xb] - qm[0];
+      if (q < 0) q = 0;
+      const int pred = predict_dc(restored, W, y, x);
+      int qv, rv;
+      rc = orc_quant(c[y * sy + x * sx] - pred, q, &qv);
+      if (!rc) rc = orc_scale(qv, q, &rv);
+      if (rc) break;
+      out[y * sy + x * sx] = qv;
+      restored[y * W + x] = rv + pred;
+    }
+  free(restored);
+  return rc;
+}
+
+/* one component of one slice at trial index q, SliceQuantiserRef::quantise_slice (EncodeStream.cpp:172-191): the LL
+ * samples (first n_ll entries of the scan list, raster inside the slice) are predicted from `restored` and update it */
+static int ld_quantise_slice(const int32_t* pl, const long* idx, int n, int n_ll, int pw, int depth, int q, const int32_t* qm,
+                             int32_t* restored, int llw, int32_t* dst) {
+  for (int i = 0; i < n; ++i) {
+    const int yy = (int)(idx[i] / pw), xx = (int)(idx[i] % pw);
+    int aq = q - qm[band_of(yy, xx, depth)];
+    if (aq < 0) aq = 0;
+    int rc;
+    if (i < n_ll) {
+      const int yl = yy >> depth, xl = xx >> depth;
+      const int pred = predict_dc(restored, llw, yl, xl);
+      int rv;
+      rc = orc_quant(pl[idx[i]] - pred, aq, &dst[i]);
+      if (!rc) rc = orc_scale(dst[i], aq, &rv);
+      if (rc) return rc;
+      restored[yl * llw + xl] = rv + pred;
+    } else {
+      rc = orc_quant(pl[idx[i]], aq, &dst[i]);
+      if (rc) return rc;
+    }
+  }
+  return ORC_OK;
+}
+static int ld_intlog2(int v) { /* Utils.cpp:40-48 */
+  int lg = 0;
+  --v;
+  while (v > 0) { v >>= 1; ++lg; }
+  return lg;
+}
+/* chroma_slice_bits (Slices.cpp:70-96): U and V coefficient by coefficient */
+static int bits_of_pair_list(const int32_t* a, const int32_t* b, int n) {
+  int gross = 0, count = 0;
+  for (int i = 0; i < n; ++i) {
+    unsigned nb, code;
+    orc_signed_vlc(a[i], &nb, &code);
+    gross += (int)nb;
+    if (nb > 1) count = gross;
+    orc_signed_vlc(b[i], &nb, &code);
+    gross += (int)nb;
+    if (nb > 1) count = gross;
+  }
+  return count;
+}
+
+int orc_ld_qindices(const int32_t* y, const int32_t* u, const int32_t* v, int lh, int lw, int ch, int cw, const int32_t* qm,
+                    int nbands, const int32_t* sbytes, int ny, int nx, int32_t* out) {
+  const int depth = (nbands - 1) / 3;
+  const plane_in P[3] = {{lh, lw, y}, {ch, cw, u}, {ch, cw, v}};
+  const size_t cap = (size_t)(lh / ny) * (lw / nx);
+  long* idx = (long*)malloc(sizeof(long) * cap);
+  int32_t* tmp[3];
+  int32_t* restored[3];
+  for (int c = 0; c < 3; ++c) {
+    tmp[c] = (int32_t*)malloc(sizeof(int32_t) * cap);
+    restored[c] = (int32_t*)calloc((size_t)(P[c].ph >> depth) * (P[c].pw >> depth), sizeof(int32_t));
+  }
+  int rc = ORC_OK;
+  for (int sy = 0; sy < ny && !rc; ++sy)
+    for (int sx = 0; sx < nx && !rc; ++sx) {
+      const int bytes = sbytes[sy * nx + sx];
+      const int avail = 8 * bytes - 7 - ld_intlog2(8 * bytes - 7);
+      int trial = 63, best = 127, delta = 64, n[3];
+      for (int pass = 0; pass < 8 && !rc; ++pass) {   /* seven probes, then the slice again with the chosen index (:232-236) */
+        const int q = pass < 7 ? trial : best;
+        for (int c = 0; c < 3 && !rc; ++c) {
+          n[c] = slice_scan(P[c].ph, P[c].pw, depth, ny, nx, sy, sx, idx);
+          const int n_ll = ((P[c].ph / ny) >> depth) * ((P[c].pw / nx) >> depth);
+          rc = ld_quantise_slice(P[c].pl, idx, n[c], n_ll, P[c].pw, depth, q, qm, restored[c], P[c].pw >> depth, tmp[c]);
+        }
+        if (rc || pass == 7) break;
+        delta >>= 1;
+        const int need = bits_of_list(tmp[0], n[0]) + bits_of_pair_list(tmp[1], tmp[2], n[1]);
+        if (need <= avail) { if (trial < best) best = trial; trial -= delta; }
+        else trial += delta;
+      }
+      out[sy * nx + sx] = best;
+    }
+  free(idx);
+  for (int c = 0; c < 3; ++c) { free(tmp[c]); free(restored[c]); }
+  return rc;
+}
+
+/* operator<<(ostream&, Slices) with LDSliceIO (Slices.cpp:195-244); planes hold QUANTISED coefficients */
+int orc_pack_slices_ld(const int32_t* y, const int32_t* u, const int32_t* v, int lh, int lw, int ch, int cw, int depth,
+                       const int32_t* qidx, int ny, int nx, const int32_t* sbytes, uint8_t* out, long cap, long* out_len) {
+  const plane_in P[3] = {{lh, lw, y}, {ch, cw, u}, {ch, cw, v}};
+  const size_t lcap = (size_t)(lh / ny) * (lw / nx);
+  long* idx = (long*)malloc(sizeof(long) * lcap);
+  int32_t* val[3];
+  for (int c = 0; c < 3; ++c) val[c] = (int32_t*)malloc(sizeof(int32_t) * lcap);
+  long pos = 0;
+  int rc = ORC_OK;
+  for (int sy = 0; sy < ny && !rc; ++sy)
+    for (int sx = 0; sx < nx && !rc; ++sx) {
+      const int size = sbytes[sy * nx + sx];
+      int n[3];
+      for (int c = 0; c < 3; ++c) {
+        n[c] = slice_scan(P[c].ph, P[c].pw, depth, ny, nx, sy, sx, idx);
+        for (int i = 0; i < n[c]; ++i) val[c][i] = P[c].pl[idx[i]];
+      }
+      const int ybits = bits_of_list(val[0], n[0]);
+      const int split = ld_intlog2(8 * size - 7);
+      const int uvbits = 8 * size - 7 - split - ybits;
+      if (uvbits < bits_of_pair_list(val[1], val[2], n[1])) { rc = ORC_ERR_LD_TOO_MANY_BYTES; break; }
+      if (pos + size > cap) { rc = ORC_ERR_CAPACITY; break; }
+      memset(out + pos, 0, (size_t)size);
+      bitw w = {out + pos, 0, 8L * size};
+      put_bits(&w, (uint32_t)qidx[sy * nx + sx] & 0x7Fu, 7);
+      put_bits(&w, (uint32_t)ybits, split);
+      /* vlc::bounded(ybits): what lies beyond the bound (only the ones of trailing zeros) is dropped */
+      w.end = 7 + split + ybits;
+      for (int i = 0; i < n[0]; ++i) {
+        unsigned nb, code;
+        orc_signed_vlc(val[0][i], &nb, &code);
+        put_bits(&w, code, (int)nb);
+      }
+      w.bit = w.end;                         /* vlc::flush */
+      w.end = 7 + split + ybits + uvbits;    /* vlc::bounded(uvbits) */
+      for (int i = 0; i < n[1]; ++i) {
+        unsigned nb, code;
+        orc_signed_vlc(val[1][i], &nb, &code);
+        put_bits(&w, code, (int)nb);
+        orc_signed_vlc(val[2][i], &nb, &code);
+        put_bits(&w, code, (int)nb);
+      }
+      pos += size;
+    }
+  free(idx);
+  for (int c = 0; c < 3; ++c) free(val[c]);
+  *out_len = pos;
   return rc;
 }
 

@@ -122,6 +122,28 @@ def dequantise_ld(coef, qidx, qmatrix):
     return _quant(lib().orc_dequantise_ld, coef, qidx, qmatrix)
 
 
+def quantise_ld(coef, qidx, qmatrix):
+    return _quant(lib().orc_quantise_ld, coef, qidx, qmatrix)
+
+
+def ld_qindices(y, u, v, qmatrix, sbytes):
+    y, u, v, qmatrix, sbytes = _i32(y), _i32(u), _i32(v), _i32(qmatrix), _i32(sbytes)
+    out = np.empty_like(sbytes)
+    _chk(lib().orc_ld_qindices(_p(y), _p(u), _p(v), y.shape[0], y.shape[1], u.shape[0], u.shape[1], _p(qmatrix), qmatrix.size,
+                               _p(sbytes), sbytes.shape[0], sbytes.shape[1], _p(out)))
+    return out
+
+
+def pack_slices_ld(y, u, v, depth, qidx, sbytes):
+    y, u, v, qidx, sb = _i32(y), _i32(u), _i32(v), _i32(qidx), _i32(sbytes)
+    cap = int(sb.sum()) + 64
+    out = np.zeros(cap, np.uint8)
+    ln = C.c_long(0)
+    _chk(lib().orc_pack_slices_ld(_p(y), _p(u), _p(v), y.shape[0], y.shape[1], u.shape[0], u.shape[1], depth, _p(qidx),
+                                  qidx.shape[0], qidx.shape[1], _p(sb), _p(out), C.c_long(cap), C.byref(ln)))
+    return out[:ln.value].tobytes()
+
+
 def slice_bytes(ny, nx, total, scalar):
     out = np.zeros((ny, nx), np.int32)
     _chk(lib().orc_slice_bytes(ny, nx, total, scalar, _p(out)))

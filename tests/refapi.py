@@ -139,6 +139,14 @@ def cbr_qindices(y, u, v, qmatrix, sbytes, scalar):
     return out
 
 
+def ld_qindices(y, u, v, qmatrix, sbytes):
+    y, u, v, qmatrix, sbytes = _i32(y), _i32(u), _i32(v), _i32(qmatrix), _i32(sbytes)
+    out = np.empty_like(sbytes)
+    _chk(lib().ref_ld_qindices(_p(y), _p(u), _p(v), y.shape[0], y.shape[1], u.shape[0], u.shape[1], _p(qmatrix), qmatrix.size,
+                               _p(sbytes), sbytes.shape[0], sbytes.shape[1], _p(out)))
+    return out
+
+
 def pack_slices(y, u, v, depth, qidx, mode, prefix, scalar, sbytes=None):
     y, u, v, qidx = _i32(y), _i32(u), _i32(v), _i32(qidx)
     sb = _i32(sbytes) if sbytes is not None else None

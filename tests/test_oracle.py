@@ -152,6 +152,26 @@ def test_hq_slices_vs_reference(ref, depth, fmt, scalar, prefix):
         assert orc.pack_slices(y, u, v, depth, qidx, 1, prefix, scalar, sb) == wantc
 
 
+@pytest.mark.parametrize("depth,fmt,total", [(2, "444", 500), (3, "422", 2500), (3, "420", 1800), (4, "422", 9000)])
+def test_ld_encoder_vs_reference(ref, depth, fmt, total):
+    """quantIndicesLD, the predictive quantiser and the LD slice writer against the compiled reference"""
+    ny, nx = 3, 4
+    y, u, v = _planes(depth, ny, nx, fmt, 20 + depth, 40.0)
+    rng = np.random.default_rng(depth)
+    for p in (y, u, v):      # a DC level, so that the prediction matters
+        p[:: 1 << depth, :: 1 << depth] += rng.integers(-900, 900, size=p[:: 1 << depth, :: 1 << depth].shape).astype(np.int32)
+    qm = ref.quant_matrix(depth % 7, depth)
+    sb = ref.slice_bytes(ny, nx, total, 1)
+    want = ref.ld_qindices(y, u, v, qm, sb)
+    got = orc.ld_qindices(y, u, v, qm, sb)
+    assert np.array_equal(got, want)
+    assert want.min() < want.max()
+    q = [ref.quantise_ld(p, want, qm) for p in (y, u, v)]
+    for p, r in zip((y, u, v), q):
+        assert np.array_equal(orc.quantise_ld(p, want, qm), r)
+    assert orc.pack_slices_ld(q[0], q[1], q[2], depth, want, sb) == ref.pack_slices(q[0], q[1], q[2], depth, want, 2, 0, 1, sb)
+
+
 def test_hq_scalar_too_small(ref):
     y, u, v = _planes(3, 2, 2, "422", 1, 4000.0)
     qidx = np.zeros((2, 2), np.int32)
