@@ -219,6 +219,7 @@ struct vc2_ctx {
   DevBuf tmp[8];   // scratch for the Library-surface (host pointer) calls
   int dwt_min_warps = 148 * 48;   // streaming DWT: cut rows into segments until the grid has at least this many warps
   int dwt_pd = 2;                 // prefetch distance in row pairs (VC2_DWT_PD)
+  int dwt_fast = 1;               // fast loop of the lifting kernels (VC2_DWT_FAST=0 turns it off)
   int dwt_seg_rows = 0;           // > 0: forced rows per warp (tuning, VC2_DWT_SEG_ROWS)
   // optional per-kernel timing with CUDA events on the launch stream (vc2_profile_*)
   bool profiling = false;
@@ -280,6 +281,7 @@ extern "C" vc2_ctx* vc2_create(int device) {
   if (const char* e = getenv("VC2_DWT_SEG_ROWS")) c->dwt_seg_rows = atoi(e) & ~1;
   if (const char* e = getenv("VC2_DWT_MIN_WARPS")) c->dwt_min_warps = atoi(e);
   if (const char* e = getenv("VC2_DWT_PD")) c->dwt_pd = atoi(e);
+  if (const char* e = getenv("VC2_DWT_FAST")) c->dwt_fast = atoi(e) != 0;
   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return nullptr; }
   c->own_stream = true;
   QuantTables t;
@@ -385,6 +387,7 @@ static cudaError_t run_dwt(vc2_ctx* ctx, bool inverse, int kernel, int depth, in
     memset(&p, 0, sizeof(p));
     p.ncomp = ncomp;
     p.pd = ctx->dwt_pd;
+    p.fast = ctx->dwt_fast;
     for (int c = 0; c < ncomp; ++c) {
       const CompBuf& B = cb[c];
       DwtComp& C = p.c[c];
@@ -950,7 +953,7 @@ extern "C" vc2_codec* vc2_codec_create(vc2_ctx* ctx, const vc2_codec_params* prm
   for (int c = 0; c < 3; ++c) {
     k->scratch_off[0][c] = s0; k->scratch_off[1][c] = s1;
     s0 += g.plane[c].size() / 4;
-    s1 += g.plane[c].size() / 16 + 1;
+    s1 += (g.plane[c].size() / 16 + 4) & ~3ll;   // every plane starts on a 16-byte boundary
   }
   k->scratch_stride[0] = s0; k->scratch_stride[1] = s1;
   R(k->scratch0, (size_t)s0 * 4 * B);

@@ -28,7 +28,7 @@ namespace {
 constexpr unsigned FULL = 0xFFFFFFFFu;
 constexpr int WARPS = 4;   // warps per CTA: four vertically adjacent row segments of one strip
 #ifndef VC2_DWT_MINB
-#define VC2_DWT_MINB 5     // resident CTAs per SM the register allocation is held to (5 -> 102 registers per thread; measured best of 4, 5, 6)
+#define VC2_DWT_MINB 4     // resident CTAs per SM the register allocation is held to (4 -> 128 registers per thread: the fast loop spills at 5)
 #endif
 
 // ---- compile-time schedule of the vertical pipeline ------------------------------------------------
@@ -58,10 +58,10 @@ struct Sched {
   static constexpr int oldestB = last_targets_A ? lag(n - 1) + reach(n - 1) : lag(n - 1);
   static constexpr int WA = oldestA / 2 + 1;
   static constexpr int WB = (oldestB - reach(0)) / 2 + 1;
-  static constexpr int U = WA * WB / cgcd(WA, WB);   // unroll period of the row-pair loop
-  // ring slot of the first row of each parity (row PA lives in A slot 0 by construction)
-  static constexpr int cB = (PA - reach(0) - PB) / 2;   // (r0 - PB) / 2 = tau + cB  (PA - PB - reach(0) is even)
-  static constexpr int firstB = pmod(-cB, WB);
+  static constexpr int WR = cmax(WA, WB);            // both rings are allocated with WR rows: the fast loop rotates them with one period
+  // smallest newest-row index for which no step of the pair needs the edge rule at the top
+  __host__ __device__ static constexpr int amin_i(int i) { return lag(i) + reach(i); }
+  static constexpr int AMIN = cmax(cmax(amin_i(0), amin_i(1)), cmax(n > 2 ? amin_i(n > 2 ? 2 : 0) : 0, n > 3 ? amin_i(n > 3 ? 3 : 0) : 0));
 };
 
 template <int K> struct Vec { static constexpr int V = (K == VC2_FIDELITY) ? 4 : 8; };
@@ -154,24 +154,24 @@ template <int K, int DIR>
 struct Rings {
   using SC = Sched<K, DIR>;
   static constexpr int V = Vec<K>::V;
-  int A[SC::WA][V];
-  int B[SC::WB][V];
+  int A[SC::WR][V];
+  int B[SC::WR][V];
   __device__ __forceinline__ void clear() {
 #pragma unroll
     for (int v = 0; v < V; ++v) {
 #pragma unroll
-      for (int i = 0; i < SC::WA; ++i) A[i][v] = 0;
+      for (int i = 0; i < SC::WR; ++i) A[i][v] = 0;
 #pragma unroll
-      for (int i = 0; i < SC::WB; ++i) B[i][v] = 0;
+      for (int i = 0; i < SC::WR; ++i) B[i][v] = 0;
     }
   }
   __device__ __forceinline__ void shift() {
 #pragma unroll
     for (int v = 0; v < V; ++v) {
 #pragma unroll
-      for (int i = SC::WA - 1; i > 0; --i) A[i][v] = A[i - 1][v];
+      for (int i = SC::WR - 1; i > 0; --i) A[i][v] = A[i - 1][v];
 #pragma unroll
-      for (int i = SC::WB - 1; i > 0; --i) B[i][v] = B[i - 1][v];
+      for (int i = SC::WR - 1; i > 0; --i) B[i][v] = B[i - 1][v];
     }
   }
 };
@@ -210,15 +210,15 @@ __device__ __forceinline__ void vstep(Rings<K, DIR>& g, int a, int r, int last) 
         l = g.B[(L + (2 * k + 1) - SC::reach(0)) / 2][v];
         rr = g.B[(L - (2 * k + 1) - SC::reach(0)) / 2][v];
         if (EDGE) {
-          if (r - (2 * k + 1) < 0) l = pick_row<SC::WB, V>(g.B, age_first, v);
-          if (r + (2 * k + 1) > last) rr = pick_row<SC::WB, V>(g.B, age_last, v);
+          if (r - (2 * k + 1) < 0) l = pick_row<SC::WR, V>(g.B, age_first, v);
+          if (r + (2 * k + 1) > last) rr = pick_row<SC::WR, V>(g.B, age_last, v);
         }
       } else {              // sources are A rows
         l = g.A[(L + (2 * k + 1)) / 2][v];
         rr = g.A[(L - (2 * k + 1)) / 2][v];
         if (EDGE) {
-          if (r - (2 * k + 1) < 0) l = pick_row<SC::WA, V>(g.A, age_first, v);
-          if (r + (2 * k + 1) > last) rr = pick_row<SC::WA, V>(g.A, age_last, v);
+          if (r - (2 * k + 1) < 0) l = pick_row<SC::WR, V>(g.A, age_first, v);
+          if (r + (2 * k + 1) > last) rr = pick_row<SC::WR, V>(g.A, age_last, v);
         }
       }
       if (ST::cl(k) == ST::cr(k)) { if (ST::cl(k) != 0) sum += (unsigned)ST::cl(k) * ((unsigned)l + (unsigned)rr); }
@@ -243,6 +243,69 @@ __device__ __forceinline__ void vstep_guarded(Rings<K, DIR>& g, int a, int H) {
   if (r - SC::reach(I) < 0 || r + SC::reach(I) > last) vstep<K, DIR, I, true>(g, a, r, last);
   else vstep<K, DIR, I, false>(g, a, r, last);
 }
+
+// ---- the fast loop: interior rows of interior strips ------------------------------------------------
+// No edge rule, no bounds or alignment tests, addresses from running pointers and 32-bit band indices.  The ring
+// accesses are written for a ROTATED ring (row of age i in slot (i + R) % WR, R a template constant); the kernels
+// use R = 0 after an ordinary shift, see the note at the loop.
+template <int K, int DIR, int I, int R>
+__device__ __forceinline__ void vstep_rot(Rings<K, DIR>& g) {
+  using SC = Sched<K, DIR>;
+  constexpr int S = SC::sidx(I);
+  using ST = Step<K, S>;
+  constexpr int V = Vec<K>::V, N = ST::N, W = SC::WR;
+  constexpr bool TA = (I % 2) == 1;
+  constexpr int L = SC::lag(I);
+  constexpr int tage = TA ? L / 2 : (L - SC::reach(0)) / 2;
+#pragma unroll
+  for (int v = 0; v < V; ++v) {
+    unsigned sum = (unsigned)ST::ADD;
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      int l, rr;
+      if constexpr (TA) {
+        l = g.B[((L + (2 * k + 1) - SC::reach(0)) / 2 + R) % W][v];
+        rr = g.B[((L - (2 * k + 1) - SC::reach(0)) / 2 + R) % W][v];
+      } else {
+        l = g.A[((L + (2 * k + 1)) / 2 + R) % W][v];
+        rr = g.A[((L - (2 * k + 1)) / 2 + R) % W][v];
+      }
+      if (ST::cl(k) == ST::cr(k)) { if (ST::cl(k) != 0) sum += (unsigned)ST::cl(k) * ((unsigned)l + (unsigned)rr); }
+      else {
+        if (ST::cl(k) != 0) sum += (unsigned)ST::cl(k) * (unsigned)l;
+        if (ST::cr(k) != 0) sum += (unsigned)ST::cr(k) * (unsigned)rr;
+      }
+    }
+    const int delta = ((int)sum) >> ST::SH;
+    int& t = TA ? g.A[(tage + R) % W][v] : g.B[(tage + R) % W][v];
+    t = (ST::SIGN * DIR > 0) ? (int)((unsigned)t + (unsigned)delta) : (int)((unsigned)t - (unsigned)delta);
+  }
+}
+template <int K, int DIR, int R>
+__device__ __forceinline__ void vsteps_rot(Rings<K, DIR>& g) {
+  vstep_rot<K, DIR, 0, R>(g);
+  vstep_rot<K, DIR, 1, R>(g);
+  if constexpr (Sched<K, DIR>::n == 4) {
+    vstep_rot<K, DIR, 2, R>(g);
+    vstep_rot<K, DIR, 3, R>(g);
+  }
+}
+
+// per-lane constants of the fast loop
+struct FastCtx {
+  int32_t* coefpic;          // this picture's coefficient block
+  int sx, kx4;               // slice column of this lane's band samples, (column inside the slice part) / 4
+  int lgbh, bhm1, bw4, nx, nc4;
+  int o_ll, o_hl, o_lh, o_hh;   // band starts, as element offsets ((base / 4) * 128)
+  int32_t* llp;              // compact LL plane at this lane's band column, or NULL (LL = band 0 of the block)
+  int ll_pitch;
+  bool store;                // this lane's columns are useful
+  __device__ __forceinline__ int idx(int by) const {   // element index of the lane's 16-byte piece in band row by (band start 0)
+    const int sy = by >> lgbh, ry = by & bhm1;
+    const int s = sy * nx + sx;
+    return ((((s >> 5) * nc4 + ry * bw4 + kx4) << 5) + (s & 31)) << 2;
+  }
+};
 
 // ---- global memory access of one lane's V columns of one row -------------------------------------------
 struct BandAddr {   // group-interleaved addressing of band samples (see vc2_common.cuh)
@@ -456,6 +519,97 @@ __device__ __forceinline__ void fwd_pair(const DwtComp& C, const StripCtx& S, co
   }
 }
 
+// ---- forward fast loop -------------------------------------------------------------------------------
+template <int K, int KIND, int PPL>
+__device__ __forceinline__ void fwd_fast_fetch(const DwtComp& C, const StripCtx& S, const uint8_t* p, int (&dst)[2 * PPL]) {
+  constexpr int V = 2 * PPL, SHIFT = Wavelet<K>::SHIFT;
+  static_assert(PPL == 4, "the fast loop moves 16-byte pieces");
+  int x[V];
+  if (KIND == SAMPLE_I32) {
+#pragma unroll
+    for (int j = 0; j < V; j += 4) {
+      const int4 q = __ldg(reinterpret_cast<const int4*>(p) + j / 4);
+      x[j] = q.x; x[j + 1] = q.y; x[j + 2] = q.z; x[j + 3] = q.w;
+    }
+  } else {
+    const uint4 q = __ldg(reinterpret_cast<const uint4*>(p));
+    const unsigned w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      x[2 * j] = (int)(__byte_perm(w[j], 0, 0x4401) >> C.sshift) - C.soffset;
+      x[2 * j + 1] = (int)(__byte_perm(w[j], 0, 0x4423) >> C.sshift) - C.soffset;
+    }
+  }
+  int e[PPL], o[PPL];
+#pragma unroll
+  for (int a = 0; a < PPL; ++a) {
+    e[a] = (int)((unsigned)x[2 * a] << SHIFT);
+    o[a] = (int)((unsigned)x[2 * a + 1] << SHIFT);
+  }
+  hsteps<K, +1, PPL>(e, o, S.lane, false, 0, 0);
+#pragma unroll
+  for (int a = 0; a < PPL; ++a) { dst[a] = e[a]; dst[PPL + a] = o[a]; }
+}
+
+template <int PPL, bool ODD>
+__device__ __forceinline__ void fwd_fast_emit(const FastCtx& F, int row, const int (&src)[2 * PPL]) {
+  if (!F.store) return;
+  const int by = row >> 1, i = F.idx(by);
+  const int4 lo = make_int4(src[0], src[1], src[2], src[3]), hi = make_int4(src[PPL], src[PPL + 1], src[PPL + 2], src[PPL + 3]);
+  if (ODD) {
+    *reinterpret_cast<int4*>(F.coefpic + i + F.o_lh) = lo;
+    *reinterpret_cast<int4*>(F.coefpic + i + F.o_hh) = hi;
+  } else {
+    if (F.llp) *reinterpret_cast<int4*>(F.llp + (long long)by * F.ll_pitch) = lo;
+    else *reinterpret_cast<int4*>(F.coefpic + i + F.o_ll) = lo;
+    *reinterpret_cast<int4*>(F.coefpic + i + F.o_hl) = hi;
+  }
+}
+
+// iteration T of a chunk; pA / pB run over the picture rows a and a - reach(0) of this lane
+template <int K, int KIND, int T>
+__device__ __forceinline__ void fwd_fast_iter(const DwtComp& C, const StripCtx& S, const FastCtx& F, Rings<K, +1>& g, int tau,
+                                              const uint8_t*& pA, const uint8_t*& pB, long long step, long long pf, int pf_last) {
+  using SC = Sched<K, +1>;
+  constexpr int V = Vec<K>::V, PPL = V / 2, n = SC::n, W = SC::WR, R = (W - 1 - T % W) % W;
+  const int a = 2 * tau + SC::PA;
+  if (a <= pf_last) { prefetch_l1(pA + pf); prefetch_l1(pB + pf); }
+  fwd_fast_fetch<K, KIND, PPL>(C, S, pA, g.A[R]);
+  fwd_fast_fetch<K, KIND, PPL>(C, S, pB, g.B[R]);
+  pA += step; pB += step;
+  vsteps_rot<K, +1, R>(g);
+  constexpr int L1 = SC::lag(n - 1), L2 = SC::lag(n - 2);
+  if constexpr (SC::last_targets_A) {
+    fwd_fast_emit<PPL, ((SC::PA - L1) & 1) != 0>(F, a - L1, g.A[(L1 / 2 + R) % W]);
+    fwd_fast_emit<PPL, ((SC::PA - L2) & 1) != 0>(F, a - L2, g.B[((L2 - SC::reach(0)) / 2 + R) % W]);
+  } else {
+    fwd_fast_emit<PPL, ((SC::PA - L1) & 1) != 0>(F, a - L1, g.B[((L1 - SC::reach(0)) / 2 + R) % W]);
+    fwd_fast_emit<PPL, ((SC::PA - L2) & 1) != 0>(F, a - L2, g.A[(L2 / 2 + R) % W]);
+  }
+}
+// band side of the fast loop: false when this level / strip has to stay on the general loop
+template <int K>
+__device__ __forceinline__ bool fast_setup(const DwtComp& C, const StripCtx& S, FastCtx& F) {
+  using G = Geo<K>;
+  constexpr int PPL = G::V / 2;
+  if (PPL != 4 || S.hedge) return false;
+  if (C.lgbh < 0 || C.lgbw < 0 || (C.bw & 3) || ((C.base_ll | C.base_hl | C.base_lh | C.base_hh) & 3)) return false;
+  const int bx0 = (S.xs >> 1) + PPL * S.lane;
+  F.coefpic = C.coef + (long long)S.pic * C.coef_pic_stride;
+  F.sx = bx0 >> C.lgbw;
+  F.kx4 = (bx0 & (C.bw - 1)) >> 2;
+  F.lgbh = C.lgbh; F.bhm1 = C.bh - 1; F.bw4 = C.bw >> 2; F.nx = C.nx; F.nc4 = C.NC >> 2;
+  F.o_ll = (C.base_ll >> 2) * 128; F.o_hl = (C.base_hl >> 2) * 128; F.o_lh = (C.base_lh >> 2) * 128; F.o_hh = (C.base_hh >> 2) * 128;
+  F.llp = nullptr; F.ll_pitch = C.ll_pitch;
+  if (C.ll) {
+    F.llp = C.ll + (long long)S.pic * C.ll_pic_stride + bx0;
+    if ((C.ll_pitch & 3) || (reinterpret_cast<uintptr_t>(C.ll + (long long)S.pic * C.ll_pic_stride) & 15)) return false;
+  }
+  if (reinterpret_cast<uintptr_t>(F.coefpic) & 15) return false;
+  F.store = S.mine;
+  return true;
+}
+
 // common strip set-up; returns false when this warp has nothing to do
 template <int K>
 __device__ __forceinline__ bool strip_setup(const DwtComp& C, int seg_rows, StripCtx& S, bool inverse) {
@@ -494,8 +648,42 @@ __global__ void __launch_bounds__(32 * WARPS, VC2_DWT_MINB) dwt_fwd_kernel(const
   // last pair: until the last step has reached row y1 - 1
   const int tau0 = max((S.y0 - SC::total_reach() - SC::PA) >> 1, 0);
   const int tau_end = (S.y1 - 1 + SC::lag(SC::n - 1) - SC::PA + 2) >> 1;
+  int tau = tau0;
+  if constexpr (Vec<K>::V == 8 && KIND != SAMPLE_U8) {
+    constexpr int W = SC::WR, esz = KIND == SAMPLE_I32 ? 4 : 2;
+    FastCtx F;
+    const uint8_t* base = (const uint8_t*)C.pix + (long long)S.pic * C.pix_pic_stride * (KIND == SAMPLE_I32 ? 4 : 1);
+    bool fast = p.fast && fast_setup<K>(C, S, F) && S.xs + Geo<K>::XW <= C.pix_w && ((C.pix_pitch * esz) & 15) == 0 &&
+                (reinterpret_cast<uintptr_t>(base) & 15) == 0;
+    // newest rows a for which the pair needs no edge rule, no row replication, and emits two rows of [y0, y1)
+    const int a_lo = max(SC::AMIN, S.y0 + SC::lag(SC::n - 1));
+    const int a_hi = min(min(S.H, C.pix_h) - 1, S.y1 - 1 + SC::lag(SC::n - 2));
+    const int tf0 = max(tau0, (a_lo - SC::PA + 1) >> 1);
+    const int nfast = ((a_hi - SC::PA) >> 1) + 1 - tf0;
+    int stop = (fast && nfast > 0) ? tf0 : tau_end;
+    for (;;) {   // general loop up to the fast range, the fast range, general loop again: ONE copy of the general body
 #pragma unroll 1
-  for (int tau = tau0; tau < tau_end; ++tau) fwd_pair<K, KIND>(C, S, ba, g, tau);
+      for (; tau < stop; ++tau) fwd_pair<K, KIND>(C, S, ba, g, tau);
+      if (stop == tau_end) break;
+      stop = tau_end;
+      const long long step = 2ll * C.pix_pitch * esz, pf = step * S.pd;
+      const int a0 = 2 * tau + SC::PA;
+      const uint8_t* pA = base + ((long long)a0 * C.pix_pitch + S.xs + 8 * S.lane) * esz;
+      const uint8_t* pB = pA - (long long)SC::reach(0) * C.pix_pitch * esz;
+      const int pf_last = C.pix_h - 1 - 2 * S.pd;
+      // one iteration per trip, rings aged by register moves (rotation index 0): unrolling a whole rotation period
+      // makes every slot index a constant and saves the moves, but the loop then outgrows the instruction caches
+      // (measured: no_instruction became the first stall reason)
+#pragma unroll 1
+      for (int i = 0; i < nfast; ++i, ++tau) {
+        g.shift();
+        fwd_fast_iter<K, KIND, W - 1>(C, S, F, g, tau, pA, pB, step, pf, pf_last);
+      }
+    }
+  } else {
+#pragma unroll 1
+    for (; tau < tau_end; ++tau) fwd_pair<K, KIND>(C, S, ba, g, tau);
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -618,6 +806,83 @@ __device__ __forceinline__ void inv_pair(const DwtComp& C, const StripCtx& S, co
   }
 }
 
+// ---- inverse fast loop -------------------------------------------------------------------------------
+template <int PPL, bool ODD>
+__device__ __forceinline__ void inv_fast_fetch(const FastCtx& F, int row, int (&dst)[2 * PPL]) {
+  const int by = row >> 1, i = F.idx(by);
+  int4 lo, hi;
+  if (ODD) {
+    lo = __ldg(reinterpret_cast<const int4*>(F.coefpic + i + F.o_lh));
+    hi = __ldg(reinterpret_cast<const int4*>(F.coefpic + i + F.o_hh));
+  } else {
+    lo = F.llp ? __ldg(reinterpret_cast<const int4*>(F.llp + (long long)by * F.ll_pitch)) : __ldg(reinterpret_cast<const int4*>(F.coefpic + i + F.o_ll));
+    hi = __ldg(reinterpret_cast<const int4*>(F.coefpic + i + F.o_hl));
+  }
+  dst[0] = lo.x; dst[1] = lo.y; dst[2] = lo.z; dst[3] = lo.w;
+  dst[PPL] = hi.x; dst[PPL + 1] = hi.y; dst[PPL + 2] = hi.z; dst[PPL + 3] = hi.w;
+}
+template <bool ODD>
+__device__ __forceinline__ void inv_fast_prefetch(const FastCtx& F, int row) {
+  const int by = row >> 1, i = F.idx(by);
+  if (ODD) { prefetch_l1(F.coefpic + i + F.o_lh); prefetch_l1(F.coefpic + i + F.o_hh); }
+  else {
+    if (F.llp) prefetch_l1(F.llp + (long long)by * F.ll_pitch); else prefetch_l1(F.coefpic + i + F.o_ll);
+    prefetch_l1(F.coefpic + i + F.o_hl);
+  }
+}
+
+template <int K, int KIND, int PPL>
+__device__ __forceinline__ void inv_fast_emit(const DwtComp& C, const StripCtx& S, const FastCtx& F, uint8_t* dst, const int (&src)[2 * PPL]) {
+  constexpr int V = 2 * PPL, SHIFT = Wavelet<K>::SHIFT;
+  int e[PPL], o[PPL];
+#pragma unroll
+  for (int a = 0; a < PPL; ++a) { e[a] = src[a]; o[a] = src[PPL + a]; }
+  hsteps<K, -1, PPL>(e, o, S.lane, false, 0, 0);
+  if (!F.store) return;
+  int v[V];
+  const int rnd = SHIFT ? (1 << (SHIFT - 1)) : 0;
+#pragma unroll
+  for (int a = 0; a < PPL; ++a) { v[2 * a] = e[a]; v[2 * a + 1] = o[a]; }
+#pragma unroll
+  for (int k = 0; k < V; ++k) {
+    if (SHIFT) v[k] = (v[k] + rnd) >> SHIFT;
+    if (KIND != SAMPLE_I32) v[k] = (int)((unsigned)(min(max(v[k], C.clip_min), C.clip_max) + C.soffset) << C.sshift);
+  }
+  if (KIND == SAMPLE_I32) {
+#pragma unroll
+    for (int j = 0; j < V; j += 4) reinterpret_cast<int4*>(dst)[j / 4] = make_int4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+  } else {
+    unsigned w[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) w[j] = __byte_perm((unsigned)v[2 * j], (unsigned)v[2 * j + 1], 0x4501);
+    *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+
+// iteration T of a chunk; p1 / p2 run over the output rows a - L1 and a - L2 of this lane
+template <int K, int KIND, int T>
+__device__ __forceinline__ void inv_fast_iter(const DwtComp& C, const StripCtx& S, const FastCtx& F, Rings<K, -1>& g, int tau,
+                                              uint8_t*& p1, uint8_t*& p2, long long step) {
+  using SC = Sched<K, -1>;
+  constexpr int V = Vec<K>::V, PPL = V / 2, n = SC::n, W = SC::WR, R = (W - 1 - T % W) % W;
+  const int a = 2 * tau + SC::PA;
+  if (a + 2 * S.pd <= S.H - 1) {
+    inv_fast_prefetch<(SC::PA & 1) != 0>(F, a + 2 * S.pd);
+    inv_fast_prefetch<((SC::PA - SC::reach(0)) & 1) != 0>(F, a + 2 * S.pd - SC::reach(0));
+  }
+  inv_fast_fetch<PPL, (SC::PA & 1) != 0>(F, a, g.A[R]);
+  inv_fast_fetch<PPL, ((SC::PA - SC::reach(0)) & 1) != 0>(F, a - SC::reach(0), g.B[R]);
+  vsteps_rot<K, -1, R>(g);
+  constexpr int L1 = SC::lag(n - 1), L2 = SC::lag(n - 2);
+  if constexpr (SC::last_targets_A) {
+    inv_fast_emit<K, KIND, PPL>(C, S, F, p1, g.A[(L1 / 2 + R) % W]);
+    inv_fast_emit<K, KIND, PPL>(C, S, F, p2, g.B[((L2 - SC::reach(0)) / 2 + R) % W]);
+  } else {
+    inv_fast_emit<K, KIND, PPL>(C, S, F, p1, g.B[((L1 - SC::reach(0)) / 2 + R) % W]);
+    inv_fast_emit<K, KIND, PPL>(C, S, F, p2, g.A[(L2 / 2 + R) % W]);
+  }
+  p1 += step; p2 += step;
+}
 template <int K, int KIND>
 __global__ void __launch_bounds__(32 * WARPS, VC2_DWT_MINB) dwt_inv_kernel(const DwtParams p, int seg_rows) {
   using SC = Sched<K, -1>;
@@ -633,8 +898,38 @@ __global__ void __launch_bounds__(32 * WARPS, VC2_DWT_MINB) dwt_inv_kernel(const
   g.clear();
   const int tau0 = max((S.y0 - SC::total_reach() - SC::PA) >> 1, 0);
   const int tau_end = (S.y1 - 1 + SC::lag(SC::n - 1) - SC::PA + 2) >> 1;
+  int tau = tau0;
+  if constexpr (Vec<K>::V == 8 && KIND != SAMPLE_U8) {
+    constexpr int W = SC::WR, esz = KIND == SAMPLE_I32 ? 4 : 2;
+    FastCtx F;
+    uint8_t* base = (uint8_t*)C.pix + (long long)S.pic * C.pix_pic_stride * (KIND == SAMPLE_I32 ? 4 : 1);
+    bool fast = p.fast && fast_setup<K>(C, S, F) && S.xs + Geo<K>::XW <= C.pix_w && ((C.pix_pitch * esz) & 15) == 0 &&
+                (reinterpret_cast<uintptr_t>(base) & 15) == 0;
+    // newest rows a for which the pair needs no edge rule and emits two rows of [y0, y1) that survive the crop
+    const int a_lo = max(SC::AMIN, S.y0 + SC::lag(SC::n - 1));
+    const int a_hi = min(S.H - 1, min(S.y1, C.pix_h) - 1 + SC::lag(SC::n - 2));
+    const int tf0 = max(tau0, (a_lo - SC::PA + 1) >> 1);
+    const int nfast = ((a_hi - SC::PA) >> 1) + 1 - tf0;
+    int stop = (fast && nfast > 0) ? tf0 : tau_end;
+    for (;;) {
 #pragma unroll 1
-  for (int tau = tau0; tau < tau_end; ++tau) inv_pair<K, KIND>(C, S, ba, g, tau);
+      for (; tau < stop; ++tau) inv_pair<K, KIND>(C, S, ba, g, tau);
+      if (stop == tau_end) break;
+      stop = tau_end;
+      const long long step = 2ll * C.pix_pitch * esz;
+      const int a0 = 2 * tau + SC::PA;
+      uint8_t* p1 = base + ((long long)(a0 - SC::lag(SC::n - 1)) * C.pix_pitch + S.xs + 8 * S.lane) * esz;
+      uint8_t* p2 = base + ((long long)(a0 - SC::lag(SC::n - 2)) * C.pix_pitch + S.xs + 8 * S.lane) * esz;
+#pragma unroll 1
+      for (int i = 0; i < nfast; ++i, ++tau) {
+        g.shift();
+        inv_fast_iter<K, KIND, W - 1>(C, S, F, g, tau, p1, p2, step);
+      }
+    }
+  } else {
+#pragma unroll 1
+    for (; tau < tau_end; ++tau) inv_pair<K, KIND>(C, S, ba, g, tau);
+  }
 }
 
 // ------------------------------------------------------------------------------------------

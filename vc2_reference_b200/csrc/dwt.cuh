@@ -97,6 +97,7 @@ struct DwtParams {
   DwtComp c[3];
   int ncomp;
   int pd;   // prefetch distance of the streaming kernels, in row pairs
+  int fast; // 1: interior rows of interior strips run the fast loop (dwt.cu); 0: general loop only (VC2_DWT_FAST=0)
 };
 
 }  // namespace vc2
