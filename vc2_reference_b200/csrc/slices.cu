@@ -162,10 +162,16 @@ __device__ __forceinline__ void walk_component(const int4* __restrict__ src, con
   const int n = g.band_start[c][g.nbands];
   int k = 0, b = 0, bend = g.band_start[c][1];
   BandP bp = band_params(q, g.qmatrix[0], badq);
-  int4 nxt = __ldg(src);
-  for (int piece = 0; piece < (n >> 2); ++piece) {
-    const int4 v4 = nxt;
-    if (piece + 1 < (n >> 2)) nxt = __ldg(src + (size_t)(piece + 1) * 32);
+  // three pieces in flight: the loads of a thread are 512 bytes apart (one piece of each of the 32 slices of the
+  // group in between), every one a fresh line, and one piece of work is too short to cover an HBM round trip
+  const int np = n >> 2;
+  int4 n0 = __ldg(src), n1 = n0, n2 = n0;
+  if (np > 1) n1 = __ldg(src + 32);
+  if (np > 2) n2 = __ldg(src + 64);
+  for (int piece = 0; piece < np; ++piece) {
+    const int4 v4 = n0;
+    n0 = n1; n1 = n2;
+    if (piece + 3 < np) n2 = __ldg(src + (size_t)(piece + 3) * 32);
     const int v[4] = {v4.x, v4.y, v4.z, v4.w};
     if (bend - k >= 4) {
 #pragma unroll
