@@ -19,5 +19,5 @@ PY
 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file gpurun_out/${tag}_launches.csv \
   python bench.py --steps 2 --warmup 3 --no-cpu-baseline --e2e-pictures 8 > gpurun_out/${tag}_ncu_bench.log 2>&1
 VC2_CODEC_SUBBATCH=1 ncu --set full --clock-control none --import-source on -s 26 -c 13 -f -o gpurun_out/prof_${tag} \
-  python tools/profile_step.py C3 1 32 > gpurun_out/${tag}_ncu_full.log 2>&1
+  python tools/profile_step.py C3 1 128 > gpurun_out/${tag}_ncu_full.log 2>&1
 ls -la gpurun_out | tail -12

@@ -174,8 +174,8 @@ __device__ __forceinline__ void walk_component(const int4* __restrict__ src, con
     if (piece + 3 < np) n2 = __ldg(src + (size_t)(piece + 3) * 32);
     const int v[4] = {v4.x, v4.y, v4.z, v4.w};
     if (bend - k >= 4) {
-#pragma unroll
-      for (int e = 0; e < 4; ++e) op(v[e], bp);
+      op.pair(v[0], v[1], bp);
+      op.pair(v[2], v[3], bp);
       k += 4;
     } else {
 #pragma unroll
@@ -281,6 +281,7 @@ struct CountOp {      // component_slice_bytes' bit count of quantise(v) (rate-c
     }
     if (mag) last = bits;
   }
+  __device__ __forceinline__ void pair(int v0, int v1, const BandP& bp) { (*this)(v0, bp); (*this)(v1, bp); }
 };
 struct SseOp {        // yss_for_slice (Quantisation.cpp:627-642): product in int, sum in long long
   long long acc;
@@ -288,6 +289,7 @@ struct SseOp {        // yss_for_slice (Quantisation.cpp:627-642): product in in
     const int d = v - scale_band(quant_band(v, bp), bp);
     acc += (long long)(int)((unsigned)d * (unsigned)d);
   }
+  __device__ __forceinline__ void pair(int v0, int v1, const BandP& bp) { (*this)(v0, bp); (*this)(v1, bp); }
 };
 template <bool QUANT>
 struct EmitOp {
@@ -302,6 +304,21 @@ struct EmitOp {
     vlc_of(lut, mag, v < 0, bigor, code, nb);
     W->put(code, nb);
     last = mag ? W->mark() : last;
+  }
+  // two coefficients of the same band: when both codes come from the table and are at most 16 bits long they go
+  // into the accumulator as ONE append (one shift, one flush test)
+  __device__ __forceinline__ void pair(int v0, int v1, const BandP& bp) {
+    const uint32_t m0 = QUANT ? quant_mag(v0, bp) : (uint32_t)abs(v0), m1 = QUANT ? quant_mag(v1, bp) : (uint32_t)abs(v1);
+    if ((m0 | m1) < 128u) {
+      const uint32_t e0 = lut[2u * m0 + (v0 < 0 ? 1u : 0u)], e1 = lut[2u * m1 + (v1 < 0 ? 1u : 0u)];
+      const int nb0 = (int)(e0 & 31u), nb1 = (int)(e1 & 31u);
+      const unsigned mid = W->mark() + (unsigned)nb0;        // the cursor behind the first code (mark() is linear in the bit position)
+      W->put(((e0 >> 5) << nb1) | (e1 >> 5), nb0 + nb1);
+      last = m1 ? W->mark() : (m0 ? mid : last);
+    } else {
+      (*this)(v0, bp);
+      (*this)(v1, bp);
+    }
   }
 };
 
