@@ -83,6 +83,17 @@ CASES += [
 ]
 
 
+# full-width pictures for every kernel family the BASELINE configs do not cover: the lifting kernels' fast loop only
+# runs on strips that lie wholly inside the picture (>= 3 strips of 240 columns)
+CASES += [
+    case("W00_Daub97_d3_422_1080p", 1920, 1080, "422", 10, 1, "HQ_ConstQ", "Daub97", 3, 1, 2, q=10, S=2, seed=500),
+    case("W01_Haar0_d4_422_1080p", 1920, 1080, "422", 10, 1, "HQ_ConstQ", "Haar0", 4, 1, 2, q=6, S=2, seed=501),
+    case("W02_LeGall_d2_444_720p", 1280, 720, "444", 12, 1, "HQ_CBR", "LeGall", 2, 1, 1, s=900000, seed=502),
+    case("W03_DD97_d3_420_1024p", 1920, 1024, "420", 8, 1, "HQ_ConstQ", "DD97", 3, 2, 2, q=14, P=1, seed=503),
+    case("W04_Haar1_d3_422_odd", 1450, 810, "422", 10, 1, "HQ_ConstQ", "Haar1", 3, 1, 2, q=8, S=2, seed=504),
+]
+
+
 def md5_file(path):
     h = hashlib.md5()
     n = 0
