@@ -753,6 +753,10 @@ __global__ void __launch_bounds__(256) assemble_kernel(const AssembleParams p) {
   const int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (s >= p.nslices) return;
   const long long sidx = (long long)pic * p.nslices + s;
+  const uint32_t* __restrict__ img = p.staging + sidx * p.wcap;
+  // the first 33 words of the image do not depend on where the slice goes: fetch them together with its offset and
+  // size instead of one DRAM round trip later (the kernel is latency bound: a slice is six 128-byte rows)
+  const uint32_t first0 = __ldg(img + lane), first1 = __ldg(img + lane + 1);
   const uint32_t* so = p.slice_off + (long long)pic * (p.nslices + 1);
   const unsigned offset = so[s];
   int total = (int)p.sizes[sidx];
@@ -762,19 +766,18 @@ __global__ void __launch_bounds__(256) assemble_kernel(const AssembleParams p) {
     if (lane == 0) atomicOr(&p.err_flags[sidx], VC2_FLAG_STREAM);
     return;
   }
-  const uint32_t* img = p.staging + sidx * p.wcap;
-  uint8_t* dst = p.out + (long long)pic * p.out_pic_stride + offset;
+  uint8_t* __restrict__ dst = p.out + (long long)pic * p.out_pic_stride + offset;
   const int head = min((int)((4 - (reinterpret_cast<uintptr_t>(dst) & 3)) & 3), total);
-  if (lane < head) dst[lane] = (uint8_t)(img[0] >> (24 - 8 * lane));
+  const uint32_t img0 = __shfl_sync(FULL, first0, 0);
+  if (lane < head) dst[lane] = (uint8_t)(img0 >> (24 - 8 * lane));
   const int nwords = (total - head) >> 2;
-  uint32_t* dw = reinterpret_cast<uint32_t*>(dst + head);
-  if (head == 0) {
-    for (int m = lane; m < nwords; m += 32) dw[m] = __byte_perm(img[m], 0, 0x0123);
-  } else {
-    for (int m = lane; m < nwords; m += 32) {
-      const uint32_t be = __funnelshift_l(img[m + 1], img[m], 8 * head);   // image bytes head+4m .. head+4m+3
-      dw[m] = __byte_perm(be, 0, 0x0123);
-    }
+  uint32_t* __restrict__ dw = reinterpret_cast<uint32_t*>(dst + head);
+  // image bytes head + 4m .. head + 4m + 3 = the funnel of words m, m + 1 (shift 0 when the slice starts aligned)
+  if (lane < nwords) dw[lane] = __byte_perm(__funnelshift_l(first1, first0, 8 * head), 0, 0x0123);
+#pragma unroll 2
+  for (int m = lane + 32; m < nwords; m += 32) {
+    const uint32_t be = __funnelshift_l(__ldg(img + m + 1), __ldg(img + m), 8 * head);
+    dw[m] = __byte_perm(be, 0, 0x0123);
   }
   const int done = head + 4 * nwords, tail = total - done;
   if (lane < tail) {
