@@ -27,6 +27,9 @@ namespace {
 
 constexpr unsigned FULL = 0xFFFFFFFFu;
 constexpr int WARPS = 4;   // warps per CTA: four vertically adjacent row segments of one strip
+#ifndef VC2_DWT_NO_SWPIPE
+#define VC2_DWT_SWPIPE 1   // forward fast loop, 16-bit samples: the next row pair is loaded before the current one is used
+#endif
 #ifndef VC2_DWT_MINB
 #define VC2_DWT_MINB 4     // resident CTAs per SM the register allocation is held to (4 -> 128 registers per thread: the fast loop spills at 5)
 #endif
@@ -551,6 +554,28 @@ __device__ __forceinline__ void fwd_fast_fetch(const DwtComp& C, const StripCtx&
   for (int a = 0; a < PPL; ++a) { dst[a] = e[a]; dst[PPL + a] = o[a]; }
 }
 
+// the same from words that are already in registers (the loop loads one row pair ahead)
+template <int K, int PPL>
+__device__ __forceinline__ void fwd_fast_convert(const DwtComp& C, const StripCtx& S, const uint4 q, int (&dst)[2 * PPL]) {
+  constexpr int V = 2 * PPL, SHIFT = Wavelet<K>::SHIFT;
+  int x[V];
+  const unsigned w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    x[2 * j] = (int)(__byte_perm(w[j], 0, 0x4401) >> C.sshift) - C.soffset;
+    x[2 * j + 1] = (int)(__byte_perm(w[j], 0, 0x4423) >> C.sshift) - C.soffset;
+  }
+  int e[PPL], o[PPL];
+#pragma unroll
+  for (int a = 0; a < PPL; ++a) {
+    e[a] = (int)((unsigned)x[2 * a] << SHIFT);
+    o[a] = (int)((unsigned)x[2 * a + 1] << SHIFT);
+  }
+  hsteps<K, +1, PPL>(e, o, S.lane, false, 0, 0);
+#pragma unroll
+  for (int a = 0; a < PPL; ++a) { dst[a] = e[a]; dst[PPL + a] = o[a]; }
+}
+
 template <int PPL, bool ODD>
 __device__ __forceinline__ void fwd_fast_emit(const FastCtx& F, int row, const int (&src)[2 * PPL]) {
   if (!F.store) return;
@@ -569,14 +594,26 @@ __device__ __forceinline__ void fwd_fast_emit(const FastCtx& F, int row, const i
 // iteration T of a chunk; pA / pB run over the picture rows a and a - reach(0) of this lane
 template <int K, int KIND, int T>
 __device__ __forceinline__ void fwd_fast_iter(const DwtComp& C, const StripCtx& S, const FastCtx& F, Rings<K, +1>& g, int tau,
-                                              const uint8_t*& pA, const uint8_t*& pB, long long step, long long pf, int pf_last) {
+                                              const uint8_t*& pA, const uint8_t*& pB, long long step, long long pf, int pf_last,
+                                              uint4& qa, uint4& qb, bool more) {
   using SC = Sched<K, +1>;
   constexpr int V = Vec<K>::V, PPL = V / 2, n = SC::n, W = SC::WR, R = (W - 1 - T % W) % W;
   const int a = 2 * tau + SC::PA;
   if (a <= pf_last) { prefetch_l1(pA + pf); prefetch_l1(pB + pf); }
-  fwd_fast_fetch<K, KIND, PPL>(C, S, pA, g.A[R]);
-  fwd_fast_fetch<K, KIND, PPL>(C, S, pB, g.B[R]);
-  pA += step; pB += step;
+#ifdef VC2_DWT_SWPIPE
+  if constexpr (KIND == SAMPLE_U16BE) {
+    const uint4 ca = qa, cb = qb;
+    pA += step; pB += step;
+    if (more) { qa = __ldg(reinterpret_cast<const uint4*>(pA)); qb = __ldg(reinterpret_cast<const uint4*>(pB)); }
+    fwd_fast_convert<K, PPL>(C, S, ca, g.A[R]);
+    fwd_fast_convert<K, PPL>(C, S, cb, g.B[R]);
+  } else
+#endif
+  {
+    fwd_fast_fetch<K, KIND, PPL>(C, S, pA, g.A[R]);
+    fwd_fast_fetch<K, KIND, PPL>(C, S, pB, g.B[R]);
+    pA += step; pB += step;
+  }
   vsteps_rot<K, +1, R>(g);
   constexpr int L1 = SC::lag(n - 1), L2 = SC::lag(n - 2);
   if constexpr (SC::last_targets_A) {
@@ -674,10 +711,14 @@ __global__ void __launch_bounds__(32 * WARPS, VC2_DWT_MINB) dwt_fwd_kernel(const
       // one iteration per trip, rings aged by register moves (rotation index 0): unrolling a whole rotation period
       // makes every slot index a constant and saves the moves, but the loop then outgrows the instruction caches
       // (measured: no_instruction became the first stall reason)
+      uint4 qa = make_uint4(0, 0, 0, 0), qb = qa;
+#ifdef VC2_DWT_SWPIPE
+      if constexpr (KIND == SAMPLE_U16BE) { qa = __ldg(reinterpret_cast<const uint4*>(pA)); qb = __ldg(reinterpret_cast<const uint4*>(pB)); }
+#endif
 #pragma unroll 1
       for (int i = 0; i < nfast; ++i, ++tau) {
         g.shift();
-        fwd_fast_iter<K, KIND, W - 1>(C, S, F, g, tau, pA, pB, step, pf, pf_last);
+        fwd_fast_iter<K, KIND, W - 1>(C, S, F, g, tau, pA, pB, step, pf, pf_last, qa, qb, i + 1 < nfast);
       }
     }
   } else {
