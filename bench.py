@@ -178,6 +178,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=128, help="pictures per step per GPU")
     ap.add_argument("--e2e-pictures", type=int, default=64, help="pictures per end-to-end step (host buffers) per GPU")
+    ap.add_argument("--e2e-slots", type=int, default=8, help="device slots of the end-to-end codecs (pictures in flight)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
 
@@ -287,7 +288,7 @@ def main():
     # One call moves E2E_N pictures through a codec that keeps E2E_SLOTS of them in flight on the device (the host
     # entry points pipeline copy-in, kernels and copy-out over the slots; a long call amortises the pipeline's fill
     # and drain).  Pictures repeat the B synthetic frames of the device-resident part.
-    E2E_N, E2E_SLOTS = args.e2e_pictures, 8
+    E2E_N, E2E_SLOTS = args.e2e_pictures, args.e2e_slots
     pin = lambda n: torch.empty(n, dtype=torch.uint8, pin_memory=True).numpy()
     h_pics = [pin(codec.picture_bytes) for _ in range(E2E_N)]
     h_out = [pin(codec.picture_bytes) for _ in range(E2E_N)]
