@@ -795,15 +795,18 @@ __global__ void __launch_bounds__(256) assemble_kernel(const AssembleParams p) {
 struct BitReader {
   const uint32_t* p;   // next aligned word to fetch
   uint32_t hi, lo;     // the window, top aligned; bits below the nb valid ones are zero
-  uint32_t nxt;        // the word that follows the window: byte swapped, bits beyond the bound forced to one
+  uint32_t nxt;        // the word that follows the window, AS LOADED: it is byte swapped and bounded only when it enters the
+                       // window, so that nothing touches the register between the load and the next refill (the swap
+                       // right behind the load was half of all stall samples of the parser, ncu source view)
   int nb;              // valid bits in hi:lo
   int left;            // real stream bits behind nxt (<= 0: only ones follow)
   __device__ __forceinline__ static uint32_t be(uint32_t x) { return __byte_perm(x, 0, 0x0123); }
   __device__ __forceinline__ void fetch() {
-    const uint32_t raw = __ldg(p++);
-    nxt = be(raw) | __funnelshift_rc(0xFFFFFFFFu, 0u, max(left, 0));   // ones from bit `left` on (none when left >= 32)
+    nxt = __ldg(p++);
     left -= 32;
   }
+  // the prefetched word as window bits: ones from the bound on (left + 32 real bits were behind the window when it was fetched)
+  __device__ __forceinline__ uint32_t next_word() const { return be(nxt) | __funnelshift_rc(0xFFFFFFFFu, 0u, max(left + 32, 0)); }
   // start reading at byte address a (any alignment); the first `bound` bits are real.  The buffers have slack
   // behind the data.  Leaves nb >= 33.
   __device__ __forceinline__ void init(const uint8_t* a, int bound) {
@@ -826,9 +829,10 @@ struct BitReader {
   }
   // nb >= 33 afterwards.  Straight-line code: the lanes of a warp (one slice each) run dry at different codes.
   __device__ __forceinline__ void ensure() {
-    if (nb <= 32) {   // lo is empty: append nxt behind the nb valid bits of hi
-      hi |= __funnelshift_rc(nxt, 0u, nb);
-      lo = __funnelshift_lc(0u, nxt, 32 - nb);
+    if (nb <= 32) {   // lo is empty: append the prefetched word behind the nb valid bits of hi
+      const uint32_t w = next_word();
+      hi |= __funnelshift_rc(w, 0u, nb);
+      lo = __funnelshift_lc(0u, w, 32 - nb);
       nb += 32;
       fetch();
     }
