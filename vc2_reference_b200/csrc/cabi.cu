@@ -1466,8 +1466,7 @@ extern "C" int vc2_codec_decode_host(vc2_codec* k, int n, const uint8_t* const* 
     return VC2_OK;
   };
   const int chunks = (n + B - 1) / B;
-  int status = VC2_OK, last_stage_slot = 0;
-  (void)last_stage_slot;
+  int status = VC2_OK;
   for (int c = 0; c < chunks && status == VC2_OK; ++c) {
     const int base = c * B, m = std::min(B, n - base);
     const int sub = stage_pictures(B);
@@ -1504,7 +1503,6 @@ extern "C" int vc2_codec_decode_host(vc2_codec* k, int n, const uint8_t* const* 
       CU(cudaMemcpyAsync(flags(c & 1) + (size_t)i * ns, k->err.as<uint32_t>() + (size_t)i * ns, (size_t)ns * 4 * mm, cudaMemcpyDeviceToHost,
                          k->copy_out));
       CU(cudaEventRecord(k->ev_out[(c & 1) * B + i], k->copy_out));
-      last_stage_slot = i;
     }
     if (status) break;
     if (c + 1 < chunks && c >= 1) status = check(c - 1);   // the flag set of chunk c+1 was last used by chunk c-1
