@@ -178,7 +178,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=128, help="pictures per step per GPU")
     ap.add_argument("--e2e-pictures", type=int, default=64, help="pictures per end-to-end step (host buffers) per GPU")
-    ap.add_argument("--e2e-slots", type=int, default=8, help="device slots of the end-to-end codecs (pictures in flight)")
+    ap.add_argument("--e2e-slots", type=int, default=4, help="device slots of the end-to-end codecs (pictures in flight)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
 
