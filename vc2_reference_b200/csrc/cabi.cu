@@ -543,7 +543,9 @@ struct PackBuffers {
 };
 
 // staging words per slice: every coefficient at the 32-bit VLC limit, plus header bytes and slack
-static int staging_words(const SliceGeom& g) { return (g.prefix + 4 + 4 * g.comp_start[3] + 3) / 4 + 4; }
+// worst case (every code 32 bits) plus slack for the assembler's look-ahead, in whole 16-byte units: the HQ packer
+// stores four words at a time (WideBitWriter)
+static int staging_words(const SliceGeom& g) { return ((g.prefix + 4 + 4 * g.comp_start[3] + 3) / 4 + 4 + 3) & ~3; }
 
 static cudaError_t run_pack(vc2_ctx* ctx, const SliceGeom& g, const int32_t* coef, int npictures, int mode, int quantise,
                             int search, int const_q, int emit, const PackBuffers& B) {

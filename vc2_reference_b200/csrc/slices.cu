@@ -267,6 +267,85 @@ struct BitWriter {
   }
 };
 
+// The HQ packer's writer: the same bit accumulator, but finished words leave the thread FOUR AT A TIME.  The slice
+// images of a warp's lanes are 4 KB apart, so every lane of a store instruction opens its own 32-byte sector: word
+// stores cost one L2 request per word (tools/stream_probe.cu: 4.1 ms per 16.6 M warp-wide scattered word stores, most
+// of the packer's time), 16-byte stores a quarter of that.  b0..b3 always hold the last four words pushed (b3 the
+// newest); they are stored when the word cursor crosses a 16-byte boundary of the (16-byte aligned) slice image, and
+// the up to three words behind the last boundary ("pending") exist only in registers until spill().
+struct WideBitWriter {
+  uint32_t* w;    // first word of the slice image (16-byte aligned: staging_words() is a multiple of four)
+  uint32_t* wp;   // next word to write
+  unsigned long long acc;   // the low nacc bits are pending
+  int nacc;
+  uint32_t b0, b1, b2, b3;
+  __device__ __forceinline__ void init(uint32_t* words) { w = wp = words; acc = 0; nacc = 0; b0 = b1 = b2 = b3 = 0u; }
+  __device__ __forceinline__ int wc() const { return (int)(wp - w); }
+  __device__ __forceinline__ int pos() const { return 32 * wc() + nacc; }
+  __device__ __forceinline__ unsigned mark() const { return 8u * (unsigned)reinterpret_cast<uintptr_t>(wp) + (unsigned)nacc; }
+  __device__ __forceinline__ int unmark(unsigned m) const { return (int)(m - 8u * (unsigned)reinterpret_cast<uintptr_t>(w)); }
+  __device__ __forceinline__ int pending() const { return (int)((reinterpret_cast<uintptr_t>(wp) >> 2) & 3u); }
+  __device__ __forceinline__ void push(bool full, uint32_t out) {   // branch free, like BitWriter::put's flush
+    b0 = full ? b1 : b0;
+    b1 = full ? b2 : b1;
+    b2 = full ? b3 : b2;
+    b3 = full ? out : b3;
+    wp += full ? 1 : 0;
+    if (full && (reinterpret_cast<uintptr_t>(wp) & 15u) == 0) *reinterpret_cast<uint4*>(wp - 4) = make_uint4(b0, b1, b2, b3);
+  }
+  __device__ __forceinline__ void put(uint32_t code, int nb) {   // nb in 0..32
+    acc = (acc << nb) | code;
+    nacc += nb;
+    const bool full = nacc >= 32;
+    push(full, (uint32_t)(acc >> ((nacc - 32) & 31)));
+    nacc -= full ? 32 : 0;
+  }
+  // make the slice image in memory complete up to wp / fetch the pending words of a moved cursor back
+  __device__ __forceinline__ void spill() {
+    const int r = pending();
+    if (r >= 1) wp[-1] = b3;
+    if (r >= 2) wp[-2] = b2;
+    if (r >= 3) wp[-3] = b1;
+  }
+  __device__ __forceinline__ void reload() {
+    const int r = pending();
+    if (r >= 1) b3 = wp[-1];
+    if (r >= 2) b2 = wp[-2];
+    if (r >= 3) b1 = wp[-3];
+  }
+  __device__ __forceinline__ void seek(int target) {   // see BitWriter::seek
+    int cur = pos();
+    while (cur < target) {
+      const int t = min(target - cur, 32);
+      put(0u, t);
+      cur += t;
+    }
+    if (target < cur) {
+      const int twc = target >> 5, tb = target & 31;
+      if (twc == wc()) acc >>= (nacc - tb);
+      else {
+        spill();
+        acc = (unsigned long long)w[twc] >> (32 - tb);
+        wp = w + twc;
+        reload();
+      }
+      nacc = tb;
+    }
+  }
+  __device__ __forceinline__ void patch_byte(int bitpos, uint32_t value) {   // see BitWriter::patch_byte
+    const int idx = bitpos >> 5;
+    if (idx < wc()) {
+      spill();
+      w[idx] |= value << (24 - (bitpos & 31));
+      reload();
+    } else acc |= (unsigned long long)value << (nacc - (bitpos - 32 * wc()) - 8);
+  }
+  __device__ __forceinline__ void finish() {
+    if (nacc > 0) { push(true, (uint32_t)(acc << (32 - nacc))); nacc = 0; }
+    spill();
+  }
+};
+
 struct CountOp {      // component_slice_bytes' bit count of quantise(v) (rate-control probe)
   const uint32_t* lut;
   int bits, last;
@@ -291,10 +370,10 @@ struct SseOp {        // yss_for_slice (Quantisation.cpp:627-642): product in in
   }
   __device__ __forceinline__ void pair(int v0, int v1, const BandP& bp) { (*this)(v0, bp); (*this)(v1, bp); }
 };
-template <bool QUANT>
+template <bool QUANT, class Writer>
 struct EmitOp {
   const uint32_t* lut;
-  BitWriter* W;
+  Writer* W;
   unsigned last;   // BitWriter::mark() behind the last non-zero coefficient
   unsigned bigor;
   __device__ __forceinline__ void operator()(int v, const BandP& bp) {
@@ -398,7 +477,7 @@ __global__ void __launch_bounds__(128) hq_pack_kernel(const PackParams p) {
   }
 
   if (p.emit) {
-    BitWriter W;
+    WideBitWriter W;
     W.init(p.staging + sidx * p.wcap);
     int total = 0;
     if (!(flags & VC2_FLAG_SEARCH_PHASE)) {
@@ -414,11 +493,11 @@ __global__ void __launch_bounds__(128) hq_pack_kernel(const PackParams p) {
         const int4* csrc = src + (size_t)(g.comp_start[c] >> 2) * 32;
         int last;
         if (p.quantise) {
-          EmitOp<true> op = {s_enc, &W, W.mark(), 0u};
+          EmitOp<true, WideBitWriter> op = {s_enc, &W, W.mark(), 0u};
           walk_component(csrc, g, c, qi, badq, op);
           last = W.unmark(op.last); bigor |= op.bigor;
         } else {
-          EmitOp<false> op = {s_enc, &W, W.mark(), 0u};
+          EmitOp<false, WideBitWriter> op = {s_enc, &W, W.mark(), 0u};
           walk_component(csrc, g, c, qi, badq, op);
           last = W.unmark(op.last); bigor |= op.bigor;
         }
