@@ -132,6 +132,9 @@ int vc2_slice_bytes(int ny, int nx, int total_bytes, int scalar, int32_t* out);
 /* quant_factor / quant_offset tables - Quantisation.cpp:40-83 */
 int vc2_quant_factor(int q);
 int vc2_quant_offset(int q);
+/* multiplier and shift the slice coders divide by quant_factor(q) with: a / quant_factor(q) == mulhi(a, m) >> shift
+ * for every a < 2^31 (the reference's own domain: (abs(v) << 2) in int, Quantisation.cpp:69-76); for the tests */
+int vc2_quant_magic31(int q, uint32_t* m, uint32_t* shift);
 /* fill a vc2_geom from picture size + colour format (0=4:4:4, 1=4:2:2, 2=4:2:0) and -u/-a slice sizes;
  * returns VC2_ERR_ARG when sliceSizeIsValid rejects the combination (EncodeStream.cpp:374-405) */
 int vc2_make_geom(int height, int width, int chroma_format, int kernel, int depth,

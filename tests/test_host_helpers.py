@@ -55,6 +55,29 @@ def test_quant_factor_table_vs_reference(ref):
     assert ref.quant_factor(130) == -1
 
 
+def test_quant_magic31_is_exact_below_2_31():
+    """The slice coders divide by quant_factor with one multiply-high and one shift (cabi.cu vc2_quant_magic31):
+    it must equal truncating division for EVERY dividend the reference can form, (abs(v) << 2) in int
+    (Quantisation.cpp:69-76), i.e. below 2^31.  Checked on every dividend below 2^22, on the multiples of the
+    divisor and their neighbours (where a rounding error would show first) up to 2^31, and on random dividends."""
+    import ctypes as C
+    rng = np.random.default_rng(31)
+    dense = np.arange(1 << 22, dtype=np.uint64)
+    rnd = rng.integers(0, 1 << 31, 1 << 20, dtype=np.uint64)
+    top = np.uint64((1 << 31) - 1)
+    for q in range(120):
+        m, sh = C.c_uint32(), C.c_uint32()
+        assert lib.vc2_quant_magic31(q, C.byref(m), C.byref(sh)) == 0
+        d = np.uint64(lib.vc2_quant_factor(q) & 0xFFFFFFFF)
+        mult = np.arange(1, 1 << 16, dtype=np.uint64) * np.uint64(max(1, ((1 << 31) // int(d)) >> 16)) * d
+        mult = mult[mult <= top]
+        edge = np.concatenate([mult, mult - np.uint64(1), np.minimum(mult + np.uint64(1), top), np.array([top, top - min(d, top), 0], np.uint64)])
+        for a in (dense, rnd, edge):
+            got = ((a * np.uint64(m.value)) >> np.uint64(32)) >> np.uint64(sh.value)
+            assert np.array_equal(got, a // d), q
+    assert lib.vc2_quant_magic31(120, C.byref(m), C.byref(sh)) != 0
+
+
 def test_slice_bytes(ref):
     assert vc2.slice_bytes(3, 4, 1000, 1).ravel().tolist() == [83, 83, 84, 83, 83, 84, 83, 83, 84, 83, 83, 84]
     assert (vc2.slice_bytes(135, 120, 2073600, 1) == 128).all()

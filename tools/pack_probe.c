@@ -150,7 +150,10 @@ int main(int argc, char** argv) {
     {"flat grey, prefix 2, CBR", 1920, 1080, 2, 8, VC2_HAAR1, 2, 2, 2, 2, 1, VC2_HQ_CBR, 0, 400000, 1, 0},
     {"noise q0 S8 4:4:4 12b", 1920, 1080, 0, 12, VC2_FIDELITY, 3, 1, 2, 1, 8, VC2_HQ_VBR, 0, 0, 2, 0},
     {"noise q0 S1 (scalar too small)", 1920, 1080, 1, 10, VC2_DAUB97, 3, 1, 2, 0, 1, VC2_HQ_VBR, 0, 0, 2, 0},
-    {"noise q30 S1 prefix 1 4:2:0", 1920, 1080, 2, 10, VC2_DD97, 2, 4, 4, 1, 1, VC2_HQ_VBR, 30, 0, 2, 0},
+    {"noise q30 S1 prefix 1 4:2:0", 1920, 1080, 2, 10, VC2_DD97, 2, 2, 4, 1, 1, VC2_HQ_VBR, 30, 0, 2, 0},
+    {"C5 LD LeGall d3 2073600", 1920, 1080, 1, 10, VC2_LEGALL, 3, 1, 2, 0, 1, VC2_LD, 0, 2073600, 0, 0},
+    {"LD noise DD137 d2 tight", 1920, 1080, 0, 8, VC2_DD137, 2, 2, 4, 0, 1, VC2_LD, 0, 700000, 2, 0},
+    {"odd slice starts: prefix 1 S1 q40", 1920, 1080, 1, 10, VC2_HAAR0, 3, 1, 2, 1, 1, VC2_HQ_VBR, 40, 0, 0, 0},
     {"noise CBR tight", 1920, 1080, 1, 10, VC2_LEGALL, 3, 1, 2, 0, 1, VC2_HQ_CBR, 0, 500000, 2, 0},
   };
   int bad = 0;

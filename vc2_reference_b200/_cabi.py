@@ -52,6 +52,7 @@ def _load():
         "vc2_slice_bytes": (C.c_int, [C.c_int] * 4 + [i32p]),
         "vc2_quant_factor": (C.c_int, [C.c_int]),
         "vc2_quant_offset": (C.c_int, [C.c_int]),
+        "vc2_quant_magic31": (C.c_int, [C.c_int, u32p, u32p]),
         "vc2_make_geom": (C.c_int, [C.c_int] * 9 + [gp]),
         "vc2_hq_index_slices": (C.c_int, [vp, C.c_size_t, C.c_int, C.c_int, C.c_int, u32p]),
         "vc2_dwt_forward": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp]),

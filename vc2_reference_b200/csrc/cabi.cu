@@ -259,6 +259,21 @@ static int cuda_fail(vc2_ctx* c, cudaError_t e) { return fail(c, VC2_ERR_CUDA, c
     if (e_ != cudaSuccess) return cuda_fail(ctx, e_);    \
   } while (0)
 
+// Truncating division by quant_factor(q) for dividends below 2^31 with ONE multiply: a / d == mulhi(a, m) >> shift,
+// m = ceil(2^(31 + l) / d), shift = l - 1, l = ceil(log2 d).  d >= 4 so l >= 2; 2^(l-1) < d <= 2^l so m < 2^32;
+// m * d - 2^(31+l) < d <= 2^l, so the error term a * (m * d - 2^(31+l)) / (d * 2^(31+l)) stays below 1 / d for
+// a < 2^31.  The dividend of the dead-zone quantiser is |v| << 2 computed in int (Quantisation.cpp:69-76): the
+// reference itself is only defined for |v| < 2^29, i.e. for dividends below 2^31.
+extern "C" int vc2_quant_magic31(int q, uint32_t* m, uint32_t* shift) {
+  if (q < 0 || q > 119 || !m || !shift) return VC2_ERR_ARG;
+  const uint64_t d = (uint64_t)(uint32_t)vc2_quant_factor(q);   // the top entries exceed INT_MAX (as in make_quant_tables)
+  uint32_t l = 0;
+  while ((1ull << l) < d) ++l;
+  *m = (uint32_t)(((1ull << (31 + l)) + d - 1) / d);
+  *shift = l - 1;
+  return VC2_OK;
+}
+
 static void make_quant_tables(QuantTables& t) {
   for (int q = 0; q < 128; ++q) {
     const uint32_t d = (uint32_t)vc2_quant_factor(std::min(q, 119));
@@ -268,6 +283,7 @@ static void make_quant_tables(QuantTables& t) {
     while ((1ull << l) < d) ++l;   // ceil(log2 d); d >= 4 so l >= 2
     t.ql[q] = l;
     t.qm[q] = (uint32_t)(((1ull << 32) * ((1ull << l) - d)) / d + 1);
+    vc2_quant_magic31(std::min(q, 119), &t.qm31[q], &t.ql31[q]);
   }
 }
 

@@ -68,7 +68,7 @@ constexpr unsigned FULL = 0xFFFFFFFFu;
 // The truncating division by the table constant uses the round-up multiply-shift of Granlund &
 // Montgomery, exact for every 32-bit dividend:  t = mulhi(m', a);  q = (t + ((a - t) >> 1)) >> (l - 1)
 struct QParam {
-  uint32_t qf, qo, qm, ql;
+  uint32_t qf, qo, qm, ql, qm31, ql31;
 };
 __device__ __forceinline__ QParam qparam(int q) {
   QParam r;
@@ -77,6 +77,8 @@ __device__ __forceinline__ QParam qparam(int q) {
   r.qo = c_qt.qo[q];
   r.qm = c_qt.qm[q];
   r.ql = c_qt.ql[q];
+  r.qm31 = c_qt.qm31[q];
+  r.ql31 = c_qt.ql31[q];
   return r;
 }
 __device__ __forceinline__ uint32_t udiv_magic(uint32_t a, uint32_t m, uint32_t l) {
@@ -127,7 +129,7 @@ __device__ __forceinline__ void vlc_code(int v, uint32_t& code, int& nb) {
 
 // quantiser parameters of one band for one slice (per lane: the slices of a warp may use different indices)
 struct BandP {
-  uint32_t qm, ql, qf, qo;   // magic multiplier, log2 ceiling, quant_factor, quant_offset
+  uint32_t qm, ql, qf, qo;   // one-multiply magic (exact below 2^31) and its shift, quant_factor, quant_offset + 2
 };
 // adjusted index max(q - qmatrix[b], 0) (Quantisation.cpp:16-20); bad when the reference would throw (:60-63)
 __device__ __forceinline__ BandP band_params(int q, int qmat, bool& bad) {
@@ -135,13 +137,11 @@ __device__ __forceinline__ BandP band_params(int q, int qmat, bool& bad) {
   if (aq > 119) bad = true;
   const QParam p = qparam(aq);
   BandP r;
-  r.qm = p.qm; r.ql = p.ql - 1u; r.qf = p.qf; r.qo = p.qo + 2u;
+  r.qm = p.qm31; r.ql = p.ql31; r.qf = p.qf; r.qo = p.qo + 2u;
   return r;
 }
 __device__ __forceinline__ int quant_band(int v, const BandP& bp) {
-  const uint32_t a = (uint32_t)abs(v) << 2;
-  const uint32_t t = __umulhi(bp.qm, a);
-  const int q = (int)((t + ((a - t) >> 1)) >> bp.ql);
+  const int q = (int)(__umulhi(bp.qm, (uint32_t)abs(v) << 2) >> bp.ql);
   return v < 0 ? -q : q;
 }
 __device__ __forceinline__ int scale_band(int v, const BandP& bp) {   // bp.qo already holds quant_offset + 2
@@ -209,9 +209,7 @@ __device__ __forceinline__ void vlc_of(const uint32_t* __restrict__ lut, uint32_
   }
 }
 __device__ __forceinline__ uint32_t quant_mag(int v, const BandP& bp) {   // |quant(v, q)|
-  const uint32_t a = (uint32_t)abs(v) << 2;
-  const uint32_t t = __umulhi(bp.qm, a);
-  return (t + ((a - t) >> 1)) >> bp.ql;
+  return __umulhi(bp.qm, (uint32_t)abs(v) << 2) >> bp.ql;
 }
 // stage a table of n 32-bit words from global into shared memory (whole CTA; caller synchronises)
 __device__ __forceinline__ void stage_table(uint32_t* dst, const uint32_t* src, int n) {
@@ -275,61 +273,56 @@ struct BitWriter {
 // the up to three words behind the last boundary ("pending") exist only in registers until spill().
 struct WideBitWriter {
   uint32_t* w;    // first word of the slice image (16-byte aligned: staging_words() is a multiple of four)
-  uint32_t* wp;   // next word to write
-  unsigned long long acc;   // the low nacc bits are pending
-  int nacc;
+  unsigned long long acc;   // the low (bp & 31) bits are pending
+  unsigned bp;    // bits written so far: ONE cursor, word index bp >> 5, so that "a word is full" and "four words are
+                  // full" are comparisons on old ^ new cursor and the packer's marks are the cursor itself
   uint32_t b0, b1, b2, b3;
-  __device__ __forceinline__ void init(uint32_t* words) { w = wp = words; acc = 0; nacc = 0; b0 = b1 = b2 = b3 = 0u; }
-  __device__ __forceinline__ int wc() const { return (int)(wp - w); }
-  __device__ __forceinline__ int pos() const { return 32 * wc() + nacc; }
-  __device__ __forceinline__ unsigned mark() const { return 8u * (unsigned)reinterpret_cast<uintptr_t>(wp) + (unsigned)nacc; }
-  __device__ __forceinline__ int unmark(unsigned m) const { return (int)(m - 8u * (unsigned)reinterpret_cast<uintptr_t>(w)); }
-  __device__ __forceinline__ int pending() const { return (int)((reinterpret_cast<uintptr_t>(wp) >> 2) & 3u); }
-  __device__ __forceinline__ void push(bool full, uint32_t out) {   // branch free, like BitWriter::put's flush
+  __device__ __forceinline__ void init(uint32_t* words) { w = words; acc = 0; bp = 0u; b0 = b1 = b2 = b3 = 0u; }
+  __device__ __forceinline__ int wc() const { return (int)(bp >> 5); }
+  __device__ __forceinline__ int pos() const { return (int)bp; }
+  __device__ __forceinline__ unsigned mark() const { return bp; }
+  __device__ __forceinline__ int unmark(unsigned m) const { return (int)m; }
+  __device__ __forceinline__ int pending() const { return (int)((bp >> 5) & 3u); }
+  __device__ __forceinline__ void put(uint32_t code, int nb) {   // nb in 0..32: at most one word boundary is crossed
+    acc = (acc << nb) | code;
+    const unsigned nbp = bp + (unsigned)nb;
+    const unsigned x = nbp ^ bp;
+    const bool full = x >= 32u;   // branch free: the lanes of a warp (one slice each) fill their words at different coefficients
+    const uint32_t out = (uint32_t)(acc >> (nbp & 31u));
     b0 = full ? b1 : b0;
     b1 = full ? b2 : b1;
     b2 = full ? b3 : b2;
     b3 = full ? out : b3;
-    wp += full ? 1 : 0;
-    if (full && (reinterpret_cast<uintptr_t>(wp) & 15u) == 0) *reinterpret_cast<uint4*>(wp - 4) = make_uint4(b0, b1, b2, b3);
+    bp = nbp;
+    if (x >= 128u) *reinterpret_cast<uint4*>(w + (nbp >> 5) - 4) = make_uint4(b0, b1, b2, b3);
   }
-  __device__ __forceinline__ void put(uint32_t code, int nb) {   // nb in 0..32
-    acc = (acc << nb) | code;
-    nacc += nb;
-    const bool full = nacc >= 32;
-    push(full, (uint32_t)(acc >> ((nacc - 32) & 31)));
-    nacc -= full ? 32 : 0;
-  }
-  // make the slice image in memory complete up to wp / fetch the pending words of a moved cursor back
+  // make the slice image in memory complete up to the cursor / fetch the pending words of a moved cursor back
   __device__ __forceinline__ void spill() {
     const int r = pending();
+    uint32_t* wp = w + wc();
     if (r >= 1) wp[-1] = b3;
     if (r >= 2) wp[-2] = b2;
     if (r >= 3) wp[-3] = b1;
   }
   __device__ __forceinline__ void reload() {
     const int r = pending();
+    const uint32_t* wp = w + wc();
     if (r >= 1) b3 = wp[-1];
     if (r >= 2) b2 = wp[-2];
     if (r >= 3) b1 = wp[-3];
   }
   __device__ __forceinline__ void seek(int target) {   // see BitWriter::seek
-    int cur = pos();
-    while (cur < target) {
-      const int t = min(target - cur, 32);
-      put(0u, t);
-      cur += t;
-    }
-    if (target < cur) {
+    while ((int)bp < target) put(0u, min(target - (int)bp, 32));
+    if (target < (int)bp) {
       const int twc = target >> 5, tb = target & 31;
-      if (twc == wc()) acc >>= (nacc - tb);
+      if (twc == wc()) acc >>= ((int)(bp & 31u) - tb);
       else {
         spill();
         acc = (unsigned long long)w[twc] >> (32 - tb);
-        wp = w + twc;
+        bp = (unsigned)target;
         reload();
       }
-      nacc = tb;
+      bp = (unsigned)target;
     }
   }
   __device__ __forceinline__ void patch_byte(int bitpos, uint32_t value) {   // see BitWriter::patch_byte
@@ -338,10 +331,10 @@ struct WideBitWriter {
       spill();
       w[idx] |= value << (24 - (bitpos & 31));
       reload();
-    } else acc |= (unsigned long long)value << (nacc - (bitpos - 32 * wc()) - 8);
+    } else acc |= (unsigned long long)value << ((int)(bp & 31u) - (bitpos & 31) - 8);
   }
   __device__ __forceinline__ void finish() {
-    if (nacc > 0) { push(true, (uint32_t)(acc << (32 - nacc))); nacc = 0; }
+    if (bp & 31u) put(0u, 32 - (int)(bp & 31u));
     spill();
   }
 };

@@ -51,12 +51,15 @@ struct PlaneGeom {
 };
 
 // quantiser tables (Quantisation.cpp:40-83), filled by the host at context creation.
-// qf = quant_factor, qo = quant_offset, (qm, ql) = Granlund-Montgomery magic for exact u32 / qf.
+// qf = quant_factor, qo = quant_offset, (qm, ql) = Granlund-Montgomery magic for exact u32 / qf,
+// (qm31, ql31) = the one-multiply magic that is exact for dividends below 2^31 (vc2_quant_magic31).
 struct QuantTables {
   uint32_t qf[128];
   uint32_t qo[128];
   uint32_t qm[128];
   uint32_t ql[128];
+  uint32_t qm31[128];
+  uint32_t ql31[128];
 };
 
 __host__ __device__ inline int band_level(int b) { return b == 0 ? 0 : (b - 1) / 3 + 1; }
