@@ -2,8 +2,8 @@
  * loads TWO builds of the C-ABI library side by side (dlopen, RTLD_LOCAL), runs the same synthetic pictures through
  * the fused encoder of each, compares the payloads byte for byte (the first library is the one the GPU parity tests
  * last passed on) and prints the per-stage CUDA-event times of both (vc2_profile_read).
- *   build: gcc -O2 tools/pack_probe.c -o gpurun_out/pack_probe -ldl
- *   run:   gpurun_out/pack_probe baseline.so candidate.so [pictures]
+ *   build: gcc -O2 tools/pack_probe.c -o tools/_probe/pack_probe -ldl   (tools/_probe/ travels to the GPU box, gpurun_out/ does not)
+ *   run:   pack_probe PICTURES baseline.so candidate.so [candidate.so ...]
  * Picture content: the generator of oracle/gen.py (SURVEY.md Appx B.3), restated in C. */
 #include <dlfcn.h>
 #include <stdint.h>
@@ -134,11 +134,12 @@ static Result run(Lib* l, const Case* c, int npic, uint8_t** pics, size_t pic_by
 }
 
 int main(int argc, char** argv) {
-  if (argc < 3) { fprintf(stderr, "usage: pack_probe baseline.so candidate.so [pictures]\n"); return 2; }
-  Lib A, B;
-  load(&A, argv[1]);
-  load(&B, argv[2]);
-  const int npic_timed = argc > 3 ? atoi(argv[3]) : 32;
+  if (argc < 3) { fprintf(stderr, "usage: pack_probe pictures baseline.so candidate.so [candidate.so ...]\n"); return 2; }
+  enum { MAXLIB = 6 };
+  Lib L[MAXLIB];
+  const int npic_timed = atoi(argv[1]);
+  int nlib = 0;
+  for (int i = 2; i < argc && nlib < MAXLIB; ++i) load(&L[nlib++], argv[i]);
   static const char* stage[VC2_NUM_STAGES] = {"dwt_l0", "dwt_deep", "pack", "unpack", "idwt_deep", "idwt_l0", "ld_dc", "assemble", "index"};
   /* name, W, H, chroma format, bits, wavelet, depth, -u, -a, prefix, scalar, mode, q, bytes, content, timed */
   const Case cases[] = {
@@ -154,6 +155,7 @@ int main(int argc, char** argv) {
     {"C5 LD LeGall d3 2073600", 1920, 1080, 1, 10, VC2_LEGALL, 3, 1, 2, 0, 1, VC2_LD, 0, 2073600, 0, 0},
     {"LD noise DD137 d2 tight", 1920, 1080, 0, 8, VC2_DD137, 2, 2, 4, 0, 1, VC2_LD, 0, 700000, 2, 0},
     {"odd slice starts: prefix 1 S1 q40", 1920, 1080, 1, 10, VC2_HAAR0, 3, 1, 2, 1, 1, VC2_HQ_VBR, 40, 0, 0, 0},
+    {"big slices -u4 -a8 d2 4:4:4", 1920, 1080, 0, 10, VC2_HAAR1, 2, 4, 8, 0, 2, VC2_HQ_VBR, 8, 0, 0, 0},
     {"noise CBR tight", 1920, 1080, 1, 10, VC2_LEGALL, 3, 1, 2, 0, 1, VC2_HQ_CBR, 0, 500000, 2, 0},
   };
   int bad = 0;
@@ -171,19 +173,26 @@ int main(int argc, char** argv) {
       gen_plane(pics[i] + 2 * (size_t)c->W * c->H, 1234u, 1, i, chh, cw, c->bits, c->content);
       gen_plane(pics[i] + 2 * ((size_t)c->W * c->H + (size_t)cw * chh), 1234u, 2, i, chh, cw, c->bits, c->content);
     }
-    const Result ra = run(&A, c, npic, pics, pic_bytes), rb = run(&B, c, npic, pics, pic_bytes);
-    const int same = ra.hash == rb.hash && ra.recon == rb.recon && ra.bytes == rb.bytes && ra.status == rb.status;
-    if (!same) bad++;
-    printf("%-32s %s  status %d/%d  payload %zu/%zu B  hash %016llx/%016llx  recon %016llx/%016llx\n", c->name, same ? "SAME" : "DIFFERENT",
-           ra.status, rb.status, ra.bytes, rb.bytes, (unsigned long long)ra.hash, (unsigned long long)rb.hash,
-           (unsigned long long)ra.recon, (unsigned long long)rb.recon);
+    Result r[MAXLIB];
+    for (int l = 0; l < nlib; ++l) r[l] = run(&L[l], c, npic, pics, pic_bytes);
+    printf("%-34s status %d  payload %zu B  hash %016llx  recon %016llx :", c->name, r[0].status, r[0].bytes,
+           (unsigned long long)r[0].hash, (unsigned long long)r[0].recon);
+    for (int l = 1; l < nlib; ++l) {
+      const int same = r[0].hash == r[l].hash && r[0].recon == r[l].recon && r[0].bytes == r[l].bytes && r[0].status == r[l].status;
+      if (!same) bad++;
+      printf(" %s", same ? "SAME" : "DIFFERENT");
+    }
+    printf("\n");
     if (c->timed)
       for (int s = 0; s < VC2_NUM_STAGES; ++s)
-        if (ra.launches[s] || rb.launches[s])
-          printf("    %-10s %8.3f ms -> %8.3f ms per %d pictures (%+.1f %%)\n", stage[s], ra.ms[s], rb.ms[s], npic, 100.0 * (rb.ms[s] / ra.ms[s] - 1.0));
+        if (r[0].launches[s]) {
+          printf("    %-10s %8.3f ms per %d pictures ->", stage[s], r[0].ms[s], npic);
+          for (int l = 1; l < nlib; ++l) printf("  %8.3f (%+.1f %%)", r[l].ms[s], 100.0 * (r[l].ms[s] / r[0].ms[s] - 1.0));
+          printf("\n");
+        }
     for (int i = 0; i < distinct; ++i) free(pics[i]);
     free(pics);
   }
-  printf(bad ? "%d case(s) DIFFER\n" : "all cases identical\n", bad);
+  printf(bad ? "%d comparison(s) DIFFER\n" : "all cases identical\n", bad);
   return bad ? 1 : 0;
 }

@@ -157,6 +157,9 @@ __device__ __forceinline__ int scale_band(int v, const BandP& bp) {   // bp.qo a
 //   src  : this lane's first piece of the component (pieces are 32 int4 apart, see vc2_common.cuh)
 //   op(v, bp) is called once per coefficient, in coding order
 // ------------------------------------------------------------------------------------------
+#ifndef VC2_WALK_UNROLL
+#define VC2_WALK_UNROLL
+#endif
 template <class Op>
 __device__ __forceinline__ void walk_component(const int4* __restrict__ src, const SliceGeom& g, int c, int q, bool& badq, Op& op) {
   const int n = g.band_start[c][g.nbands];
@@ -168,16 +171,36 @@ __device__ __forceinline__ void walk_component(const int4* __restrict__ src, con
   int4 n0 = __ldg(src), n1 = n0, n2 = n0;
   if (np > 1) n1 = __ldg(src + 32);
   if (np > 2) n2 = __ldg(src + 64);
-  for (int piece = 0; piece < np; ++piece) {
-    const int4 v4 = n0;
-    n0 = n1; n1 = n2;
-    if (piece + 3 < np) n2 = __ldg(src + (size_t)(piece + 3) * 32);
-    const int v[4] = {v4.x, v4.y, v4.z, v4.w};
-    if (bend - k >= 4) {
-      op.pair(v[0], v[1], bp);
-      op.pair(v[2], v[3], bp);
-      k += 4;
+  int piece = 0;
+  while (piece < np) {
+    while (k == bend) {   // coefficient k exists (piece < np), so does its band
+      ++b;
+      bend = g.band_start[c][b + 1];
+      bp = band_params(q, g.qmatrix[b], badq);
+    }
+    // the whole pieces inside the current band are one inner loop: band bookkeeping (constant-bank look-ups, the
+    // quantiser parameters) stays outside it
+    const int run = min((bend - k) >> 2, np - piece);
+    if (run > 0) {
+      k += 4 * run;
+      const int4* pf = src + (size_t)(piece + 3) * 32;
+      int ahead = np - (piece + 3);   // pieces that can still be prefetched
+      piece += run;
+      VC2_WALK_UNROLL
+      for (int i = 0; i < run; ++i) {
+        const int4 v4 = n0;
+        n0 = n1; n1 = n2;
+        if (ahead > 0) n2 = __ldg(pf);
+        pf += 32; --ahead;
+        op.pair(v4.x, v4.y, bp);
+        op.pair(v4.z, v4.w, bp);
+      }
     } else {
+      const int4 v4 = n0;
+      n0 = n1; n1 = n2;
+      if (piece + 3 < np) n2 = __ldg(src + (size_t)(piece + 3) * 32);
+      ++piece;
+      const int v[4] = {v4.x, v4.y, v4.z, v4.w};
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         while (k == bend) {
