@@ -155,7 +155,7 @@ int main(int argc, char** argv) {
     {"C5 LD LeGall d3 2073600", 1920, 1080, 1, 10, VC2_LEGALL, 3, 1, 2, 0, 1, VC2_LD, 0, 2073600, 0, 0},
     {"LD noise DD137 d2 tight", 1920, 1080, 0, 8, VC2_DD137, 2, 2, 4, 0, 1, VC2_LD, 0, 700000, 2, 0},
     {"odd slice starts: prefix 1 S1 q40", 1920, 1080, 1, 10, VC2_HAAR0, 3, 1, 2, 1, 1, VC2_HQ_VBR, 40, 0, 0, 0},
-    {"big slices -u4 -a8 d2 4:4:4", 1920, 1080, 0, 10, VC2_HAAR1, 2, 4, 8, 0, 2, VC2_HQ_VBR, 8, 0, 0, 0},
+    {"big slices -u2 -a8 d2 4:4:4", 1920, 1080, 0, 10, VC2_HAAR1, 2, 2, 8, 0, 2, VC2_HQ_VBR, 8, 0, 0, 0},
     {"noise CBR tight", 1920, 1080, 1, 10, VC2_LEGALL, 3, 1, 2, 0, 1, VC2_HQ_CBR, 0, 500000, 2, 0},
   };
   int bad = 0;

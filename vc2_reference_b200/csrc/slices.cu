@@ -1035,17 +1035,32 @@ __global__ void __launch_bounds__(128) slice_unpack_kernel(const UnpackParams p)
       BandP bp = band_params(qi, g.qmatrix[0], badq);
       int4* cdst = dst + (size_t)(g.comp_start[c] >> 2) * 32;
       const int n = g.band_start[c][g.nbands];
-      for (int piece = 0; piece < (n >> 2); ++piece) {
-        int v[4];
-        if (bend - k >= 4) {   // warp uniform: the four coefficients belong to the current band
-          br.get_vlc2(s_dec, range_err, v[0], v[1]);
-          br.get_vlc2(s_dec, range_err, v[2], v[3]);
-          if (DEQ) {
+      const int np = n >> 2;
+      int piece = 0;
+      while (piece < np) {
+        while (k == bend) {   // coefficient k exists (piece < np), so does its band
+          ++b;
+          bend = g.band_start[c][b + 1];
+          bp = band_params(qi, g.qmatrix[b], badq);
+        }
+        // warp uniform: the whole pieces inside the current band are one inner loop (see walk_component)
+        const int run = min((bend - k) >> 2, np - piece);
+        if (run > 0) {
+          k += 4 * run;
+          piece += run;
+          for (int i = 0; i < run; ++i) {
+            int v[4];
+            br.get_vlc2(s_dec, range_err, v[0], v[1]);
+            br.get_vlc2(s_dec, range_err, v[2], v[3]);
+            if (DEQ) {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) v[e] = scale_band(v[e], bp);
+              for (int e = 0; e < 4; ++e) v[e] = scale_band(v[e], bp);
+            }
+            *cdst = make_int4(v[0], v[1], v[2], v[3]);
+            cdst += 32;
           }
-          k += 4;
         } else {
+          int v[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             while (k == bend) {
@@ -1057,8 +1072,10 @@ __global__ void __launch_bounds__(128) slice_unpack_kernel(const UnpackParams p)
             v[e] = DEQ ? scale_band(x, bp) : x;
             ++k;
           }
+          *cdst = make_int4(v[0], v[1], v[2], v[3]);
+          cdst += 32;
+          ++piece;
         }
-        cdst[(size_t)piece * 32] = make_int4(v[0], v[1], v[2], v[3]);
       }
     }
     if (bad) flags |= VC2_FLAG_STREAM;
