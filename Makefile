@@ -41,6 +41,16 @@ $(CSRC)/dwt_inv.o: $(CSRC)/dwt.cu $(CSRC)/*.cuh include/vc2_cabi.h
 $(LIB): $(OBJS)
 	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -lcudart
 
+# A/B probe (tools/pack_probe.c): `make probe-baseline` once on a build the GPU tests passed on, change a kernel,
+# `make probe`, then on the GPU box: tools/_probe/pack_probe 32 tools/_probe/baseline.so vc2_reference_b200/libvc2b200.so
+# (about 25 s of box time per call: no Python start-up).  tools/_probe/ is git-ignored but travels with gpurun.
+probe: $(LIB)
+	mkdir -p tools/_probe
+	$(CC) -O2 -Wall tools/pack_probe.c -o tools/_probe/pack_probe -ldl
+probe-baseline: $(LIB)
+	mkdir -p tools/_probe
+	cp $(LIB) tools/_probe/baseline.so
+
 clean:
 	rm -f $(OBJS) $(LIB) $(HOSTLIB) $(BIN)/EncodeStream $(BIN)/DecodeStream $(BIN)/DecodeFrame
-.PHONY: all clean
+.PHONY: all clean probe probe-baseline
