@@ -8,7 +8,7 @@ NVFLAGS   := -O3 -std=c++17 -lineinfo -diag-suppress 177 $(ARCH) -Xcompiler -fPI
 PKG       := vc2_reference_b200
 CSRC      := $(PKG)/csrc
 LIB       := $(PKG)/libvc2b200.so
-OBJS      := $(CSRC)/dwt_fwd.o $(CSRC)/dwt_inv.o $(CSRC)/slices.o $(CSRC)/cabi.o
+OBJS      := $(CSRC)/dwt_fwd.o $(CSRC)/dwt_inv.o $(CSRC)/dwt_tile_fwd.o $(CSRC)/dwt_tile_inv.o $(CSRC)/slices.o $(CSRC)/cabi.o
 
 ORACLE    := oracle/_build/libvc2oracle.so
 
@@ -36,6 +36,11 @@ $(CSRC)/%.o: $(CSRC)/%.cu $(CSRC)/*.cuh include/vc2_cabi.h
 $(CSRC)/dwt_fwd.o: $(CSRC)/dwt.cu $(CSRC)/*.cuh include/vc2_cabi.h
 	$(NVCC) $(NVFLAGS) -DVC2_DWT_PART=1 -c $< -o $@
 $(CSRC)/dwt_inv.o: $(CSRC)/dwt.cu $(CSRC)/*.cuh include/vc2_cabi.h
+	$(NVCC) $(NVFLAGS) -DVC2_DWT_PART=2 -c $< -o $@
+
+$(CSRC)/dwt_tile_fwd.o: $(CSRC)/dwt_tile.cu $(CSRC)/*.cuh include/vc2_cabi.h
+	$(NVCC) $(NVFLAGS) -DVC2_DWT_PART=1 -c $< -o $@
+$(CSRC)/dwt_tile_inv.o: $(CSRC)/dwt_tile.cu $(CSRC)/*.cuh include/vc2_cabi.h
 	$(NVCC) $(NVFLAGS) -DVC2_DWT_PART=2 -c $< -o $@
 
 $(LIB): $(OBJS)

@@ -19,6 +19,8 @@
 namespace vc2 {
 cudaError_t dwt_fwd_launch(cudaStream_t s, int kernel, int sample_kind, const DwtParams& p, int npictures, int seg_rows);
 cudaError_t dwt_inv_launch(cudaStream_t s, int kernel, int sample_kind, const DwtParams& p, int npictures, int seg_rows);
+cudaError_t dwt_tile_fwd_launch(cudaStream_t s, int kernel, int sample_kind, const DwtParams& p, int npictures, int cfg);
+cudaError_t dwt_tile_inv_launch(cudaStream_t s, int kernel, int sample_kind, const DwtParams& p, int npictures, int cfg);
 }  // namespace vc2
 
 using namespace vc2;
@@ -221,6 +223,7 @@ struct vc2_ctx {
   int dwt_pd = 2;                 // prefetch distance in row pairs (VC2_DWT_PD)
   int dwt_fast = 1;               // fast loop of the lifting kernels (VC2_DWT_FAST=0 turns it off)
   int dwt_seg_rows = 0;           // > 0: forced rows per warp (tuning, VC2_DWT_SEG_ROWS)
+  int dwt_tile = 0;               // lifting kernels: 0 = streaming register rings (dwt.cu), 1 / 2 = shared-memory tiles (dwt_tile.cu, VC2_DWT_TILE)
   // optional per-kernel timing with CUDA events on the launch stream (vc2_profile_*)
   bool profiling = false;
   struct Span { int stage; cudaEvent_t a, b; };
@@ -298,6 +301,7 @@ extern "C" vc2_ctx* vc2_create(int device) {
   if (const char* e = getenv("VC2_DWT_MIN_WARPS")) c->dwt_min_warps = atoi(e);
   if (const char* e = getenv("VC2_DWT_PD")) c->dwt_pd = atoi(e);
   if (const char* e = getenv("VC2_DWT_FAST")) c->dwt_fast = atoi(e) != 0;
+  if (const char* e = getenv("VC2_DWT_TILE")) c->dwt_tile = atoi(e);
   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return nullptr; }
   c->own_stream = true;
   QuantTables t;
@@ -440,8 +444,12 @@ static cudaError_t run_dwt(vc2_ctx* ctx, bool inverse, int kernel, int depth, in
     int seg_rows = 256;
     while (seg_rows > 32 && (cols / 240 + ncomp) * ((maxh + seg_rows - 1) / seg_rows) * npictures < ctx->dwt_min_warps) seg_rows >>= 1;
     if (ctx->dwt_seg_rows > 0) seg_rows = ctx->dwt_seg_rows;
-    cudaError_t e = inverse ? dwt_inv_launch(ctx->stream, kernel, l == 0 ? sample_kind : SAMPLE_I32, p, npictures, seg_rows)
-                            : dwt_fwd_launch(ctx->stream, kernel, l == 0 ? sample_kind : SAMPLE_I32, p, npictures, seg_rows);
+    const int kind = l == 0 ? sample_kind : SAMPLE_I32;
+    cudaError_t e;
+    if (ctx->dwt_tile) e = inverse ? dwt_tile_inv_launch(ctx->stream, kernel, kind, p, npictures, ctx->dwt_tile)
+                                   : dwt_tile_fwd_launch(ctx->stream, kernel, kind, p, npictures, ctx->dwt_tile);
+    else e = inverse ? dwt_inv_launch(ctx->stream, kernel, kind, p, npictures, seg_rows)
+                     : dwt_fwd_launch(ctx->stream, kernel, kind, p, npictures, seg_rows);
     if (e != cudaSuccess) return e;
     ctx->launches++;
   }

@@ -14,8 +14,7 @@
 // is reproduced by an "edge" variant of each step taken only for rows near the top/bottom (the tap
 // is redirected to the first row of that parity, or to a register copy of the last one), and by
 // extending the source-parity sequence past the left/right border before each horizontal step.
-#include "dwt.cuh"
-#include "slices.cuh"
+#include "dwt_lift.cuh"
 
 #ifndef VC2_DWT_PART
 #error "compile with -DVC2_DWT_PART=1 (forward) or =2 (inverse + layout)"
@@ -25,7 +24,6 @@ namespace vc2 {
 
 namespace {
 
-constexpr unsigned FULL = 0xFFFFFFFFu;
 constexpr int WARPS = 4;   // warps per CTA: four vertically adjacent row segments of one strip
 #ifndef VC2_DWT_NO_SWPIPE
 #define VC2_DWT_SWPIPE 1   // forward fast loop, 16-bit samples: the next row pair is loaded before the current one is used
@@ -35,10 +33,6 @@ constexpr int WARPS = 4;   // warps per CTA: four vertically adjacent row segmen
 #endif
 
 // ---- compile-time schedule of the vertical pipeline ------------------------------------------------
-__host__ __device__ constexpr int cmax(int a, int b) { return a > b ? a : b; }
-__host__ __device__ constexpr int cgcd(int a, int b) { return b == 0 ? a : cgcd(b, a % b); }
-__host__ __device__ constexpr int pmod(int a, int m) { return ((a % m) + m) % m; }
-
 template <int K, int DIR>
 struct Sched {
   static constexpr int n = Wavelet<K>::NSTEPS;
@@ -78,77 +72,6 @@ struct Geo {
   static constexpr int XU = XW - 2 * HX;              // useful columns per warp
 };
 
-// ---- horizontal lifting step in registers ------------------------------------------------------
-// A lane holds pairs PPL*lane .. PPL*lane+PPL-1 of a row segment: e[a] / o[a] = even / odd sample of
-// pair PPL*lane+a.  Neighbouring pairs come from other lanes by shuffle.  When the segment touches
-// the left/right edge of the lattice (hedge), the source-parity sequence is first extended beyond
-// [plo, phi] with its edge value = the reference's tap clamping.
-template <int PPL>
-__device__ __forceinline__ int pick(const int (&x)[PPL], int i) {
-  int v = x[0];
-#pragma unroll
-  for (int a = 1; a < PPL; ++a) v = (i == a) ? x[a] : v;
-  return v;
-}
-
-template <int K, int S, int DIR, int PPL>
-__device__ __forceinline__ void hstep(int (&e)[PPL], int (&o)[PPL], int lane, bool hedge, int plo, int phi) {
-  using ST = Step<K, S>;
-  constexpr int P = ST::P, N = ST::N;
-  int (&src)[PPL] = P ? e : o;
-  int (&tgt)[PPL] = P ? o : e;
-  if (hedge) {
-    const int vlo = __shfl_sync(FULL, pick<PPL>(src, plo % PPL), plo / PPL);
-    const int vhi = __shfl_sync(FULL, pick<PPL>(src, phi % PPL), phi / PPL);
-#pragma unroll
-    for (int a = 0; a < PPL; ++a) {
-      const int p = PPL * lane + a;
-      if (p < plo) src[a] = vlo; else if (p > phi) src[a] = vhi;
-    }
-  }
-  constexpr int QMIN = -(P ? N - 1 : N), QMAX = PPL - 1 + (P ? N : N - 1);
-  int nb[QMAX - QMIN + 1];   // source values at pair offsets QMIN..QMAX from pair PPL*lane
-#pragma unroll
-  for (int q = QMIN; q <= QMAX; ++q) {
-    const int r = pmod(q, PPL), dl = (q - r) / PPL;
-    nb[q - QMIN] = dl == 0 ? src[r] : __shfl_sync(FULL, src[r], lane + dl);
-  }
-#pragma unroll
-  for (int a = 0; a < PPL; ++a) {
-    unsigned sum = (unsigned)ST::ADD;
-#pragma unroll
-    for (int k = 0; k < N; ++k) {
-      const unsigned l = (unsigned)nb[a - (P ? k : k + 1) - QMIN], r = (unsigned)nb[a + (P ? k + 1 : k) - QMIN];
-      if (ST::cl(k) == ST::cr(k)) { if (ST::cl(k) != 0) sum += (unsigned)ST::cl(k) * (l + r); }
-      else {
-        if (ST::cl(k) != 0) sum += (unsigned)ST::cl(k) * l;
-        if (ST::cr(k) != 0) sum += (unsigned)ST::cr(k) * r;
-      }
-    }
-    const int delta = ((int)sum) >> ST::SH;
-    tgt[a] = (ST::SIGN * DIR > 0) ? (int)((unsigned)tgt[a] + (unsigned)delta) : (int)((unsigned)tgt[a] - (unsigned)delta);
-  }
-}
-
-template <int K, int DIR, int PPL>
-__device__ __forceinline__ void hsteps(int (&e)[PPL], int (&o)[PPL], int lane, bool hedge, int plo, int phi) {
-  constexpr int N = Wavelet<K>::NSTEPS;
-  if constexpr (DIR > 0) {
-    hstep<K, 0, DIR, PPL>(e, o, lane, hedge, plo, phi);
-    hstep<K, 1, DIR, PPL>(e, o, lane, hedge, plo, phi);
-    if constexpr (N == 4) {
-      hstep<K, 2, DIR, PPL>(e, o, lane, hedge, plo, phi);
-      hstep<K, 3, DIR, PPL>(e, o, lane, hedge, plo, phi);
-    }
-  } else {
-    if constexpr (N == 4) {
-      hstep<K, 3, DIR, PPL>(e, o, lane, hedge, plo, phi);
-      hstep<K, 2, DIR, PPL>(e, o, lane, hedge, plo, phi);
-    }
-    hstep<K, 1, DIR, PPL>(e, o, lane, hedge, plo, phi);
-    hstep<K, 0, DIR, PPL>(e, o, lane, hedge, plo, phi);
-  }
-}
 
 // ---- the per-lane state of the vertical pipeline ---------------------------------------------------
 // Rings are indexed by AGE: A[i] = A row (a - 2i), B[i] = B row (r0 - 2i), a = newest A row of the current
@@ -205,7 +128,7 @@ __device__ __forceinline__ void vstep(Rings<K, DIR>& g, int a, int r, int last) 
   const int age_first = (newest - spar) >> 1, age_last = (newest - (last - 1 + spar)) >> 1;
 #pragma unroll
   for (int v = 0; v < V; ++v) {
-    unsigned sum = (unsigned)ST::ADD;
+    int lv[N], rv[N];
 #pragma unroll
     for (int k = 0; k < N; ++k) {
       int l, rr;
@@ -224,15 +147,10 @@ __device__ __forceinline__ void vstep(Rings<K, DIR>& g, int a, int r, int last) 
           if (r + (2 * k + 1) > last) rr = pick_row<SC::WR, V>(g.A, age_last, v);
         }
       }
-      if (ST::cl(k) == ST::cr(k)) { if (ST::cl(k) != 0) sum += (unsigned)ST::cl(k) * ((unsigned)l + (unsigned)rr); }
-      else {
-        if (ST::cl(k) != 0) sum += (unsigned)ST::cl(k) * (unsigned)l;
-        if (ST::cr(k) != 0) sum += (unsigned)ST::cr(k) * (unsigned)rr;
-      }
+      lv[k] = l; rv[k] = rr;
     }
-    const int delta = ((int)sum) >> ST::SH;
     int& t = TA ? g.A[tage][v] : g.B[tage][v];
-    t = (ST::SIGN * DIR > 0) ? (int)((unsigned)t + (unsigned)delta) : (int)((unsigned)t - (unsigned)delta);
+    t = lift_update<K, S, DIR>(t, [&](int k, bool right) { return right ? rv[k] : lv[k]; });
   }
 }
 
@@ -262,26 +180,11 @@ __device__ __forceinline__ void vstep_rot(Rings<K, DIR>& g) {
   constexpr int tage = TA ? L / 2 : (L - SC::reach(0)) / 2;
 #pragma unroll
   for (int v = 0; v < V; ++v) {
-    unsigned sum = (unsigned)ST::ADD;
-#pragma unroll
-    for (int k = 0; k < N; ++k) {
-      int l, rr;
-      if constexpr (TA) {
-        l = g.B[((L + (2 * k + 1) - SC::reach(0)) / 2 + R) % W][v];
-        rr = g.B[((L - (2 * k + 1) - SC::reach(0)) / 2 + R) % W][v];
-      } else {
-        l = g.A[((L + (2 * k + 1)) / 2 + R) % W][v];
-        rr = g.A[((L - (2 * k + 1)) / 2 + R) % W][v];
-      }
-      if (ST::cl(k) == ST::cr(k)) { if (ST::cl(k) != 0) sum += (unsigned)ST::cl(k) * ((unsigned)l + (unsigned)rr); }
-      else {
-        if (ST::cl(k) != 0) sum += (unsigned)ST::cl(k) * (unsigned)l;
-        if (ST::cr(k) != 0) sum += (unsigned)ST::cr(k) * (unsigned)rr;
-      }
-    }
-    const int delta = ((int)sum) >> ST::SH;
     int& t = TA ? g.A[(tage + R) % W][v] : g.B[(tage + R) % W][v];
-    t = (ST::SIGN * DIR > 0) ? (int)((unsigned)t + (unsigned)delta) : (int)((unsigned)t - (unsigned)delta);
+    t = lift_update<K, S, DIR>(t, [&](int k, bool right) {
+      if constexpr (TA) return right ? g.B[((L - (2 * k + 1) - SC::reach(0)) / 2 + R) % W][v] : g.B[((L + (2 * k + 1) - SC::reach(0)) / 2 + R) % W][v];
+      else return right ? g.A[((L - (2 * k + 1)) / 2 + R) % W][v] : g.A[((L + (2 * k + 1)) / 2 + R) % W][v];
+    });
   }
 }
 template <int K, int DIR, int R>
@@ -310,130 +213,6 @@ struct FastCtx {
   }
 };
 
-// ---- global memory access of one lane's V columns of one row -------------------------------------------
-struct BandAddr {   // group-interleaved addressing of band samples (see vc2_common.cuh)
-  int bh, bw, lgbh, lgbw, nx, nc4;
-  __device__ __forceinline__ long long at(int base, int by, int bx) const {
-    const int sy = lgbh >= 0 ? (by >> lgbh) : (by / bh);
-    const int sx = lgbw >= 0 ? (bx >> lgbw) : (bx / bw);
-    return coef_index(sy * nx + sx, base + (by - sy * bh) * bw + (bx - sx * bw), nc4);
-  }
-};
-
-__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
-// prefetch distance in row pairs: StripCtx::pd (DwtParams::pd, host tuned)
-
-// forward: touch the cache line(s) of this lane's samples of picture row `row`
-template <int KIND, int V>
-__device__ __forceinline__ void prefetch_pix(const DwtComp& C, int pic, int row, int gx) {
-  if (row > C.pix_h - 1 || gx < 0 || gx + V - 1 >= C.pix_w) return;
-  const int esz = KIND == SAMPLE_I32 ? 4 : KIND == SAMPLE_U16BE ? 2 : 1;
-  const uint8_t* base = (const uint8_t*)C.pix + (KIND == SAMPLE_I32 ? (long long)pic * C.pix_pic_stride * 4 : (long long)pic * C.pix_pic_stride);
-  prefetch_l1(base + ((long long)row * C.pix_pitch + gx) * esz);
-}
-
-__device__ __forceinline__ int sample_u16be(unsigned w, int sshift, int soffset) {
-  return (int)(__byte_perm(w, 0, 0x4401) >> sshift) - soffset;
-}
-
-// forward: load V consecutive samples of picture row `row` starting at column gx (may be negative / past the edge)
-template <int KIND, int V>
-__device__ __forceinline__ void load_pix(const DwtComp& C, int pic, int row, int gx, int (&x)[V]) {
-  const int sy = min(row, C.pix_h - 1);                 // waveletPad: replicate the last row (WaveletTransform.cpp:88)
-  const bool inside = gx >= 0 && gx + V - 1 < C.pix_w;   // all V samples are real picture samples
-  if (KIND == SAMPLE_I32) {
-    const int* rp = (const int*)C.pix + (long long)pic * C.pix_pic_stride + (long long)sy * C.pix_pitch;
-    if (inside && ((reinterpret_cast<uintptr_t>(rp + gx) & 15) == 0)) {
-#pragma unroll
-      for (int j = 0; j < V; j += 4) {
-        const int4 q = __ldg(reinterpret_cast<const int4*>(rp + gx + j));
-        x[j] = q.x; x[j + 1] = q.y; x[j + 2] = q.z; x[j + 3] = q.w;
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < V; ++j) x[j] = rp[min(max(gx + j, 0), C.pix_w - 1)];   // :89 replicate the last column
-    }
-  } else if (KIND == SAMPLE_U16BE) {
-    const uint16_t* rp = (const uint16_t*)((const uint8_t*)C.pix + (long long)pic * C.pix_pic_stride) + (long long)sy * C.pix_pitch;
-    if (inside && ((reinterpret_cast<uintptr_t>(rp + gx) & (2 * V - 1)) == 0)) {
-      unsigned w[V / 2];
-      if (V == 8) {
-        const uint4 q = __ldg(reinterpret_cast<const uint4*>(rp + gx));
-        w[0] = q.x; w[1] = q.y; w[V / 2 - 2] = q.z; w[V / 2 - 1] = q.w;
-      } else {
-        const uint2 q = __ldg(reinterpret_cast<const uint2*>(rp + gx));
-        w[0] = q.x; w[1] = q.y;
-      }
-#pragma unroll
-      for (int j = 0; j < V / 2; ++j) {
-        x[2 * j] = sample_u16be(w[j] & 0xFFFFu, C.sshift, C.soffset);
-        x[2 * j + 1] = (int)(__byte_perm(w[j], 0, 0x4423) >> C.sshift) - C.soffset;
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < V; ++j) x[j] = sample_u16be(rp[min(max(gx + j, 0), C.pix_w - 1)], C.sshift, C.soffset);
-    }
-  } else {
-    const uint8_t* rp = (const uint8_t*)C.pix + (long long)pic * C.pix_pic_stride + (long long)sy * C.pix_pitch;
-#pragma unroll
-    for (int j = 0; j < V; ++j) x[j] = (int)((unsigned)rp[min(max(gx + j, 0), C.pix_w - 1)] >> C.sshift) - C.soffset;
-  }
-}
-
-// PPL consecutive samples of band row `by` starting at band column bx0 (multiple of PPL): vector access when
-// the run is one aligned piece of the interleaved layout, else element by element
-template <int PPL, bool STORE>
-__device__ __forceinline__ void band_access(int32_t* coef, const BandAddr& ba, int base, int by, int bx0, int bxmax, int (&x)[PPL]) {
-  if (bx0 < 0 || bx0 > bxmax) {
-    if (!STORE) {
-#pragma unroll
-      for (int j = 0; j < PPL; ++j) x[j] = 0;
-    }
-    return;
-  }
-  const bool vec = PPL == 4 && (ba.bw & 3) == 0 && (base & 3) == 0 && bx0 + 3 <= bxmax;
-  if (vec) {
-    int4* p = reinterpret_cast<int4*>(coef + ba.at(base, by, bx0));
-    if (STORE) *p = make_int4(x[0], x[1], x[PPL > 2 ? 2 : 0], x[PPL > 3 ? 3 : 0]);
-    else { const int4 q = __ldg(p); x[0] = q.x; x[1] = q.y; x[PPL > 2 ? 2 : 0] = q.z; x[PPL > 3 ? 3 : 0] = q.w; }
-  } else {
-#pragma unroll
-    for (int j = 0; j < PPL; ++j) {
-      if (bx0 + j <= bxmax) {
-        int32_t* p = coef + ba.at(base, by, bx0 + j);
-        if (STORE) *p = x[j]; else x[j] = *p;
-      } else if (!STORE) x[j] = 0;
-    }
-  }
-}
-template <int PPL>
-__device__ __forceinline__ void band_prefetch(const int32_t* coef, const BandAddr& ba, int base, int by, int bx0, int bxmax) {
-  if (bx0 < 0 || bx0 > bxmax) return;
-  prefetch_l1(coef + ba.at(base, by, bx0));
-}
-// same for the compact LL plane between levels
-template <int PPL, bool STORE>
-__device__ __forceinline__ void ll_access(int32_t* ll, long long pitch, int by, int bx0, int bxmax, int (&x)[PPL]) {
-  if (bx0 < 0 || bx0 > bxmax) {
-    if (!STORE) {
-#pragma unroll
-      for (int j = 0; j < PPL; ++j) x[j] = 0;
-    }
-    return;
-  }
-  int32_t* p = ll + (long long)by * pitch + bx0;
-  if (PPL == 4 && bx0 + 3 <= bxmax && ((reinterpret_cast<uintptr_t>(p) & 15) == 0)) {
-    int4* q = reinterpret_cast<int4*>(p);
-    if (STORE) *q = make_int4(x[0], x[1], x[PPL > 2 ? 2 : 0], x[PPL > 3 ? 3 : 0]);
-    else { const int4 t = __ldg(q); x[0] = t.x; x[1] = t.y; x[PPL > 2 ? 2 : 0] = t.z; x[PPL > 3 ? 3 : 0] = t.w; }
-  } else {
-#pragma unroll
-    for (int j = 0; j < PPL; ++j) {
-      if (bx0 + j <= bxmax) { if (STORE) p[j] = x[j]; else x[j] = p[j]; }
-      else if (!STORE) x[j] = 0;
-    }
-  }
-}
 
 // per-warp constants of one strip segment
 struct StripCtx {
@@ -773,43 +552,9 @@ __device__ __forceinline__ void inv_emit_row(const DwtComp& C, const StripCtx& S
   const int gx = S.xs + V * S.lane;
   if (!S.mine || row >= C.pix_h || gx >= C.pix_w) return;
   int v[V];
-  const int rnd = SHIFT ? (1 << (SHIFT - 1)) : 0;
 #pragma unroll
   for (int a = 0; a < PPL; ++a) { v[2 * a] = e[a]; v[2 * a + 1] = o[a]; }
-#pragma unroll
-  for (int k = 0; k < V; ++k) {
-    if (SHIFT) v[k] = (v[k] + rnd) >> SHIFT;
-    if (KIND != SAMPLE_I32) v[k] = (int)((unsigned)(min(max(v[k], C.clip_min), C.clip_max) + C.soffset) << C.sshift);
-  }
-  const long long rowoff = (long long)row * C.pix_pitch;
-  const bool whole = gx + V - 1 < C.pix_w;
-  if (KIND == SAMPLE_I32) {
-    int* dst = (int*)C.pix + (long long)S.pic * C.pix_pic_stride + rowoff + gx;
-    if (whole && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
-#pragma unroll
-      for (int j = 0; j < V; j += 4) *reinterpret_cast<int4*>(dst + j) = make_int4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-    } else {
-#pragma unroll
-      for (int k = 0; k < V; ++k) if (gx + k < C.pix_w) dst[k] = v[k];
-    }
-  } else if (KIND == SAMPLE_U16BE) {
-    // offset binary, MSB justified, big endian (Arrays.cpp:396-414)
-    uint16_t* dst = (uint16_t*)((uint8_t*)C.pix + (long long)S.pic * C.pix_pic_stride) + rowoff + gx;
-    unsigned w[V / 2];
-#pragma unroll
-    for (int j = 0; j < V / 2; ++j) w[j] = __byte_perm((unsigned)v[2 * j], (unsigned)v[2 * j + 1], 0x4501);
-    if (whole && ((reinterpret_cast<uintptr_t>(dst) & (2 * V - 1)) == 0)) {
-      if (V == 8) *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[V / 2 - 2], w[V / 2 - 1]);
-      else *reinterpret_cast<uint2*>(dst) = make_uint2(w[0], w[1]);
-    } else {
-#pragma unroll
-      for (int k = 0; k < V; ++k) if (gx + k < C.pix_w) dst[k] = (uint16_t)((k & 1) ? (w[k / 2] >> 16) : (w[k / 2] & 0xFFFFu));
-    }
-  } else {
-    uint8_t* dst = (uint8_t*)C.pix + (long long)S.pic * C.pix_pic_stride + rowoff + gx;
-#pragma unroll
-    for (int k = 0; k < V; ++k) if (gx + k < C.pix_w) dst[k] = (uint8_t)v[k];
-  }
+  store_pix<K, KIND, V>(C, S.pic, row, gx, v);
 }
 
 template <int K, int KIND>
