@@ -4,7 +4,7 @@ NVCC      ?= nvcc
 CXX       ?= g++
 CC        ?= gcc
 ARCH      := -gencode arch=compute_100a,code=sm_100a
-NVFLAGS   := -O3 -std=c++17 -lineinfo -diag-suppress 177 $(ARCH) -Xcompiler -fPIC
+NVFLAGS   := -O3 -std=c++17 -lineinfo -diag-suppress 177 $(ARCH) -Xcompiler -fPIC $(EXTRA)
 PKG       := vc2_reference_b200
 CSRC      := $(PKG)/csrc
 LIB       := $(PKG)/libvc2b200.so

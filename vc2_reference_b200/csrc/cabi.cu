@@ -223,7 +223,7 @@ struct vc2_ctx {
   int dwt_pd = 2;                 // prefetch distance in row pairs (VC2_DWT_PD)
   int dwt_fast = 1;               // fast loop of the lifting kernels (VC2_DWT_FAST=0 turns it off)
   int dwt_seg_rows = 0;           // > 0: forced rows per warp (tuning, VC2_DWT_SEG_ROWS)
-  int dwt_tile = 0;               // lifting kernels: 0 = streaming register rings (dwt.cu), 1 / 2 = shared-memory tiles (dwt_tile.cu, VC2_DWT_TILE)
+  int dwt_tile = 1;               // lifting kernels: 1 = shared-memory tiles (dwt_tile.cu), 0 = streaming register rings (dwt.cu; VC2_DWT_TILE=0)
   // optional per-kernel timing with CUDA events on the launch stream (vc2_profile_*)
   bool profiling = false;
   struct Span { int stage; cudaEvent_t a, b; };

@@ -91,13 +91,30 @@ struct DwtComp {
   // raw sample conversion (Arrays.cpp:351-376, 396-397): v = (word >> sshift) - soffset
   int sshift, soffset;
   int clip_min, clip_max;    // inverse level 0 on the fused path (Picture.cpp:284-292)
+  // NARROW coefficient block (tile kernels only): the block holds QUANTISED coefficients as 16-bit sign-magnitude words
+  // t = 2 * |q| + (q < 0) - the index of the packer's code table - in the same group-interleaved order.  The forward
+  // kernels quantise on the way out (Quantisation.cpp:69-76, one index per band: HQ_ConstQ), the inverse kernels
+  // scale on the way in (Quantisation.cpp:86-95, the index of the slice each piece belongs to).  [0..3] = LL, HL, LH, HH.
+  uint32_t qmul[4];          // forward: |q| = (|v| * qmul) >> qsh for |v| < VC2_NARROW_FAST_MAX (host-verified) ...
+  int qsh[4];
+  uint32_t qm31[4];          // ... else the one-multiply-high division of vc2_quant_magic31: |q| = mulhi(|v| << 2, qm31) >> ql31
+  int ql31[4];
+  int qmat[4];               // inverse: quantisation matrix entries of the four bands (Quantisation.cpp:16-20)
 };
+#define VC2_NARROW_FAST_MAX 8192
+#define VC2_NARROW_MAX_MAG 32767
 
 struct DwtParams {
   DwtComp c[3];
   int ncomp;
   int pd;   // prefetch distance of the streaming kernels, in row pairs
   int fast; // 1: interior rows of interior strips run the fast loop (dwt.cu); 0: general loop only (VC2_DWT_FAST=0)
+  // narrow coefficient block (see DwtComp)
+  int narrow;
+  uint32_t* narrow_ovf;      // [picture] set when a quantised magnitude does not fit 15 bits: the caller re-runs the picture wide
+  const int32_t* qidx;       // inverse: [picture][slice] quantisation index of every slice
+  int nslices;
+  const uint2* scale_tab;    // inverse: [128] (quant_factor, quant_offset + 2) in device memory
 };
 
 }  // namespace vc2

@@ -29,6 +29,18 @@ __device__ __forceinline__ int pick(const int (&x)[PPL], int i) {
 // One lifting update, x[t] += SIGN * ((ADD + sum_k CLk*x[t-(2k+1)] + CRk*x[t+(2k+1)]) >> SH)  (forward; the inverse
 // flips the sign).  A subtraction is folded into the sum: -(s >> n) == (2^n - 1 - s) >> n for an arithmetic shift, so
 // every update is "multiply-add chain, shift, add" (the shift-and-add is one LEA.HI.SX32).
+// c + (sa ? -a : a) + (sb ? -b : b) as one three-input add: the asm block keeps the compiler from re-associating the
+// rounding constant away from the two unit-weight taps
+template <bool SA, bool SB>
+__device__ __forceinline__ int add3(int c, int a, int b) {
+  int r;
+  if (SA && SB) asm("{ .reg .s32 t; sub.s32 t, %1, %2; sub.s32 %0, t, %3; }" : "=r"(r) : "r"(c), "r"(a), "r"(b));
+  else if (SA) asm("{ .reg .s32 t; sub.s32 t, %1, %2; add.s32 %0, t, %3; }" : "=r"(r) : "r"(c), "r"(a), "r"(b));
+  else if (SB) asm("{ .reg .s32 t; add.s32 t, %1, %2; sub.s32 %0, t, %3; }" : "=r"(r) : "r"(c), "r"(a), "r"(b));
+  else asm("{ .reg .s32 t; add.s32 t, %1, %2; add.s32 %0, t, %3; }" : "=r"(r) : "r"(c), "r"(a), "r"(b));
+  return r;
+}
+
 template <int K, int S, int DIR, class Tap>
 __device__ __forceinline__ int lift_update(int t, Tap tap) {   // tap(k, right) = source value at distance 2k+1 to the left / right
   using ST = Step<K, S>;
@@ -39,8 +51,16 @@ __device__ __forceinline__ int lift_update(int t, Tap tap) {   // tap(k, right) 
 #pragma unroll
   for (int k = 0; k < ST::N; ++k) {
     const int cl = NEG ? -ST::cl(k) : ST::cl(k), cr = NEG ? -ST::cr(k) : ST::cr(k);
-    if (cl == 1) u += tap(k, false); else if (cl == -1) u -= tap(k, false);
-    if (cr == 1) u += tap(k, true); else if (cr == -1) u -= tap(k, true);
+    const bool ul = cl == 1 || cl == -1, ur = cr == 1 || cr == -1;
+    if (ul && ur) {
+      if (cl < 0 && cr < 0) u = add3<true, true>(u, tap(k, false), tap(k, true));
+      else if (cl < 0) u = add3<true, false>(u, tap(k, false), tap(k, true));
+      else if (cr < 0) u = add3<false, true>(u, tap(k, false), tap(k, true));
+      else u = add3<false, false>(u, tap(k, false), tap(k, true));
+    } else {
+      if (cl == 1) u += tap(k, false); else if (cl == -1) u -= tap(k, false);
+      if (cr == 1) u += tap(k, true); else if (cr == -1) u -= tap(k, true);
+    }
   }
 #pragma unroll
   for (int k = 0; k < ST::N; ++k) {
@@ -99,6 +119,64 @@ __device__ __forceinline__ void hsteps(int (&e)[PPL], int (&o)[PPL], int lane, b
     }
     hstep<K, 1, DIR, PPL, WIDTH>(e, o, lane, hedge, plo, phi);
     hstep<K, 0, DIR, PPL, WIDTH>(e, o, lane, hedge, plo, phi);
+  }
+}
+
+// The same for NR independent row segments at once (the tile kernels lift several rows / columns per call so that the
+// shuffles of one segment overlap the arithmetic of another): e[r] / o[r] = pairs of segment r.
+template <int K, int S, int DIR, int PPL, int WIDTH, int NR>
+__device__ __forceinline__ void hstep_rows(int (&e)[NR][PPL], int (&o)[NR][PPL], int lane, bool hedge, int plo, int phi) {
+  using ST = Step<K, S>;
+  constexpr int P = ST::P, N = ST::N;
+  int (&src)[NR][PPL] = P ? e : o;
+  int (&tgt)[NR][PPL] = P ? o : e;
+  if (hedge) {
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+      const int vlo = __shfl_sync(FULL, pick<PPL>(src[r], plo % PPL), plo / PPL, WIDTH);
+      const int vhi = __shfl_sync(FULL, pick<PPL>(src[r], phi % PPL), phi / PPL, WIDTH);
+#pragma unroll
+      for (int a = 0; a < PPL; ++a) {
+        const int p = PPL * lane + a;
+        if (p < plo) src[r][a] = vlo; else if (p > phi) src[r][a] = vhi;
+      }
+    }
+  }
+  constexpr int QMIN = -(P ? N - 1 : N), QMAX = PPL - 1 + (P ? N : N - 1);
+  int nb[NR][QMAX - QMIN + 1];
+#pragma unroll
+  for (int r = 0; r < NR; ++r) {
+#pragma unroll
+    for (int q = QMIN; q <= QMAX; ++q) {
+      const int m = pmod(q, PPL), dl = (q - m) / PPL;
+      nb[r][q - QMIN] = dl == 0 ? src[r][m] : __shfl_sync(FULL, src[r][m], lane + dl, WIDTH);
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < NR; ++r) {
+#pragma unroll
+    for (int a = 0; a < PPL; ++a)
+      tgt[r][a] = lift_update<K, S, DIR>(tgt[r][a], [&](int k, bool right) { return right ? nb[r][a + (P ? k + 1 : k) - QMIN] : nb[r][a - (P ? k : k + 1) - QMIN]; });
+  }
+}
+
+template <int K, int DIR, int PPL, int WIDTH, int NR>
+__device__ __forceinline__ void hsteps_rows(int (&e)[NR][PPL], int (&o)[NR][PPL], int lane, bool hedge, int plo, int phi) {
+  constexpr int N = Wavelet<K>::NSTEPS;
+  if constexpr (DIR > 0) {
+    hstep_rows<K, 0, DIR, PPL, WIDTH, NR>(e, o, lane, hedge, plo, phi);
+    hstep_rows<K, 1, DIR, PPL, WIDTH, NR>(e, o, lane, hedge, plo, phi);
+    if constexpr (N == 4) {
+      hstep_rows<K, 2, DIR, PPL, WIDTH, NR>(e, o, lane, hedge, plo, phi);
+      hstep_rows<K, 3, DIR, PPL, WIDTH, NR>(e, o, lane, hedge, plo, phi);
+    }
+  } else {
+    if constexpr (N == 4) {
+      hstep_rows<K, 3, DIR, PPL, WIDTH, NR>(e, o, lane, hedge, plo, phi);
+      hstep_rows<K, 2, DIR, PPL, WIDTH, NR>(e, o, lane, hedge, plo, phi);
+    }
+    hstep_rows<K, 1, DIR, PPL, WIDTH, NR>(e, o, lane, hedge, plo, phi);
+    hstep_rows<K, 0, DIR, PPL, WIDTH, NR>(e, o, lane, hedge, plo, phi);
   }
 }
 

@@ -32,7 +32,7 @@ namespace vc2 {
 namespace {
 
 // TWL lanes per tile row (8 samples each), TVL lanes per tile column group (8 rows each), NW warps per CTA
-template <int K, int TWL_, int TVL_, int NW_, int MINB_>
+template <int K, int TWL_, int TVL_, int NW_, int MINB_, int TPC_>
 struct Tile {
   static constexpr int TWL = TWL_, TVL = TVL_, NW = NW_, MINB = MINB_;   // MINB: resident CTAs per SM the registers are held to
   static constexpr int HL = (Wavelet<K>::R + 7) / 8;      // halo, in lanes, on each side (both directions)
@@ -41,44 +41,47 @@ struct Tile {
   static constexpr int CHUNKS = 2 * TWL;                  // 16-byte chunks per tile row: TWL of even columns, then TWL of odd ones
   static constexpr int RPW = 32 / TWL;                    // rows per warp and iteration in the row phases
   static constexpr int TPW = 32 / TVL;                    // column tasks per warp and iteration in the column phase
+  static constexpr int NG = NW * RPW;                     // row groups: a group is TWL lanes working on one row at a time
   static constexpr int SMEM = TH * TW * 4;
-  static_assert(TH % (NW * RPW) == 0 && YU % (NW * RPW) == 0, "row phases run without a tail");
+  static constexpr int TPC = TPC_;                        // horizontally adjacent tiles per CTA (amortises the set-up)
+  static_assert(TH == 8 * NG, "a row group owns one swizzle block of eight tile rows");
 };
 
-struct TileList {     // flat list of the tiles of one picture: component c owns tiles [start[c], start[c + 1])
-  int tx[3], start[4];
+struct TileList {     // grid.x = CTA in its tile row, grid.y = tile row (both: the largest component), grid.z = picture * ncomp + component
+  int cx[3], tx[3], ty[3];   // CTAs per tile row, tiles per tile row, tile rows
 };
 
 __device__ __forceinline__ int swz(int row) { return (row >> 3) & 7; }
 
-// per-lane constants of the vectorised band access (band part widths are multiples of four, power-of-two part heights)
+// per-lane constants of the vectorised band access (band part widths are multiples of four, power-of-two part heights):
+// the 16-byte piece of band row `by` at this lane's band columns sits at element idx(by) behind the band's start
 struct BandFast {
-  int32_t* coefpic;
-  int sx, kx4, lgbh, bhm1, bw4, nx, nc4;
-  int o_ll, o_hl, o_lh, o_hh;
-  int32_t* llp;
+  int32_t *p_ll, *p_hl, *p_lh, *p_hh;   // picture block + band start (p_ll: compact LL plane at this lane's columns when plane_ll)
+  bool plane_ll;
   int ll_pitch;
+  int sx, kx4, lgbh, bhm1, bw4, nx, nc4;
   __device__ __forceinline__ int idx(int by) const {
     const int sy = by >> lgbh, ry = by & bhm1;
     const int s = sy * nx + sx;
     return ((((s >> 5) * nc4 + ry * bw4 + kx4) << 5) + (s & 31)) << 2;
   }
 };
-// false when this level / tile has to use the element-wise access
+// false when this level / lane has to use the element-wise access
 __device__ __forceinline__ bool band_fast_setup(const DwtComp& C, int pic, int bx0, bool inside, BandFast& F) {
   if (!inside) return false;
   if (C.lgbh < 0 || C.lgbw < 0 || (C.bw & 3) || ((C.base_ll | C.base_hl | C.base_lh | C.base_hh) & 3)) return false;
-  F.coefpic = C.coef + (long long)pic * C.coef_pic_stride;
+  int32_t* coefpic = C.coef + (long long)pic * C.coef_pic_stride;
   F.sx = bx0 >> C.lgbw;
   F.kx4 = (bx0 & (C.bw - 1)) >> 2;
   F.lgbh = C.lgbh; F.bhm1 = C.bh - 1; F.bw4 = C.bw >> 2; F.nx = C.nx; F.nc4 = C.NC >> 2;
-  F.o_ll = (C.base_ll >> 2) * 128; F.o_hl = (C.base_hl >> 2) * 128; F.o_lh = (C.base_lh >> 2) * 128; F.o_hh = (C.base_hh >> 2) * 128;
-  F.llp = nullptr; F.ll_pitch = C.ll_pitch;
+  F.p_ll = coefpic + (C.base_ll >> 2) * 128; F.p_hl = coefpic + (C.base_hl >> 2) * 128;
+  F.p_lh = coefpic + (C.base_lh >> 2) * 128; F.p_hh = coefpic + (C.base_hh >> 2) * 128;
+  F.plane_ll = C.ll != nullptr; F.ll_pitch = C.ll_pitch;
   if (C.ll) {
-    F.llp = C.ll + (long long)pic * C.ll_pic_stride + bx0;
+    F.p_ll = C.ll + (long long)pic * C.ll_pic_stride + bx0;
     if ((C.ll_pitch & 3) || (reinterpret_cast<uintptr_t>(C.ll + (long long)pic * C.ll_pic_stride) & 15)) return false;
   }
-  if (reinterpret_cast<uintptr_t>(F.coefpic) & 15) return false;
+  if (reinterpret_cast<uintptr_t>(coefpic) & 15) return false;
   return true;
 }
 
@@ -87,27 +90,35 @@ struct TileCtx {
   int x0, y0, xs, ys;          // first useful sample; first sample of the tile (halo included)
   int plo, phi, vplo, vphi;    // valid pair range of a tile row / of a tile column, in pairs from the tile origin
   bool hedge, vedge;
+  int tx, tx_end;              // this CTA's tiles of the tile row: [tx, tx_end)
 };
 
+// the CTA's place; false when the component is smaller than the grid (chroma)
 template <class T>
 __device__ __forceinline__ bool tile_setup(const DwtParams& p, const TileList& tl, TileCtx& S) {
-  const int per_pic = tl.start[p.ncomp];
-  const int t = blockIdx.x;
-  S.pic = t / per_pic;
-  int r = t - S.pic * per_pic;
-  S.comp = (p.ncomp > 1 && r >= tl.start[1]) + (p.ncomp > 2 && r >= tl.start[2]);
-  r -= tl.start[S.comp];
+  const int z = blockIdx.z;
+  S.pic = p.ncomp == 3 ? z / 3 : z;
+  S.comp = p.ncomp == 3 ? z - 3 * S.pic : 0;
+  const int cx = blockIdx.x, ty = blockIdx.y;
+  const int ncx = S.comp == 0 ? tl.cx[0] : tl.cx[1], nty = S.comp == 0 ? tl.ty[0] : tl.ty[1];   // the chroma planes are alike
+  if (cx >= ncx || ty >= nty) return false;
   const DwtComp& C = p.c[S.comp];
-  const int ty = r / tl.tx[S.comp], tx = r - ty * tl.tx[S.comp];
-  S.x0 = tx * T::XU; S.y0 = ty * T::YU;
-  S.xs = S.x0 - 8 * T::HL; S.ys = S.y0 - 8 * T::HL;
-  S.plo = max(0, -S.xs / 2);
-  S.phi = min(T::TW / 2 - 1, (C.lat_w - 2 - S.xs) / 2);
-  S.hedge = S.xs < 0 || S.xs + T::TW > C.lat_w;
+  S.tx = cx * T::TPC;
+  S.tx_end = min(S.tx + T::TPC, S.comp == 0 ? tl.tx[0] : tl.tx[1]);
+  S.y0 = ty * T::YU;
+  S.ys = S.y0 - 8 * T::HL;
   S.vplo = max(0, -S.ys / 2);
   S.vphi = min(T::TH / 2 - 1, (C.lat_h - 2 - S.ys) / 2);
   S.vedge = S.ys < 0 || S.ys + T::TH > C.lat_h;
   return true;
+}
+template <class T>
+__device__ __forceinline__ void tile_column_setup(const DwtComp& C, TileCtx& S, int tx) {
+  S.x0 = tx * T::XU;
+  S.xs = S.x0 - 8 * T::HL;
+  S.plo = max(0, -S.xs / 2);
+  S.phi = min(T::TW / 2 - 1, (C.lat_w - 2 - S.xs) / 2);
+  S.hedge = S.xs < 0 || S.xs + T::TW > C.lat_w;
 }
 
 // P2 of both directions: vertical lifting of the column chunks [first, first + count) of each half of the tile rows
@@ -128,8 +139,7 @@ __device__ __forceinline__ void tile_columns(int4* mid, const TileCtx& S, int fi
       e[0][a] = q0.x; e[1][a] = q0.y; e[2][a] = q0.z; e[3][a] = q0.w;
       o[0][a] = q1.x; o[1][a] = q1.y; o[2][a] = q1.z; o[3][a] = q1.w;
     }
-#pragma unroll
-    for (int c = 0; c < 4; ++c) hsteps<K, DIR, 4, T::TVL>(e[c], o[c], j, S.vedge, S.vplo, S.vphi);
+    hsteps_rows<K, DIR, 4, T::TVL, 4>(e, o, j, S.vedge, S.vplo, S.vphi);
     if (keep) {
 #pragma unroll
       for (int a = 0; a < 4; ++a) {
@@ -140,7 +150,65 @@ __device__ __forceinline__ void tile_columns(int4* mid, const TileCtx& S, int fi
   }
 }
 
+__device__ __forceinline__ int mad_lo(int a, int b, int c) {   // a * b + c as ONE multiply-add (not re-associated by the compiler)
+  int r;
+  asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+  return r;
+}
+
 #if VC2_DWT_PART == 1
+// per-lane constants of the picture row loads
+struct RowLoad {
+  const uint8_t* lane_base;   // first byte of this lane's eight samples in picture row 0
+  int pitchB;                 // bytes per picture row (a plane stays below 2 GB)
+  int last_row;               // waveletPad: rows beyond it replicate it (WaveletTransform.cpp:88)
+  int mul, nsub;              // v = (word >> sshift) * mul + nsub: sample offset and accuracy shift in one multiply-add
+  int sshift;
+  bool vec, skip;             // whole 16-byte pieces inside the picture | nothing of this lane is inside the lattice
+};
+
+// the raw words of this lane's eight samples of lattice row y (whole 16-byte pieces inside the picture)
+template <int KIND> struct RawRow { uint4 a, b; };
+template <int KIND>
+__device__ __forceinline__ RawRow<KIND> tile_load_raw(const RowLoad& L, int y) {
+  RawRow<KIND> r;
+  r.a = make_uint4(0, 0, 0, 0); r.b = r.a;
+  if (L.vec) {
+    const uint8_t* p = L.lane_base + (unsigned)(min(max(y, 0), L.last_row) * L.pitchB);
+    r.a = __ldg(reinterpret_cast<const uint4*>(p));
+    if (KIND == SAMPLE_I32) r.b = __ldg(reinterpret_cast<const uint4*>(p) + 1);
+  }
+  return r;
+}
+// converted and shifted (Arrays.cpp:351-376, WaveletTransform.cpp:270), as four pairs
+template <int KIND>
+__device__ __forceinline__ void tile_convert(const RowLoad& L, const RawRow<KIND>& r, int (&e)[4], int (&o)[4]) {
+  if (KIND == SAMPLE_I32) {
+    e[0] = (int)r.a.x * L.mul; o[0] = (int)r.a.y * L.mul; e[1] = (int)r.a.z * L.mul; o[1] = (int)r.a.w * L.mul;
+    e[2] = (int)r.b.x * L.mul; o[2] = (int)r.b.y * L.mul; e[3] = (int)r.b.z * L.mul; o[3] = (int)r.b.w * L.mul;
+  } else {
+    const unsigned w[4] = {r.a.x, r.a.y, r.a.z, r.a.w};
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      e[a] = mad_lo((int)(__byte_perm(w[a], 0, 0x4401) >> L.sshift), L.mul, L.nsub);
+      o[a] = mad_lo((int)(__byte_perm(w[a], 0, 0x4423) >> L.sshift), L.mul, L.nsub);
+    }
+  }
+}
+// the same for a row that is not made of whole aligned pieces (picture edge, odd widths, 8-bit samples)
+template <int KIND>
+__device__ __forceinline__ void tile_load_row_slow(const DwtComp& C, int pic, const RowLoad& L, int y, int gx, int (&e)[4], int (&o)[4]) {
+  if (!L.skip) {
+    int x[8];
+    load_pix<KIND, 8>(C, pic, min(max(y, 0), L.last_row), gx, x);
+#pragma unroll
+    for (int a = 0; a < 4; ++a) { e[a] = x[2 * a] * L.mul; o[a] = x[2 * a + 1] * L.mul; }
+  } else {
+#pragma unroll
+    for (int a = 0; a < 4; ++a) { e[a] = 0; o[a] = 0; }
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // forward level:  pix (dense plane)  ->  LL (compact plane or band 0), HL, LH, HH (interleaved)
 // ------------------------------------------------------------------------------------------
@@ -148,71 +216,110 @@ template <int K, int KIND, class T>
 __global__ void __launch_bounds__(32 * T::NW, T::MINB) dwt_tile_fwd_kernel(const DwtParams p, const TileList tl) {
   extern __shared__ int4 mid[];
   TileCtx S;
-  tile_setup<T>(p, tl, S);
+  if (!tile_setup<T>(p, tl, S)) return;
   const DwtComp& C = p.c[S.comp];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int hl = lane & (T::TWL - 1), sub = lane / T::TWL;
+  const int hl = lane & (T::TWL - 1), g = warp * T::RPW + lane / T::TWL;   // lane inside its row, row group
   constexpr int SHIFT = Wavelet<K>::SHIFT;
-
-  // P1: load, convert, shift in the accuracy bit (WaveletTransform.cpp:270), horizontal lifting
-#pragma unroll 2
-  for (int r = warp * T::RPW + sub; r < T::TH; r += T::NW * T::RPW) {
-    const int y = min(max(S.ys + r, 0), C.lat_h - 1);   // rows outside the lattice are never used: any row will do
-    int x[8];
-    load_pix<KIND, 8>(C, S.pic, y, S.xs + 8 * hl, x);
-    int e[4], o[4];
-#pragma unroll
-    for (int a = 0; a < 4; ++a) {
-      e[a] = (int)((unsigned)x[2 * a] << SHIFT);
-      o[a] = (int)((unsigned)x[2 * a + 1] << SHIFT);
-    }
-    hsteps<K, +1, 4, T::TWL>(e, o, hl, S.hedge, S.plo, S.phi);
-    int4* row = mid + r * T::CHUNKS;
-    row[hl ^ swz(r)] = make_int4(e[0], e[1], e[2], e[3]);
-    row[(T::TWL + hl) ^ swz(r)] = make_int4(o[0], o[1], o[2], o[3]);
-  }
-  __syncthreads();
-
-  // P2: vertical lifting of the useful columns
-  tile_columns<K, +1, T>(mid, S, T::HL, T::TWL - 2 * T::HL);
-  __syncthreads();
-
-  // P3: the useful rows leave as band rows
-  const int gx = S.xs + 8 * hl;
-  const bool mine = hl >= T::HL && hl < T::TWL - T::HL && gx < C.lat_w;
-  const int bx0 = (S.xs >> 1) + 4 * hl, bxmax = C.lat_w / 2 - 1;
-  BandFast F;
-  const bool fast = band_fast_setup(C, S.pic, bx0, mine && bx0 + 3 <= bxmax, F);
+  constexpr int esz = KIND == SAMPLE_I32 ? 4 : KIND == SAMPLE_U16BE ? 2 : 1;
+  const uint8_t* picbase = (const uint8_t*)C.pix + (long long)S.pic * C.pix_pic_stride * (KIND == SAMPLE_I32 ? 4 : 1);
   const BandAddr ba = {C.bh, C.bw, C.lgbh, C.lgbw, C.nx, C.NC >> 2};
   int32_t* coef = C.coef + (long long)S.pic * C.coef_pic_stride;
+  const int bxmax = C.lat_w / 2 - 1;
+  const int r0 = 8 * g;                                   // P1: this group's eight tile rows
+  int4* rows = mid + r0 * T::CHUNKS;
+  const int ce = hl ^ swz(r0), co = (T::TWL + hl) ^ swz(r0);
+
 #pragma unroll 1
-  for (int r = 8 * T::HL + warp * T::RPW + sub; r < T::TH - 8 * T::HL; r += T::NW * T::RPW) {
-    const int y = S.ys + r;
-    if (y >= C.lat_h || !mine) continue;
-    const int4* row = mid + r * T::CHUNKS;
-    const int4 lo4 = row[hl ^ swz(r)], hi4 = row[(T::TWL + hl) ^ swz(r)];
-    const int by = y >> 1;
-    if (fast) {
-      const int i = F.idx(by);
-      if (y & 1) {
-        *reinterpret_cast<int4*>(F.coefpic + i + F.o_lh) = lo4;
-        *reinterpret_cast<int4*>(F.coefpic + i + F.o_hh) = hi4;
+  for (int tx = S.tx; tx < S.tx_end; ++tx) {
+    tile_column_setup<T>(C, S, tx);
+    const int gx = S.xs + 8 * hl;
+    // P1: load, convert, shift in the accuracy bit, horizontal lifting
+    {
+      RowLoad L;
+      L.pitchB = C.pix_pitch * esz;
+      L.lane_base = picbase + (long long)gx * esz;
+      L.last_row = min(C.lat_h, C.pix_h) - 1;
+      L.sshift = C.sshift;
+      L.mul = 1 << SHIFT;
+      L.nsub = KIND == SAMPLE_I32 ? 0 : -(C.soffset << SHIFT);
+      L.vec = KIND != SAMPLE_U8 && gx >= 0 && gx + 7 < C.pix_w && ((L.pitchB | reinterpret_cast<uintptr_t>(L.lane_base)) & 15) == 0;
+      L.skip = gx + 7 < 0 || gx >= C.lat_w;
+      auto lift_store = [&](int i, int (&e)[2][4], int (&o)[2][4]) {
+        hsteps_rows<K, +1, 4, T::TWL, 2>(e, o, hl, S.hedge, S.plo, S.phi);
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          rows[(i + k) * T::CHUNKS + ce] = make_int4(e[k][0], e[k][1], e[k][2], e[k][3]);
+          rows[(i + k) * T::CHUNKS + co] = make_int4(o[k][0], o[k][1], o[k][2], o[k][3]);
+        }
+      };
+      if (__all_sync(FULL, L.vec || L.skip)) {
+        // every load of the row group is in flight before the first one is used: one memory round trip per tile
+        constexpr int NB = KIND == SAMPLE_I32 ? 4 : 8;   // rows per batch (32 registers of raw words)
+#pragma unroll 1
+        for (int b = 0; b < 8; b += NB) {
+          RawRow<KIND> raw[NB];
+#pragma unroll
+          for (int i = 0; i < NB; ++i) raw[i] = tile_load_raw<KIND>(L, S.ys + r0 + b + i);
+#pragma unroll
+          for (int i = 0; i < NB; i += 2) {
+            int e[2][4], o[2][4];
+            tile_convert<KIND>(L, raw[i], e[0], o[0]);
+            tile_convert<KIND>(L, raw[i + 1], e[1], o[1]);
+            lift_store(b + i, e, o);
+          }
+        }
       } else {
-        if (F.llp) *reinterpret_cast<int4*>(F.llp + (long long)by * F.ll_pitch) = lo4;
-        else *reinterpret_cast<int4*>(F.coefpic + i + F.o_ll) = lo4;
-        *reinterpret_cast<int4*>(F.coefpic + i + F.o_hl) = hi4;
-      }
-    } else {
-      int lo[4] = {lo4.x, lo4.y, lo4.z, lo4.w}, hi[4] = {hi4.x, hi4.y, hi4.z, hi4.w};
-      if (y & 1) {
-        band_access<4, true>(coef, ba, C.base_lh, by, bx0, bxmax, lo);
-        band_access<4, true>(coef, ba, C.base_hh, by, bx0, bxmax, hi);
-      } else {
-        if (C.ll) ll_access<4, true>(C.ll + (long long)S.pic * C.ll_pic_stride, C.ll_pitch, by, bx0, bxmax, lo);
-        else band_access<4, true>(coef, ba, C.base_ll, by, bx0, bxmax, lo);
-        band_access<4, true>(coef, ba, C.base_hl, by, bx0, bxmax, hi);
+#pragma unroll 1
+        for (int i = 0; i < 8; i += 2) {
+          int e[2][4], o[2][4];
+          tile_load_row_slow<KIND>(C, S.pic, L, S.ys + r0 + i, gx, e[0], o[0]);
+          tile_load_row_slow<KIND>(C, S.pic, L, S.ys + r0 + i + 1, gx, e[1], o[1]);
+          lift_store(i, e, o);
+        }
       }
     }
+    __syncthreads();
+
+    // P2: vertical lifting of the useful columns
+    tile_columns<K, +1, T>(mid, S, T::HL, T::TWL - 2 * T::HL);
+    __syncthreads();
+
+    // P3: the useful rows leave as band rows, two lattice rows (one band row of LL | HL and of LH | HH) at a time
+    const bool mine = hl >= T::HL && hl < T::TWL - T::HL && gx < C.lat_w;
+    if (mine) {
+      const int bx0 = (S.xs >> 1) + 4 * hl;
+      BandFast F;
+      const bool fast = band_fast_setup(C, S.pic, bx0, bx0 + 3 <= bxmax, F);
+#pragma unroll 1
+      for (int m = 4 * T::HL + g; m < T::TH / 2 - 4 * T::HL; m += T::NG) {
+        const int y = S.ys + 2 * m;
+        if (y >= C.lat_h) break;
+        const int4* row = mid + 2 * m * T::CHUNKS;
+        const int c0 = hl ^ swz(2 * m), c1 = (T::TWL + hl) ^ swz(2 * m);
+        const int4 ll4 = row[c0], hl4 = row[c1], lh4 = row[T::CHUNKS + c0], hh4 = row[T::CHUNKS + c1];
+        const int by = y >> 1;
+        if (fast) {
+          const int i = F.idx(by);
+          if (F.plane_ll) *reinterpret_cast<int4*>(F.p_ll + by * F.ll_pitch) = ll4;
+          else *reinterpret_cast<int4*>(F.p_ll + i) = ll4;
+          *reinterpret_cast<int4*>(F.p_hl + i) = hl4;
+          *reinterpret_cast<int4*>(F.p_lh + i) = lh4;
+          *reinterpret_cast<int4*>(F.p_hh + i) = hh4;
+        } else {
+          int v[4] = {ll4.x, ll4.y, ll4.z, ll4.w};
+          if (C.ll) ll_access<4, true>(C.ll + (long long)S.pic * C.ll_pic_stride, C.ll_pitch, by, bx0, bxmax, v);
+          else band_access<4, true>(coef, ba, C.base_ll, by, bx0, bxmax, v);
+          v[0] = hl4.x; v[1] = hl4.y; v[2] = hl4.z; v[3] = hl4.w;
+          band_access<4, true>(coef, ba, C.base_hl, by, bx0, bxmax, v);
+          v[0] = lh4.x; v[1] = lh4.y; v[2] = lh4.z; v[3] = lh4.w;
+          band_access<4, true>(coef, ba, C.base_lh, by, bx0, bxmax, v);
+          v[0] = hh4.x; v[1] = hh4.y; v[2] = hh4.z; v[3] = hh4.w;
+          band_access<4, true>(coef, ba, C.base_hh, by, bx0, bxmax, v);
+        }
+      }
+    }
+    __syncthreads();   // the tile is free for the CTA's next column
   }
 }
 #else
@@ -223,73 +330,80 @@ template <int K, int KIND, class T>
 __global__ void __launch_bounds__(32 * T::NW, T::MINB) dwt_tile_inv_kernel(const DwtParams p, const TileList tl) {
   extern __shared__ int4 mid[];
   TileCtx S;
-  tile_setup<T>(p, tl, S);
+  if (!tile_setup<T>(p, tl, S)) return;
   const DwtComp& C = p.c[S.comp];
-  if (S.x0 >= C.pix_w || S.y0 >= C.pix_h) return;   // nothing of this tile survives the crop (WaveletTransform.cpp:340)
+  if (S.y0 >= C.pix_h) return;   // nothing of this tile row survives the crop (WaveletTransform.cpp:340)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int hl = lane & (T::TWL - 1), sub = lane / T::TWL;
-  const int gx = S.xs + 8 * hl;
-  const int bx0 = (S.xs >> 1) + 4 * hl, bxmax = C.lat_w / 2 - 1;
+  const int hl = lane & (T::TWL - 1), g = warp * T::RPW + lane / T::TWL;
+  const int bxmax = C.lat_w / 2 - 1;
+  const BandAddr ba = {C.bh, C.bw, C.lgbh, C.lgbw, C.nx, C.NC >> 2};
+  int32_t* coef = C.coef + (long long)S.pic * C.coef_pic_stride;
 
-  // P1: band rows into the tile
-  {
-    BandFast F;
-    const bool fast = band_fast_setup(C, S.pic, bx0, bx0 >= 0 && bx0 + 3 <= bxmax, F);
-    const BandAddr ba = {C.bh, C.bw, C.lgbh, C.lgbw, C.nx, C.NC >> 2};
-    int32_t* coef = C.coef + (long long)S.pic * C.coef_pic_stride;
-#pragma unroll 2
-    for (int r = warp * T::RPW + sub; r < T::TH; r += T::NW * T::RPW) {
-      const int y = S.ys + r;
-      if (y < 0 || y >= C.lat_h) continue;     // never used (the column phase extends the sequence inside the lattice)
-      const int by = y >> 1;
-      int4 lo4, hi4;
-      if (fast) {
-        const int i = F.idx(by);
-        if (y & 1) {
-          lo4 = __ldg(reinterpret_cast<const int4*>(F.coefpic + i + F.o_lh));
-          hi4 = __ldg(reinterpret_cast<const int4*>(F.coefpic + i + F.o_hh));
-        } else {
-          lo4 = F.llp ? __ldg(reinterpret_cast<const int4*>(F.llp + (long long)by * F.ll_pitch)) : __ldg(reinterpret_cast<const int4*>(F.coefpic + i + F.o_ll));
-          hi4 = __ldg(reinterpret_cast<const int4*>(F.coefpic + i + F.o_hl));
-        }
-      } else {
-        int lo[4], hi[4];
-        if (y & 1) {
-          band_access<4, false>(coef, ba, C.base_lh, by, bx0, bxmax, lo);
-          band_access<4, false>(coef, ba, C.base_hh, by, bx0, bxmax, hi);
-        } else {
-          if (C.ll) ll_access<4, false>(C.ll + (long long)S.pic * C.ll_pic_stride, C.ll_pitch, by, bx0, bxmax, lo);
-          else band_access<4, false>(coef, ba, C.base_ll, by, bx0, bxmax, lo);
-          band_access<4, false>(coef, ba, C.base_hl, by, bx0, bxmax, hi);
-        }
-        lo4 = make_int4(lo[0], lo[1], lo[2], lo[3]);
-        hi4 = make_int4(hi[0], hi[1], hi[2], hi[3]);
-      }
-      int4* row = mid + r * T::CHUNKS;
-      row[hl ^ swz(r)] = lo4;
-      row[(T::TWL + hl) ^ swz(r)] = hi4;
-    }
-  }
-  __syncthreads();
-
-  // P2: vertical inverse lifting of every column (the row phase reaches into the halo columns)
-  tile_columns<K, -1, T>(mid, S, 0, T::TWL);
-  __syncthreads();
-
-  // P3: horizontal inverse lifting, rounding, clip, sample format
-  const bool mine = hl >= T::HL && hl < T::TWL - T::HL && gx < C.pix_w;
 #pragma unroll 1
-  for (int r = 8 * T::HL + warp * T::RPW + sub; r < T::TH - 8 * T::HL; r += T::NW * T::RPW) {
-    const int y = S.ys + r;
-    const int4* row = mid + r * T::CHUNKS;
-    const int4 lo4 = row[hl ^ swz(r)], hi4 = row[(T::TWL + hl) ^ swz(r)];
-    int e[4] = {lo4.x, lo4.y, lo4.z, lo4.w}, o[4] = {hi4.x, hi4.y, hi4.z, hi4.w};
-    hsteps<K, -1, 4, T::TWL>(e, o, hl, S.hedge, S.plo, S.phi);
-    if (!mine || y >= C.pix_h) continue;
-    int v[8];
+  for (int tx = S.tx; tx < S.tx_end; ++tx) {
+    tile_column_setup<T>(C, S, tx);
+    if (S.x0 >= C.pix_w) break;
+    const int gx = S.xs + 8 * hl;
+    const int bx0 = (S.xs >> 1) + 4 * hl;
+    // P1: band rows into the tile, two lattice rows (one band row of LL | HL and of LH | HH) at a time
+    {
+      BandFast F;
+      const bool fast = band_fast_setup(C, S.pic, bx0, bx0 >= 0 && bx0 + 3 <= bxmax, F);
 #pragma unroll
-    for (int a = 0; a < 4; ++a) { v[2 * a] = e[a]; v[2 * a + 1] = o[a]; }
-    store_pix<K, KIND, 8>(C, S.pic, y, gx, v);
+      for (int m = g; m < T::TH / 2; m += T::NG) {   // unrolled: all the loads of the lane are in flight together
+        const int y = S.ys + 2 * m;
+        if (y < 0 || y >= C.lat_h) continue;     // never used (the column phase extends the sequence inside the lattice)
+        const int by = y >> 1;
+        int4 ll4, hl4, lh4, hh4;
+        if (fast) {
+          const int k = F.idx(by);
+          ll4 = F.plane_ll ? __ldg(reinterpret_cast<const int4*>(F.p_ll + by * F.ll_pitch)) : __ldg(reinterpret_cast<const int4*>(F.p_ll + k));
+          hl4 = __ldg(reinterpret_cast<const int4*>(F.p_hl + k));
+          lh4 = __ldg(reinterpret_cast<const int4*>(F.p_lh + k));
+          hh4 = __ldg(reinterpret_cast<const int4*>(F.p_hh + k));
+        } else {
+          int v[4];
+          if (C.ll) ll_access<4, false>(C.ll + (long long)S.pic * C.ll_pic_stride, C.ll_pitch, by, bx0, bxmax, v);
+          else band_access<4, false>(coef, ba, C.base_ll, by, bx0, bxmax, v);
+          ll4 = make_int4(v[0], v[1], v[2], v[3]);
+          band_access<4, false>(coef, ba, C.base_hl, by, bx0, bxmax, v);
+          hl4 = make_int4(v[0], v[1], v[2], v[3]);
+          band_access<4, false>(coef, ba, C.base_lh, by, bx0, bxmax, v);
+          lh4 = make_int4(v[0], v[1], v[2], v[3]);
+          band_access<4, false>(coef, ba, C.base_hh, by, bx0, bxmax, v);
+          hh4 = make_int4(v[0], v[1], v[2], v[3]);
+        }
+        int4* row = mid + 2 * m * T::CHUNKS;
+        const int c0 = hl ^ swz(2 * m), c1 = (T::TWL + hl) ^ swz(2 * m);
+        row[c0] = ll4; row[c1] = hl4; row[T::CHUNKS + c0] = lh4; row[T::CHUNKS + c1] = hh4;
+      }
+    }
+    __syncthreads();
+
+    // P2: vertical inverse lifting of every column (the row phase reaches into the halo columns)
+    tile_columns<K, -1, T>(mid, S, 0, T::TWL);
+    __syncthreads();
+
+    // P3: horizontal inverse lifting, rounding, clip, sample format, two rows at a time
+    const bool mine = hl >= T::HL && hl < T::TWL - T::HL && gx < C.pix_w;
+#pragma unroll 1
+    for (int m = 4 * T::HL + g; m < T::TH / 2 - 4 * T::HL; m += T::NG) {
+      const int4* row = mid + 2 * m * T::CHUNKS;
+      const int c0 = hl ^ swz(2 * m), c1 = (T::TWL + hl) ^ swz(2 * m);
+      const int4 a0 = row[c0], a1 = row[c1], b0 = row[T::CHUNKS + c0], b1 = row[T::CHUNKS + c1];
+      int e[2][4] = {{a0.x, a0.y, a0.z, a0.w}, {b0.x, b0.y, b0.z, b0.w}}, o[2][4] = {{a1.x, a1.y, a1.z, a1.w}, {b1.x, b1.y, b1.z, b1.w}};
+      hsteps_rows<K, -1, 4, T::TWL, 2>(e, o, hl, S.hedge, S.plo, S.phi);
+      const int y = S.ys + 2 * m;
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        if (!mine || y + k >= C.pix_h) continue;
+        int v[8];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) { v[2 * a] = e[k][a]; v[2 * a + 1] = o[k][a]; }
+        store_pix<K, KIND, 8>(C, S.pic, y + k, gx, v);
+      }
+    }
+    __syncthreads();   // the tile is free for the CTA's next column
   }
 }
 #endif
@@ -297,17 +411,19 @@ __global__ void __launch_bounds__(32 * T::NW, T::MINB) dwt_tile_inv_kernel(const
 template <int K, int KIND, class T>
 cudaError_t launch_tile(cudaStream_t s, const DwtParams& p, int npictures) {
   TileList tl;
-  int n = 0;
+  int gx = 0, gy = 0;
+  if (p.ncomp != 1 && p.ncomp != 3) return cudaErrorInvalidValue;
+  if (p.ncomp == 3 && (p.c[1].lat_w != p.c[2].lat_w || p.c[1].lat_h != p.c[2].lat_h)) return cudaErrorInvalidValue;
   for (int c = 0; c < 3; ++c) {
-    tl.start[c] = n;
-    tl.tx[c] = 1;
+    tl.tx[c] = tl.cx[c] = tl.ty[c] = 1;
     if (c < p.ncomp) {
       tl.tx[c] = (p.c[c].lat_w + T::XU - 1) / T::XU;
-      n += tl.tx[c] * ((p.c[c].lat_h + T::YU - 1) / T::YU);
+      tl.cx[c] = (tl.tx[c] + T::TPC - 1) / T::TPC;
+      tl.ty[c] = (p.c[c].lat_h + T::YU - 1) / T::YU;
+      gx = tl.cx[c] > gx ? tl.cx[c] : gx;
+      gy = tl.ty[c] > gy ? tl.ty[c] : gy;
     }
   }
-  tl.start[3] = n;
-  for (int c = p.ncomp; c < 3; ++c) tl.start[c] = n;
 #if VC2_DWT_PART == 1
   auto kern = dwt_tile_fwd_kernel<K, KIND, T>;
 #else
@@ -321,14 +437,21 @@ cudaError_t launch_tile(cudaStream_t s, const DwtParams& p, int npictures) {
     if (e != cudaSuccess) return e;
     if (dev >= 0 && dev < 16) configured[dev] = true;
   }
-  kern<<<(unsigned)((long long)n * npictures), 32 * T::NW, T::SMEM, s>>>(p, tl);
+  if (gy > 65535 || (long long)npictures * p.ncomp > 65535) return cudaErrorInvalidValue;
+  kern<<<dim3((unsigned)gx, (unsigned)gy, (unsigned)(npictures * p.ncomp)), 32 * T::NW, T::SMEM, s>>>(p, tl);
   return cudaGetLastError();
 }
 
 template <int K, int KIND>
 cudaError_t pick_tile(cudaStream_t s, const DwtParams& p, int npictures, int cfg) {
-  if (cfg == 2) return launch_tile<K, KIND, Tile<K, 16, 16, 8, 3>>(s, p, npictures);   // 128 x 128 tile, 64 KB, three CTAs per SM
-  return launch_tile<K, KIND, Tile<K, 32, 16, 16, 1>>(s, p, npictures);               // 128 rows x 256 columns, 128 KB, one CTA per SM
+#ifdef VC2_TILE_EXPERIMENT   // more shapes of the bench wavelet for A/B runs on the GPU box
+  if constexpr (K == VC2_DD137 && KIND != SAMPLE_U8) {
+    if (cfg == 2) return launch_tile<K, KIND, Tile<K, 16, 16, 8, 3, 4>>(s, p, npictures);
+    if (cfg == 4) return launch_tile<K, KIND, Tile<K, 16, 16, 8, 2, 1>>(s, p, npictures);
+    if (cfg == 5) return launch_tile<K, KIND, Tile<K, 32, 16, 16, 1, 1>>(s, p, npictures);
+  }
+#endif
+  return launch_tile<K, KIND, Tile<K, 16, 16, 8, 3, 1>>(s, p, npictures);   // 128 x 128 tile, 64 KB, three CTAs of 8 warps per SM
 }
 
 template <int KIND>
@@ -344,7 +467,7 @@ cudaError_t dispatch_tile(cudaStream_t s, int kernel, const DwtParams& p, int np
 
 }  // namespace
 
-// cfg: 1 = 128 x 256 tile (one CTA of 16 warps per SM), 2 = 128 x 128 tile (three CTAs of 8 warps per SM)
+// cfg: tile shape for A/B runs (VC2_TILE_EXPERIMENT builds); the product uses 128 x 128 tiles, three CTAs of 8 warps per SM
 #if VC2_DWT_PART == 1
 cudaError_t dwt_tile_fwd_launch(cudaStream_t s, int kernel, int sample_kind, const DwtParams& p, int npictures, int cfg) {
 #else
