@@ -66,3 +66,59 @@ def test_codec_vs_oracle(ctx, c):
         pic = orc.decode_picture_hq(want, c["h"], c["w"], ch, cw, c["bits"], kern, c["depth"], g.slices_y, g.slices_x, c["P"], c["S"])
         assert k.download_picture(i) == pic, (c, i)
     k.close()
+
+
+def _noise_frame(seed, w, h, fmt, bits):
+    """full-range noise, MSB justified big-endian words: coefficients far beyond 15 bits at q = 0"""
+    ch, cw = gen.chroma_dims(w, h, fmt)
+    rng = np.random.default_rng(seed)
+    v = rng.integers(0, 1 << bits, size=w * h + 2 * ch * cw, dtype=np.uint32) << (16 - bits)
+    return v.astype(">u2").tobytes()
+
+
+@pytest.mark.parametrize("kernel,depth,bits", [("DD137", 3, 13), ("Daub97", 3, 13), ("LeGall", 2, 10)])
+def test_narrow_block_overflow_falls_back_to_32_bit(ctx, kernel, depth, bits):
+    """HQ_ConstQ encodes and HQ decodes keep 16-bit quantised coefficients between the lifting kernels and the slice
+    coders; q = 0 on full-range noise overflows that block (the LeGall case stays inside it), and the slot has to come out
+    exactly as through the 32-bit path: device-resident calls, the status / download entry points, the host-buffer calls"""
+    w, h, fmt, q, P, S = 416, 256, "422", 0, 1, 16
+    g = vc2.make_geom(h, w, fmt, kernel, depth, 1, 2, P, S)
+    ch, cw = gen.chroma_dims(w, h, fmt)
+    kern = vc2.KERNELS[kernel]
+    frames = [_noise_frame(77 + i, w, h, fmt, bits) if i != 1 else gen.frame_bytes(5, i, w, h, fmt, bits) for i in range(3)]
+    want, pics = [], []
+    for f in frames:
+        try:
+            want.append(orc.encode_picture_hq_constq(f, h, w, ch, cw, bits, kern, depth, g.slices_y, g.slices_x, q, P, S))
+        except orc.OrcError:
+            pytest.skip("the reference rejects this content at q = 0 (slice scalar)")
+        pics.append(orc.decode_picture_hq(want[-1], h, w, ch, cw, bits, kern, depth, g.slices_y, g.slices_x, P, S))
+    k = vc2.Codec(ctx, g, "HQ_ConstQ", qindex=q, luma_depth=bits, max_pictures=4)
+    for i, f in enumerate(frames):
+        k.upload_picture(i, f)
+    k.encode(3)
+    k.decode(3)                       # round trip in the slot, then ask for the results in both orders
+    assert k.download_picture(2) == pics[2]
+    for i in range(3):
+        assert k.download_payload(i)[0] == want[i], (kernel, i)
+        assert k.download_picture(i) == pics[i], (kernel, i)
+    # a separate decoder fed with the payloads
+    d = vc2.Codec(ctx, g, "HQ_ConstQ", qindex=q, luma_depth=bits, max_pictures=4)
+    for i in range(3):
+        d.upload_payload(i, want[i])
+    d.decode(3)
+    for i in range(3):
+        d.slot_status(i)
+        assert d.download_picture(i) == pics[i], (kernel, i)
+    # host-buffer calls, more pictures than slots
+    src = [np.frombuffer(frames[i % 3], np.uint8).copy() for i in range(7)]
+    bufs = [np.zeros(k.payload_capacity, np.uint8) for _ in src]
+    lens = k.encode_host(src, bufs)
+    for i in range(7):
+        assert bufs[i][:lens[i]].tobytes() == want[i % 3], (kernel, "encode_host", i)
+    outs = [np.zeros(k.picture_bytes, np.uint8) for _ in src]
+    d.decode_host(bufs, lens, outs)
+    for i in range(7):
+        assert outs[i].tobytes() == pics[i % 3], (kernel, "decode_host", i)
+    k.close()
+    d.close()

@@ -9,6 +9,7 @@
 
 #include <algorithm>
 #include <new>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -224,6 +225,8 @@ struct vc2_ctx {
   int dwt_fast = 1;               // fast loop of the lifting kernels (VC2_DWT_FAST=0 turns it off)
   int dwt_seg_rows = 0;           // > 0: forced rows per warp (tuning, VC2_DWT_SEG_ROWS)
   int dwt_tile = 1;               // lifting kernels: 1 = shared-memory tiles (dwt_tile.cu), 0 = streaming register rings (dwt.cu; VC2_DWT_TILE=0)
+  int narrow = 1;                 // codecs keep quantised 16-bit coefficients between the lifting kernels and the slice coders (VC2_NARROW=0: 32-bit)
+  DevBuf scale_tab;               // [128] (quant_factor, quant_offset + 2) for the inverse lifting kernels of the narrow path
   // optional per-kernel timing with CUDA events on the launch stream (vc2_profile_*)
   bool profiling = false;
   struct Span { int stage; cudaEvent_t a, b; };
@@ -302,11 +305,17 @@ extern "C" vc2_ctx* vc2_create(int device) {
   if (const char* e = getenv("VC2_DWT_PD")) c->dwt_pd = atoi(e);
   if (const char* e = getenv("VC2_DWT_FAST")) c->dwt_fast = atoi(e) != 0;
   if (const char* e = getenv("VC2_DWT_TILE")) c->dwt_tile = atoi(e);
+  if (const char* e = getenv("VC2_NARROW")) c->narrow = atoi(e) != 0;
   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return nullptr; }
   c->own_stream = true;
   QuantTables t;
   make_quant_tables(t);
   if (upload_quant_tables(t) != cudaSuccess) { cudaStreamDestroy(c->stream); delete c; return nullptr; }
+  uint32_t st[256];
+  for (int q = 0; q < 128; ++q) { st[2 * q] = t.qf[q]; st[2 * q + 1] = t.qo[q] + 2u; }
+  if (c->scale_tab.reserve(sizeof(st)) != cudaSuccess || cudaMemcpy(c->scale_tab.p, st, sizeof(st), cudaMemcpyHostToDevice) != cudaSuccess) {
+    c->scale_tab.release(); cudaStreamDestroy(c->stream); delete c; return nullptr;
+  }
   return c;
 }
 
@@ -315,6 +324,7 @@ extern "C" void vc2_destroy(vc2_ctx* c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   for (auto& b : c->tmp) b.release();
+  c->scale_tab.release();
   for (auto& sp : c->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
   for (auto e : c->event_pool) cudaEventDestroy(e);
   if (c->own_stream) cudaStreamDestroy(c->stream);
@@ -398,8 +408,41 @@ static int ilog2_or_neg(int v) {
   return l;
 }
 
+// The narrow path's forward quantiser: |q| = (|v| * mul) >> sh == (|v| << 2) / quant_factor(q) for every |v| below
+// VC2_NARROW_FAST_MAX, with a product that stays inside 32 bits.  Found by trying the shifts in turn and checking every
+// dividend (once per index and process); an index without such a pair keeps mul = 0, sh = -1 and the kernels never take
+// the fast form for it (cannot happen for the table of Quantisation.cpp:42-59, but nothing relies on that).
+struct NarrowMagic { uint32_t mul; int sh; };
+static const NarrowMagic& narrow_magic(int q) {
+  static NarrowMagic tab[120];
+  static std::once_flag once;
+  std::call_once(once, [] {
+    for (int i = 0; i < 120; ++i) {
+      const uint64_t d = (uint64_t)(uint32_t)vc2_quant_factor(i);
+      tab[i].mul = 0; tab[i].sh = -1;
+      for (int sh = 0; sh < 32 && tab[i].sh < 0; ++sh) {
+        const uint64_t mul = ((4ull << sh) + d - 1) / d;
+        if (mul * (VC2_NARROW_FAST_MAX - 1) >= (1ull << 32)) break;
+        bool ok = true;
+        for (uint64_t v = 0; v < VC2_NARROW_FAST_MAX && ok; ++v) ok = ((v * mul) >> sh) == (4 * v) / d;
+        if (ok) { tab[i].mul = (uint32_t)mul; tab[i].sh = sh; }
+      }
+    }
+  });
+  return tab[std::min(std::max(q, 0), 119)];
+}
+
+// narrow coefficient block (dwt.cuh): off, forward with one quantisation index (HQ_ConstQ), or inverse with the index of every slice
+struct NarrowCfg {
+  int on = 0;
+  int qindex = 0;                 // forward
+  const int32_t* qidx = nullptr;  // inverse: [picture][slice]
+  uint32_t* ovf = nullptr;        // [picture]
+};
+
 static cudaError_t run_dwt(vc2_ctx* ctx, bool inverse, int kernel, int depth, int sample_kind, const SliceGeom& g, const CompBuf* cb,
-                           int ncomp, int npictures) {
+                           int ncomp, int npictures, const NarrowCfg& nw = NarrowCfg()) {
+  if (nw.on && !ctx->dwt_tile) return cudaErrorInvalidValue;   // only the tile kernels know the narrow block
   for (int step = 0; step < depth; ++step) {
     const int l = inverse ? depth - 1 - step : step;   // 0 = finest
     const int L = depth - l;                           // VC-2 level of the bands touched
@@ -408,6 +451,11 @@ static cudaError_t run_dwt(vc2_ctx* ctx, bool inverse, int kernel, int depth, in
     p.ncomp = ncomp;
     p.pd = ctx->dwt_pd;
     p.fast = ctx->dwt_fast;
+    p.narrow = nw.on;
+    p.narrow_ovf = nw.ovf;
+    p.qidx = nw.qidx;
+    p.nslices = g.slices_x * g.slices_y;
+    p.scale_tab = ctx->scale_tab.as<uint2>();
     for (int c = 0; c < ncomp; ++c) {
       const CompBuf& B = cb[c];
       DwtComp& C = p.c[c];
@@ -435,6 +483,19 @@ static cudaError_t run_dwt(vc2_ctx* ctx, bool inverse, int kernel, int depth, in
       C.base_lh = g.comp_start[cc] + g.band_start[cc][bhl + 1];
       C.base_hh = g.comp_start[cc] + g.band_start[cc][bhl + 2];
       C.sshift = B.sshift; C.soffset = B.soffset; C.clip_min = B.clip_min; C.clip_max = B.clip_max;
+      if (nw.on) {
+        const int band[4] = {0, bhl, bhl + 1, bhl + 2};
+        for (int i = 0; i < 4; ++i) {
+          C.qmat[i] = g.qmatrix[band[i]];
+          const int q = std::min(std::max(nw.qindex - g.qmatrix[band[i]], 0), 119);   // Quantisation.cpp:16-20; beyond 119 the packer raises the error
+          const NarrowMagic& m = narrow_magic(q);
+          C.qmul[i] = m.mul; C.qsh[i] = m.sh < 0 ? 0 : m.sh;
+          uint32_t mm = 0, ll = 0;
+          vc2_quant_magic31(q, &mm, &ll);
+          C.qm31[i] = mm; C.ql31[i] = (int)ll;
+          if (m.sh < 0) { C.qmul[i] = 0; C.qsh[i] = 0; }
+        }
+      }
     }
     ProfScope ps(ctx, inverse ? (l == 0 ? VC2_STAGE_IDWT_L0 : VC2_STAGE_IDWT_DEEP) : (l == 0 ? VC2_STAGE_DWT_L0 : VC2_STAGE_DWT_DEEP));
     // rows per warp: long segments amortise the warm-up rows of the streaming kernels, short ones fill the GPU
@@ -572,11 +633,12 @@ struct PackBuffers {
 static int staging_words(const SliceGeom& g) { return ((g.prefix + 4 + 4 * g.comp_start[3] + 3) / 4 + 4 + 3) & ~3; }
 
 static cudaError_t run_pack(vc2_ctx* ctx, const SliceGeom& g, const int32_t* coef, int npictures, int mode, int quantise,
-                            int search, int const_q, int emit, const PackBuffers& B) {
+                            int search, int const_q, int emit, const PackBuffers& B, int narrow = 0) {
   PackParams p;
   memset(&p, 0, sizeof(p));
   p.g = g;
   p.coef = coef;
+  p.narrow = narrow;
   p.mode = mode; p.quantise = quantise; p.search = search; p.const_q = const_q; p.emit = emit;
   p.qidx = B.qidx; p.slice_bytes = B.slice_bytes_dev;
   p.staging = B.staging; p.wcap = staging_words(g); p.sizes = B.sizes; p.err_flags = B.err_flags;
@@ -876,6 +938,19 @@ struct vc2_codec {
   // device buffers
   DevBuf samples, recon, coef, scratch0, scratch1, payload, slice_off, err, qidx, staging, sizes, sbytes, fixed, tmp_plane, tmp_q;
   DevBuf dev_len;                     // [B] payload bytes of each slot: written by the encoder's scan or by upload_payload
+  // narrow coefficient block (dwt.cuh): HQ_ConstQ encodes and HQ decodes keep 16-bit quantised coefficients between the
+  // lifting kernels and the slice coders.  A magnitude beyond 15 bits raises narrow_ovf[slot]; whoever looks at the
+  // slot's result next (status, downloads, taps, the host-buffer calls) first runs the slot again through the 32-bit path.
+  bool narrow_enc = false, narrow_dec = false;
+  DevBuf narrow_ovf;                  // [2][B]: overflow flags of the encodes, of the decodes
+  struct SlotState {
+    bool enc_unchecked = false;       // the payload comes from a narrow encode whose overflow flag has not been looked at
+    bool dec_unchecked = false;       // the same for the reconstructed picture and a narrow decode
+    bool dec_after_enc = false;       // a decode read that payload
+    uint8_t coef = 0;                 // what the coefficient block holds: 0 = 32-bit, 1 = narrow (encode), 2 = narrow (decode)
+  };
+  std::vector<SlotState> slot_state;
+  uint32_t* host_novf = nullptr;      // pinned [2 * B]: overflow flags of the host-buffer pipelines
   DevBuf ld_qcoef, ld_acbits, ld_restored;   // LD encoder only, allocated at its first use
   long long ld_ll_stride = 0;
   int ld_ll_off[3] = {0, 0, 0}, ld_ll_w[3] = {0, 0, 0};
@@ -915,10 +990,11 @@ static void codec_free(vc2_codec* k) {
   cudaStreamSynchronize(k->ctx->stream);
   DevBuf* all[] = {&k->samples, &k->recon, &k->coef, &k->scratch0, &k->scratch1, &k->payload, &k->slice_off, &k->err,
                    &k->qidx, &k->staging, &k->sizes, &k->sbytes, &k->fixed, &k->tmp_plane, &k->tmp_q, &k->dev_len,
-                   &k->ld_qcoef, &k->ld_acbits, &k->ld_restored};
+                   &k->ld_qcoef, &k->ld_acbits, &k->ld_restored, &k->narrow_ovf};
   for (DevBuf* b : all) b->release();
   if (k->host_flags) cudaFreeHost(k->host_flags);
   if (k->host_len) cudaFreeHost(k->host_len);
+  if (k->host_novf) cudaFreeHost(k->host_novf);
   for (auto e : k->ev_in) cudaEventDestroy(e);
   for (auto e : k->ev_done) cudaEventDestroy(e);
   for (auto e : k->ev_out) cudaEventDestroy(e);
@@ -995,6 +1071,11 @@ extern "C" vc2_codec* vc2_codec_create(vc2_ctx* ctx, const vc2_codec_params* prm
   R(k->tmp_plane, (size_t)g.plane[0].size() * 4);
   R(k->tmp_q, (size_t)g.plane[0].size() * 4);
   R(k->dev_len, (size_t)B * 4);
+  R(k->narrow_ovf, (size_t)B * 4 * 2);
+  k->narrow_enc = ctx->narrow && ctx->dwt_tile && prm->mode == VC2_HQ_VBR;
+  k->narrow_dec = ctx->narrow && ctx->dwt_tile && prm->mode != VC2_LD;
+  k->slot_state.assign(B, vc2_codec::SlotState());
+  if (ok && cudaMallocHost((void**)&k->host_novf, (size_t)4 * 2 * B) != cudaSuccess) ok = false;
   k->len32.assign(B, 0);
   if (ok && cudaMallocHost((void**)&k->host_flags, (size_t)k->nslices * 4 * 2 * B) != cudaSuccess) ok = false;
   if (ok && cudaMallocHost((void**)&k->host_len, (size_t)4 * B) != cudaSuccess) ok = false;
@@ -1030,6 +1111,7 @@ extern "C" vc2_codec* vc2_codec_create(vc2_ctx* ctx, const vc2_codec_params* prm
   }
   if (ok) ok = cudaMemset(k->err.p, 0, (size_t)k->nslices * 4 * B) == cudaSuccess;
   if (ok) ok = cudaMemset(k->dev_len.p, 0, (size_t)B * 4) == cudaSuccess;
+  if (ok) ok = cudaMemset(k->narrow_ovf.p, 0, (size_t)B * 4 * 2) == cudaSuccess;
   if (!ok) { fail(ctx, VC2_ERR_CUDA, "codec allocation failed"); codec_free(k); return nullptr; }
   k->payload_len.assign(B, 0);
   return k;
@@ -1085,11 +1167,21 @@ static int codec_ld_buffers(vc2_codec* k) {
   return VC2_OK;
 }
 
-static int codec_encode_range(vc2_codec* k, int first, int n) {
+static int codec_encode_range(vc2_codec* k, int first, int n, bool wide = false) {
   vc2_ctx* ctx = k->ctx;
   CompBuf cb[3];
   codec_compbufs(k, cb, first, false);
-  CU(run_dwt(ctx, false, k->prm.geom.kernel, k->prm.geom.depth, k->sample_kind, k->g, cb, 3, n));
+  const bool narrow = k->narrow_enc && !wide;
+  NarrowCfg nw;
+  if (narrow) {
+    nw.on = 1; nw.qindex = k->prm.qindex; nw.ovf = k->narrow_ovf.as<uint32_t>() + first;
+    CU(cudaMemsetAsync(nw.ovf, 0, (size_t)n * 4, ctx->stream));
+  }
+  for (int i = 0; i < n; ++i) {
+    vc2_codec::SlotState& ss = k->slot_state[first + i];
+    ss.enc_unchecked = narrow; ss.dec_after_enc = false; ss.coef = narrow ? 1 : 0;
+  }
+  CU(run_dwt(ctx, false, k->prm.geom.kernel, k->prm.geom.depth, k->sample_kind, k->g, cb, 3, n, nw));
   if (k->prm.mode == VC2_LD) {
     // EncodeStream.cpp:141-245 (rate control), Quantisation.cpp:213-282 (predictive quantiser), Slices.cpp:195-244 (writer)
     const int st = codec_ld_buffers(k);
@@ -1143,7 +1235,7 @@ static int codec_encode_range(vc2_codec* k, int first, int n) {
   B.fixed_off_dev = cbr ? k->fixed.as<uint32_t>() : nullptr;
   B.total_len = k->dev_len.as<uint32_t>() + first;
   const int32_t* coef = k->coef.as<int32_t>() + (long long)first * k->g.coef_pic_stride;
-  CU(run_pack(ctx, k->g, coef, n, k->prm.mode, 1, cbr ? 1 : 0, cbr ? -1 : k->prm.qindex, 1, B));
+  CU(run_pack(ctx, k->g, coef, n, k->prm.mode, 1, cbr ? 1 : 0, cbr ? -1 : k->prm.qindex, 1, B, narrow ? 1 : 0));
   return VC2_OK;
 }
 
@@ -1202,10 +1294,20 @@ extern "C" int vc2_codec_encode_dev(vc2_codec* k, int n) {
   return codec_run_split(k, n, [&](int first, int cnt) { return codec_encode_range(k, first, cnt); });
 }
 
-static int codec_decode_range(vc2_codec* k, int first, int n, bool index_here) {
+static int codec_decode_range(vc2_codec* k, int first, int n, bool index_here, bool wide = false) {
   vc2_ctx* ctx = k->ctx;
   const SliceGeom& g = k->g;
   const bool ld = k->prm.mode == VC2_LD;
+  const bool narrow = k->narrow_dec && !wide;
+  NarrowCfg nw;
+  if (narrow) {
+    nw.on = 1; nw.qidx = k->qidx.as<int32_t>() + (size_t)first * k->nslices; nw.ovf = k->narrow_ovf.as<uint32_t>() + k->prm.max_pictures + first;
+    CU(cudaMemsetAsync(nw.ovf, 0, (size_t)n * 4, ctx->stream));
+  }
+  for (int i = 0; i < n; ++i) {
+    vc2_codec::SlotState& ss = k->slot_state[first + i];
+    ss.dec_unchecked = narrow; ss.dec_after_enc = true; ss.coef = narrow ? 2 : 0;
+  }
   const bool shared_off = ld;   // HQ pictures are always indexed from their own length bytes (DecodeStream.cpp:512)
   CU(cudaMemsetAsync(k->err.as<uint32_t>() + (size_t)first * k->nslices, 0, (size_t)k->nslices * 4 * n, ctx->stream));
   UnpackParams p;
@@ -1220,6 +1322,8 @@ static int codec_decode_range(vc2_codec* k, int first, int n, bool index_here) {
   p.err_flags = k->err.as<uint32_t>() + (size_t)first * k->nslices;
   p.dequantise = 1;
   p.ld = ld ? 1 : 0;
+  p.narrow = narrow ? 1 : 0;
+  p.narrow_ovf = nw.ovf;
   if (index_here && !ld) {
     // the reader's walk over the length bytes of every slice (Slices.cpp:544-605): the slice offsets are always
     // derived from the payload itself, never taken from the encoder
@@ -1257,7 +1361,75 @@ static int codec_decode_range(vc2_codec* k, int first, int n, bool index_here) {
   }
   CompBuf cb[3];
   codec_compbufs(k, cb, first, true);
-  CU(run_dwt(ctx, true, k->prm.geom.kernel, k->prm.geom.depth, k->sample_kind, k->g, cb, 3, n));
+  CU(run_dwt(ctx, true, k->prm.geom.kernel, k->prm.geom.depth, k->sample_kind, k->g, cb, 3, n, nw));
+  return VC2_OK;
+}
+
+// Slots that went through the narrow block: did a coefficient overflow it?  Then the slot runs again through the 32-bit
+// path - the inputs (samples, or payload and slice offsets) are still in the slot - and a decode that consumed the payload
+// of such an encode is repeated as well.  Synchronises the stream when there is something to look at.
+static int codec_fix_narrow(vc2_codec* k, int slot) {
+  vc2_ctx* ctx = k->ctx;
+  vc2_codec::SlotState& ss = k->slot_state[slot];
+  const int B = k->prm.max_pictures;
+  if (ss.enc_unchecked) {
+    uint32_t ovf = 0;
+    CU(cudaMemcpyAsync(&ovf, k->narrow_ovf.as<uint32_t>() + slot, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ss.enc_unchecked = false;
+    if (ovf) {
+      k->main_dirty = true;
+      const bool again = ss.dec_after_enc;
+      int st = codec_encode_range(k, slot, 1, true);
+      if (st) return st;
+      if (again) {
+        st = codec_decode_range(k, slot, 1, true);
+        if (st) return st;
+      }
+    }
+  }
+  if (ss.dec_unchecked) {
+    uint32_t ovf = 0;
+    CU(cudaMemcpyAsync(&ovf, k->narrow_ovf.as<uint32_t>() + B + slot, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ss.dec_unchecked = false;
+    if (ovf) {
+      k->main_dirty = true;
+      const int st = codec_decode_range(k, slot, 1, false, true);
+      if (st) return st;
+    }
+  }
+  return VC2_OK;
+}
+// the coefficient taps read the 32-bit block: rebuild it for a slot that was run narrow (forward transform, or parse + scale)
+static int codec_make_wide(vc2_codec* k, int slot) {
+  vc2_ctx* ctx = k->ctx;
+  int st = codec_fix_narrow(k, slot);
+  if (st) return st;
+  const int state = k->slot_state[slot].coef;
+  if (state == 0) return VC2_OK;
+  k->main_dirty = true;
+  if (state == 1) {
+    CompBuf cb[3];
+    codec_compbufs(k, cb, slot, false);
+    CU(run_dwt(ctx, false, k->prm.geom.kernel, k->prm.geom.depth, k->sample_kind, k->g, cb, 3, 1));
+  } else {
+    const SliceGeom& g = k->g;
+    UnpackParams p;
+    memset(&p, 0, sizeof(p));
+    p.g = g;
+    p.in = k->payload.as<uint8_t>() + (size_t)slot * k->payload_cap;
+    p.in_pic_stride = (long long)k->payload_cap;
+    p.slice_off = k->slice_off.as<uint32_t>() + (size_t)slot * (k->nslices + 1);
+    p.slice_off_pic_stride = k->nslices + 1;
+    p.coef = k->coef.as<int32_t>() + (long long)slot * g.coef_pic_stride;
+    p.qidx = k->qidx.as<int32_t>() + (size_t)slot * k->nslices;
+    p.err_flags = k->err.as<uint32_t>() + (size_t)slot * k->nslices;
+    p.dequantise = 1;
+    CU(unpack_launch(ctx->stream, p, 1));
+    ctx->launches++;
+  }
+  k->slot_state[slot].coef = 0;
   return VC2_OK;
 }
 
@@ -1302,6 +1474,7 @@ extern "C" int vc2_codec_download_picture(vc2_codec* k, int slot, void* raw) {
   KARG(k && raw && slot >= 0 && slot < k->prm.max_pictures);
   vc2_ctx* ctx = k->ctx;
   CU(cudaSetDevice(ctx->device));
+  { const int st = codec_fix_narrow(k, slot); if (st) return st; }
   CU(cudaMemcpyAsync(raw, vc2_codec_recon_dev(k, slot), k->pic_bytes, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   return VC2_OK;
@@ -1316,6 +1489,7 @@ extern "C" int vc2_codec_upload_payload(vc2_codec* k, int slot, const uint8_t* p
   // bytes and length only: decode_dev walks the slice length bytes on the device (hq_index_kernel)
   CU(cudaMemcpyAsync(vc2_codec_payload_dev(k, slot), payload, len, cudaMemcpyHostToDevice, ctx->stream));
   k->payload_len[slot] = len;
+  k->slot_state[slot].enc_unchecked = false;   // the payload is the caller's now
   k->len32[slot] = (uint32_t)len;
   CU(cudaMemcpyAsync(k->dev_len.as<uint32_t>() + slot, &k->len32[slot], 4, cudaMemcpyHostToDevice, ctx->stream));
   k->main_dirty = true;
@@ -1326,6 +1500,7 @@ extern "C" int vc2_codec_slot_status(vc2_codec* k, int slot) {
   KARG(k && slot >= 0 && slot < k->prm.max_pictures);
   vc2_ctx* ctx = k->ctx;
   CU(cudaSetDevice(ctx->device));
+  { const int st = codec_fix_narrow(k, slot); if (st) return st; }
   std::vector<uint32_t> flags(k->nslices);
   CU(cudaMemcpyAsync(flags.data(), k->err.as<uint32_t>() + (size_t)slot * k->nslices, (size_t)k->nslices * 4,
                      cudaMemcpyDeviceToHost, ctx->stream));
@@ -1356,6 +1531,7 @@ extern "C" int vc2_codec_read_transform(vc2_codec* k, int slot, int32_t* y, int3
   vc2_ctx* ctx = k->ctx;
   CU(cudaSetDevice(ctx->device));
   int32_t* dst[3] = {y, u, v};
+  { const int st = codec_make_wide(k, slot); if (st) return st; }
   for (int c = 0; c < 3; ++c) {
     if (!dst[c]) continue;
     CU(layout_launch(ctx->stream, false, vc2_codec_coeffs_dev(k, slot), k->tmp_plane.as<int32_t>(), k->g, c));
@@ -1371,6 +1547,7 @@ extern "C" int vc2_codec_read_quantised(vc2_codec* k, int slot, int32_t* y, int3
   vc2_ctx* ctx = k->ctx;
   CU(cudaSetDevice(ctx->device));
   int32_t* dst[3] = {y, u, v};
+  { const int st = codec_make_wide(k, slot); if (st) return st; }
   for (int c = 0; c < 3; ++c) {
     if (!dst[c]) continue;
     const PlaneGeom& pg = k->g.plane[c];
@@ -1427,11 +1604,13 @@ extern "C" int vc2_codec_encode_host(vc2_codec* k, int n, const void* const* pic
   const int lag = std::min(2, nstage_slots - 1);   // stages in flight behind the newest upload
   const int nstages = (n + sub - 1) / sub;
   int status = VC2_OK;
+  std::vector<int> redo;                // pictures that overflowed the narrow coefficient block: encoded again at the end, 32-bit
   auto drain = [&](int st) -> int {     // stage st: wait for its kernels, then send its payloads home
     const int slot0 = (st % nstage_slots) * sub, first = st * sub, m = std::min(sub, n - first);
     cudaError_t e = cudaEventSynchronize(k->ev_done[slot0]);
     if (e != cudaSuccess) return cuda_fail(ctx, e);
     for (int j = 0; j < m; ++j) {
+      if (k->narrow_enc && k->host_novf[slot0 + j]) { redo.push_back(first + j); payload_len[first + j] = 0; continue; }
       const int er = first_error(k->host_flags + (size_t)(slot0 + j) * ns, ns);
       if (er) return fail(ctx, er);
       payload_len[first + j] = k->host_len[slot0 + j];
@@ -1457,12 +1636,20 @@ extern "C" int vc2_codec_encode_host(vc2_codec* k, int n, const void* const* pic
                          cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaMemcpyAsync(k->host_flags + (size_t)slot0 * ns, k->err.as<uint32_t>() + (size_t)slot0 * ns, (size_t)ns * 4 * m,
                        cudaMemcpyDeviceToHost, ctx->stream));
+    if (k->narrow_enc) CU(cudaMemcpyAsync(k->host_novf + slot0, k->narrow_ovf.as<uint32_t>() + slot0, (size_t)4 * m, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaEventRecord(k->ev_done[slot0], ctx->stream));
     if (st >= lag) status = drain(st - lag);
   }
   for (int st = std::max(0, nstages - lag); st < nstages && status == VC2_OK; ++st) status = drain(st);
   cudaStreamSynchronize(k->copy_out);
   cudaStreamSynchronize(ctx->stream);
+  for (size_t r = 0; r < redo.size() && status == VC2_OK; ++r) {   // slot 0, one at a time, 32-bit coefficient block
+    const int i = redo[r];
+    CU(cudaMemcpyAsync(vc2_codec_samples_dev(k, 0), pictures[i], k->pic_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    status = codec_encode_range(k, 0, 1, true);
+    if (status) break;
+    status = vc2_codec_download_payload(k, 0, payloads[i], cap, &payload_len[i], nullptr, nullptr);
+  }
   return status;
 }
 
@@ -1480,12 +1667,14 @@ extern "C" int vc2_codec_decode_host(vc2_codec* k, int n, const uint8_t* const* 
   }
   CU(cudaStreamSynchronize(ctx->stream));
   auto flags = [&](int set) { return k->host_flags + (size_t)set * B * ns; };
+  std::vector<int> redo;             // pictures that overflowed the narrow coefficient block: decoded again at the end, 32-bit
   auto check = [&](int c) -> int {   // wait for chunk c and look at its error flags
     const int m = std::min(B, n - c * B);
     const int sub = stage_pictures(B);
     cudaError_t e = cudaEventSynchronize(k->ev_out[(c & 1) * B + (m - 1) / sub * sub]);
     if (e != cudaSuccess) return cuda_fail(ctx, e);
     for (int i = 0; i < m; ++i) {
+      if (k->narrow_dec && k->host_novf[(c & 1) * B + i]) { redo.push_back(c * B + i); continue; }
       const int st = first_error(flags(c & 1) + (size_t)i * ns, ns);
       if (st && st != VC2_ERR_VLC_RANGE) return fail(ctx, st);
     }
@@ -1522,6 +1711,7 @@ extern "C" int vc2_codec_decode_host(vc2_codec* k, int n, const uint8_t* const* 
       if (c > 0) CU(cudaStreamWaitEvent(ctx->stream, k->ev_out[((c - 1) & 1) * B + i], 0));   // the previous pictures have left these slots
       status = codec_decode_range(k, i, mm, false);
       if (status) break;
+      if (k->narrow_dec) CU(cudaMemcpyAsync(k->host_novf + (c & 1) * B + i, k->narrow_ovf.as<uint32_t>() + B + i, (size_t)4 * mm, cudaMemcpyDeviceToHost, ctx->stream));
       CU(cudaEventRecord(k->ev_done[i], ctx->stream));
       CU(cudaStreamWaitEvent(k->copy_out, k->ev_done[i], 0));
       for (int j = i; j < i + mm; ++j)
@@ -1537,5 +1727,16 @@ extern "C" int vc2_codec_decode_host(vc2_codec* k, int n, const uint8_t* const* 
   if (status == VC2_OK) status = check(chunks - 1);
   cudaStreamSynchronize(k->copy_out);
   cudaStreamSynchronize(ctx->stream);
+  for (size_t r = 0; r < redo.size() && status == VC2_OK; ++r) {   // slot 0, one at a time, 32-bit coefficient block
+    const int i = redo[r];
+    status = vc2_codec_upload_payload(k, 0, payloads[i], payload_len[i]);
+    if (status) break;
+    status = codec_decode_range(k, 0, 1, hq, true);
+    if (status) break;
+    status = vc2_codec_slot_status(k, 0);
+    if (status == VC2_ERR_VLC_RANGE) status = VC2_OK;
+    if (status) break;
+    status = vc2_codec_download_picture(k, 0, pictures[i]);
+  }
   return status;
 }

@@ -101,8 +101,7 @@ struct DwtComp {
   int ql31[4];
   int qmat[4];               // inverse: quantisation matrix entries of the four bands (Quantisation.cpp:16-20)
 };
-#define VC2_NARROW_FAST_MAX 8192
-#define VC2_NARROW_MAX_MAG 32767
+
 
 struct DwtParams {
   DwtComp c[3];

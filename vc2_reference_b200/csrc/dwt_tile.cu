@@ -54,35 +54,97 @@ struct TileList {     // grid.x = CTA in its tile row, grid.y = tile row (both: 
 __device__ __forceinline__ int swz(int row) { return (row >> 3) & 7; }
 
 // per-lane constants of the vectorised band access (band part widths are multiples of four, power-of-two part heights):
-// the 16-byte piece of band row `by` at this lane's band columns sits at element idx(by) behind the band's start
+// the piece (four coefficients) of band row `by` at this lane's band columns sits at element idx(by) behind the band's start
 struct BandFast {
-  int32_t *p_ll, *p_hl, *p_lh, *p_hh;   // picture block + band start (p_ll: compact LL plane at this lane's columns when plane_ll)
+  uint8_t *p_ll, *p_hl, *p_lh, *p_hh;   // picture block + band start (p_ll: compact LL plane at this lane's columns when plane_ll)
   bool plane_ll;
   int ll_pitch;
+  int esh;                              // log2 of the element size of the block: 2 (int32) or 1 (narrow, 16-bit)
   int sx, kx4, lgbh, bhm1, bw4, nx, nc4;
+  __device__ __forceinline__ int slice(int by) const { return (by >> lgbh) * nx + sx; }
   __device__ __forceinline__ int idx(int by) const {
-    const int sy = by >> lgbh, ry = by & bhm1;
-    const int s = sy * nx + sx;
+    const int ry = by & bhm1, s = slice(by);
     return ((((s >> 5) * nc4 + ry * bw4 + kx4) << 5) + (s & 31)) << 2;
   }
+  template <class V> __device__ __forceinline__ V* at(uint8_t* band, int i) const { return reinterpret_cast<V*>(band + ((unsigned)i << esh)); }
+  __device__ __forceinline__ int4* ll_row(int by) const { return reinterpret_cast<int4*>(p_ll + (((long long)by * ll_pitch) << 2)); }
 };
 // false when this level / lane has to use the element-wise access
-__device__ __forceinline__ bool band_fast_setup(const DwtComp& C, int pic, int bx0, bool inside, BandFast& F) {
+__device__ __forceinline__ bool band_fast_setup(const DwtComp& C, int pic, int narrow, int bx0, bool inside, BandFast& F) {
   if (!inside) return false;
   if (C.lgbh < 0 || C.lgbw < 0 || (C.bw & 3) || ((C.base_ll | C.base_hl | C.base_lh | C.base_hh) & 3)) return false;
-  int32_t* coefpic = C.coef + (long long)pic * C.coef_pic_stride;
+  F.esh = narrow ? 1 : 2;
+  uint8_t* coefpic = reinterpret_cast<uint8_t*>(C.coef) + (((long long)pic * C.coef_pic_stride) << F.esh);
   F.sx = bx0 >> C.lgbw;
   F.kx4 = (bx0 & (C.bw - 1)) >> 2;
   F.lgbh = C.lgbh; F.bhm1 = C.bh - 1; F.bw4 = C.bw >> 2; F.nx = C.nx; F.nc4 = C.NC >> 2;
-  F.p_ll = coefpic + (C.base_ll >> 2) * 128; F.p_hl = coefpic + (C.base_hl >> 2) * 128;
-  F.p_lh = coefpic + (C.base_lh >> 2) * 128; F.p_hh = coefpic + (C.base_hh >> 2) * 128;
+  F.p_ll = coefpic + (((C.base_ll >> 2) * 128) << F.esh); F.p_hl = coefpic + (((C.base_hl >> 2) * 128) << F.esh);
+  F.p_lh = coefpic + (((C.base_lh >> 2) * 128) << F.esh); F.p_hh = coefpic + (((C.base_hh >> 2) * 128) << F.esh);
   F.plane_ll = C.ll != nullptr; F.ll_pitch = C.ll_pitch;
   if (C.ll) {
-    F.p_ll = C.ll + (long long)pic * C.ll_pic_stride + bx0;
+    F.p_ll = reinterpret_cast<uint8_t*>(C.ll + (long long)pic * C.ll_pic_stride + bx0);
     if ((C.ll_pitch & 3) || (reinterpret_cast<uintptr_t>(C.ll + (long long)pic * C.ll_pic_stride) & 15)) return false;
   }
   if (reinterpret_cast<uintptr_t>(coefpic) & 15) return false;
   return true;
+}
+
+// ---- narrow coefficient block: quantised, 16-bit sign-magnitude (see dwt.cuh) ----------------------------------------
+// |quant(v, q)| (Quantisation.cpp:69-76) of four coefficients of band b as sign-magnitude words, two per register
+__device__ __forceinline__ uint2 quant4_smag(const DwtComp& C, int b, const int4 v, bool& ovf) {
+  const unsigned a0 = (unsigned)abs(v.x), a1 = (unsigned)abs(v.y), a2 = (unsigned)abs(v.z), a3 = (unsigned)abs(v.w);
+  unsigned m0, m1, m2, m3;
+  if ((a0 | a1 | a2 | a3) < (unsigned)VC2_NARROW_FAST_MAX) {   // one full-rate multiply: exact below the bound (checked by the host)
+    const unsigned mul = C.qmul[b];
+    const int sh = C.qsh[b];
+    m0 = (a0 * mul) >> sh; m1 = (a1 * mul) >> sh; m2 = (a2 * mul) >> sh; m3 = (a3 * mul) >> sh;
+  } else {
+    const unsigned mm = C.qm31[b];
+    const int sh = C.ql31[b];
+    m0 = __umulhi(a0 << 2, mm) >> sh; m1 = __umulhi(a1 << 2, mm) >> sh; m2 = __umulhi(a2 << 2, mm) >> sh; m3 = __umulhi(a3 << 2, mm) >> sh;
+    if ((m0 | m1 | m2 | m3) > (unsigned)VC2_NARROW_MAX_MAG) {
+      ovf = true;
+      m0 = min(m0, (unsigned)VC2_NARROW_MAX_MAG); m1 = min(m1, (unsigned)VC2_NARROW_MAX_MAG);
+      m2 = min(m2, (unsigned)VC2_NARROW_MAX_MAG); m3 = min(m3, (unsigned)VC2_NARROW_MAX_MAG);
+    }
+  }
+  const unsigned t0 = 2u * m0 + ((unsigned)v.x >> 31), t1 = 2u * m1 + ((unsigned)v.y >> 31);
+  const unsigned t2 = 2u * m2 + ((unsigned)v.z >> 31), t3 = 2u * m3 + ((unsigned)v.w >> 31);
+  return make_uint2(t0 | (t1 << 16), t2 | (t3 << 16));
+}
+// scale(q, index) (Quantisation.cpp:86-95) of four sign-magnitude words; fo = (quant_factor, quant_offset + 2)
+__device__ __forceinline__ int scale1_smag(unsigned t, const uint2 fo) {
+  const unsigned mag = t >> 1;
+  const unsigned m = mag ? (mag * fo.x + fo.y) >> 2 : 0u;
+  return (t & 1u) ? -(int)m : (int)m;
+}
+__device__ __forceinline__ int4 scale4_smag(const uint2 w, const uint2 fo) {
+  return make_int4(scale1_smag(w.x & 0xFFFFu, fo), scale1_smag(w.x >> 16, fo), scale1_smag(w.y & 0xFFFFu, fo), scale1_smag(w.y >> 16, fo));
+}
+__device__ __forceinline__ uint2 scale_params(const DwtParams& p, const DwtComp& C, int pic, int slice, int b) {
+  const int q = min(max(__ldg(p.qidx + (long long)pic * p.nslices + slice) - C.qmat[b], 0), 127);
+  return __ldg(p.scale_tab + q);
+}
+// element-wise access to the narrow block (small band parts at the deep levels, picture edges)
+template <bool STORE>
+__device__ __forceinline__ void band_access16(const DwtParams& p, const DwtComp& C, int pic, const BandAddr& ba, int b, int base, int by, int bx0, int bxmax,
+                                              int (&x)[4], bool& ovf) {
+  uint16_t* coef = reinterpret_cast<uint16_t*>(C.coef) + (long long)pic * C.coef_pic_stride;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int bx = bx0 + j;
+    if (bx < 0 || bx > bxmax) { if (!STORE) x[j] = 0; continue; }
+    uint16_t* e = coef + ba.at(base, by, bx);
+    if (STORE) {
+      const unsigned a = (unsigned)abs(x[j]);
+      unsigned m = a < (unsigned)VC2_NARROW_FAST_MAX ? (a * C.qmul[b]) >> C.qsh[b] : __umulhi(a << 2, C.qm31[b]) >> C.ql31[b];
+      if (m > (unsigned)VC2_NARROW_MAX_MAG) { ovf = true; m = VC2_NARROW_MAX_MAG; }
+      *e = (uint16_t)(2u * m + ((unsigned)x[j] >> 31));
+    } else {
+      const int sy = ba.lgbh >= 0 ? (by >> ba.lgbh) : (by / ba.bh), sx = ba.lgbw >= 0 ? (bx >> ba.lgbw) : (bx / ba.bw);
+      x[j] = scale1_smag(*e, scale_params(p, C, pic, sy * ba.nx + sx, b));
+    }
+  }
 }
 
 struct TileCtx {
@@ -290,7 +352,8 @@ __global__ void __launch_bounds__(32 * T::NW, T::MINB) dwt_tile_fwd_kernel(const
     if (mine) {
       const int bx0 = (S.xs >> 1) + 4 * hl;
       BandFast F;
-      const bool fast = band_fast_setup(C, S.pic, bx0, bx0 + 3 <= bxmax, F);
+      const bool fast = band_fast_setup(C, S.pic, p.narrow, bx0, bx0 + 3 <= bxmax, F);
+      bool ovf = false;
 #pragma unroll 1
       for (int m = 4 * T::HL + g; m < T::TH / 2 - 4 * T::HL; m += T::NG) {
         const int y = S.ys + 2 * m;
@@ -301,23 +364,36 @@ __global__ void __launch_bounds__(32 * T::NW, T::MINB) dwt_tile_fwd_kernel(const
         const int by = y >> 1;
         if (fast) {
           const int i = F.idx(by);
-          if (F.plane_ll) *reinterpret_cast<int4*>(F.p_ll + by * F.ll_pitch) = ll4;
-          else *reinterpret_cast<int4*>(F.p_ll + i) = ll4;
-          *reinterpret_cast<int4*>(F.p_hl + i) = hl4;
-          *reinterpret_cast<int4*>(F.p_lh + i) = lh4;
-          *reinterpret_cast<int4*>(F.p_hh + i) = hh4;
+          if (p.narrow) {
+            if (F.plane_ll) *F.ll_row(by) = ll4;
+            else *F.at<uint2>(F.p_ll, i) = quant4_smag(C, 0, ll4, ovf);
+            *F.at<uint2>(F.p_hl, i) = quant4_smag(C, 1, hl4, ovf);
+            *F.at<uint2>(F.p_lh, i) = quant4_smag(C, 2, lh4, ovf);
+            *F.at<uint2>(F.p_hh, i) = quant4_smag(C, 3, hh4, ovf);
+          } else {
+            if (F.plane_ll) *F.ll_row(by) = ll4;
+            else *F.at<int4>(F.p_ll, i) = ll4;
+            *F.at<int4>(F.p_hl, i) = hl4;
+            *F.at<int4>(F.p_lh, i) = lh4;
+            *F.at<int4>(F.p_hh, i) = hh4;
+          }
         } else {
           int v[4] = {ll4.x, ll4.y, ll4.z, ll4.w};
           if (C.ll) ll_access<4, true>(C.ll + (long long)S.pic * C.ll_pic_stride, C.ll_pitch, by, bx0, bxmax, v);
+          else if (p.narrow) band_access16<true>(p, C, S.pic, ba, 0, C.base_ll, by, bx0, bxmax, v, ovf);
           else band_access<4, true>(coef, ba, C.base_ll, by, bx0, bxmax, v);
           v[0] = hl4.x; v[1] = hl4.y; v[2] = hl4.z; v[3] = hl4.w;
-          band_access<4, true>(coef, ba, C.base_hl, by, bx0, bxmax, v);
+          if (p.narrow) band_access16<true>(p, C, S.pic, ba, 1, C.base_hl, by, bx0, bxmax, v, ovf);
+          else band_access<4, true>(coef, ba, C.base_hl, by, bx0, bxmax, v);
           v[0] = lh4.x; v[1] = lh4.y; v[2] = lh4.z; v[3] = lh4.w;
-          band_access<4, true>(coef, ba, C.base_lh, by, bx0, bxmax, v);
+          if (p.narrow) band_access16<true>(p, C, S.pic, ba, 2, C.base_lh, by, bx0, bxmax, v, ovf);
+          else band_access<4, true>(coef, ba, C.base_lh, by, bx0, bxmax, v);
           v[0] = hh4.x; v[1] = hh4.y; v[2] = hh4.z; v[3] = hh4.w;
-          band_access<4, true>(coef, ba, C.base_hh, by, bx0, bxmax, v);
+          if (p.narrow) band_access16<true>(p, C, S.pic, ba, 3, C.base_hh, by, bx0, bxmax, v, ovf);
+          else band_access<4, true>(coef, ba, C.base_hh, by, bx0, bxmax, v);
         }
       }
+      if (ovf) atomicOr(p.narrow_ovf + S.pic, 1u);
     }
     __syncthreads();   // the tile is free for the CTA's next column
   }
@@ -348,7 +424,8 @@ __global__ void __launch_bounds__(32 * T::NW, T::MINB) dwt_tile_inv_kernel(const
     // P1: band rows into the tile, two lattice rows (one band row of LL | HL and of LH | HH) at a time
     {
       BandFast F;
-      const bool fast = band_fast_setup(C, S.pic, bx0, bx0 >= 0 && bx0 + 3 <= bxmax, F);
+      const bool fast = band_fast_setup(C, S.pic, p.narrow, bx0, bx0 >= 0 && bx0 + 3 <= bxmax, F);
+      bool never = false;
 #pragma unroll
       for (int m = g; m < T::TH / 2; m += T::NG) {   // unrolled: all the loads of the lane are in flight together
         const int y = S.ys + 2 * m;
@@ -357,20 +434,34 @@ __global__ void __launch_bounds__(32 * T::NW, T::MINB) dwt_tile_inv_kernel(const
         int4 ll4, hl4, lh4, hh4;
         if (fast) {
           const int k = F.idx(by);
-          ll4 = F.plane_ll ? __ldg(reinterpret_cast<const int4*>(F.p_ll + by * F.ll_pitch)) : __ldg(reinterpret_cast<const int4*>(F.p_ll + k));
-          hl4 = __ldg(reinterpret_cast<const int4*>(F.p_hl + k));
-          lh4 = __ldg(reinterpret_cast<const int4*>(F.p_lh + k));
-          hh4 = __ldg(reinterpret_cast<const int4*>(F.p_hh + k));
+          if (p.narrow) {
+            const uint2 wl = F.plane_ll ? make_uint2(0, 0) : __ldg(F.at<const uint2>(F.p_ll, k));
+            const uint2 w1 = __ldg(F.at<const uint2>(F.p_hl, k)), w2 = __ldg(F.at<const uint2>(F.p_lh, k)), w3 = __ldg(F.at<const uint2>(F.p_hh, k));
+            const int sl = F.slice(by);
+            ll4 = F.plane_ll ? __ldg(F.ll_row(by)) : scale4_smag(wl, scale_params(p, C, S.pic, sl, 0));
+            hl4 = scale4_smag(w1, scale_params(p, C, S.pic, sl, 1));
+            lh4 = scale4_smag(w2, scale_params(p, C, S.pic, sl, 2));
+            hh4 = scale4_smag(w3, scale_params(p, C, S.pic, sl, 3));
+          } else {
+            ll4 = F.plane_ll ? __ldg(F.ll_row(by)) : __ldg(F.at<const int4>(F.p_ll, k));
+            hl4 = __ldg(F.at<const int4>(F.p_hl, k));
+            lh4 = __ldg(F.at<const int4>(F.p_lh, k));
+            hh4 = __ldg(F.at<const int4>(F.p_hh, k));
+          }
         } else {
           int v[4];
           if (C.ll) ll_access<4, false>(C.ll + (long long)S.pic * C.ll_pic_stride, C.ll_pitch, by, bx0, bxmax, v);
+          else if (p.narrow) band_access16<false>(p, C, S.pic, ba, 0, C.base_ll, by, bx0, bxmax, v, never);
           else band_access<4, false>(coef, ba, C.base_ll, by, bx0, bxmax, v);
           ll4 = make_int4(v[0], v[1], v[2], v[3]);
-          band_access<4, false>(coef, ba, C.base_hl, by, bx0, bxmax, v);
+          if (p.narrow) band_access16<false>(p, C, S.pic, ba, 1, C.base_hl, by, bx0, bxmax, v, never);
+          else band_access<4, false>(coef, ba, C.base_hl, by, bx0, bxmax, v);
           hl4 = make_int4(v[0], v[1], v[2], v[3]);
-          band_access<4, false>(coef, ba, C.base_lh, by, bx0, bxmax, v);
+          if (p.narrow) band_access16<false>(p, C, S.pic, ba, 2, C.base_lh, by, bx0, bxmax, v, never);
+          else band_access<4, false>(coef, ba, C.base_lh, by, bx0, bxmax, v);
           lh4 = make_int4(v[0], v[1], v[2], v[3]);
-          band_access<4, false>(coef, ba, C.base_hh, by, bx0, bxmax, v);
+          if (p.narrow) band_access16<false>(p, C, S.pic, ba, 3, C.base_hh, by, bx0, bxmax, v, never);
+          else band_access<4, false>(coef, ba, C.base_hh, by, bx0, bxmax, v);
           hh4 = make_int4(v[0], v[1], v[2], v[3]);
         }
         int4* row = mid + 2 * m * T::CHUNKS;

@@ -469,6 +469,102 @@ __global__ void __launch_bounds__(128) hq_pack_kernel(const PackParams p) {
 }
 
 // ------------------------------------------------------------------------------------------
+// HQ slice encoder over the NARROW coefficient block (HQ_ConstQ): the lifting kernels have already quantised, a
+// coefficient arrives as the 16-bit word t = 2 * |q| + (q < 0), which IS the index of the code table.  No band
+// bookkeeping is left: a component is one flat run of 8-byte pieces (four coefficients), 256 bytes apart per lane.
+// Same slice syntax, writer and staging images as hq_pack_kernel.
+// ------------------------------------------------------------------------------------------
+struct NarrowEmit {
+  const uint32_t* lut;
+  WideBitWriter* W;
+  unsigned last;   // cursor behind the last non-zero coefficient
+  __device__ __forceinline__ void one(uint32_t t) {
+    uint32_t code;
+    int nb;
+    if (t < 2u * (uint32_t)ENC_LUT_MAG) {
+      const uint32_t e = lut[t];
+      nb = (int)(e & 31u);
+      code = e >> 5;
+    } else {   // magnitudes up to 32767: m = |q| + 1 <= 2^15, 2 * 15 + 2 = 32 bits at most
+      const uint32_t m = (t >> 1) + 1u;
+      const int k = 31 - __clz(m);
+      nb = 2 * k + 2;
+      code = (spread16(m ^ (1u << k)) << 2) | 2u | (t & 1u);
+    }
+    W->put(code, nb);
+    last = t >= 2u ? W->mark() : last;
+  }
+  // two coefficients whose codes come from the table and are at most 16 bits long: ONE append
+  __device__ __forceinline__ void pair(uint32_t t0, uint32_t t1) {
+    if ((t0 | t1) < 256u) {
+      const uint32_t e0 = lut[t0], e1 = lut[t1];
+      const int nb0 = (int)(e0 & 31u), nb1 = (int)(e1 & 31u);
+      const unsigned mid = W->mark() + (unsigned)nb0;
+      W->put(((e0 >> 5) << nb1) | (e1 >> 5), nb0 + nb1);
+      last = t1 >= 2u ? W->mark() : (t0 >= 2u ? mid : last);
+    } else {
+      one(t0);
+      one(t1);
+    }
+  }
+};
+
+__global__ void __launch_bounds__(128) hq_pack_narrow_kernel(const PackParams p) {
+  __shared__ uint32_t s_enc[2 * ENC_LUT_MAG];
+  stage_table(s_enc, d_enc_lut, 2 * ENC_LUT_MAG);
+  __syncthreads();
+  const SliceGeom& g = p.g;
+  const int nslices = g.slices_x * g.slices_y;
+  const int pic = blockIdx.y;
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= nslices) return;
+  const int nc4 = g.comp_start[3] >> 2;
+  const uint2* src = reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(p.coef) + (long long)pic * g.coef_pic_stride) +
+                     (size_t)(s >> 5) * nc4 * 32 + (s & 31);
+  const long long sidx = (long long)pic * nslices + s;
+  unsigned flags = 0;
+  const int qi = p.const_q;
+  p.qidx[sidx] = qi;
+  // the reference rejects an index beyond its quantiser table when it quantises (Quantisation.cpp:60-63)
+  for (int b = 0; b < g.nbands; ++b) if (max(qi - g.qmatrix[b], 0) > 119) flags |= VC2_FLAG_QUANT_INDEX;
+  WideBitWriter W;
+  W.init(p.staging + sidx * p.wcap);
+  for (int i = 0; i < g.prefix; ++i) W.put(0u, 8);
+  W.put((uint32_t)qi & 0xFFu, 8);
+  bool too_big = false;
+  int lensum = 0;
+  for (int c = 0; c < 3; ++c) {
+    const int len_pos = W.pos();
+    W.put(0u, 8);
+    const int data_start = W.pos();
+    const uint2* csrc = src + (size_t)(g.comp_start[c] >> 2) * 32;
+    const int np = g.band_start[c][g.nbands] >> 2;
+    NarrowEmit op = {s_enc, &W, W.mark()};
+    // three pieces in flight (every one a fresh line, see walk_component)
+    uint2 n0 = __ldg(csrc), n1 = n0, n2 = n0;
+    if (np > 1) n1 = __ldg(csrc + 32);
+    if (np > 2) n2 = __ldg(csrc + 64);
+    const uint2* pf = csrc + 96;
+    for (int i = 0; i < np; ++i) {
+      const uint2 w = n0;
+      n0 = n1; n1 = n2;
+      if (i + 3 < np) n2 = __ldg(pf);
+      pf += 32;
+      op.pair(w.x & 0xFFFFu, w.x >> 16);
+      op.pair(w.y & 0xFFFFu, w.y >> 16);
+    }
+    const int L = scaled_bytes(W.unmark(op.last) - data_start, g.scalar, too_big);
+    if (too_big) { flags |= VC2_FLAG_SCALAR_TOO_SMALL; break; }
+    lensum += L;
+    W.seek(data_start + 8 * L);
+    W.patch_byte(len_pos, (uint32_t)(L / g.scalar) & 0xFFu);
+  }
+  W.finish();
+  p.sizes[sidx] = flags ? 0u : (uint32_t)(g.prefix + 4 + lensum);
+  p.err_flags[sidx] = flags;
+}
+
+// ------------------------------------------------------------------------------------------
 // LD encoder.  The reference picks the slice quantisers in raster order (quantIndicesLD,
 // EncodeStream.cpp:193-245): seven probes of a binary search per slice, each probe quantising the whole
 // slice - with the LL band predicted from its already decoded neighbours, which is what chains the slices
@@ -1057,6 +1153,68 @@ __global__ void __launch_bounds__(128) slice_unpack_kernel(const UnpackParams p)
 }
 
 // ------------------------------------------------------------------------------------------
+// HQ slice decoder into the NARROW coefficient block: the parsed (still quantised) coefficients are stored as 16-bit
+// sign-magnitude words, the inverse lifting kernels scale them on the way in.  A magnitude that does not fit 15 bits
+// raises narrow_ovf[picture]: the caller decodes that picture again through the 32-bit path.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) slice_unpack_narrow_kernel(const UnpackParams p) {
+  __shared__ int16_t s_dec[1 << DEC_LUT_BITS];
+  stage_table(reinterpret_cast<uint32_t*>(s_dec), reinterpret_cast<const uint32_t*>(d_dec_lut), (1 << DEC_LUT_BITS) / 2);
+  __syncthreads();
+  const SliceGeom& g = p.g;
+  const int nslices = g.slices_x * g.slices_y;
+  const int pic = blockIdx.y;
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= nslices) return;
+  const int nc4 = g.comp_start[3] >> 2;
+  uint2* dst = reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(p.coef) + (long long)pic * g.coef_pic_stride) + (size_t)(s >> 5) * nc4 * 32 + (s & 31);
+  const uint32_t* so = p.slice_off + (long long)pic * p.slice_off_pic_stride;
+  const uint8_t* bytes = p.in + (long long)pic * p.in_pic_stride + so[s];
+  const int size = (int)(so[s + 1] - so[s]);
+  const long long sidx = (long long)pic * nslices + s;
+  unsigned flags = 0, big = 0;
+  bool range_err = false;
+  BitReader br;
+  // prefix | qindex | len | data | len | data | len | data   (Slices.cpp:544-605)
+  bool bad = size < g.prefix + 4;
+  const int qi = bad ? 0 : bytes[g.prefix];
+  int pos = g.prefix + 1;
+  for (int c = 0; c < 3; ++c) {
+    int len = 0;
+    if (!bad) {
+      len = bytes[pos] * g.scalar;
+      if (pos + 1 + len + (2 - c) > size) { bad = true; len = 0; }
+    }
+    const int start = pos + 1;
+    pos = start + len;
+    br.init(bytes + (bad ? 0 : start), 8 * len);
+    uint2* cdst = dst + (size_t)(g.comp_start[c] >> 2) * 32;
+    const int np = g.band_start[c][g.nbands] >> 2;
+    for (int i = 0; i < np; ++i) {
+      int v[4];
+      br.get_vlc2(s_dec, range_err, v[0], v[1]);
+      br.get_vlc2(s_dec, range_err, v[2], v[3]);
+      unsigned t[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const unsigned a = (unsigned)abs(v[e]);
+        big |= a;
+        t[e] = 2u * min(a, (unsigned)VC2_NARROW_MAX_MAG) + ((unsigned)v[e] >> 31);
+      }
+      *cdst = make_uint2(t[0] | (t[1] << 16), t[2] | (t[3] << 16));
+      cdst += 32;
+    }
+  }
+  if (bad) flags |= VC2_FLAG_STREAM;
+  if (big > (unsigned)VC2_NARROW_MAX_MAG) atomicOr(p.narrow_ovf + pic, 1u);
+  // the reference scales every band of the slice: an index beyond the quantiser table is an error (Quantisation.cpp:60-63)
+  for (int b = 0; b < g.nbands; ++b) if (max(qi - g.qmatrix[b], 0) > 119) flags |= VC2_FLAG_QUANT_INDEX;
+  p.qidx[sidx] = qi;
+  if (range_err) flags |= VC2_FLAG_VLC_RANGE;
+  if (flags) atomicOr(&p.err_flags[sidx], flags);
+}
+
+// ------------------------------------------------------------------------------------------
 // Slice index of an HQ payload: slice s+1 starts where the three length-prefixed components of slice s
 // end (Slices.cpp:544-605), a chain of dependent byte loads.  One CTA per picture: warps 1..7 stream the
 // payload through a shared-memory ring while thread 0 walks the chain inside it (three dependent
@@ -1250,6 +1408,11 @@ __global__ void __launch_bounds__(1024) ld_dc_kernel(const LdDcParams p) {
 
 cudaError_t pack_launch(cudaStream_t s, const PackParams& p, int npictures) {
   const int nslices = p.g.slices_x * p.g.slices_y;
+  if (p.narrow) {
+    if (p.search || p.const_q < 0 || !p.emit || p.mode != VC2_HQ_VBR) return cudaErrorInvalidValue;
+    hq_pack_narrow_kernel<<<dim3((nslices + 127) / 128, npictures), 128, 0, s>>>(p);
+    return cudaGetLastError();
+  }
   hq_pack_kernel<<<dim3((nslices + 127) / 128, npictures), 128, 0, s>>>(p);
   return cudaGetLastError();
 }
@@ -1277,6 +1440,11 @@ cudaError_t assemble_launch(cudaStream_t s, const AssembleParams& p, int npictur
 cudaError_t unpack_launch(cudaStream_t s, const UnpackParams& p, int npictures) {
   const int nslices = p.g.slices_x * p.g.slices_y;
   const dim3 grid((nslices + 127) / 128, npictures);
+  if (p.narrow) {
+    if (p.ld) return cudaErrorInvalidValue;
+    slice_unpack_narrow_kernel<<<grid, 128, 0, s>>>(p);
+    return cudaGetLastError();
+  }
   if (p.ld) {
     if (p.dequantise) slice_unpack_kernel<true, true><<<grid, 128, 0, s>>>(p);
     else slice_unpack_kernel<true, false><<<grid, 128, 0, s>>>(p);

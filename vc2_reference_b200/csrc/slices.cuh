@@ -39,6 +39,7 @@ struct PackParams {
   int wcap;                     // staging words per slice (worst case: every code 32 bits)
   uint32_t* sizes;              // [pic][slices] out: bytes of each coded slice
   uint32_t* err_flags;          // [pic][slices] out (VC2_FLAG_*)
+  int narrow;                   // 1: coef is the narrow block (16-bit sign-magnitude, already quantised; HQ_ConstQ only)
 };
 
 struct AssembleParams {         // exclusive scan of the slice sizes and the gather into the payload
@@ -66,6 +67,8 @@ struct UnpackParams {
   uint32_t* err_flags;          // [pic][slices]
   int dequantise;               // 1: store scale(v, q'); 0: store the quantised value
   int ld;                       // 1: LD slice syntax (Slices.cpp:246-303); LL band left quantised
+  int narrow;                   // 1: coef is the narrow block: 16-bit sign-magnitude words of the QUANTISED coefficients (HQ only)
+  uint32_t* narrow_ovf;         // [pic] set when a magnitude does not fit the narrow block
 };
 
 // slice index of HQ payloads on the device (the reader's walk over the length bytes, Slices.cpp:544-605)

@@ -6,6 +6,9 @@
 
 #define VC2_MAX_DEPTH 6
 #define VC2_MAX_BANDS (3 * VC2_MAX_DEPTH + 1)
+// narrow coefficient block (dwt.cuh): 16-bit sign-magnitude words 2 * |q| + (q < 0)
+#define VC2_NARROW_MAX_MAG 32767   /* largest |q| the block holds */
+#define VC2_NARROW_FAST_MAX 8192   /* |v| below this: the quantiser's one-multiply form (verified by the host per band) */
 
 namespace vc2 {
 
