@@ -225,6 +225,8 @@ struct vc2_ctx {
   int dwt_fast = 1;               // fast loop of the lifting kernels (VC2_DWT_FAST=0 turns it off)
   int dwt_seg_rows = 0;           // > 0: forced rows per warp (tuning, VC2_DWT_SEG_ROWS)
   int dwt_tile = 1;               // lifting kernels: 1 = shared-memory tiles (dwt_tile.cu), 0 = streaming register rings (dwt.cu; VC2_DWT_TILE=0)
+  int fuse_gather = 0;            // narrow packer: scan + gather inside the packing kernel (VC2_FUSE_GATHER=1).  Off: measured slower - the
+                                  // images of all resident warps (3700 x 25 KB) do not stay in L2 until their warp gathers them
   int narrow = 1;                 // codecs keep quantised 16-bit coefficients between the lifting kernels and the slice coders (VC2_NARROW=0: 32-bit)
   DevBuf scale_tab;               // [128] (quant_factor, quant_offset + 2) for the inverse lifting kernels of the narrow path
   // optional per-kernel timing with CUDA events on the launch stream (vc2_profile_*)
@@ -306,6 +308,7 @@ extern "C" vc2_ctx* vc2_create(int device) {
   if (const char* e = getenv("VC2_DWT_FAST")) c->dwt_fast = atoi(e) != 0;
   if (const char* e = getenv("VC2_DWT_TILE")) c->dwt_tile = atoi(e);
   if (const char* e = getenv("VC2_NARROW")) c->narrow = atoi(e) != 0;
+  if (const char* e = getenv("VC2_FUSE_GATHER")) c->fuse_gather = atoi(e) != 0;
   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return nullptr; }
   c->own_stream = true;
   QuantTables t;
@@ -438,6 +441,7 @@ struct NarrowCfg {
   int qindex = 0;                 // forward
   const int32_t* qidx = nullptr;  // inverse: [picture][slice]
   uint32_t* ovf = nullptr;        // [picture]
+  const BandScale* band_scale = nullptr; // inverse: [picture], see UnpackParams::band_scale
 };
 
 static cudaError_t run_dwt(vc2_ctx* ctx, bool inverse, int kernel, int depth, int sample_kind, const SliceGeom& g, const CompBuf* cb,
@@ -454,6 +458,7 @@ static cudaError_t run_dwt(vc2_ctx* ctx, bool inverse, int kernel, int depth, in
     p.narrow = nw.on;
     p.narrow_ovf = nw.ovf;
     p.qidx = nw.qidx;
+    p.band_scale = nw.band_scale;
     p.nslices = g.slices_x * g.slices_y;
     p.scale_tab = ctx->scale_tab.as<uint2>();
     for (int c = 0; c < ncomp; ++c) {
@@ -487,6 +492,7 @@ static cudaError_t run_dwt(vc2_ctx* ctx, bool inverse, int kernel, int depth, in
         const int band[4] = {0, bhl, bhl + 1, bhl + 2};
         for (int i = 0; i < 4; ++i) {
           C.qmat[i] = g.qmatrix[band[i]];
+          C.band[i] = band[i];
           const int q = std::min(std::max(nw.qindex - g.qmatrix[band[i]], 0), 119);   // Quantisation.cpp:16-20; beyond 119 the packer raises the error
           const NarrowMagic& m = narrow_magic(q);
           C.qmul[i] = m.mul; C.qsh[i] = m.sh < 0 ? 0 : m.sh;
@@ -625,7 +631,10 @@ struct PackBuffers {
   uint32_t* staging; uint32_t* sizes;
   const int32_t* slice_bytes_dev; const uint32_t* fixed_off_dev;
   uint32_t* total_len = nullptr;   // [pic] payload bytes, device memory (optional)
+  // fused scan + gather of the narrow packer: [pic][tiles] 64-bit tile states followed by [pic] 32-bit tickets (NULL: separate scan and gather)
+  unsigned long long* tile_state = nullptr;
 };
+static size_t tile_state_bytes(int nslices, int npictures) { return ((size_t)((nslices + 127) / 128) * 8 + 8) * npictures; }
 
 // staging words per slice: every coefficient at the 32-bit VLC limit, plus header bytes and slack
 // worst case (every code 32 bits) plus slack for the assembler's look-ahead, in whole 16-byte units: the HQ packer
@@ -643,13 +652,25 @@ static cudaError_t run_pack(vc2_ctx* ctx, const SliceGeom& g, const int32_t* coe
   p.qidx = B.qidx; p.slice_bytes = B.slice_bytes_dev;
   p.staging = B.staging; p.wcap = staging_words(g); p.sizes = B.sizes; p.err_flags = B.err_flags;
   cudaError_t e;
+  const bool fuse = narrow && B.tile_state && ctx->fuse_gather;
+  if (fuse) {
+    const int nslices = g.slices_x * g.slices_y;
+    p.fuse = 1;
+    p.tiles = (nslices + 127) / 128;
+    p.tile_state = B.tile_state;
+    p.tile_ticket = reinterpret_cast<uint32_t*>(B.tile_state + (size_t)p.tiles * npictures);
+    p.out = B.out; p.out_pic_stride = B.out_stride; p.out_capacity = B.out_capacity;
+    p.slice_off = B.slice_off; p.total_len = B.total_len;
+    e = cudaMemsetAsync(B.tile_state, 0, tile_state_bytes(nslices, npictures), ctx->stream);
+    if (e != cudaSuccess) return e;
+  }
   {
     ProfScope ps(ctx, VC2_STAGE_PACK);
     e = pack_launch(ctx->stream, p, npictures);
   }
   if (e != cudaSuccess) return e;
   ctx->launches++;
-  if (!emit) return cudaSuccess;
+  if (!emit || fuse) return cudaSuccess;
   AssembleParams a;
   memset(&a, 0, sizeof(a));
   a.nslices = g.slices_x * g.slices_y;
@@ -943,6 +964,8 @@ struct vc2_codec {
   // slot's result next (status, downloads, taps, the host-buffer calls) first runs the slot again through the 32-bit path.
   bool narrow_enc = false, narrow_dec = false;
   DevBuf narrow_ovf;                  // [2][B]: overflow flags of the encodes, of the decodes
+  DevBuf band_scale;                  // [B] BandScale of the decodes
+  DevBuf tile_state;                  // fused scan + gather of the narrow packer (PackBuffers::tile_state), one region per slot
   struct SlotState {
     bool enc_unchecked = false;       // the payload comes from a narrow encode whose overflow flag has not been looked at
     bool dec_unchecked = false;       // the same for the reconstructed picture and a narrow decode
@@ -990,7 +1013,7 @@ static void codec_free(vc2_codec* k) {
   cudaStreamSynchronize(k->ctx->stream);
   DevBuf* all[] = {&k->samples, &k->recon, &k->coef, &k->scratch0, &k->scratch1, &k->payload, &k->slice_off, &k->err,
                    &k->qidx, &k->staging, &k->sizes, &k->sbytes, &k->fixed, &k->tmp_plane, &k->tmp_q, &k->dev_len,
-                   &k->ld_qcoef, &k->ld_acbits, &k->ld_restored, &k->narrow_ovf};
+                   &k->ld_qcoef, &k->ld_acbits, &k->ld_restored, &k->narrow_ovf, &k->tile_state, &k->band_scale};
   for (DevBuf* b : all) b->release();
   if (k->host_flags) cudaFreeHost(k->host_flags);
   if (k->host_len) cudaFreeHost(k->host_len);
@@ -1072,6 +1095,8 @@ extern "C" vc2_codec* vc2_codec_create(vc2_ctx* ctx, const vc2_codec_params* prm
   R(k->tmp_q, (size_t)g.plane[0].size() * 4);
   R(k->dev_len, (size_t)B * 4);
   R(k->narrow_ovf, (size_t)B * 4 * 2);
+  R(k->band_scale, sizeof(BandScale) * B);
+  R(k->tile_state, tile_state_bytes(k->nslices, 1) * B);
   k->narrow_enc = ctx->narrow && ctx->dwt_tile && prm->mode == VC2_HQ_VBR;
   k->narrow_dec = ctx->narrow && ctx->dwt_tile && prm->mode != VC2_LD;
   k->slot_state.assign(B, vc2_codec::SlotState());
@@ -1234,6 +1259,7 @@ static int codec_encode_range(vc2_codec* k, int first, int n, bool wide = false)
   B.slice_bytes_dev = cbr ? k->sbytes.as<int32_t>() : nullptr;
   B.fixed_off_dev = cbr ? k->fixed.as<uint32_t>() : nullptr;
   B.total_len = k->dev_len.as<uint32_t>() + first;
+  B.tile_state = reinterpret_cast<unsigned long long*>(k->tile_state.as<uint8_t>() + tile_state_bytes(k->nslices, 1) * first);
   const int32_t* coef = k->coef.as<int32_t>() + (long long)first * k->g.coef_pic_stride;
   CU(run_pack(ctx, k->g, coef, n, k->prm.mode, 1, cbr ? 1 : 0, cbr ? -1 : k->prm.qindex, 1, B, narrow ? 1 : 0));
   return VC2_OK;
@@ -1302,7 +1328,10 @@ static int codec_decode_range(vc2_codec* k, int first, int n, bool index_here, b
   NarrowCfg nw;
   if (narrow) {
     nw.on = 1; nw.qidx = k->qidx.as<int32_t>() + (size_t)first * k->nslices; nw.ovf = k->narrow_ovf.as<uint32_t>() + k->prm.max_pictures + first;
+    BandScale* bs = k->band_scale.as<BandScale>() + first;
+    nw.band_scale = bs;
     CU(cudaMemsetAsync(nw.ovf, 0, (size_t)n * 4, ctx->stream));
+    CU(cudaMemsetAsync(bs, 0, sizeof(BandScale) * n, ctx->stream));
   }
   for (int i = 0; i < n; ++i) {
     vc2_codec::SlotState& ss = k->slot_state[first + i];
@@ -1324,6 +1353,7 @@ static int codec_decode_range(vc2_codec* k, int first, int n, bool index_here, b
   p.ld = ld ? 1 : 0;
   p.narrow = narrow ? 1 : 0;
   p.narrow_ovf = nw.ovf;
+  p.band_scale = const_cast<BandScale*>(nw.band_scale);
   if (index_here && !ld) {
     // the reader's walk over the length bytes of every slice (Slices.cpp:544-605): the slice offsets are always
     // derived from the payload itself, never taken from the encoder
@@ -1339,9 +1369,9 @@ static int codec_decode_range(vc2_codec* k, int first, int n, bool index_here, b
   }
   {
     ProfScope ps(ctx, VC2_STAGE_UNPACK);
-    CU(unpack_launch(ctx->stream, p, n));
+    CU(unpack_launch(ctx->stream, p, n, ctx->scale_tab.as<uint2>()));
   }
-  ctx->launches++;
+  ctx->launches += narrow ? 2 : 1;
   if (ld) {
     // LL band: DC-predicted reconstruction, one wavefront CTA per (picture, component)
     for (int i = 0; i < n; ++i)

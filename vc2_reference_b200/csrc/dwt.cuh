@@ -100,6 +100,7 @@ struct DwtComp {
   uint32_t qm31[4];          // ... else the one-multiply-high division of vc2_quant_magic31: |q| = mulhi(|v| << 2, qm31) >> ql31
   int ql31[4];
   int qmat[4];               // inverse: quantisation matrix entries of the four bands (Quantisation.cpp:16-20)
+  int band[4];               // ... and their band numbers
 };
 
 
@@ -112,6 +113,7 @@ struct DwtParams {
   int narrow;
   uint32_t* narrow_ovf;      // [picture] set when a quantised magnitude does not fit 15 bits: the caller re-runs the picture wide
   const int32_t* qidx;       // inverse: [picture][slice] quantisation index of every slice
+  const BandScale* band_scale;   // inverse: [picture] one index for the whole picture? then its scale factors per band
   int nslices;
   const uint2* scale_tab;    // inverse: [128] (quant_factor, quant_offset + 2) in device memory
 };

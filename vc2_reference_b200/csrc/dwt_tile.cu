@@ -126,9 +126,10 @@ __device__ __forceinline__ uint2 scale_params(const DwtParams& p, const DwtComp&
   return __ldg(p.scale_tab + q);
 }
 // element-wise access to the narrow block (small band parts at the deep levels, picture edges)
+// uni: the whole picture has one index, fo_uni = its scale factors for this band
 template <bool STORE>
 __device__ __forceinline__ void band_access16(const DwtParams& p, const DwtComp& C, int pic, const BandAddr& ba, int b, int base, int by, int bx0, int bxmax,
-                                              int (&x)[4], bool& ovf) {
+                                              int (&x)[4], bool& ovf, bool uni = false, uint2 fo_uni = make_uint2(0, 0)) {
   uint16_t* coef = reinterpret_cast<uint16_t*>(C.coef) + (long long)pic * C.coef_pic_stride;
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
@@ -141,8 +142,11 @@ __device__ __forceinline__ void band_access16(const DwtParams& p, const DwtComp&
       if (m > (unsigned)VC2_NARROW_MAX_MAG) { ovf = true; m = VC2_NARROW_MAX_MAG; }
       *e = (uint16_t)(2u * m + ((unsigned)x[j] >> 31));
     } else {
-      const int sy = ba.lgbh >= 0 ? (by >> ba.lgbh) : (by / ba.bh), sx = ba.lgbw >= 0 ? (bx >> ba.lgbw) : (bx / ba.bw);
-      x[j] = scale1_smag(*e, scale_params(p, C, pic, sy * ba.nx + sx, b));
+      if (uni) x[j] = scale1_smag(*e, fo_uni);
+      else {
+        const int sy = ba.lgbh >= 0 ? (by >> ba.lgbh) : (by / ba.bh), sx = ba.lgbw >= 0 ? (bx >> ba.lgbw) : (bx / ba.bw);
+        x[j] = scale1_smag(*e, scale_params(p, C, pic, sy * ba.nx + sx, b));
+      }
     }
   }
 }
@@ -279,7 +283,7 @@ __global__ void __launch_bounds__(32 * T::NW, T::MINB) dwt_tile_fwd_kernel(const
   extern __shared__ int4 mid[];
   TileCtx S;
   if (!tile_setup<T>(p, tl, S)) return;
-  const DwtComp& C = p.c[S.comp];
+  const DwtComp& C = p.c[S.comp];   // (a copy in shared memory instead of these indexed constant loads was measured: 10 % slower)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int hl = lane & (T::TWL - 1), g = warp * T::RPW + lane / T::TWL;   // lane inside its row, row group
   constexpr int SHIFT = Wavelet<K>::SHIFT;
@@ -407,7 +411,7 @@ __global__ void __launch_bounds__(32 * T::NW, T::MINB) dwt_tile_inv_kernel(const
   extern __shared__ int4 mid[];
   TileCtx S;
   if (!tile_setup<T>(p, tl, S)) return;
-  const DwtComp& C = p.c[S.comp];
+  const DwtComp& C = p.c[S.comp];   // (a copy in shared memory instead of these indexed constant loads was measured: 10 % slower)
   if (S.y0 >= C.pix_h) return;   // nothing of this tile row survives the crop (WaveletTransform.cpp:340)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int hl = lane & (T::TWL - 1), g = warp * T::RPW + lane / T::TWL;
@@ -426,47 +430,88 @@ __global__ void __launch_bounds__(32 * T::NW, T::MINB) dwt_tile_inv_kernel(const
       BandFast F;
       const bool fast = band_fast_setup(C, S.pic, p.narrow, bx0, bx0 >= 0 && bx0 + 3 <= bxmax, F);
       bool never = false;
+      // one index for the whole picture (HQ_ConstQ streams): the scale factors are four constants, left behind by the parser
+      bool uni = false;
+      uint2 fu[4] = {make_uint2(0, 0), make_uint2(0, 0), make_uint2(0, 0), make_uint2(0, 0)};
+      if (p.narrow) {
+        const BandScale* bs = p.band_scale + S.pic;
+        uni = __ldg(&bs->diff) == 0u;
 #pragma unroll
-      for (int m = g; m < T::TH / 2; m += T::NG) {   // unrolled: all the loads of the lane are in flight together
-        const int y = S.ys + 2 * m;
-        if (y < 0 || y >= C.lat_h) continue;     // never used (the column phase extends the sequence inside the lattice)
-        const int by = y >> 1;
-        int4 ll4, hl4, lh4, hh4;
-        if (fast) {
-          const int k = F.idx(by);
-          if (p.narrow) {
-            const uint2 wl = F.plane_ll ? make_uint2(0, 0) : __ldg(F.at<const uint2>(F.p_ll, k));
-            const uint2 w1 = __ldg(F.at<const uint2>(F.p_hl, k)), w2 = __ldg(F.at<const uint2>(F.p_lh, k)), w3 = __ldg(F.at<const uint2>(F.p_hh, k));
-            const int sl = F.slice(by);
-            ll4 = F.plane_ll ? __ldg(F.ll_row(by)) : scale4_smag(wl, scale_params(p, C, S.pic, sl, 0));
-            hl4 = scale4_smag(w1, scale_params(p, C, S.pic, sl, 1));
-            lh4 = scale4_smag(w2, scale_params(p, C, S.pic, sl, 2));
-            hh4 = scale4_smag(w3, scale_params(p, C, S.pic, sl, 3));
-          } else {
-            ll4 = F.plane_ll ? __ldg(F.ll_row(by)) : __ldg(F.at<const int4>(F.p_ll, k));
-            hl4 = __ldg(F.at<const int4>(F.p_hl, k));
-            lh4 = __ldg(F.at<const int4>(F.p_lh, k));
-            hh4 = __ldg(F.at<const int4>(F.p_hh, k));
-          }
-        } else {
-          int v[4];
-          if (C.ll) ll_access<4, false>(C.ll + (long long)S.pic * C.ll_pic_stride, C.ll_pitch, by, bx0, bxmax, v);
-          else if (p.narrow) band_access16<false>(p, C, S.pic, ba, 0, C.base_ll, by, bx0, bxmax, v, never);
-          else band_access<4, false>(coef, ba, C.base_ll, by, bx0, bxmax, v);
-          ll4 = make_int4(v[0], v[1], v[2], v[3]);
-          if (p.narrow) band_access16<false>(p, C, S.pic, ba, 1, C.base_hl, by, bx0, bxmax, v, never);
-          else band_access<4, false>(coef, ba, C.base_hl, by, bx0, bxmax, v);
-          hl4 = make_int4(v[0], v[1], v[2], v[3]);
-          if (p.narrow) band_access16<false>(p, C, S.pic, ba, 2, C.base_lh, by, bx0, bxmax, v, never);
-          else band_access<4, false>(coef, ba, C.base_lh, by, bx0, bxmax, v);
-          lh4 = make_int4(v[0], v[1], v[2], v[3]);
-          if (p.narrow) band_access16<false>(p, C, S.pic, ba, 3, C.base_hh, by, bx0, bxmax, v, never);
-          else band_access<4, false>(coef, ba, C.base_hh, by, bx0, bxmax, v);
-          hh4 = make_int4(v[0], v[1], v[2], v[3]);
-        }
+        for (int b = 0; b < 4; ++b) fu[b] = __ldg(&bs->fo[C.band[b]]);
+      }
+      auto put = [&](int m, const int4& ll4, const int4& hl4, const int4& lh4, const int4& hh4) {
         int4* row = mid + 2 * m * T::CHUNKS;
         const int c0 = hl ^ swz(2 * m), c1 = (T::TWL + hl) ^ swz(2 * m);
         row[c0] = ll4; row[c1] = hl4; row[T::CHUNKS + c0] = lh4; row[T::CHUNKS + c1] = hh4;
+      };
+      const bool lane_out = bx0 + 3 < 0 || bx0 > bxmax;   // nothing of this lane is inside the lattice: its columns are never used
+      if (__all_sync(FULL, fast || lane_out)) {
+        // whole pieces only.  Unrolled: all the loads of the lane are in flight together
+        if (p.narrow) {
+          constexpr int NI = T::TH / 2 / T::NG, NB = 2;   // band rows per lane, and per batch of loads
+          static_assert(NI % NB == 0, "whole batches");
+#pragma unroll 1
+          for (int i0 = 0; i0 < NI; i0 += NB) {
+            uint2 w[NB][4];
+            int4 l4[NB];
+#pragma unroll
+            for (int i = 0; i < NB; ++i) {
+              const int m = g + (i0 + i) * T::NG, y = S.ys + 2 * m;
+              const bool on = fast && y >= 0 && y < C.lat_h;
+              const int by = on ? y >> 1 : 0, k = on ? F.idx(by) : 0;
+              l4[i] = make_int4(0, 0, 0, 0);
+              w[i][0] = make_uint2(0, 0);
+              if (on) {
+                if (F.plane_ll) l4[i] = __ldg(F.ll_row(by)); else w[i][0] = __ldg(F.at<const uint2>(F.p_ll, k));
+                w[i][1] = __ldg(F.at<const uint2>(F.p_hl, k)); w[i][2] = __ldg(F.at<const uint2>(F.p_lh, k)); w[i][3] = __ldg(F.at<const uint2>(F.p_hh, k));
+              }
+            }
+#pragma unroll
+            for (int i = 0; i < NB; ++i) {
+              const int m = g + (i0 + i) * T::NG, y = S.ys + 2 * m;
+              if (!fast || y < 0 || y >= C.lat_h) continue;
+              uint2 f0 = fu[0], f1 = fu[1], f2 = fu[2], f3 = fu[3];
+              if (!uni) {
+                const int sl = F.slice(y >> 1);
+                f0 = scale_params(p, C, S.pic, sl, 0); f1 = scale_params(p, C, S.pic, sl, 1);
+                f2 = scale_params(p, C, S.pic, sl, 2); f3 = scale_params(p, C, S.pic, sl, 3);
+              }
+              put(m, F.plane_ll ? l4[i] : scale4_smag(w[i][0], f0), scale4_smag(w[i][1], f1), scale4_smag(w[i][2], f2), scale4_smag(w[i][3], f3));
+            }
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < T::TH / 2 / T::NG; ++i) {
+            const int m = g + i * T::NG, y = S.ys + 2 * m;
+            if (!fast || y < 0 || y >= C.lat_h) continue;
+            const int by = y >> 1, k = F.idx(by);
+            put(m, F.plane_ll ? __ldg(F.ll_row(by)) : __ldg(F.at<const int4>(F.p_ll, k)), __ldg(F.at<const int4>(F.p_hl, k)),
+                __ldg(F.at<const int4>(F.p_lh, k)), __ldg(F.at<const int4>(F.p_hh, k)));
+          }
+        }
+      } else {
+#pragma unroll 1
+        for (int m = g; m < T::TH / 2; m += T::NG) {
+          const int y = S.ys + 2 * m;
+          if (y < 0 || y >= C.lat_h) continue;     // never used (the column phase extends the sequence inside the lattice)
+          const int by = y >> 1;
+          int4 ll4, hl4, lh4, hh4;
+          int v[4];
+          if (C.ll) ll_access<4, false>(C.ll + (long long)S.pic * C.ll_pic_stride, C.ll_pitch, by, bx0, bxmax, v);
+          else if (p.narrow) band_access16<false>(p, C, S.pic, ba, 0, C.base_ll, by, bx0, bxmax, v, never, uni, fu[0]);
+          else band_access<4, false>(coef, ba, C.base_ll, by, bx0, bxmax, v);
+          ll4 = make_int4(v[0], v[1], v[2], v[3]);
+          if (p.narrow) band_access16<false>(p, C, S.pic, ba, 1, C.base_hl, by, bx0, bxmax, v, never, uni, fu[1]);
+          else band_access<4, false>(coef, ba, C.base_hl, by, bx0, bxmax, v);
+          hl4 = make_int4(v[0], v[1], v[2], v[3]);
+          if (p.narrow) band_access16<false>(p, C, S.pic, ba, 2, C.base_lh, by, bx0, bxmax, v, never, uni, fu[2]);
+          else band_access<4, false>(coef, ba, C.base_lh, by, bx0, bxmax, v);
+          lh4 = make_int4(v[0], v[1], v[2], v[3]);
+          if (p.narrow) band_access16<false>(p, C, S.pic, ba, 3, C.base_hh, by, bx0, bxmax, v, never, uni, fu[3]);
+          else band_access<4, false>(coef, ba, C.base_hh, by, bx0, bxmax, v);
+          hh4 = make_int4(v[0], v[1], v[2], v[3]);
+          put(m, ll4, hl4, lh4, hh4);
+        }
       }
     }
     __syncthreads();

@@ -474,15 +474,23 @@ __global__ void __launch_bounds__(128) hq_pack_kernel(const PackParams p) {
 // bookkeeping is left: a component is one flat run of 8-byte pieces (four coefficients), 256 bytes apart per lane.
 // Same slice syntax, writer and staging images as hq_pack_kernel.
 // ------------------------------------------------------------------------------------------
+template <bool RO>
+__device__ __forceinline__ void copy_slice_image(const uint32_t* img, uint8_t* dst, int total, int lane, uint32_t first0, uint32_t first1);
+
 struct NarrowEmit {
-  const uint32_t* lut;
+  unsigned lut;    // shared-memory address of the code table (kept in a register: the look-up is one LDS behind a shift-add)
   WideBitWriter* W;
   unsigned last;   // cursor behind the last non-zero coefficient
+  __device__ __forceinline__ uint32_t entry(uint32_t t) const {
+    uint32_t e;
+    asm("ld.shared.u32 %0, [%1];" : "=r"(e) : "r"(lut + 4u * t));
+    return e;
+  }
   __device__ __forceinline__ void one(uint32_t t) {
     uint32_t code;
     int nb;
     if (t < 2u * (uint32_t)ENC_LUT_MAG) {
-      const uint32_t e = lut[t];
+      const uint32_t e = entry(t);
       nb = (int)(e & 31u);
       code = e >> 5;
     } else {   // magnitudes up to 32767: m = |q| + 1 <= 2^15, 2 * 15 + 2 = 32 bits at most
@@ -494,10 +502,11 @@ struct NarrowEmit {
     W->put(code, nb);
     last = t >= 2u ? W->mark() : last;
   }
-  // two coefficients whose codes come from the table and are at most 16 bits long: ONE append
-  __device__ __forceinline__ void pair(uint32_t t0, uint32_t t1) {
-    if ((t0 | t1) < 256u) {
-      const uint32_t e0 = lut[t0], e1 = lut[t1];
+  // two coefficients (the two halves of w) whose codes come from the table and are at most 16 bits long: ONE append
+  __device__ __forceinline__ void pair(uint32_t w) {
+    const uint32_t t0 = w & 0xFFFFu, t1 = w >> 16;
+    if ((w & 0xFF00FF00u) == 0u) {
+      const uint32_t e0 = entry(t0), e1 = entry(t1);
       const int nb0 = (int)(e0 & 31u), nb1 = (int)(e1 & 31u);
       const unsigned mid = W->mark() + (unsigned)nb0;
       W->put(((e0 >> 5) << nb1) | (e1 >> 5), nb0 + nb1);
@@ -511,13 +520,18 @@ struct NarrowEmit {
 
 __global__ void __launch_bounds__(128) hq_pack_narrow_kernel(const PackParams p) {
   __shared__ uint32_t s_enc[2 * ENC_LUT_MAG];
+  __shared__ unsigned s_tile, s_warp_sum[4], s_before;
+  const int pic = blockIdx.y;
+  if (p.fuse && threadIdx.x == 0) s_tile = atomicAdd(p.tile_ticket + pic, 1u);
   stage_table(s_enc, d_enc_lut, 2 * ENC_LUT_MAG);
   __syncthreads();
   const SliceGeom& g = p.g;
   const int nslices = g.slices_x * g.slices_y;
-  const int pic = blockIdx.y;
-  const int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= nslices) return;
+  const int tile = p.fuse ? (int)s_tile : (int)blockIdx.x;
+  const int s = tile * blockDim.x + threadIdx.x;
+  if (!p.fuse && s >= nslices) return;
+  unsigned size = 0;
+  if (s < nslices) {
   const int nc4 = g.comp_start[3] >> 2;
   const uint2* src = reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(p.coef) + (long long)pic * g.coef_pic_stride) +
                      (size_t)(s >> 5) * nc4 * 32 + (s & 31);
@@ -539,8 +553,10 @@ __global__ void __launch_bounds__(128) hq_pack_narrow_kernel(const PackParams p)
     const int data_start = W.pos();
     const uint2* csrc = src + (size_t)(g.comp_start[c] >> 2) * 32;
     const int np = g.band_start[c][g.nbands] >> 2;
-    NarrowEmit op = {s_enc, &W, W.mark()};
-    // three pieces in flight (every one a fresh line, see walk_component)
+    NarrowEmit op = {(unsigned)__cvta_generic_to_shared(s_enc), &W, W.mark()};
+    // three pieces in registers (every one a fresh line, see walk_component), the lines of the pieces PF ahead on their
+    // way into L1: a piece is 8 bytes per lane, the warp walks its group 256 bytes at a time
+    constexpr int PF = 8;
     uint2 n0 = __ldg(csrc), n1 = n0, n2 = n0;
     if (np > 1) n1 = __ldg(csrc + 32);
     if (np > 2) n2 = __ldg(csrc + 64);
@@ -549,9 +565,10 @@ __global__ void __launch_bounds__(128) hq_pack_narrow_kernel(const PackParams p)
       const uint2 w = n0;
       n0 = n1; n1 = n2;
       if (i + 3 < np) n2 = __ldg(pf);
+      if (i + 3 + PF < np) asm volatile("prefetch.global.L1 [%0];" ::"l"(pf + 32 * PF));
       pf += 32;
-      op.pair(w.x & 0xFFFFu, w.x >> 16);
-      op.pair(w.y & 0xFFFFu, w.y >> 16);
+      op.pair(w.x);
+      op.pair(w.y);
     }
     const int L = scaled_bytes(W.unmark(op.last) - data_start, g.scalar, too_big);
     if (too_big) { flags |= VC2_FLAG_SCALAR_TOO_SMALL; break; }
@@ -560,8 +577,68 @@ __global__ void __launch_bounds__(128) hq_pack_narrow_kernel(const PackParams p)
     W.patch_byte(len_pos, (uint32_t)(L / g.scalar) & 0xFFu);
   }
   W.finish();
-  p.sizes[sidx] = flags ? 0u : (uint32_t)(g.prefix + 4 + lensum);
+  size = flags ? 0u : (uint32_t)(g.prefix + 4 + lensum);
+  p.sizes[sidx] = size;
   p.err_flags[sidx] = flags;
+  }
+  if (!p.fuse) return;
+
+  // ---- where do this CTA's slices go?  scan inside the CTA, then the bytes of all the tiles in front of it
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned incl = size;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const unsigned v = __shfl_up_sync(FULL, incl, d);
+    if (lane >= d) incl += v;
+  }
+  if (lane == 31) s_warp_sum[warp] = incl;
+  __syncthreads();
+  unsigned before_warp = 0, cta_total = 0;
+#pragma unroll
+  for (int w = 0; w < 4; ++w) {
+    if (w < warp) before_warp += s_warp_sum[w];
+    cta_total += s_warp_sum[w];
+  }
+  if (threadIdx.x == 0) {
+    volatile unsigned long long* st = p.tile_state + (long long)pic * p.tiles;
+    unsigned before = 0;
+    if (tile == 0) st[0] = (2ull << 32) | cta_total;
+    else {
+      st[tile] = (1ull << 32) | cta_total;
+      for (int j = tile - 1;; --j) {
+        unsigned long long v;
+        do { v = st[j]; } while ((v >> 32) == 0);   // tile j started before this one (tickets): it will publish
+        before += (unsigned)v;
+        if ((v >> 32) == 2) break;
+      }
+      st[tile] = (2ull << 32) | (before + cta_total);
+    }
+    s_before = before;
+  }
+  __syncthreads();
+  const unsigned offset = s_before + before_warp + incl - size;
+  uint32_t* so = p.slice_off + (long long)pic * (nslices + 1);
+  if (s < nslices) so[s] = offset;
+  if (s == nslices - 1) {
+    so[nslices] = offset + size;
+    if (p.total_len) p.total_len[pic] = offset + size;
+  }
+  // ---- gather: the warp copies its 32 slice images (written a moment ago: L2 hits) to their place in the payload
+  __threadfence_block();
+  __syncwarp();
+  const long long sidx0 = (long long)pic * nslices + (s - lane);
+  uint8_t* out = p.out + (long long)pic * p.out_pic_stride;
+  for (int j = 0; j < 32; ++j) {
+    const unsigned off_j = __shfl_sync(FULL, offset, j);
+    const int total = (int)__shfl_sync(FULL, size, j);
+    if (total <= 0) continue;
+    if ((long long)off_j + total > p.out_capacity) {
+      if (lane == 0) atomicOr(&p.err_flags[sidx0 + j], VC2_FLAG_STREAM);
+      continue;
+    }
+    const uint32_t* img = p.staging + (sidx0 + j) * p.wcap;
+    copy_slice_image<false>(img, out + off_j, total, lane, img[lane], img[lane + 1]);
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -865,6 +942,30 @@ __global__ void __launch_bounds__(1024) slice_scan_kernel(const AssembleParams p
 // Gather: one warp copies one slice image from the staging words (MSB-first) to its byte offset in
 // the payload.  Head bytes up to 4-byte alignment, aligned 32-bit words, tail bytes.
 // ------------------------------------------------------------------------------------------
+// one warp copies `total` bytes of a slice image (MSB-first words) to dst: head bytes up to 4-byte alignment, aligned
+// 32-bit words, tail bytes.  first0 / first1 = image words lane, lane + 1 (fetched by the caller, early).  RO: the images were
+// written by an earlier kernel (read-only path); else by this kernel (plain loads)
+template <bool RO>
+__device__ __forceinline__ void copy_slice_image(const uint32_t* img, uint8_t* dst, int total, int lane, uint32_t first0, uint32_t first1) {
+  const int head = min((int)((4 - (reinterpret_cast<uintptr_t>(dst) & 3)) & 3), total);
+  const uint32_t img0 = __shfl_sync(FULL, first0, 0);
+  if (lane < head) dst[lane] = (uint8_t)(img0 >> (24 - 8 * lane));
+  const int nwords = (total - head) >> 2;
+  uint32_t* __restrict__ dw = reinterpret_cast<uint32_t*>(dst + head);
+  // image bytes head + 4m .. head + 4m + 3 = the funnel of words m, m + 1 (shift 0 when the slice starts aligned)
+  if (lane < nwords) dw[lane] = __byte_perm(__funnelshift_l(first1, first0, 8 * head), 0, 0x0123);
+#pragma unroll 2
+  for (int m = lane + 32; m < nwords; m += 32) {
+    const uint32_t be = RO ? __funnelshift_l(__ldg(img + m + 1), __ldg(img + m), 8 * head) : __funnelshift_l(img[m + 1], img[m], 8 * head);
+    dw[m] = __byte_perm(be, 0, 0x0123);
+  }
+  const int done = head + 4 * nwords, tail = total - done;
+  if (lane < tail) {
+    const int i = done + lane;
+    dst[i] = (uint8_t)(img[i >> 2] >> (24 - 8 * (i & 3)));
+  }
+}
+
 __global__ void __launch_bounds__(256) assemble_kernel(const AssembleParams p) {
   const int pic = blockIdx.y;
   const int lane = threadIdx.x & 31;
@@ -884,24 +985,7 @@ __global__ void __launch_bounds__(256) assemble_kernel(const AssembleParams p) {
     if (lane == 0) atomicOr(&p.err_flags[sidx], VC2_FLAG_STREAM);
     return;
   }
-  uint8_t* __restrict__ dst = p.out + (long long)pic * p.out_pic_stride + offset;
-  const int head = min((int)((4 - (reinterpret_cast<uintptr_t>(dst) & 3)) & 3), total);
-  const uint32_t img0 = __shfl_sync(FULL, first0, 0);
-  if (lane < head) dst[lane] = (uint8_t)(img0 >> (24 - 8 * lane));
-  const int nwords = (total - head) >> 2;
-  uint32_t* __restrict__ dw = reinterpret_cast<uint32_t*>(dst + head);
-  // image bytes head + 4m .. head + 4m + 3 = the funnel of words m, m + 1 (shift 0 when the slice starts aligned)
-  if (lane < nwords) dw[lane] = __byte_perm(__funnelshift_l(first1, first0, 8 * head), 0, 0x0123);
-#pragma unroll 2
-  for (int m = lane + 32; m < nwords; m += 32) {
-    const uint32_t be = __funnelshift_l(__ldg(img + m + 1), __ldg(img + m), 8 * head);
-    dw[m] = __byte_perm(be, 0, 0x0123);
-  }
-  const int done = head + 4 * nwords, tail = total - done;
-  if (lane < tail) {
-    const int i = done + lane;
-    dst[i] = (uint8_t)(img[i >> 2] >> (24 - 8 * (i & 3)));
-  }
+  copy_slice_image<true>(img, p.out + (long long)pic * p.out_pic_stride + offset, total, lane, first0, first1);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1207,11 +1291,26 @@ __global__ void __launch_bounds__(128) slice_unpack_narrow_kernel(const UnpackPa
   }
   if (bad) flags |= VC2_FLAG_STREAM;
   if (big > (unsigned)VC2_NARROW_MAX_MAG) atomicOr(p.narrow_ovf + pic, 1u);
+  {   // does the whole picture use one index?  (HQ_ConstQ streams: the inverse lifting kernels then scale with per-band constants)
+    const uint8_t* first = p.in + (long long)pic * p.in_pic_stride + so[0];
+    const int q0 = (int)(so[1] - so[0]) >= g.prefix + 4 ? first[g.prefix] : 0;
+    if (qi != q0) atomicOr(&p.band_scale[pic].diff, (unsigned)(qi ^ q0) | 0x100u);
+  }
   // the reference scales every band of the slice: an index beyond the quantiser table is an error (Quantisation.cpp:60-63)
   for (int b = 0; b < g.nbands; ++b) if (max(qi - g.qmatrix[b], 0) > 119) flags |= VC2_FLAG_QUANT_INDEX;
   p.qidx[sidx] = qi;
   if (range_err) flags |= VC2_FLAG_VLC_RANGE;
   if (flags) atomicOr(&p.err_flags[sidx], flags);
+}
+
+// per picture: the scale factors of every band for the index of slice 0 - what the inverse lifting kernels use when the
+// parser found one index for the whole picture (BandScale::diff == 0)
+__global__ void narrow_scale_kernel(const UnpackParams p, const uint2* __restrict__ tab) {
+  const int pic = blockIdx.x, b = threadIdx.x;
+  const int nslices = p.g.slices_x * p.g.slices_y;
+  if (b >= p.g.nbands) return;
+  const int q = min(max(p.qidx[(long long)pic * nslices] - p.g.qmatrix[b], 0), 127);
+  p.band_scale[pic].fo[b] = tab[q];
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1410,6 +1509,7 @@ cudaError_t pack_launch(cudaStream_t s, const PackParams& p, int npictures) {
   const int nslices = p.g.slices_x * p.g.slices_y;
   if (p.narrow) {
     if (p.search || p.const_q < 0 || !p.emit || p.mode != VC2_HQ_VBR) return cudaErrorInvalidValue;
+    if (p.fuse && p.tiles != (nslices + 127) / 128) return cudaErrorInvalidValue;
     hq_pack_narrow_kernel<<<dim3((nslices + 127) / 128, npictures), 128, 0, s>>>(p);
     return cudaGetLastError();
   }
@@ -1437,12 +1537,15 @@ cudaError_t assemble_launch(cudaStream_t s, const AssembleParams& p, int npictur
   return cudaGetLastError();
 }
 
-cudaError_t unpack_launch(cudaStream_t s, const UnpackParams& p, int npictures) {
+cudaError_t unpack_launch(cudaStream_t s, const UnpackParams& p, int npictures, const uint2* scale_tab) {
   const int nslices = p.g.slices_x * p.g.slices_y;
   const dim3 grid((nslices + 127) / 128, npictures);
   if (p.narrow) {
     if (p.ld) return cudaErrorInvalidValue;
     slice_unpack_narrow_kernel<<<grid, 128, 0, s>>>(p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    narrow_scale_kernel<<<npictures, 32, 0, s>>>(p, scale_tab);
     return cudaGetLastError();
   }
   if (p.ld) {

@@ -40,6 +40,17 @@ struct PackParams {
   uint32_t* sizes;              // [pic][slices] out: bytes of each coded slice
   uint32_t* err_flags;          // [pic][slices] out (VC2_FLAG_*)
   int narrow;                   // 1: coef is the narrow block (16-bit sign-magnitude, already quantised; HQ_ConstQ only)
+  // fused scan + gather (narrow packer): the CTA scans its slice sizes, learns the bytes in front of it from the CTAs
+  // before it (decoupled look-back over tile_state) and copies its slice images - still in L2 - to their place in the
+  // payload: no second pass over the staging buffer, no scan / gather launches
+  int fuse;
+  unsigned long long* tile_state;   // [pic][tiles]: (state << 32) | bytes; state 0 = nothing, 1 = the tile's own bytes, 2 = all bytes up to and with it
+  uint32_t* tile_ticket;            // [pic] next tile to hand out (tiles are taken in arrival order: a tile never waits for one that has not started)
+  int tiles;                        // CTAs per picture
+  uint8_t* out;                     // payload [pic]
+  long long out_pic_stride, out_capacity;
+  uint32_t* slice_off;              // [pic][slices + 1] out
+  uint32_t* total_len;              // [pic] out (may be NULL)
 };
 
 struct AssembleParams {         // exclusive scan of the slice sizes and the gather into the payload
@@ -69,6 +80,7 @@ struct UnpackParams {
   int ld;                       // 1: LD slice syntax (Slices.cpp:246-303); LL band left quantised
   int narrow;                   // 1: coef is the narrow block: 16-bit sign-magnitude words of the QUANTISED coefficients (HQ only)
   uint32_t* narrow_ovf;         // [pic] set when a magnitude does not fit the narrow block
+  BandScale* band_scale;        // [pic] narrow: one index for the whole picture? and its scale factors (for the inverse lifting kernels)
 };
 
 // slice index of HQ payloads on the device (the reader's walk over the length bytes, Slices.cpp:544-605)
@@ -128,7 +140,7 @@ cudaError_t ld_encode_launch(cudaStream_t s, const LdEncParams& p, int npictures
 cudaError_t upload_quant_tables(const QuantTables& t);
 cudaError_t pack_launch(cudaStream_t s, const PackParams& p, int npictures);
 cudaError_t assemble_launch(cudaStream_t s, const AssembleParams& p, int npictures);
-cudaError_t unpack_launch(cudaStream_t s, const UnpackParams& p, int npictures);
+cudaError_t unpack_launch(cudaStream_t s, const UnpackParams& p, int npictures, const uint2* scale_tab = nullptr);
 cudaError_t index_launch(cudaStream_t s, const IndexParams& p, int npictures);
 cudaError_t layout_launch(cudaStream_t s, bool to_slice_major, const int32_t* src, int32_t* dst, const SliceGeom& g, int c);
 cudaError_t quant_launch(cudaStream_t s, const QuantParams& p);

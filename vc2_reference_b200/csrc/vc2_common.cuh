@@ -65,6 +65,13 @@ struct QuantTables {
   uint32_t ql31[128];
 };
 
+// narrow decode, per picture (written by the parser, read by the inverse lifting kernels)
+struct BandScale {
+  uint32_t diff;                 // OR over the slices of (qindex ^ qindex of slice 0), 0 = one index for the whole picture
+  uint32_t pad;
+  uint2 fo[VC2_MAX_BANDS];       // (quant_factor, quant_offset + 2) of every band for the index of slice 0
+};
+
 __host__ __device__ inline int band_level(int b) { return b == 0 ? 0 : (b - 1) / 3 + 1; }
 
 }  // namespace vc2
