@@ -1373,21 +1373,25 @@ static int codec_decode_range(vc2_codec* k, int first, int n, bool index_here, b
   }
   ctx->launches += narrow ? 2 : 1;
   if (ld) {
-    // LL band: DC-predicted reconstruction, one wavefront CTA per (picture, component)
-    for (int i = 0; i < n; ++i)
-      for (int c = 0; c < 3; ++c) {
-        LdDcParams d;
-        memset(&d, 0, sizeof(d));
-        d.base = p.coef + (long long)i * g.coef_pic_stride;
-        d.qidx = p.qidx + (size_t)i * k->nslices;
-        d.H = g.plane[c].ph >> g.depth; d.W = g.plane[c].pw >> g.depth;
-        d.interleaved = 1; d.bh = g.part_h[c][0]; d.bw = g.part_w[c][0];
-        d.k0 = g.comp_start[c]; d.nc4 = g.comp_start[3] >> 2;   // band 0 starts each component
-        d.slices_y = g.slices_y; d.slices_x = g.slices_x; d.qm0 = g.qmatrix[0];
-        ProfScope ps(ctx, VC2_STAGE_LD_DC);
-        CU(ld_dc_launch(ctx->stream, d));
-        ctx->launches++;
-      }
+    // LL band: DC-predicted reconstruction, one wavefront CTA per (picture, component), the whole batch in one launch
+    LdDcBatch bt;
+    memset(&bt, 0, sizeof(bt));
+    bt.nplanes = 3;
+    for (int c = 0; c < 3; ++c) {
+      LdDcParams& d = bt.c[c];
+      d.base = p.coef;
+      d.qidx = p.qidx;
+      d.base_pic_stride = g.coef_pic_stride; d.qidx_pic_stride = k->nslices;
+      d.H = g.plane[c].ph >> g.depth; d.W = g.plane[c].pw >> g.depth;
+      d.interleaved = 1; d.bh = g.part_h[c][0]; d.bw = g.part_w[c][0];
+      d.k0 = g.comp_start[c]; d.nc4 = g.comp_start[3] >> 2;   // band 0 starts each component
+      d.slices_y = g.slices_y; d.slices_x = g.slices_x; d.qm0 = g.qmatrix[0];
+    }
+    {
+      ProfScope ps(ctx, VC2_STAGE_LD_DC);
+      CU(ld_dc_batch_launch(ctx->stream, bt, n));
+    }
+    ctx->launches++;
   }
   CompBuf cb[3];
   codec_compbufs(k, cb, first, true);

@@ -448,7 +448,10 @@ __global__ void __launch_bounds__(32 * T::NW, T::MINB) dwt_tile_inv_kernel(const
       if (__all_sync(FULL, fast || lane_out)) {
         // whole pieces only.  Unrolled: all the loads of the lane are in flight together
         if (p.narrow) {
-          constexpr int NI = T::TH / 2 / T::NG, NB = 2;   // band rows per lane, and per batch of loads
+#ifndef VC2_INV_NB
+#define VC2_INV_NB 2
+#endif
+          constexpr int NI = T::TH / 2 / T::NG, NB = VC2_INV_NB;   // band rows per lane, and per batch of loads
           static_assert(NI % NB == 0, "whole batches");
 #pragma unroll 1
           for (int i0 = 0; i0 < NI; i0 += NB) {
@@ -587,7 +590,10 @@ cudaError_t pick_tile(cudaStream_t s, const DwtParams& p, int npictures, int cfg
     if (cfg == 5) return launch_tile<K, KIND, Tile<K, 32, 16, 16, 1, 1>>(s, p, npictures);
   }
 #endif
-  return launch_tile<K, KIND, Tile<K, 16, 16, 8, 3, 1>>(s, p, npictures);   // 128 x 128 tile, 64 KB, three CTAs of 8 warps per SM
+#ifndef VC2_TILE_MINB
+#define VC2_TILE_MINB 3
+#endif
+  return launch_tile<K, KIND, Tile<K, 16, 16, 8, VC2_TILE_MINB, 1>>(s, p, npictures);   // 128 x 128 tile, 64 KB, three CTAs of 8 warps per SM
 }
 
 template <int KIND>

@@ -1475,7 +1475,7 @@ __global__ void quant_kernel(const QuantParams p) {
 // recurrence over the whole band (Quantisation.cpp:191-208, 287-306).  One CTA per plane runs
 // the anti-diagonal wavefront: element (y, x) depends on (y-1, x-1), (y-1, x), (y, x-1).
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) ld_dc_kernel(const LdDcParams p) {
+__device__ __forceinline__ void ld_dc_body(LdDcParams p) {
   const int H = p.H, Wd = p.W;
   auto at = [&](int y, int x) -> int32_t* {
     if (!p.interleaved) return p.base + (((long long)y * p.pitch + x) << p.depth);
@@ -1501,6 +1501,15 @@ __global__ void __launch_bounds__(1024) ld_dc_kernel(const LdDcParams p) {
     }
     __syncthreads();
   }
+}
+
+__global__ void __launch_bounds__(1024) ld_dc_kernel(const LdDcParams p) { ld_dc_body(p); }
+// one CTA per (picture, plane): the wavefronts of a batch run side by side
+__global__ void __launch_bounds__(1024) ld_dc_batch_kernel(const LdDcBatch b) {
+  LdDcParams p = b.c[blockIdx.y];
+  p.base += (long long)blockIdx.x * p.base_pic_stride;
+  p.qidx += (long long)blockIdx.x * p.qidx_pic_stride;
+  ld_dc_body(p);
 }
 
 }  // namespace
@@ -1569,6 +1578,11 @@ cudaError_t index_launch(cudaStream_t s, const IndexParams& p, int npictures) {
 cudaError_t quant_launch(cudaStream_t s, const QuantParams& p) {
   const dim3 block(32, 8), grid((p.pw + 31) / 32, (p.ph + 7) / 8);
   quant_kernel<<<grid, block, 0, s>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t ld_dc_batch_launch(cudaStream_t s, const LdDcBatch& b, int npictures) {
+  ld_dc_batch_kernel<<<dim3(npictures, b.nplanes), 1024, 0, s>>>(b);
   return cudaGetLastError();
 }
 

@@ -116,7 +116,11 @@ struct LdDcParams {             // LD LL-band reconstruction with DC prediction 
   int k0, nc4;                  // interleaved: comp_start of the component, NC / 4
   int slices_y, slices_x;
   int qm0;
+  // a batch: grid.x = picture, grid.y = plane; picture i of plane j starts at base + i * base_pic_stride (+ the plane's own base)
+  long long base_pic_stride, qidx_pic_stride;
 };
+struct LdDcBatch { LdDcParams c[3]; int nplanes; };
+cudaError_t ld_dc_batch_launch(cudaStream_t s, const LdDcBatch& b, int npictures);
 
 // LD encoder (EncodeStream.cpp:139-245 quantIndicesLD, Quantisation.cpp:213-282 predictive quantiser,
 // Slices.cpp:51-96 slice bit counts, :195-244 LD slice writer)
