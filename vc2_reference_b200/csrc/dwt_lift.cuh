@@ -257,10 +257,11 @@ template <int K, int KIND, int V>
 __device__ __forceinline__ void store_pix(const DwtComp& C, int pic, int row, int gx, int (&v)[V]) {
   constexpr int SHIFT = Wavelet<K>::SHIFT;
   const int rnd = SHIFT ? (1 << (SHIFT - 1)) : 0;
+  const int lo = C.clip_min + C.soffset, hi = C.clip_max + C.soffset;   // clip(v) + offset == min(max(v + offset, lo), hi): add-and-max is one instruction
 #pragma unroll
   for (int k = 0; k < V; ++k) {
     if (SHIFT) v[k] = (v[k] + rnd) >> SHIFT;
-    if (KIND != SAMPLE_I32) v[k] = (int)((unsigned)(min(max(v[k], C.clip_min), C.clip_max) + C.soffset) << C.sshift);
+    if (KIND != SAMPLE_I32) v[k] = (int)((unsigned)min(__viaddmax_s32(v[k], C.soffset, lo), hi) << C.sshift);
   }
   const long long rowoff = (long long)row * C.pix_pitch;
   const bool whole = gx + V - 1 < C.pix_w;

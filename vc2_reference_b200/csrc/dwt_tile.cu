@@ -22,6 +22,7 @@
 // 3..5 of the row number so that the eight lanes of a shared-memory phase, which sit eight rows apart in P2, hit eight
 // different bank groups.
 #include "dwt_lift.cuh"
+#include <cuda.h>   // CUtensorMap (the encoder is fetched through cudaGetDriverEntryPoint: no link against libcuda)
 
 #ifndef VC2_DWT_PART
 #error "compile with -DVC2_DWT_PART=1 (forward) or =2 (inverse)"
@@ -46,6 +47,29 @@ struct Tile {
   static constexpr int TPC = TPC_;                        // horizontally adjacent tiles per CTA (amortises the set-up)
   static_assert(TH == 8 * NG, "a row group owns one swizzle block of eight tile rows");
 };
+
+// TMA staging of the forward level-0 input (16-bit samples, no padding, 16-byte aligned rows): one thread asks the
+// copy engine for the tile's 128 x 128 samples (cp.async.bulk.tensor, zero fill outside the picture), the CTA waits
+// on an mbarrier, every lane takes its eight rows out of shared memory.  The raw tile (32 KB) lives in the upper
+// half of the lifting tile (64 KB): all lanes hold their rows in registers before the first lifted row is written.
+struct TileMaps { CUtensorMap m[3]; };
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}"
+      ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, unsigned long long* bar, int x, int y, int z) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+               ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z) : "memory");
+}
 
 struct TileList {     // grid.x = CTA in its tile row, grid.y = tile row (both: the largest component), grid.z = picture * ncomp + component
   int cx[3], tx[3], ty[3];   // CTAs per tile row, tiles per tile row, tile rows
@@ -279,8 +303,9 @@ __device__ __forceinline__ void tile_load_row_slow(const DwtComp& C, int pic, co
 // forward level:  pix (dense plane)  ->  LL (compact plane or band 0), HL, LH, HH (interleaved)
 // ------------------------------------------------------------------------------------------
 template <int K, int KIND, class T>
-__global__ void __launch_bounds__(32 * T::NW, T::MINB) dwt_tile_fwd_kernel(const DwtParams p, const TileList tl) {
-  extern __shared__ int4 mid[];
+__global__ void __launch_bounds__(32 * T::NW, T::MINB) dwt_tile_fwd_kernel(const DwtParams p, const TileList tl, const __grid_constant__ TileMaps maps, const int use_tma) {
+  extern __shared__ __align__(128) int4 mid[];
+  __shared__ unsigned long long tma_bar;
   TileCtx S;
   if (!tile_setup<T>(p, tl, S)) return;
   const DwtComp& C = p.c[S.comp];   // (a copy in shared memory instead of these indexed constant loads was measured: 10 % slower)
@@ -319,7 +344,33 @@ __global__ void __launch_bounds__(32 * T::NW, T::MINB) dwt_tile_fwd_kernel(const
           rows[(i + k) * T::CHUNKS + co] = make_int4(o[k][0], o[k][1], o[k][2], o[k][3]);
         }
       };
-      if (__all_sync(FULL, L.vec || L.skip)) {
+      if (KIND == SAMPLE_U16BE && use_tma) {
+        // the tile's raw samples through the copy engine (coordinates may lie outside the picture: zero fill, never used)
+        uint8_t* rawt = reinterpret_cast<uint8_t*>(mid) + T::SMEM / 2;
+        const unsigned phase = (unsigned)(tx - S.tx) & 1u;
+        if (threadIdx.x == 0) {
+          if (tx == S.tx) mbar_init(&tma_bar, 1);
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the tile's earlier generic-proxy accesses are ordered before the copy
+          mbar_expect_tx(&tma_bar, T::TH * T::TW * 2);
+          tma_load_3d(rawt, &maps.m[S.comp], &tma_bar, S.xs, S.ys, S.pic);
+        }
+        __syncthreads();            // the barrier is initialised (first tile) before anyone waits on it
+        mbar_wait(&tma_bar, phase);
+        RawRow<KIND> raw[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          raw[i].a = *reinterpret_cast<const uint4*>(rawt + (r0 + i) * (T::TW * 2) + hl * 16);
+          raw[i].b = raw[i].a;
+        }
+        __syncthreads();            // every lane holds its rows: the lifted rows may overwrite the raw tile
+#pragma unroll
+        for (int i = 0; i < 8; i += 2) {
+          int e[2][4], o[2][4];
+          tile_convert<KIND>(L, raw[i], e[0], o[0]);
+          tile_convert<KIND>(L, raw[i + 1], e[1], o[1]);
+          lift_store(i, e, o);
+        }
+      } else if (__all_sync(FULL, L.vec || L.skip)) {
         // every load of the row group is in flight before the first one is used: one memory round trip per tile
         constexpr int NB = KIND == SAMPLE_I32 ? 4 : 8;   // rows per batch (32 registers of raw words)
 #pragma unroll 1
@@ -547,6 +598,32 @@ __global__ void __launch_bounds__(32 * T::NW, T::MINB) dwt_tile_inv_kernel(const
 }
 #endif
 
+#if VC2_DWT_PART == 1
+static bool tma_wanted() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("VC2_DWT_TMA"); v = e ? atoi(e) != 0 : 0; }
+  return v != 0;
+}
+// tensor map of one component plane of a batch: (columns, rows, pictures) of 16-bit words, box = one tile
+static int make_tile_map(CUtensorMap* m, const void* base, int w, int h, int npictures, unsigned long long pitchB, unsigned long long picB, int box_w, int box_h) {
+  typedef CUresult (*Encode)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                             CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static Encode enc = nullptr;
+  if (!enc) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn) return 0;
+    enc = reinterpret_cast<Encode>(fn);
+  }
+  const cuuint64_t dims[3] = {(cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)npictures};
+  const cuuint64_t strides[2] = {pitchB, picB};
+  const cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT16, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS ? 1 : 0;
+}
+#endif
+
 template <int K, int KIND, class T>
 cudaError_t launch_tile(cudaStream_t s, const DwtParams& p, int npictures) {
   TileList tl;
@@ -565,6 +642,19 @@ cudaError_t launch_tile(cudaStream_t s, const DwtParams& p, int npictures) {
   }
 #if VC2_DWT_PART == 1
   auto kern = dwt_tile_fwd_kernel<K, KIND, T>;
+  // TMA staging of the input: 16-bit samples, no padding, rows and pictures on 16-byte boundaries (VC2_DWT_TMA=1)
+  alignas(64) TileMaps maps;   // (contents irrelevant when use_tma == 0)
+  memset(&maps, 0, sizeof(maps));
+  int use_tma = 0;
+  if (KIND == SAMPLE_U16BE && tma_wanted()) {
+    use_tma = 1;
+    for (int c = 0; c < p.ncomp && use_tma; ++c) {
+      const DwtComp& C = p.c[c];
+      const unsigned long long pitchB = (unsigned long long)C.pix_pitch * 2;
+      if (C.pix_w != C.lat_w || C.pix_h != C.lat_h || (pitchB & 15) || (C.pix_pic_stride & 15) || (reinterpret_cast<uintptr_t>(C.pix) & 15)) use_tma = 0;
+      else use_tma = make_tile_map(&maps.m[c], C.pix, C.pix_w, C.pix_h, npictures, pitchB, (unsigned long long)C.pix_pic_stride, T::TW, T::TH);
+    }
+  }
 #else
   auto kern = dwt_tile_inv_kernel<K, KIND, T>;
 #endif
@@ -577,7 +667,11 @@ cudaError_t launch_tile(cudaStream_t s, const DwtParams& p, int npictures) {
     if (dev >= 0 && dev < 16) configured[dev] = true;
   }
   if (gy > 65535 || (long long)npictures * p.ncomp > 65535) return cudaErrorInvalidValue;
+#if VC2_DWT_PART == 1
+  kern<<<dim3((unsigned)gx, (unsigned)gy, (unsigned)(npictures * p.ncomp)), 32 * T::NW, T::SMEM, s>>>(p, tl, maps, use_tma);
+#else
   kern<<<dim3((unsigned)gx, (unsigned)gy, (unsigned)(npictures * p.ncomp)), 32 * T::NW, T::SMEM, s>>>(p, tl);
+#endif
   return cudaGetLastError();
 }
 
