@@ -114,7 +114,8 @@ enum vc2_stage {
   VC2_STAGE_LD_DC = 6,     /* LD LL-band DC prediction wavefront                         */
   VC2_STAGE_ASSEMBLE = 7,  /* slice size scan + gather of the slice images into the payload */
   VC2_STAGE_INDEX = 8,     /* HQ slice index: the walk over the slice length bytes of a payload */
-  VC2_NUM_STAGES = 9
+  VC2_STAGE_SEARCH = 9,    /* HQ_CBR rate control: quantIndicesCBR per slice (its own launch, before the packing launch) */
+  VC2_NUM_STAGES = 10
 };
 int vc2_profile_enable(vc2_ctx* ctx, int on);
 int vc2_profile_read(vc2_ctx* ctx, float* ms, int* launches, int nstages);

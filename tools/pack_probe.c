@@ -140,7 +140,7 @@ int main(int argc, char** argv) {
   const int npic_timed = atoi(argv[1]);
   int nlib = 0;
   for (int i = 2; i < argc && nlib < MAXLIB; ++i) load(&L[nlib++], argv[i]);
-  static const char* stage[VC2_NUM_STAGES] = {"dwt_l0", "dwt_deep", "pack", "unpack", "idwt_deep", "idwt_l0", "ld_dc", "assemble", "index"};
+  static const char* stage[VC2_NUM_STAGES] = {"dwt_l0", "dwt_deep", "pack", "unpack", "idwt_deep", "idwt_l0", "ld_dc", "assemble", "index", "search"};
   /* name, W, H, chroma format, bits, wavelet, depth, -u, -a, prefix, scalar, mode, q, bytes, content, timed */
   const Case cases[] = {
     {"C3 DD137 d4 q16 S4 (bench)", 3840, 2160, 1, 10, VC2_DD137, 4, 1, 2, 0, 4, VC2_HQ_VBR, 16, 0, 0, 1},

@@ -90,7 +90,7 @@ class Context:
     def kernel_launches(self, reset=False):
         return lib.vc2_kernel_launches(self.h, 1 if reset else 0)
 
-    STAGES = ["dwt_l0", "dwt_deep", "pack", "unpack", "idwt_deep", "idwt_l0", "ld_dc", "assemble", "index"]
+    STAGES = ["dwt_l0", "dwt_deep", "pack", "unpack", "idwt_deep", "idwt_l0", "ld_dc", "assemble", "index", "search"]
 
     def profile_enable(self, on=True):
         _check(lib.vc2_profile_enable(self.h, 1 if on else 0), self.h)

@@ -282,6 +282,8 @@ extern "C" int vc2_quant_magic31(int q, uint32_t* m, uint32_t* shift) {
   return VC2_OK;
 }
 
+struct NarrowMagic { uint32_t mul; int sh; };
+static const NarrowMagic& narrow_magic(int q);
 static void make_quant_tables(QuantTables& t) {
   for (int q = 0; q < 128; ++q) {
     const uint32_t d = (uint32_t)vc2_quant_factor(std::min(q, 119));
@@ -292,6 +294,9 @@ static void make_quant_tables(QuantTables& t) {
     t.ql[q] = l;
     t.qm[q] = (uint32_t)(((1ull << 32) * ((1ull << l) - d)) / d + 1);
     vc2_quant_magic31(std::min(q, 119), &t.qm31[q], &t.ql31[q]);
+    const NarrowMagic& m = narrow_magic(std::min(q, 119));
+    t.qmul16[q] = m.sh < 0 ? 0u : m.mul;
+    t.qsh16[q] = m.sh < 0 ? 0u : (uint32_t)m.sh;
   }
 }
 
@@ -415,7 +420,6 @@ static int ilog2_or_neg(int v) {
 // VC2_NARROW_FAST_MAX, with a product that stays inside 32 bits.  Found by trying the shifts in turn and checking every
 // dividend (once per index and process); an index without such a pair keeps mul = 0, sh = -1 and the kernels never take
 // the fast form for it (cannot happen for the table of Quantisation.cpp:42-59, but nothing relies on that).
-struct NarrowMagic { uint32_t mul; int sh; };
 static const NarrowMagic& narrow_magic(int q) {
   static NarrowMagic tab[120];
   static std::once_flag once;
@@ -663,6 +667,19 @@ static cudaError_t run_pack(vc2_ctx* ctx, const SliceGeom& g, const int32_t* coe
     p.slice_off = B.slice_off; p.total_len = B.total_len;
     e = cudaMemsetAsync(B.tile_state, 0, tile_state_bytes(nslices, npictures), ctx->stream);
     if (e != cudaSuccess) return e;
+  }
+  if (search && emit) {
+    // HQ_CBR: rate control and packing as two launches - the search leaves the index of every slice (and its error
+    // flags), the packer reads them - so that the two are timed apart (VC2_STAGE_SEARCH)
+    PackParams q = p;
+    q.emit = 0;
+    {
+      ProfScope ps(ctx, VC2_STAGE_SEARCH);
+      e = pack_launch(ctx->stream, q, npictures);
+    }
+    if (e != cudaSuccess) return e;
+    ctx->launches++;
+    p.search = 0; p.const_q = -1; p.after_search = 1;
   }
   {
     ProfScope ps(ctx, VC2_STAGE_PACK);
@@ -1097,6 +1114,8 @@ extern "C" vc2_codec* vc2_codec_create(vc2_ctx* ctx, const vc2_codec_params* prm
   R(k->narrow_ovf, (size_t)B * 4 * 2);
   R(k->band_scale, sizeof(BandScale) * B);
   R(k->tile_state, tile_state_bytes(k->nslices, 1) * B);
+  // (HQ_CBR keeps the 32-bit block: an unquantised 16-bit block for its rate control was measured 7 % SLOWER - the search
+  // is bound by instruction issue, not by the bytes it reads, and the sign extension adds instructions)
   k->narrow_enc = ctx->narrow && ctx->dwt_tile && prm->mode == VC2_HQ_VBR;
   k->narrow_dec = ctx->narrow && ctx->dwt_tile && prm->mode != VC2_LD;
   k->slot_state.assign(B, vc2_codec::SlotState());
@@ -1261,7 +1280,7 @@ static int codec_encode_range(vc2_codec* k, int first, int n, bool wide = false)
   B.total_len = k->dev_len.as<uint32_t>() + first;
   B.tile_state = reinterpret_cast<unsigned long long*>(k->tile_state.as<uint8_t>() + tile_state_bytes(k->nslices, 1) * first);
   const int32_t* coef = k->coef.as<int32_t>() + (long long)first * k->g.coef_pic_stride;
-  CU(run_pack(ctx, k->g, coef, n, k->prm.mode, 1, cbr ? 1 : 0, cbr ? -1 : k->prm.qindex, 1, B, narrow ? 1 : 0));
+  CU(run_pack(ctx, k->g, coef, n, k->prm.mode, 1, cbr ? 1 : 0, cbr ? -1 : k->prm.qindex, 1, B, narrow ? nw.on : 0));
   return VC2_OK;
 }
 

@@ -69,7 +69,7 @@ constexpr unsigned FULL = 0xFFFFFFFFu;
 // The truncating division by the table constant uses the round-up multiply-shift of Granlund &
 // Montgomery, exact for every 32-bit dividend:  t = mulhi(m', a);  q = (t + ((a - t) >> 1)) >> (l - 1)
 struct QParam {
-  uint32_t qf, qo, qm, ql, qm31, ql31;
+  uint32_t qf, qo, qm, ql, qm31, ql31, qmul16, qsh16;
 };
 __device__ __forceinline__ QParam qparam(int q) {
   QParam r;
@@ -80,6 +80,8 @@ __device__ __forceinline__ QParam qparam(int q) {
   r.ql = c_qt.ql[q];
   r.qm31 = c_qt.qm31[q];
   r.ql31 = c_qt.ql31[q];
+  r.qmul16 = c_qt.qmul16[q];
+  r.qsh16 = c_qt.qsh16[q];
   return r;
 }
 __device__ __forceinline__ uint32_t udiv_magic(uint32_t a, uint32_t m, uint32_t l) {
@@ -131,6 +133,7 @@ __device__ __forceinline__ void vlc_code(int v, uint32_t& code, int& nb) {
 // quantiser parameters of one band for one slice (per lane: the slices of a warp may use different indices)
 struct BandP {
   uint32_t qm, ql, qf, qo;   // one-multiply magic (exact below 2^31) and its shift, quant_factor, quant_offset + 2
+  uint32_t mul16, sh16;      // full-rate form for |v| < VC2_NARROW_FAST_MAX (mul16 == 0: not available)
 };
 // adjusted index max(q - qmatrix[b], 0) (Quantisation.cpp:16-20); bad when the reference would throw (:60-63)
 __device__ __forceinline__ BandP band_params(int q, int qmat, bool& bad) {
@@ -139,6 +142,7 @@ __device__ __forceinline__ BandP band_params(int q, int qmat, bool& bad) {
   const QParam p = qparam(aq);
   BandP r;
   r.qm = p.qm31; r.ql = p.ql31; r.qf = p.qf; r.qo = p.qo + 2u;
+  r.mul16 = p.qmul16; r.sh16 = p.qsh16;
   return r;
 }
 __device__ __forceinline__ int quant_band(int v, const BandP& bp) {
@@ -162,16 +166,16 @@ __device__ __forceinline__ int scale_band(int v, const BandP& bp) {   // bp.qo a
 #define VC2_WALK_UNROLL
 #endif
 template <class Op>
-__device__ __forceinline__ void walk_component(const int4* __restrict__ src, const SliceGeom& g, int c, int q, bool& badq, Op& op) {
+__device__ __forceinline__ void walk_component(const int4* __restrict__ base, size_t first, const SliceGeom& g, int c, int q, bool& badq, Op& op) {
   const int n = g.band_start[c][g.nbands];
   int k = 0, b = 0, bend = g.band_start[c][1];
   BandP bp = band_params(q, g.qmatrix[0], badq);
   // three pieces in flight: the loads of a thread are 512 bytes apart (one piece of each of the 32 slices of the
   // group in between), every one a fresh line, and one piece of work is too short to cover an HBM round trip
   const int np = n >> 2;
-  int4 n0 = __ldg(src), n1 = n0, n2 = n0;
-  if (np > 1) n1 = __ldg(src + 32);
-  if (np > 2) n2 = __ldg(src + 64);
+  int4 n0 = __ldg(base + first), n1 = n0, n2 = n0;
+  if (np > 1) n1 = __ldg(base + first + 32);
+  if (np > 2) n2 = __ldg(base + first + 64);
   int piece = 0;
   while (piece < np) {
     while (k == bend) {   // coefficient k exists (piece < np), so does its band
@@ -184,14 +188,14 @@ __device__ __forceinline__ void walk_component(const int4* __restrict__ src, con
     const int run = min((bend - k) >> 2, np - piece);
     if (run > 0) {
       k += 4 * run;
-      const int4* pf = src + (size_t)(piece + 3) * 32;
+      size_t pf = first + (size_t)(piece + 3) * 32;
       int ahead = np - (piece + 3);   // pieces that can still be prefetched
       piece += run;
       VC2_WALK_UNROLL
       for (int i = 0; i < run; ++i) {
         const int4 v4 = n0;
         n0 = n1; n1 = n2;
-        if (ahead > 0) n2 = __ldg(pf);
+        if (ahead > 0) n2 = __ldg(base + pf);
         pf += 32; --ahead;
         op.pair(v4.x, v4.y, bp);
         op.pair(v4.z, v4.w, bp);
@@ -199,7 +203,7 @@ __device__ __forceinline__ void walk_component(const int4* __restrict__ src, con
     } else {
       const int4 v4 = n0;
       n0 = n1; n1 = n2;
-      if (piece + 3 < np) n2 = __ldg(src + (size_t)(piece + 3) * 32);
+      if (piece + 3 < np) n2 = __ldg(base + first + (size_t)(piece + 3) * 32);
       ++piece;
       const int v[4] = {v4.x, v4.y, v4.z, v4.w};
 #pragma unroll
@@ -303,7 +307,27 @@ struct CountOp {      // component_slice_bytes' bit count of quantise(v) (rate-c
     }
     if (mag) last = bits;
   }
-  __device__ __forceinline__ void pair(int v0, int v1, const BandP& bp) { (*this)(v0, bp); (*this)(v1, bp); }
+  __device__ __forceinline__ void count(uint32_t mag) {
+    if (mag < (uint32_t)ENC_LUT_MAG) bits += (int)(lut[2u * mag] & 31u);
+    else {
+      const uint32_t m = mag + 1u;
+      bigor |= m;
+      bits += 2 * (31 - __clz(min(m, 65535u))) + 2;
+    }
+    if (mag) last = bits;
+  }
+  // the probes of the rate control quantise every coefficient seven times: small coefficients (nearly all of them) take
+  // the full-rate multiply instead of the multiply-high
+  __device__ __forceinline__ void pair(int v0, int v1, const BandP& bp) {
+    const uint32_t a0 = (uint32_t)abs(v0), a1 = (uint32_t)abs(v1);
+    if (bp.mul16 != 0u && (a0 | a1) < (uint32_t)VC2_NARROW_FAST_MAX) {
+      count((a0 * bp.mul16) >> bp.sh16);
+      count((a1 * bp.mul16) >> bp.sh16);
+    } else {
+      (*this)(v0, bp);
+      (*this)(v1, bp);
+    }
+  }
 };
 struct SseOp {        // yss_for_slice (Quantisation.cpp:627-642): product in int, sum in long long
   long long acc;
@@ -368,7 +392,9 @@ __global__ void __launch_bounds__(128) hq_pack_kernel(const PackParams p) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= nslices) return;
   const int nc4 = g.comp_start[3] >> 2;
-  const int4* src = reinterpret_cast<const int4*>(p.coef + (long long)pic * g.coef_pic_stride) + (size_t)(s >> 5) * nc4 * 32 + (s & 31);
+  // this picture's block and the lane's first piece in it
+  const int4* base = reinterpret_cast<const int4*>(p.coef + (long long)pic * g.coef_pic_stride);
+  const size_t src = (size_t)(s >> 5) * nc4 * 32 + (s & 31);
   const long long sidx = (long long)pic * nslices + s;
   unsigned flags = 0;
   int qi = 0;
@@ -384,7 +410,7 @@ __global__ void __launch_bounds__(128) hq_pack_kernel(const PackParams p) {
       bool too_big = false, badq = false;
       for (int c = 0; c < 3; ++c) {
         CountOp op = {s_enc, 0, 0, 0u};
-        walk_component(src + (size_t)(g.comp_start[c] >> 2) * 32, g, c, trialQ, badq, op);
+        walk_component(base, src + (size_t)(g.comp_start[c] >> 2) * 32, g, c, trialQ, badq, op);
         need += scaled_bytes(op.last, g.scalar, too_big);
       }
       if (badq) { flags |= VC2_FLAG_QUANT_INDEX | VC2_FLAG_SEARCH_PHASE; dead = true; break; }
@@ -397,11 +423,11 @@ __global__ void __launch_bounds__(128) hq_pack_kernel(const PackParams p) {
       trialQ = q;
       bool badq = false;
       SseOp prev = {0};
-      walk_component(src, g, 0, trialQ, badq, prev);
+      walk_component(base, src, g, 0, trialQ, badq, prev);
       while (!badq) {
         ++trialQ;
         SseOp cur = {0};
-        walk_component(src, g, 0, trialQ, badq, cur);
+        walk_component(base, src, g, 0, trialQ, badq, cur);
         if (badq) break;
         const long long d = cur.acc - prev.acc;
         prev = cur;
@@ -417,6 +443,7 @@ __global__ void __launch_bounds__(128) hq_pack_kernel(const PackParams p) {
     p.qidx[sidx] = qi;
   } else {
     qi = p.qidx[sidx];
+    if (p.after_search) flags = p.err_flags[sidx];
   }
 
   if (p.emit) {
@@ -433,15 +460,15 @@ __global__ void __launch_bounds__(128) hq_pack_kernel(const PackParams p) {
         const int len_pos = W.pos();
         W.put(0u, 8);
         const int data_start = W.pos();
-        const int4* csrc = src + (size_t)(g.comp_start[c] >> 2) * 32;
+        const size_t csrc = src + (size_t)(g.comp_start[c] >> 2) * 32;
         int last;
         if (p.quantise) {
           EmitOp<true, WideBitWriter> op = {s_enc, &W, W.mark(), 0u};
-          walk_component(csrc, g, c, qi, badq, op);
+          walk_component(base, csrc, g, c, qi, badq, op);
           last = W.unmark(op.last); bigor |= op.bigor;
         } else {
           EmitOp<false, WideBitWriter> op = {s_enc, &W, W.mark(), 0u};
-          walk_component(csrc, g, c, qi, badq, op);
+          walk_component(base, csrc, g, c, qi, badq, op);
           last = W.unmark(op.last); bigor |= op.bigor;
         }
         int L = scaled_bytes(last - data_start, g.scalar, too_big);

@@ -33,6 +33,7 @@ struct PackParams {
   int search;                   // 1: run quantIndicesCBR per slice and use (and store) its result
   int const_q;                  // >= 0: every slice uses this index (HQ_ConstQ); < 0: read qidx[]
   int emit;                     // 0: rate control only (vc2_cbr_qindices)
+  int after_search;             // 1: a rate control launch has left qidx[] and err_flags[] (a slice it flagged is not packed)
   int32_t* qidx;                // [pic][slices] in (search == 0 && const_q < 0) or out
   const int32_t* slice_bytes;   // [slices] per-slice byte budget (CBR), same for every picture
   uint32_t* staging;            // [pic][slices][wcap] slice images as MSB-first 32-bit words

@@ -63,6 +63,8 @@ struct QuantTables {
   uint32_t ql[128];
   uint32_t qm31[128];
   uint32_t ql31[128];
+  uint32_t qmul16[128];   // |q| = (|v| * qmul16) >> qsh16 for |v| < VC2_NARROW_FAST_MAX: one full-rate multiply (0 / 0 when no such pair exists)
+  uint32_t qsh16[128];
 };
 
 // narrow decode, per picture (written by the parser, read by the inverse lifting kernels)
