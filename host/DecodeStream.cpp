@@ -36,6 +36,13 @@ namespace {
 
 enum Output { TRANSFORM, QUANTISED, INDICES, DECODED };
 
+// DecodeStream.cpp:312: bytes of a whole LD picture from the slice-bytes ratio (the header is untrusted: no division by zero)
+static int ld_picture_bytes(const PicturePreamble& pre) {
+  if (pre.slice_bytes.denominator == 0) throw std::logic_error("Stream Error: slice bytes denominator is zero");
+  if (pre.slices_y < 1 || pre.slices_x < 1) throw std::logic_error("Stream Error: slice counts must be positive");
+  return (int)((long long)pre.slice_bytes.numerator * pre.slices_y * pre.slices_x / pre.slice_bytes.denominator);
+}
+
 struct PictureUnit {
   const uint8_t* data;
   size_t len;
@@ -154,14 +161,20 @@ class Decoder {
     cfg_ = c;
     codecs_.clear();
     vc2_codec_params cp;
-    const int depth = c.pre.depth, cell = 1 << depth;
+    // untrusted header fields are checked before anything is computed from them
+    const int depth = c.pre.depth;
+    if (depth < 1 || depth > 6) throw std::logic_error("Stream Error: wavelet depth outside 1..6");
+    if (c.pre.slices_y < 1 || c.pre.slices_x < 1) throw std::logic_error("Stream Error: slice counts must be positive");
+    if (c.ld && c.pre.slice_bytes.denominator == 0) throw std::logic_error("Stream Error: slice bytes denominator is zero");
     const PictureFormat f(c.height, c.width, c.cf);
-    // slice sizes in units of 2^depth from the slice counts (the inverse of sliceSizeIsValid)
-    const int ph = paddedSize(f.lumaHeight(), depth), pw = paddedSize(f.lumaWidth(), depth);
-    if (c.pre.slices_y < 1 || c.pre.slices_x < 1 || ph % (c.pre.slices_y * cell) || pw % (c.pre.slices_x * cell))
-      throw std::logic_error("Stream Error: slice counts do not divide the padded picture");
-    if (vc2_make_geom(c.height, c.width, (int)c.cf, (int)c.pre.wavelet_kernel, depth, ph / c.pre.slices_y / cell, pw / c.pre.slices_x / cell,
-                      c.ld ? 0 : c.pre.slice_prefix, c.ld ? 1 : c.pre.slice_size_scalar, &cp.geom) != VC2_OK)
+    // the decoder takes the slice counts as they are in the stream: sliceSizeIsValid (Utils.cpp) is an encoder-side rule, the
+    // codec itself only needs every slice to be a whole number of 2^depth cells in both components (geom_ok in cabi.cu)
+    cp.geom.luma_h = f.lumaHeight(); cp.geom.luma_w = f.lumaWidth();
+    cp.geom.chroma_h = f.chromaHeight(); cp.geom.chroma_w = f.chromaWidth();
+    cp.geom.kernel = (int)c.pre.wavelet_kernel; cp.geom.depth = depth;
+    cp.geom.slices_y = c.pre.slices_y; cp.geom.slices_x = c.pre.slices_x;
+    cp.geom.prefix = c.ld ? 0 : c.pre.slice_prefix; cp.geom.scalar = c.ld ? 1 : c.pre.slice_size_scalar;
+    if (cp.geom.kernel < 0 || cp.geom.kernel > 6 || cp.geom.prefix < 0 || cp.geom.scalar < 1)
       throw std::logic_error("Stream Error: unsupported picture / slice geometry");
     cp.fmt.bytes_per_sample = c.bits == 8 ? 1 : 2;            // DecodeStream.cpp:268-271
     cp.fmt.luma_depth = c.bits; cp.fmt.chroma_depth = c.bits;   // :265-266: the luma depth serves both
@@ -314,7 +327,7 @@ int main(int argc, char** argv) {
           u.data = stream.data() + rd.pos();
           if (ld) {
             // DecodeStream.cpp:312: bytes of the whole picture from the slice-bytes ratio
-            cfg.compressedBytes = (int)((long long)pre.slice_bytes.numerator * pre.slices_y * pre.slices_x / pre.slice_bytes.denominator);
+            cfg.compressedBytes = ld_picture_bytes(pre);
             u.len = (size_t)cfg.compressedBytes;
             if (rd.pos() + u.len > streamLen) throw std::logic_error("Stream Error: LD picture runs past the end of the stream");
           } else {
@@ -337,7 +350,7 @@ int main(int argc, char** argv) {
             FragmentedPicture fp;
             fp.cfg.ld = ld; fp.cfg.height = seq.interlace ? seq.height / 2 : seq.height; fp.cfg.width = seq.width; fp.cfg.bits = seq.bitdepth;
             fp.cfg.cf = seq.chromaFormat; fp.cfg.pre = pre; fp.cfg.interlace = seq.interlace; fp.cfg.tff = seq.topFieldFirst;
-            if (ld) fp.cfg.compressedBytes = (int)((long long)pre.slice_bytes.numerator * pre.slices_y * pre.slices_x / pre.slice_bytes.denominator);
+            if (ld) fp.cfg.compressedBytes = ld_picture_bytes(pre);
             fp.needed = pre.slices_x * pre.slices_y;
             fragments[fh.picture_number] = fp;
             if (unitEnd) rd.seek(unitEnd);

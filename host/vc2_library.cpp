@@ -189,7 +189,7 @@ const Picture inverseWaveletTransform(const Picture& t, WaveletKernel kernel, in
                  inverseWaveletTransform(t.c2(), kernel, depth, f.chromaHeight(), f.chromaWidth()));
 }
 const Array1D quantMatrix(WaveletKernel kernel, int depth) {
-  if (depth > 4) throw std::domain_error("quantMatrix: depth must be 4 or less");   // WaveletTransform.cpp:348
+  if (depth < 0) throw std::domain_error("wavelet depth may not be < 0");   // WaveletTransform.cpp:348 (any depth >= 0 is computed)
   Array1D m(3 * depth + 1);
   if (vc2_quant_matrix((int)kernel, depth, m.data()) != VC2_OK) throw std::invalid_argument("quantMatrix: invalid kernel or depth");
   return m;

@@ -26,7 +26,7 @@ const Picture waveletTransform(const Picture& picture, WaveletKernel kernel, int
 // inverseWaveletTransform(..., shape) - :321-342: crops to `height x width` / `format`
 const Array2D inverseWaveletTransform(const Array2D& transform, WaveletKernel kernel, int depth, int height, int width);
 const Picture inverseWaveletTransform(const Picture& transform, WaveletKernel kernel, int depth, const PictureFormat& format);
-// quantMatrix(kernel, depth) - :345-423 (std::domain_error for depth > 4 as in :348)
+// quantMatrix(kernel, depth) - :345-423 (std::domain_error for depth < 0 as in :348; depth is bounded by VC2_MAX_DEPTH here)
 const Array1D quantMatrix(WaveletKernel kernel, int depth);
 
 }  // namespace vc2

@@ -93,6 +93,14 @@ CASES += [
     case("W04_Haar1_d3_422_odd", 1450, 810, "422", 10, 1, "HQ_ConstQ", "Haar1", 3, 1, 2, q=8, S=2, seed=504),
 ]
 
+# wavelet depths beyond the four that the BASELINE configs use: the reference computes quantMatrix for any depth >= 0
+# (WaveletTransform.cpp:345-423) and the kernels here take 1..6
+CASES += [
+    case("D5_DD97_d5_422", 640, 384, "422", 10, 2, "HQ_ConstQ", "DD97", 5, 1, 2, q=9, S=16, seed=600),
+    case("D6_LeGall_d6_444", 512, 256, "444", 10, 2, "HQ_CBR", "LeGall", 6, 1, 1, s=200000, S=32, seed=601),
+    case("D5_Haar0_d5_422_pad", 640, 330, "422", 8, 2, "HQ_ConstQ", "Haar0", 5, 1, 2, q=5, S=16, seed=602),
+]
+
 
 def md5_file(path):
     h = hashlib.md5()

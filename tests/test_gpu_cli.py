@@ -46,6 +46,8 @@ def run(cmd):
 
 @pytest.mark.parametrize("name", ["S01_LeGall_d3_422", "S04_Haar1_d4_420", "S05_Fidelity_d2_422", "S08_DD137_d4_422",
                                   "B00_DD97_d2_420", "B06_Daub97_d3_444", "C1", "C2",
+                                  # wavelet depths 5 and 6 (quantMatrix is computed for any depth, WaveletTransform.cpp:345-423)
+                                  "D5_DD97_d5_422", "D6_LeGall_d6_444",
                                   # interlaced coding (two field pictures per frame) and fragmented pictures
                                   "I00_LeGall_d3_422_tff", "I01_DD137_d2_420_bff", "I02_Haar1_d3_444_tff",
                                   "F00_DD97_d3_422", "F01_LeGall_d2_420_small", "F02_Fidelity_d2_422_il",
@@ -58,7 +60,7 @@ def test_command_lines_vs_golden(tmp_path, name):
     src = str(tmp_path / "in.yuv")
     write_input(c, src)
     # a batch smaller than the clip and (when there are several GPUs) two devices: chunking and reassembly
-    extra = ["-B", "1", "-G", "2"] if name[0] in "SI" else ["-B", "3"] if name[0] in "FL" else []
+    extra = ["-B", "1", "-G", "2"] if name[0] in "SID" else ["-B", "3"] if name[0] in "FL" else []
     small = not name.startswith("C")       # the 1080p configs: stream and pictures only (each run pays a CUDA start-up)
     for tap in ["Stream"] + (["Packaged", "Transform", "Quantised"] if small else []) + (["Indices"] if c["mode"] != "HQ_ConstQ" else []):
         dst = str(tmp_path / ("enc_" + tap))

@@ -4,6 +4,7 @@ Function names mirror the reference Library functions they reach through the C-A
 (/root/reference/src/Library/{WaveletTransform,Quantisation,Slices}.h).
 """
 import ctypes as C
+import weakref
 
 import numpy as np
 
@@ -70,11 +71,14 @@ class Context:
         self.h = lib.vc2_create(device)
         if not self.h:
             raise Vc2Error(-2, "vc2_create failed: no usable CUDA device (there is no CPU fallback)")
+        self._codecs = weakref.WeakSet()   # live codecs: destroyed before the context they point into
         if stream is not None:
             _check(lib.vc2_set_stream(self.h, C.c_void_p(stream)), self.h)
 
     def close(self):
         if self.h:
+            for k in list(self._codecs):
+                k.close()
             lib.vc2_destroy(self.h)
             self.h = None
 
@@ -192,13 +196,15 @@ class Codec:
         self.h = lib.vc2_codec_create(ctx.h, C.byref(p))
         if not self.h:
             raise Vc2Error(-1, lib.vc2_last_error(ctx.h).decode())
+        ctx._codecs.add(self)
         self.picture_bytes = lib.vc2_codec_picture_in_bytes(self.h)
         self.payload_capacity = lib.vc2_codec_payload_capacity(self.h)
         self.n_slices = g.slices_x * g.slices_y
 
     def close(self):
         if self.h:
-            lib.vc2_codec_destroy(self.h)
+            if self.ctx.h:   # a closed context has already destroyed its codecs (Context.close)
+                lib.vc2_codec_destroy(self.h)
             self.h = None
 
     def __del__(self):

@@ -621,11 +621,13 @@ static int flags_to_status(unsigned f) {
   return VC2_OK;
 }
 // reference throw order: rate control for every slice (raster) runs before any slice is written
-static int first_error(const uint32_t* flags, int n) {
+// `ignore`: flag bits the caller does not treat as errors (the decoders pass VC2_FLAG_VLC_RANGE: a parsed value beyond the
+// encoder's domain is still decoded, but a malformed slice behind it must not hide behind that)
+static int first_error(const uint32_t* flags, int n, uint32_t ignore = 0) {
   for (int i = 0; i < n; ++i)
-    if (flags[i] & VC2_FLAG_SEARCH_PHASE) return flags_to_status(flags[i]);
+    if (flags[i] & VC2_FLAG_SEARCH_PHASE & ~ignore) return flags_to_status(flags[i] & ~ignore);
   for (int i = 0; i < n; ++i)
-    if (flags[i]) return flags_to_status(flags[i]);
+    if (flags[i] & ~ignore) return flags_to_status(flags[i] & ~ignore);
   return VC2_OK;
 }
 
@@ -944,8 +946,8 @@ static int unpack_host(vc2_ctx* ctx, const uint8_t* in, size_t len, const vc2_ge
   CU(cudaMemcpyAsync(flags.data(), p.err_flags, (size_t)nslices * 4, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaMemcpyAsync(qidx, p.qidx, (size_t)nslices * 4, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
-  st = first_error(flags.data(), nslices);
-  if (st && st != VC2_ERR_VLC_RANGE) return fail(ctx, st);
+  st = first_error(flags.data(), nslices, VC2_FLAG_VLC_RANGE);
+  if (st) return fail(ctx, st);
   return VC2_OK;
 }
 
@@ -1549,7 +1551,7 @@ extern "C" int vc2_codec_upload_payload(vc2_codec* k, int slot, const uint8_t* p
   return VC2_OK;
 }
 
-extern "C" int vc2_codec_slot_status(vc2_codec* k, int slot) {
+static int codec_slot_status(vc2_codec* k, int slot, uint32_t ignore) {
   KARG(k && slot >= 0 && slot < k->prm.max_pictures);
   vc2_ctx* ctx = k->ctx;
   CU(cudaSetDevice(ctx->device));
@@ -1558,10 +1560,11 @@ extern "C" int vc2_codec_slot_status(vc2_codec* k, int slot) {
   CU(cudaMemcpyAsync(flags.data(), k->err.as<uint32_t>() + (size_t)slot * k->nslices, (size_t)k->nslices * 4,
                      cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
-  const int st = first_error(flags.data(), k->nslices);
+  const int st = first_error(flags.data(), k->nslices, ignore);
   if (st) return fail(ctx, st);
   return VC2_OK;
 }
+extern "C" int vc2_codec_slot_status(vc2_codec* k, int slot) { return codec_slot_status(k, slot, 0); }
 
 extern "C" int vc2_codec_download_payload(vc2_codec* k, int slot, uint8_t* payload, size_t cap, size_t* len, int32_t* qidx,
                                           uint32_t* slice_off) {
@@ -1728,8 +1731,8 @@ extern "C" int vc2_codec_decode_host(vc2_codec* k, int n, const uint8_t* const* 
     if (e != cudaSuccess) return cuda_fail(ctx, e);
     for (int i = 0; i < m; ++i) {
       if (k->narrow_dec && k->host_novf[(c & 1) * B + i]) { redo.push_back(c * B + i); continue; }
-      const int st = first_error(flags(c & 1) + (size_t)i * ns, ns);
-      if (st && st != VC2_ERR_VLC_RANGE) return fail(ctx, st);
+      const int st = first_error(flags(c & 1) + (size_t)i * ns, ns, VC2_FLAG_VLC_RANGE);
+      if (st) return fail(ctx, st);
     }
     return VC2_OK;
   };
@@ -1786,8 +1789,7 @@ extern "C" int vc2_codec_decode_host(vc2_codec* k, int n, const uint8_t* const* 
     if (status) break;
     status = codec_decode_range(k, 0, 1, hq, true);
     if (status) break;
-    status = vc2_codec_slot_status(k, 0);
-    if (status == VC2_ERR_VLC_RANGE) status = VC2_OK;
+    status = codec_slot_status(k, 0, VC2_FLAG_VLC_RANGE);
     if (status) break;
     status = vc2_codec_download_picture(k, 0, pictures[i]);
   }

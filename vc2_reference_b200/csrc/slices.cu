@@ -1030,8 +1030,11 @@ struct BitReader {
   int nb;              // valid bits in hi:lo
   int left;            // real stream bits behind nxt (<= 0: only ones follow)
   __device__ __forceinline__ static uint32_t be(uint32_t x) { return __byte_perm(x, 0, 0x0123); }
+  // Past the bound nothing is loaded: a component whose length byte is too small for its coefficients would otherwise walk
+  // one word per 32 coefficients beyond its slice (and, for the last slice, beyond the payload buffer).
   __device__ __forceinline__ void fetch() {
-    nxt = __ldg(p++);
+    nxt = left > 0 ? __ldg(p) : 0xFFFFFFFFu;   // left <= 0: the word holds no real bit, next_word() makes it all ones anyway
+    ++p;
     left -= 32;
   }
   // the prefetched word as window bits: ones from the bound on (left + 32 real bits were behind the window when it was fetched)
