@@ -174,6 +174,23 @@ int vc2_hq_unpack(vc2_ctx*, const uint8_t* in, size_t len, const vc2_geom* g,
 /* operator>>(istream&, Slices) with the LD reader - Slices.cpp:246-303 ; slice_bytes[ny*nx] */
 int vc2_ld_unpack(vc2_ctx*, const uint8_t* in, size_t len, const vc2_geom* g, const int32_t* slice_bytes,
                   int32_t* qY, int32_t* qU, int32_t* qV, int32_t* qidx);
+/* operator<<(ostream&, Slices) with the LD writer - Slices.cpp:195-244, 645-660.  qY/qU/qV: quantised padded planes
+ * (LL band: the quantised prediction residuals of quantise_transform); slice_bytes[ny*nx] */
+int vc2_ld_pack(vc2_ctx*, const int32_t* qY, const int32_t* qU, const int32_t* qV, const vc2_geom* g,
+                const int32_t* qidx, const int32_t* slice_bytes, uint8_t* out, size_t cap, size_t* out_len);
+/* quantise_transform(Array2D, qIndices, qMatrix), the LD quantiser with DC prediction of the LL band -
+ * Quantisation.cpp:213-282, 353-367 */
+int vc2_quantise_ld(vc2_ctx*, const int32_t* coef, int ph, int pw, int depth, const int32_t* qmatrix,
+                    const int32_t* qidx, int ny, int nx, int32_t* out);
+/* luma_slice_bits (q2 == NULL) / chroma_slice_bits (q, q2 walked interleaved) - Slices.cpp:51-96: for every slice of
+ * the quantised in-place plane(s), the bits of its code list up to and including its last non-zero coefficient;
+ * bits[ny*nx] */
+int vc2_slice_bits(vc2_ctx*, const int32_t* q, const int32_t* q2, int ph, int pw, int depth, int ny, int nx,
+                   int32_t* bits);
+/* component_slice_bytes - Slices.cpp:97-119, for every slice of one quantised in-place plane; bytes[ny*nx];
+ * VC2_ERR_SCALAR_TOO_SMALL as the reference throws */
+int vc2_hq_slice_sizes(vc2_ctx*, const int32_t* q, int ph, int pw, int depth, int ny, int nx, int scalar,
+                       int32_t* bytes);
 /* quantIndicesCBR - EncodeStream.cpp:73-125 ; cY/cU/cV: UNQUANTISED padded planes */
 int vc2_cbr_qindices(vc2_ctx*, const int32_t* cY, const int32_t* cU, const int32_t* cV, const vc2_geom* g,
                      const int32_t* qmatrix, const int32_t* slice_bytes, int32_t* qidx_out,

@@ -153,6 +153,13 @@ int ref_component_slice_bytes(const int* slice, int h, int w, int depth, int sca
   TAP_CATCH
 }
 
+// Slices.cpp:51-96: luma_slice_bits of one slice (v == NULL) or chroma_slice_bits of a U/V slice pair
+int ref_slice_bits(const int* u, const int* v, int h, int w, int depth, int* out) {
+  TAP_TRY
+  *out = v ? chroma_slice_bits(to_array(u, h, w), to_array(v, h, w), depth) : luma_slice_bits(to_array(u, h, w), depth);
+  TAP_CATCH
+}
+
 // Quantisation.cpp:627-642
 int ref_yss_for_slice(const int* y, const int* u, const int* v, int lh, int lw, int ch, int cw,
                       int q, const int* qmatrix, int nbands, long long* out) {

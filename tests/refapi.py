@@ -131,6 +131,14 @@ def component_slice_bytes(sl, depth, scalar):
     return o.value
 
 
+def slice_bits(u, v, depth):
+    u = _i32(u)
+    v = _i32(v) if v is not None else None
+    o = C.c_int(0)
+    _chk(lib().ref_slice_bits(_p(u), _p(v), u.shape[0], u.shape[1], depth, C.byref(o)))
+    return o.value
+
+
 def cbr_qindices(y, u, v, qmatrix, sbytes, scalar):
     y, u, v, qmatrix, sbytes = _i32(y), _i32(u), _i32(v), _i32(qmatrix), _i32(sbytes)
     out = np.empty_like(sbytes)

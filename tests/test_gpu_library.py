@@ -205,3 +205,63 @@ def test_ld_unpack_vs_reference(ctx, ref):
     same(y, ry, "Y")
     same(u, ru, "U")
     same(v, rv, "V")
+
+
+@pytest.mark.parametrize("case", PACK_CASES[:4])
+def test_slice_bits_and_component_bytes_vs_reference(ctx, ref, case):
+    """vc2_slice_bits / vc2_hq_slice_sizes against luma_slice_bits, chroma_slice_bits and component_slice_bytes
+    (Slices.cpp:51-119) called slice by slice on the compiled reference"""
+    h, w, cf, kernel, depth, u, a, prefix, scalar = case
+    g = vc2.make_geom(h, w, cf, kernel, depth, u, a, prefix, scalar)
+    planes, quant, qidx, qm = _quantised_picture(ref, g, kernel, 11)
+    ny, nx = g.slices_y, g.slices_x
+    got_y = ctx.slice_bits(quant[0], None, depth, ny, nx)
+    got_uv = ctx.slice_bits(quant[1], quant[2], depth, ny, nx)
+    scalar_b = max(scalar, 4)
+    got_bytes = ctx.component_slice_bytes(quant[0], depth, ny, nx, scalar_b)
+    sh, sw = quant[0].shape[0] // ny, quant[0].shape[1] // nx
+    ch, cw = quant[1].shape[0] // ny, quant[1].shape[1] // nx
+    for sy in range(ny):
+        for sx in range(nx):
+            ys = quant[0][sy * sh:(sy + 1) * sh, sx * sw:(sx + 1) * sw]
+            us = quant[1][sy * ch:(sy + 1) * ch, sx * cw:(sx + 1) * cw]
+            vs = quant[2][sy * ch:(sy + 1) * ch, sx * cw:(sx + 1) * cw]
+            assert got_y[sy, sx] == ref.slice_bits(ys, None, depth), (sy, sx)
+            assert got_uv[sy, sx] == ref.slice_bits(us, vs, depth), (sy, sx)
+            assert got_bytes[sy, sx] == ref.component_slice_bytes(ys, depth, scalar_b), (sy, sx)
+
+
+def test_component_slice_bytes_scalar_too_small(ctx, ref):
+    q = rnd((32, 64), -30000, 30000, 5)
+    with pytest.raises(vc2.Vc2Error) as e:
+        ctx.component_slice_bytes(q, 2, 1, 1, 1)
+    assert "Slice scalar is too small" in str(e.value)
+
+
+@pytest.mark.parametrize("depth,kernel,cf", [(3, "LeGall", "422"), (2, "DD97", "420"), (4, "Haar1", "444")])
+def test_ld_quantise_and_pack_vs_reference(ctx, ref, depth, kernel, cf):
+    """vc2_quantise_ld (quantise_transform with DC prediction) and vc2_ld_pack (the LD slice writer) against the reference"""
+    g = vc2.make_geom(96, 192, cf, kernel, depth, 1, 2 if cf != "444" else 1)
+    (ph, pw), (ch, cw) = vc2.api.padded_dims(g)
+    qm = vc2.quant_matrix(kernel, depth)
+    planes = [rnd((ph, pw), -300, 300, 21), rnd((ch, cw), -300, 300, 22), rnd((ch, cw), -300, 300, 23)]
+    for p in planes:       # a DC level, so that the prediction matters
+        p[::1 << depth, ::1 << depth] += 700
+    qidx = rnd((g.slices_y, g.slices_x), 10, 34, 24)
+    want_q = [ref.quantise_ld(p, qidx, qm) for p in planes]
+    got_q = [ctx.quantise_transform(p, qidx, qm) for p in planes]
+    for a, b, n in zip(got_q, want_q, "YUV"):
+        same(a, b, "quantise_transform " + n)
+    same(ctx.inverse_quantise_transform(want_q[0], qidx, qm), ref.dequantise_ld(want_q[0], qidx, qm), "inverse")
+    n = g.slices_y * g.slices_x
+    sb = vc2.slice_bytes(g.slices_y, g.slices_x, 260 * n + 7, 1)
+    want = ref.pack_slices(want_q[0], want_q[1], want_q[2], depth, qidx, 2, 0, 1, sb)
+    got = ctx.ld_pack(want_q[0], want_q[1], want_q[2], g, qidx, sb)
+    assert got == want
+    # a budget the chroma does not fit: the reference throws, so does the C-ABI
+    tight = np.full((g.slices_y, g.slices_x), 12, np.int32)
+    with pytest.raises(Exception) as e_ref:
+        ref.pack_slices(want_q[0], want_q[1], want_q[2], depth, qidx, 2, 0, 1, tight)
+    with pytest.raises(vc2.Vc2Error) as e:
+        ctx.ld_pack(want_q[0], want_q[1], want_q[2], g, qidx, tight)
+    assert "Too many bytes" in str(e_ref.value) and "Too many bytes" in str(e.value)

@@ -64,6 +64,10 @@ def _load():
         "vc2_hq_unpack": (C.c_int, [vp, vp, C.c_size_t, gp, vp, vp, vp, vp]),
         "vc2_ld_unpack": (C.c_int, [vp, vp, C.c_size_t, gp, vp, vp, vp, vp, vp]),
         "vc2_cbr_qindices": (C.c_int, [vp, vp, vp, vp, gp, vp, vp, vp, vp]),
+        "vc2_ld_pack": (C.c_int, [vp, vp, vp, vp, gp, vp, vp, vp, C.c_size_t, szp]),
+        "vc2_quantise_ld": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, C.c_int, C.c_int, vp]),
+        "vc2_slice_bits": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
+        "vc2_hq_slice_sizes": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
         "vc2_codec_create": (vp, [vp, C.POINTER(CodecParams)]),
         "vc2_codec_destroy": (None, [vp]),
         "vc2_codec_picture_in_bytes": (C.c_size_t, [vp]),

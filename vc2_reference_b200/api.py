@@ -139,6 +139,31 @@ class Context:
     def inverse_quantise_transform(self, coef, qidx, qmatrix):   # LD, DC predicted
         return self._quant(lib.vc2_dequantise_ld, coef, qidx, qmatrix)
 
+    def quantise_transform(self, coef, qidx, qmatrix):   # LD, DC predicted
+        return self._quant(lib.vc2_quantise_ld, coef, qidx, qmatrix)
+
+    def slice_bits(self, q, q2, depth, ny, nx):
+        """luma_slice_bits (q2 None) / chroma_slice_bits of every slice of the quantised in-place plane(s)"""
+        q = _i32(q)
+        q2 = _i32(q2) if q2 is not None else None
+        out = np.empty((ny, nx), np.int32)
+        _check(lib.vc2_slice_bits(self.h, _p(q), _p(q2), q.shape[0], q.shape[1], depth, ny, nx, _p(out)), self.h)
+        return out
+
+    def component_slice_bytes(self, q, depth, ny, nx, scalar):
+        q = _i32(q)
+        out = np.empty((ny, nx), np.int32)
+        _check(lib.vc2_hq_slice_sizes(self.h, _p(q), q.shape[0], q.shape[1], depth, ny, nx, scalar, _p(out)), self.h)
+        return out
+
+    def ld_pack(self, y, u, v, g, qidx, slice_bytes_):
+        y, u, v, q, sb = _i32(y), _i32(u), _i32(v), _i32(qidx), _i32(slice_bytes_)
+        cap = int(sb.sum()) + 64
+        out = np.zeros(cap, np.uint8)
+        ln = C.c_size_t(0)
+        _check(lib.vc2_ld_pack(self.h, _p(y), _p(u), _p(v), C.byref(g), _p(q), _p(sb), _p(out), cap, C.byref(ln)), self.h)
+        return out[:ln.value].tobytes()
+
     def hq_pack(self, y, u, v, g, qidx, mode="HQ_VBR", slice_bytes_=None, cap=None):
         y, u, v, q = _i32(y), _i32(u), _i32(v), _i32(qidx)
         sb = _i32(slice_bytes_) if slice_bytes_ is not None else None

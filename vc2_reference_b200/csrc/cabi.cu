@@ -786,13 +786,21 @@ static int quant_host(vc2_ctx* ctx, const int32_t* coef, int ph, int pw, int dep
   for (int b = 0; b < 3 * depth + 1; ++b) p.qmatrix[b] = qmatrix[b];
   CU(quant_launch(ctx->stream, p));
   ctx->launches++;
-  if (ld) {
+  if (ld && inverse) {
     LdDcParams d;
     memset(&d, 0, sizeof(d));
     d.base = p.dst; d.qidx = p.qidx; d.H = ph >> depth; d.W = pw >> depth;
     d.interleaved = 0; d.pitch = pw; d.depth = depth;
     d.slices_y = ny; d.slices_x = nx; d.qm0 = qmatrix[0];
     CU(ld_dc_launch(ctx->stream, d));
+    ctx->launches++;
+  } else if (ld) {
+    LdDcQuantParams d;
+    CU(ctx->tmp[3].reserve((size_t)(ph >> depth) * (pw >> depth) * 4));
+    d.src = p.src; d.dst = p.dst; d.restored = ctx->tmp[3].as<int32_t>(); d.qidx = p.qidx;
+    d.H = ph >> depth; d.W = pw >> depth; d.pitch = pw; d.depth = depth;
+    d.slices_y = ny; d.slices_x = nx; d.qm0 = qmatrix[0];
+    CU(ld_dc_quant_launch(ctx->stream, d));
     ctx->launches++;
   }
   CU(cudaMemcpyAsync(out, ctx->tmp[1].p, n, cudaMemcpyDeviceToHost, ctx->stream));
@@ -907,6 +915,108 @@ extern "C" int vc2_cbr_qindices(vc2_ctx* ctx, const int32_t* cY, const int32_t* 
                                 const int32_t* qmatrix, const int32_t* slice_bytes, int32_t* qidx_out, uint32_t* err_flags) {
   if (!qmatrix || !qidx_out) return fail(ctx, VC2_ERR_ARG);
   return pack_host(ctx, cY, cU, cV, g, qmatrix, nullptr, qidx_out, VC2_HQ_CBR, 1, 0, slice_bytes, nullptr, 0, nullptr, nullptr, err_flags);
+}
+
+// operator<<(ostream&, Slices) with the LD writer (Slices.cpp:195-244, 645-660) on already quantised planes
+extern "C" int vc2_ld_pack(vc2_ctx* ctx, const int32_t* qY, const int32_t* qU, const int32_t* qV, const vc2_geom* vg,
+                           const int32_t* qidx, const int32_t* slice_bytes, uint8_t* out, size_t cap, size_t* out_len) {
+  if (!ctx || !qY || !qU || !qV || !geom_ok(vg) || !qidx || !slice_bytes || !out) return fail(ctx, VC2_ERR_ARG);
+  CU(cudaSetDevice(ctx->device));
+  vc2_geom lg = *vg;
+  lg.prefix = 0; lg.scalar = 1;
+  SliceGeom g;
+  fill_slice_geom(g, lg, nullptr);
+  const int nslices = g.slices_x * g.slices_y;
+  std::vector<uint32_t> fixed(nslices + 1, 0);
+  for (int i = 0; i < nslices; ++i) {
+    if (slice_bytes[i] < 1) return fail(ctx, VC2_ERR_ARG);
+    fixed[i + 1] = fixed[i] + (uint32_t)slice_bytes[i];
+  }
+  const size_t total = fixed[nslices];
+  if (out_len) *out_len = total;
+  if (total > cap) return fail(ctx, VC2_ERR_CAPACITY);
+  int st = upload_planes(ctx, g, qY, qU, qV);
+  if (st) return st;
+  int maxb = 0;
+  for (int i = 0; i < nslices; ++i) maxb = std::max(maxb, slice_bytes[i]);
+  const int wcap = std::max(staging_words(g), (maxb + 3) / 4 + 4);
+  // tmp[2]: payload | slice_off | err | sizes | qidx | slice_bytes | fixed ; tmp[3]: staging
+  const size_t o_off = (total + 259) / 256 * 256, o_err = o_off + (size_t)(nslices + 1) * 4, o_sz = o_err + (size_t)nslices * 4,
+               o_q = o_sz + (size_t)nslices * 4, o_sb = o_q + (size_t)nslices * 4, o_fx = o_sb + (size_t)nslices * 4,
+               o_end = o_fx + (size_t)(nslices + 1) * 4;
+  CU(ctx->tmp[2].reserve(o_end));
+  CU(ctx->tmp[3].reserve((size_t)wcap * 4 * nslices));
+  uint8_t* base = ctx->tmp[2].as<uint8_t>();
+  CU(cudaMemsetAsync(base + o_off, 0, o_q - o_off, ctx->stream));
+  CU(cudaMemcpyAsync(base + o_q, qidx, (size_t)nslices * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(base + o_sb, slice_bytes, (size_t)nslices * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(base + o_fx, fixed.data(), (size_t)(nslices + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
+  LdEncParams p;
+  memset(&p, 0, sizeof(p));
+  p.g = g;
+  p.coef = ctx->tmp[1].as<int32_t>(); p.qcoef = ctx->tmp[1].as<int32_t>(); p.prequantised = 1;
+  p.qidx = (int32_t*)(base + o_q); p.slice_bytes = (const int32_t*)(base + o_sb);
+  p.staging = ctx->tmp[3].as<uint32_t>(); p.wcap = wcap;
+  p.sizes = (uint32_t*)(base + o_sz); p.err_flags = (uint32_t*)(base + o_err);
+  CU(ld_pack_launch(ctx->stream, p, 1));
+  ctx->launches++;
+  AssembleParams a;
+  memset(&a, 0, sizeof(a));
+  a.nslices = nslices; a.sizes = p.sizes; a.fixed_off = (const uint32_t*)(base + o_fx);
+  a.slice_off = (uint32_t*)(base + o_off); a.staging = p.staging; a.wcap = wcap;
+  a.out = base; a.out_pic_stride = 0; a.out_capacity = (long long)total; a.err_flags = p.err_flags;
+  CU(assemble_launch(ctx->stream, a, 1));
+  ctx->launches += 2;
+  std::vector<uint32_t> flags(nslices);
+  CU(cudaMemcpyAsync(flags.data(), p.err_flags, (size_t)nslices * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  st = first_error(flags.data(), nslices, VC2_FLAG_VLC_RANGE);
+  if (st) return fail(ctx, st);
+  CU(cudaMemcpy(out, base, total, cudaMemcpyDeviceToHost));
+  return VC2_OK;
+}
+
+// luma_slice_bits / chroma_slice_bits (Slices.cpp:51-96) for every slice of one plane (or of a U/V pair walked interleaved)
+extern "C" int vc2_slice_bits(vc2_ctx* ctx, const int32_t* q, const int32_t* q2, int ph, int pw, int depth, int ny, int nx,
+                              int32_t* bits) {
+  if (!ctx || !q || !bits || depth < 1 || depth > VC2_MAX_DEPTH || ny < 1 || nx < 1 || ph < 1 || pw < 1) return fail(ctx, VC2_ERR_ARG);
+  if (ph % ny || pw % nx || (ph / ny) % (1 << depth) || (pw / nx) % (1 << depth)) return fail(ctx, VC2_ERR_ARG);
+  CU(cudaSetDevice(ctx->device));
+  const size_t n = (size_t)ph * pw * 4;
+  CU(ctx->tmp[0].reserve(n));
+  CU(ctx->tmp[1].reserve(n));
+  CU(ctx->tmp[2].reserve((size_t)ny * nx * 4));
+  CU(cudaMemcpyAsync(ctx->tmp[0].p, q, n, cudaMemcpyHostToDevice, ctx->stream));
+  if (q2) CU(cudaMemcpyAsync(ctx->tmp[1].p, q2, n, cudaMemcpyHostToDevice, ctx->stream));
+  SliceBitsParams p;
+  p.q = ctx->tmp[0].as<int32_t>(); p.q2 = q2 ? ctx->tmp[1].as<int32_t>() : nullptr;
+  p.ph = ph; p.pw = pw; p.depth = depth; p.slices_y = ny; p.slices_x = nx; p.bits = ctx->tmp[2].as<int32_t>();
+  CU(slice_bits_launch(ctx->stream, p));
+  ctx->launches++;
+  CU(cudaMemcpyAsync(bits, p.bits, (size_t)ny * nx * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return VC2_OK;
+}
+
+// component_slice_bytes (Slices.cpp:97-119) for every slice of one quantised in-place plane
+extern "C" int vc2_hq_slice_sizes(vc2_ctx* ctx, const int32_t* q, int ph, int pw, int depth, int ny, int nx, int scalar,
+                                  int32_t* bytes) {
+  if (scalar < 1) return fail(ctx, VC2_ERR_ARG);
+  const int st = vc2_slice_bits(ctx, q, nullptr, ph, pw, depth, ny, nx, bytes);
+  if (st) return st;
+  for (int i = 0; i < ny * nx; ++i) {
+    const int scaled = ((bytes[i] + 7) / 8 + scalar - 1) / scalar;
+    if (scaled > 0xFF) return fail(ctx, VC2_ERR_SCALAR_TOO_SMALL);
+    bytes[i] = scaled * scalar;
+  }
+  return VC2_OK;
+}
+
+// quantise_transform(Array2D, qIndices, qMatrix) - the LD quantiser with DC prediction of the LL band
+// (Quantisation.cpp:213-282, 353-367)
+extern "C" int vc2_quantise_ld(vc2_ctx* ctx, const int32_t* coef, int ph, int pw, int depth, const int32_t* qmatrix,
+                               const int32_t* qidx, int ny, int nx, int32_t* out) {
+  return quant_host(ctx, coef, ph, pw, depth, qmatrix, qidx, ny, nx, out, 0, 1);
 }
 
 static int unpack_host(vc2_ctx* ctx, const uint8_t* in, size_t len, const vc2_geom* vg, const int32_t* slice_bytes, int ld,

@@ -870,13 +870,13 @@ __global__ void __launch_bounds__(128) ld_pack_kernel(const LdEncParams p) {
 #pragma unroll
       for (int e = 0; e < 4; ++e, ++k) {
         while (k == bend) { ++b; bend = g.band_start[c][b + 1]; bp = band_params(qi, g.qmatrix[b], badq); }
-        if (k >= nll) uq[e] = quant_band(u[e], bp);
+        if (k >= nll && !p.prequantised) uq[e] = quant_band(u[e], bp);
         uint32_t mag = (uint32_t)abs(uq[e]);
         if (mag >= (uint32_t)ENC_LUT_MAG) bigor |= mag + 1u;
         gross += lut_bits(s_enc, mag);
         if (mag) last = gross;
         if (cls) {
-          if (k >= nll) vq[e] = quant_band(v[e], bp);
+          if (k >= nll && !p.prequantised) vq[e] = quant_band(v[e], bp);
           mag = (uint32_t)abs(vq[e]);
           if (mag >= (uint32_t)ENC_LUT_MAG) bigor |= mag + 1u;
           gross += lut_bits(s_enc, mag);
@@ -892,7 +892,7 @@ __global__ void __launch_bounds__(128) ld_pack_kernel(const LdEncParams p) {
   const int split = ld_intlog2(8 * size - 7);
   const int uvbits = 8 * size - 7 - split - ybits;
   if (uvbits < uvbits_needed) flags |= VC2_FLAG_LD_TOO_MANY_BYTES;
-  if (badq) flags |= VC2_FLAG_QUANT_INDEX;
+  if (badq && !p.prequantised) flags |= VC2_FLAG_QUANT_INDEX;   // the writer alone never evaluates quant_factor
   if (bigor >> 16) flags |= VC2_FLAG_VLC_RANGE;
   if (flags & ~VC2_FLAG_VLC_RANGE) { p.err_flags[sidx] = flags; p.sizes[sidx] = 0; return; }
   // pass 2: qindex (7 bits) | luma length | luma, bounded to its exact length | U/V interleaved, bounded to the rest
@@ -1534,6 +1534,69 @@ __device__ __forceinline__ void ld_dc_body(LdDcParams p) {
 }
 
 __global__ void __launch_bounds__(1024) ld_dc_kernel(const LdDcParams p) { ld_dc_body(p); }
+// ------------------------------------------------------------------------------------------
+// Library surface: code-list bits of every slice of an in-place ordered quantised plane (one thread per slice;
+// the slice's bands in coding order, raster inside the slice's part of each band - split_into_subbands of the slice)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int signed_vlc_bits(int v) {   // SignedVLC(v).numOfBits(), VLC.cpp:21-52, 78-85
+  if (v == 0) return 1;
+  const uint32_t m = (uint32_t)abs(v) + 1u;
+  return 2 * (31 - __clz(m)) + 2;
+}
+__global__ void slice_bits_kernel(const SliceBitsParams p) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= p.slices_y * p.slices_x) return;
+  const int sh = p.ph / p.slices_y, sw = p.pw / p.slices_x;
+  const int y0 = (s / p.slices_x) * sh, x0 = (s % p.slices_x) * sw;
+  int gross = 0, count = 0;
+  for (int band = 0; band < 3 * p.depth + 1; ++band) {
+    const int level = band == 0 ? 0 : (band - 1) / 3 + 1;
+    const int stride = band == 0 ? (1 << p.depth) : (1 << (p.depth + 1 - level));
+    const int kind = band == 0 ? -1 : (band - 1) % 3;              // 0 HL, 1 LH, 2 HH
+    const int oy = (kind == 1 || kind == 2) ? stride / 2 : 0, ox = (kind == 0 || kind == 2) ? stride / 2 : 0;
+    for (int y = y0 + oy; y < y0 + sh; y += stride)
+      for (int x = x0 + ox; x < x0 + sw; x += stride) {
+        const long long i = (long long)y * p.pw + x;
+        int nb = signed_vlc_bits(p.q[i]);
+        gross += nb;
+        if (nb > 1) count = gross;
+        if (p.q2) {
+          nb = signed_vlc_bits(p.q2[i]);
+          gross += nb;
+          if (nb > 1) count = gross;
+        }
+      }
+  }
+  p.bits[s] = count;
+}
+
+// forward counterpart of ld_dc_kernel: anti-diagonal wavefront, the prediction comes from the locally decoded band
+__global__ void __launch_bounds__(1024) ld_dc_quant_kernel(const LdDcQuantParams p) {
+  const int H = p.H, Wd = p.W;
+  for (int diag = 0; diag < H + Wd - 1; ++diag) {
+    const int ylo = max(0, diag - (Wd - 1)), yhi = min(H - 1, diag);
+    for (int y = ylo + (int)threadIdx.x; y <= yhi; y += blockDim.x) {
+      const int x = diag - y;
+      const int yb = ((y + 1) * p.slices_y - 1) / H, xb = ((x + 1) * p.slices_x - 1) / Wd;
+      const int q = max(p.qidx[yb * p.slices_x + xb] - p.qm0, 0);
+      const QParam qp = qparam(q);
+      const int32_t* r = p.restored;
+      int pred;
+      if (y > 0 && x > 0) {
+        const int sum = r[(y - 1) * Wd + x - 1] + r[(y - 1) * Wd + x] + r[y * Wd + x - 1];
+        pred = sum >= 0 ? (sum + 1) / 3 : (sum - 1) / 3;
+      } else if (y > 0) pred = r[(y - 1) * Wd + x];
+      else if (x > 0) pred = r[y * Wd + x - 1];
+      else pred = 0;
+      const long long i = ((long long)y * p.pitch + x) << p.depth;
+      const int qv = quant_one(p.src[i] - pred, qp.qm, qp.ql);
+      p.dst[i] = qv;
+      p.restored[y * Wd + x] = scale_one(qv, qp.qf, qp.qo) + pred;
+    }
+    __syncthreads();
+  }
+}
+
 // one CTA per (picture, plane): the wavefronts of a batch run side by side
 __global__ void __launch_bounds__(1024) ld_dc_batch_kernel(const LdDcBatch b) {
   LdDcParams p = b.c[blockIdx.y];
@@ -1565,6 +1628,24 @@ cudaError_t ld_encode_launch(cudaStream_t s, const LdEncParams& p, int npictures
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   ld_pack_kernel<<<dim3((nslices + 127) / 128, npictures), 128, 0, s>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t ld_pack_launch(cudaStream_t s, const LdEncParams& p, int npictures) {
+  if (!p.prequantised) return cudaErrorInvalidValue;
+  const int nslices = p.g.slices_x * p.g.slices_y;
+  ld_pack_kernel<<<dim3((nslices + 127) / 128, npictures), 128, 0, s>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t slice_bits_launch(cudaStream_t s, const SliceBitsParams& p) {
+  const int n = p.slices_y * p.slices_x;
+  slice_bits_kernel<<<(n + 63) / 64, 64, 0, s>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t ld_dc_quant_launch(cudaStream_t s, const LdDcQuantParams& p) {
+  ld_dc_quant_kernel<<<1, 1024, 0, s>>>(p);
   return cudaGetLastError();
 }
 

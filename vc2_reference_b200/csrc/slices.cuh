@@ -139,8 +139,34 @@ struct LdEncParams {
   int wcap;
   uint32_t* sizes;              // [pic][slices] out
   uint32_t* err_flags;          // [pic][slices] out
+  int prequantised;             // 1 (ld_pack_launch): qcoef already holds every quantised coefficient, qidx is an input
 };
 cudaError_t ld_encode_launch(cudaStream_t s, const LdEncParams& p, int npictures);
+// the LD slice writer alone, on an already quantised block (operator<<(ostream&, Slices) in LD mode, Slices.cpp:195-244)
+cudaError_t ld_pack_launch(cudaStream_t s, const LdEncParams& p, int npictures);
+
+// bits of every slice's code list up to and including its last non-zero coefficient, on IN-PLACE ordered quantised planes
+// (luma_slice_bits / chroma_slice_bits / the count inside component_slice_bytes, Slices.cpp:51-119); q2 != NULL: the two
+// planes are walked interleaved, as the LD chroma list is
+struct SliceBitsParams {
+  const int32_t* q;
+  const int32_t* q2;
+  int ph, pw, depth, slices_y, slices_x;
+  int32_t* bits;                // [slices_y][slices_x] out
+};
+cudaError_t slice_bits_launch(cudaStream_t s, const SliceBitsParams& p);
+
+// forward LD LL-band quantiser with DC prediction (quantise_LLSubband, Quantisation.cpp:213-236) on an in-place plane
+struct LdDcQuantParams {
+  const int32_t* src;           // in-place plane of transform coefficients
+  int32_t* dst;                 // in-place plane: the LL positions receive the quantised prediction residuals
+  int32_t* restored;            // [H][W] scratch: the locally decoded LL band
+  const int32_t* qidx;          // [slices_y][slices_x]
+  int H, W;                     // LL band dims
+  long long pitch;              // padded plane width
+  int depth, slices_y, slices_x, qm0;
+};
+cudaError_t ld_dc_quant_launch(cudaStream_t s, const LdDcQuantParams& p);
 
 cudaError_t upload_quant_tables(const QuantTables& t);
 cudaError_t pack_launch(cudaStream_t s, const PackParams& p, int npictures);
