@@ -21,7 +21,12 @@
 #include <thread>
 #include <vector>
 
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
 #include "cmdline.h"
+#include "pipeline.h"
 #include "vc2/Codec.h"
 #include "vc2/DataUnit.h"
 #include "vc2/Quantisation.h"
@@ -111,43 +116,64 @@ class Decoder {
           std::vector<const uint8_t*> pay(cnt);
           std::vector<size_t> len(cnt);
           std::vector<void*> pics(cnt);
-          for (int i = 0; i < cnt; ++i) { pay[i] = pending_[first + i].data; len[i] = pending_[first + i].len; pics[i] = recon_[first + i].data(); }
+          for (int i = 0; i < cnt; ++i) { pay[i] = pending_[first + i].data; len[i] = pending_[first + i].len; pics[i] = recon_[cur_][first + i].data(); }
           codecs_[g]->decode(cnt, pay.data(), len.data(), pics.data());
         } catch (const std::exception& e) { errors[g] = e.what(); }
       });
     }
     for (auto& t : th) t.join();
     for (int g = 0; g < G_; ++g) if (!errors[g].empty()) throw std::logic_error(errors[g]);
+    // the pictures of this batch are written by a second thread while the next batch is parsed and decoded into the other
+    // set of buffers (the reference decodes and writes one picture at a time, DecodeStream.cpp:512-605)
+    finishWrite();
+    const int set = cur_;
+    const Config cfg = cfg_;
+    writer_ = std::thread([this, set, n, cfg]() {
+      try { writeSet(set, n, cfg); } catch (const std::exception& e) { writeError_ = e.what(); }
+    });
+    cur_ ^= 1;
+    pending_.clear();
+    owned_.clear();
+  }
+
+  // wait for the batch being written; called before its buffers are reused, on a geometry change and at the end
+  void finishWrite() {
+    if (writer_.joinable()) writer_.join();
+    if (!writeError_.empty()) { const std::string e = writeError_; writeError_.clear(); throw std::runtime_error(e); }
+  }
+  ~Decoder() { if (writer_.joinable()) writer_.join(); }
+
+  long frames() { finishWrite(); return frames_; }
+
+ private:
+  void writeSet(int set, int n, const Config& cfg) {
+    const size_t bytes = recon_[set][0].size();
     for (int i = 0; i < n; ++i) {
-      if (cfg_.interlace) {
+      const uint8_t* pic = recon_[set][i].data();
+      if (cfg.interlace) {
         // DecodeStream.cpp:566-583: the first picture of a pair is the first field, the second completes the frame
-        if (field_.empty()) { field_ = recon_[i]; continue; }
-        weave(field_, recon_[i]);
+        if (field_.empty()) { field_.assign(pic, pic + bytes); continue; }
+        weave(cfg, field_.data(), pic, bytes);
         field_.clear();
         out_.write(reinterpret_cast<const char*>(frame_.data()), (std::streamsize)frame_.size());
       } else {
-        out_.write(reinterpret_cast<const char*>(recon_[i].data()), (std::streamsize)recon_[i].size());
+        out_.write(reinterpret_cast<const char*>(pic), (std::streamsize)bytes);
       }
       if (verbose_) clog << "Decoded frame number " << frames_ << endl;
       ++frames_;
     }
     if (!out_) throw std::runtime_error("Failed to write output file");
-    pending_.clear();
-    owned_.clear();
   }
 
-  long frames() const { return frames_; }
-
- private:
   // two field pictures -> the rows of one frame (Frame::firstField / secondField, Frame.cpp:40-110)
-  void weave(const std::vector<uint8_t>& first, const std::vector<uint8_t>& second) {
-    const PictureFormat ff(cfg_.height, cfg_.width, cfg_.cf);
-    const int bytes = cfg_.bits == 8 ? 1 : 2;
+  void weave(const Config& cfg, const uint8_t* first, const uint8_t* second, size_t fieldBytes) {
+    const PictureFormat ff(cfg.height, cfg.width, cfg.cf);
+    const int bytes = cfg.bits == 8 ? 1 : 2;
     const int h[3] = {ff.lumaHeight(), ff.chromaHeight(), ff.chromaHeight()};
     const size_t w[3] = {(size_t)ff.lumaWidth() * bytes, (size_t)ff.chromaWidth() * bytes, (size_t)ff.chromaWidth() * bytes};
-    frame_.resize(first.size() + second.size());
-    const uint8_t* top = cfg_.tff ? first.data() : second.data();
-    const uint8_t* bot = cfg_.tff ? second.data() : first.data();
+    frame_.resize(2 * fieldBytes);
+    const uint8_t* top = cfg.tff ? first : second;
+    const uint8_t* bot = cfg.tff ? second : first;
     uint8_t* dst = frame_.data();
     for (int c = 0; c < 3; ++c)
       for (int y = 0; y < h[c]; ++y) {
@@ -157,6 +183,7 @@ class Decoder {
   }
 
   void open(const Config& c) {
+    finishWrite();   // the writer thread still reads the old geometry's buffers
     if (!cfg_.same(c)) field_.clear();
     cfg_ = c;
     codecs_.clear();
@@ -185,7 +212,10 @@ class Decoder {
       const int G = std::min(G_, std::max(1, vc2_device_count()));
       G_ = G;
       for (int g = 0; g < G; ++g) codecs_.emplace_back(new Codec(g, cp));
-      recon_.assign((size_t)G * B_, std::vector<uint8_t>(codecs_[0]->pictureBytes()));
+      for (int set = 0; set < 2; ++set) {
+        recon_[set].clear();
+        for (int i = 0; i < G * B_; ++i) recon_[set].emplace_back(codecs_[0]->pictureBytes());
+      }
     }
   }
 
@@ -224,7 +254,10 @@ class Decoder {
   Config cfg_;
   vc2_geom geom_;
   std::vector<std::unique_ptr<Codec>> codecs_;
-  std::vector<std::vector<uint8_t>> recon_;
+  std::vector<vc2cli::HostBuf> recon_[2];   // two sets of decoded pictures: one is written out while the other is decoded into
+  int cur_ = 0;
+  std::thread writer_;
+  std::string writeError_;
   std::vector<PictureUnit> pending_;
   std::deque<std::vector<uint8_t>> owned_;
   std::vector<uint8_t> field_, frame_;   // interlaced output: the first field waiting for its partner, the woven frame
@@ -269,12 +302,24 @@ int main(int argc, char** argv) {
       std::cerr << "Error: " << e.what() << endl;
       return EXIT_FAILURE;
     }
+    // the whole stream in memory, read in large pieces
     std::vector<uint8_t> stream;
-    if (inName == "-") stream.assign(std::istreambuf_iterator<char>(std::cin), std::istreambuf_iterator<char>());
-    else {
-      std::ifstream f(inName.c_str(), std::ios::in | std::ios::binary);
-      if (!f) { perror(("Failed to open input file \"" + inName + "\"").c_str()); return EXIT_FAILURE; }
-      stream.assign(std::istreambuf_iterator<char>(f), std::istreambuf_iterator<char>());
+    {
+      int fd = 0;
+      if (inName != "-") {
+        fd = ::open(inName.c_str(), O_RDONLY);
+        if (fd < 0) { perror(("Failed to open input file \"" + inName + "\"").c_str()); return EXIT_FAILURE; }
+        struct stat st;
+        if (fstat(fd, &st) == 0 && S_ISREG(st.st_mode)) stream.reserve((size_t)st.st_size + 64);
+      }
+      const size_t piece = 16u << 20;
+      for (size_t have = 0;;) {
+        if (stream.size() < have + piece) stream.resize(have + piece);
+        const ssize_t r = ::read(fd, stream.data() + have, piece);
+        if (r <= 0) { stream.resize(have); break; }
+        have += (size_t)r;
+      }
+      if (fd > 0) ::close(fd);
     }
     stream.resize(stream.size() + 64, 0);   // slack behind the last payload for the parser's word reads
     const size_t streamLen = stream.size() - 64;
@@ -388,6 +433,7 @@ int main(int argc, char** argv) {
       }
     }
     dec.flush();
+    dec.finishWrite();
     out->flush();
     clog << "End of data stream reached successfully, exiting." << endl;
   } catch (const std::exception& ex) {   // DecodeStream.cpp:985-988

@@ -8,6 +8,7 @@
 // -o PSNR (EncodeStream.cpp:676-767) reports, per frame, the mean / standard deviation of the slice quantiser indices
 // and the PSNR of the local decode, with the reference's float arithmetic.
 // LD mode (-m LD; quantIndicesLD EncodeStream.cpp:139-245, LD slice and data unit syntax) runs on the same codec.
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <cmath>
@@ -22,7 +23,12 @@
 #include <thread>
 #include <vector>
 
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
 #include "cmdline.h"
+#include "pipeline.h"
 #include "vc2/Codec.h"
 #include "vc2/DataUnit.h"
 #include "vc2/Quantisation.h"
@@ -170,9 +176,61 @@ void merge_fields(uint8_t* frame, const uint8_t* first, const uint8_t* second, c
 
 struct Worker {
   std::unique_ptr<Codec> codec;
-  std::vector<std::vector<uint8_t>> payload;   // per slot
-  std::vector<size_t> len;
   std::string error;
+};
+
+// One round of the pipeline: up to G batches of B pictures.  A round is filled by the reader, encoded by one host thread
+// per GPU and written out in picture order; with three rounds in flight the three stages overlap (the reference reads,
+// codes and writes one frame at a time, EncodeStream.cpp:452-770).
+struct Round {
+  std::vector<std::vector<vc2cli::HostBuf>> frames;    // [G][B] raw planar pictures
+  std::vector<std::vector<vc2cli::HostBuf>> payload;   // [G][B] coded slices
+  std::vector<std::vector<size_t>> len;                // [G][B]
+  std::vector<int> count;                              // [G] pictures in each batch
+  bool last = false;                                   // the input ended in (or before) this round
+  bool noFrame0 = false;                               // not even the first frame could be read
+};
+
+// input frames: a regular file is read with pread() by several threads, anything else (a pipe, standard input) in order
+class FrameSource {
+ public:
+  FrameSource(const std::string& name, size_t frameBytes) : fd_(0), frameBytes_(frameBytes), total_(-1), next_(0) {
+    if (name != "-") {
+      fd_ = ::open(name.c_str(), O_RDONLY);
+      if (fd_ < 0) return;
+      struct stat st;
+      if (fstat(fd_, &st) == 0 && S_ISREG(st.st_mode)) total_ = (long long)(st.st_size / (off_t)frameBytes);
+    }
+  }
+  ~FrameSource() { if (fd_ > 0) ::close(fd_); }
+  bool ok() const { return fd_ >= 0; }
+  bool seekable() const { return total_ >= 0; }
+  // frames still to come, when known
+  long long remaining() const { return total_ - next_; }
+  // claim the next n frame numbers (seekable input)
+  long long claim(int n) { const long long f = next_; next_ += n; return f; }
+  bool readAt(long long frame, uint8_t* dst) const {
+    size_t got = 0;
+    while (got < frameBytes_) {
+      const ssize_t r = ::pread(fd_, dst + got, frameBytes_ - got, (off_t)(frame * (long long)frameBytes_ + (long long)got));
+      if (r <= 0) return false;
+      got += (size_t)r;
+    }
+    return true;
+  }
+  bool readNext(uint8_t* dst) {
+    size_t got = 0;
+    while (got < frameBytes_) {
+      const ssize_t r = ::read(fd_, dst + got, frameBytes_ - got);
+      if (r <= 0) return false;
+      got += (size_t)r;
+    }
+    return true;
+  }
+ private:
+  int fd_;
+  size_t frameBytes_;
+  long long total_, next_;
 };
 
 }  // namespace
@@ -189,12 +247,10 @@ int main(int argc, char** argv) {
       std::cerr << "Error: " << e.what() << endl;
       return EXIT_FAILURE;
     }
-    std::ifstream inF;
-    std::istream* in = &std::cin;
     if (p.inFile != "-") {
-      inF.open(p.inFile.c_str(), std::ios::in | std::ios::binary);
-      if (!inF) { perror(("Failed to open input file \"" + p.inFile + "\"").c_str()); return EXIT_FAILURE; }
-      in = &inF;
+      const int probe = ::open(p.inFile.c_str(), O_RDONLY);
+      if (probe < 0) { perror(("Failed to open input file \"" + p.inFile + "\"").c_str()); return EXIT_FAILURE; }
+      ::close(probe);
     }
     std::ofstream outF;
     std::ostream* out = &std::cout;
@@ -246,11 +302,7 @@ int main(int argc, char** argv) {
     const int B = p.interlaced ? (p.batch + 1) / 2 * 2 : p.batch;   // both fields of a frame in one batch
     cp.max_pictures = B;
     std::vector<Worker> workers(G);
-    for (int g = 0; g < G; ++g) {
-      workers[g].codec.reset(new Codec(g, cp));
-      workers[g].payload.assign(B, std::vector<uint8_t>(workers[g].codec->payloadCapacity()));
-      workers[g].len.assign(B, 0);
-    }
+    for (int g = 0; g < G; ++g) workers[g].codec.reset(new Codec(g, cp));
     const size_t picBytes = workers[0].codec->pictureBytes();
     const size_t cap = workers[0].codec->payloadCapacity();
 
@@ -275,64 +327,142 @@ int main(int argc, char** argv) {
       for (int i = 0; i < ySlices * xSlices; ++i) sliceOff[i + 1] = sliceOff[i] + (uint32_t)(sb.data()[i] + (ld ? 0 : p.prefix));
     }
 
-    // one round = up to G batches of B pictures; frames[g][i] is picture number frame0 + g*B + i
-    std::vector<std::vector<std::vector<uint8_t>>> frames(G, std::vector<std::vector<uint8_t>>(B, std::vector<uint8_t>(picBytes)));
+    // one round = up to G batches of B pictures; frames[g][i] is picture number frame0 + g*B + i.
+    // -o Stream / Packaged: three rounds in flight - the reader fills one while the GPUs code the second and this thread
+    // writes the third.  The other outputs read codec slots back after the encode, so they keep to one round.
+    const bool pipelined = p.output == STREAM || p.output == PACKAGED;
+    const int NR = pipelined ? 3 : 1;
+    std::vector<Round> rounds(NR);
+    for (Round& r : rounds) {
+      r.frames.resize(G); r.payload.resize(G); r.len.assign(G, std::vector<size_t>(B, 0)); r.count.assign(G, 0);
+      for (int g = 0; g < G; ++g)
+        for (int i = 0; i < B; ++i) { r.frames[g].emplace_back(picBytes); r.payload[g].emplace_back(cap); }
+    }
     std::vector<std::vector<uint8_t>> recon;
     if (p.output == DECODED || p.output == PSNR) recon.assign(B, std::vector<uint8_t>(picBytes));
     std::vector<uint8_t> frameBuf(p.interlaced ? 2 * picBytes : 0);
-    unsigned long long frame = 0, psnrFrame = 0;
-    bool eof = false;
-    while (!eof) {
-      std::vector<int> count(G, 0);
-      for (int g = 0; g < G && !eof; ++g)
-        for (int i = 0; i < B; i += framePics) {
-          uint8_t* dst = p.interlaced ? frameBuf.data() : frames[g][i].data();
-          in->read(reinterpret_cast<char*>(dst), (std::streamsize)(picBytes * framePics));
-          if ((size_t)in->gcount() != picBytes * framePics) {
-            if (frame == 0 && g == 0 && i == 0) { std::cerr << "\rFailed to read input frame number 0" << endl; return EXIT_FAILURE; }
-            eof = true;
-            break;
-          }
-          if (p.interlaced) split_fields(frameBuf.data(), frames[g][i].data(), frames[g][i + 1].data(), format, p.bytes, p.topFieldFirst);
-          count[g] += framePics;
+    FrameSource source(p.inFile, picBytes * framePics);
+    vc2cli::Channel<int> freeQ, readQ, codedQ;
+    for (int r = 0; r < NR; ++r) freeQ.push(r);
+    std::atomic<bool> stop(false);
+
+    // stage 1: read
+    std::thread reader([&]() {
+      bool eof = false, first = true;
+      std::vector<uint8_t> fieldsIn(p.interlaced ? 2 * picBytes : 0);
+      while (!eof) {
+        const int ri = freeQ.pop();
+        Round& r = rounds[ri];
+        std::fill(r.count.begin(), r.count.end(), 0);
+        r.last = false; r.noFrame0 = false;
+        if (stop) { r.last = true; readQ.push(ri); return; }
+        const int framesPerBatch = B / framePics;
+        if (source.seekable()) {
+          // frame f of this round goes to batch f / framesPerBatch; the reads are independent: several threads
+          const long long want = (long long)G * framesPerBatch, have = std::min(want, std::max(0LL, source.remaining()));
+          const long long f0 = source.claim((int)have);
+          if (have < want) eof = true;
+          const int T = (int)std::min<long long>(have, 4);
+          std::vector<std::thread> th;
+          std::vector<char> bad(T > 0 ? T : 1, 0);
+          for (int t = 0; t < T; ++t)
+            th.emplace_back([&, t]() {
+              std::vector<uint8_t> both(p.interlaced ? 2 * picBytes : 0);
+              for (long long f = t; f < have; f += T) {
+                const int g = (int)(f / framesPerBatch), i = (int)(f % framesPerBatch) * framePics;
+                uint8_t* dst = p.interlaced ? both.data() : r.frames[g][i].data();
+                if (!source.readAt(f0 + f, dst)) { bad[t] = 1; return; }
+                if (p.interlaced) split_fields(both.data(), r.frames[g][i].data(), r.frames[g][i + 1].data(), format, p.bytes, p.topFieldFirst);
+              }
+            });
+          for (auto& t : th) t.join();
+          for (int t = 0; t < T; ++t) if (bad[t]) eof = true;   // a file that shrank under us: stop after this round
+          for (long long f = 0; f < have; ++f) r.count[(int)(f / framesPerBatch)] += framePics;
+          if (first && have == 0) r.noFrame0 = true;
+        } else {
+          for (int g = 0; g < G && !eof; ++g)
+            for (int i = 0; i < B; i += framePics) {
+              uint8_t* dst = p.interlaced ? fieldsIn.data() : r.frames[g][i].data();
+              if (!source.readNext(dst)) {
+                if (first && g == 0 && i == 0) r.noFrame0 = true;
+                eof = true;
+                break;
+              }
+              if (p.interlaced) split_fields(fieldsIn.data(), r.frames[g][i].data(), r.frames[g][i + 1].data(), format, p.bytes, p.topFieldFirst);
+              r.count[g] += framePics;
+            }
         }
-      // encode: one host thread per GPU
-      std::vector<std::thread> th;
-      for (int g = 0; g < G; ++g) {
-        if (!count[g]) continue;
-        th.emplace_back([&, g]() {
-          Worker& w = workers[g];
-          try {
-            std::vector<const void*> pics(count[g]);
-            std::vector<uint8_t*> pay(count[g]);
-            for (int i = 0; i < count[g]; ++i) { pics[i] = frames[g][i].data(); pay[i] = w.payload[i].data(); }
-            w.codec->encode(count[g], pics.data(), pay.data(), cap, w.len.data());
-          } catch (const std::exception& e) { w.error = e.what(); }
-        });
+        first = false;
+        r.last = eof;
+        readQ.push(ri);
       }
-      for (auto& t : th) t.join();
+    });
+
+    // stage 2: encode, one host thread per GPU
+    std::thread coder([&]() {
+      for (;;) {
+        const int ri = readQ.pop();
+        Round& r = rounds[ri];
+        std::vector<std::thread> th;
+        for (int g = 0; g < G; ++g) {
+          if (!r.count[g] || r.noFrame0) continue;
+          th.emplace_back([&, g]() {
+            Worker& w = workers[g];
+            try {
+              std::vector<const void*> pics(r.count[g]);
+              std::vector<uint8_t*> pay(r.count[g]);
+              for (int i = 0; i < r.count[g]; ++i) { pics[i] = r.frames[g][i].data(); pay[i] = r.payload[g][i].data(); }
+              w.codec->encode(r.count[g], pics.data(), pay.data(), cap, r.len[g].data());
+            } catch (const std::exception& e) { w.error = e.what(); }
+          });
+        }
+        for (auto& t : th) t.join();
+        const bool last = r.last;
+        codedQ.push(ri);
+        if (last) break;
+      }
+    });
+    // every way out of the loop below ends the two threads first: a stopped reader hands on an empty last round
+    auto shutdown = [&]() {
+      stop = true;
+      for (int r = 0; r < NR; ++r) freeQ.push(r);
+      if (reader.joinable()) reader.join();
+      if (coder.joinable()) coder.join();
+    };
+
+    // stage 3 (this thread): ordered reassembly and output
+    unsigned long long frame = 0, psnrFrame = 0;
+    std::string failure;
+    try {
+    for (bool done = false; !done;) {
+      const int ri = codedQ.pop();
+      Round& r = rounds[ri];
+      done = r.last;
+      if (r.noFrame0) { failure = "\rFailed to read input frame number 0"; break; }
+      std::vector<int>& count = r.count;
+      std::vector<std::vector<vc2cli::HostBuf>>& frames = r.frames;
       // ordered reassembly
       for (int g = 0; g < G; ++g) {
         Worker& w = workers[g];
         if (!count[g]) continue;
         if (!w.error.empty()) throw std::logic_error(w.error);
         for (int i = 0; i < count[g]; ++i, ++frame) {
-          if (p.verbose) clog << "Encoded frame number " << frame << " (" << w.len[i] << " bytes)" << endl;
+          if (p.verbose) clog << "Encoded frame number " << frame << " (" << r.len[g][i] << " bytes)" << endl;
           if (p.output == STREAM) {
             unit.clear();
             // picture number = field + frame * fields per frame, wrapping at 2^32 (Utils.cpp:52-63)
             if (p.fragment > 0) {
-              if (w.len[i] != sliceOff.back()) throw std::logic_error("fragment writer: payload length does not match the slice table");
-              if (ld) writer.ldFragmentedPicture(unit, (unsigned long)(frame & 0xFFFFFFFFull), pre, w.payload[i].data(), sliceOff.data(), p.fragment);
-              else writer.hqFragmentedPicture(unit, (unsigned long)(frame & 0xFFFFFFFFull), pre, w.payload[i].data(), sliceOff.data(), p.fragment);
+              if (r.len[g][i] != sliceOff.back()) throw std::logic_error("fragment writer: payload length does not match the slice table");
+              if (ld) writer.ldFragmentedPicture(unit, (unsigned long)(frame & 0xFFFFFFFFull), pre, r.payload[g][i].data(), sliceOff.data(), p.fragment);
+              else writer.hqFragmentedPicture(unit, (unsigned long)(frame & 0xFFFFFFFFull), pre, r.payload[g][i].data(), sliceOff.data(), p.fragment);
             } else if (ld) {
-              writer.ldPicture(unit, (unsigned long)(frame & 0xFFFFFFFFull), pre, w.payload[i].data(), w.len[i]);
+              writer.ldPicture(unit, (unsigned long)(frame & 0xFFFFFFFFull), pre, r.payload[g][i].data(), r.len[g][i]);
             } else {
-              writer.hqPicture(unit, (unsigned long)(frame & 0xFFFFFFFFull), pre, w.payload[i].data(), w.len[i]);
+              writer.hqPicture(unit, (unsigned long)(frame & 0xFFFFFFFFull), pre, r.payload[g][i].data(), r.len[g][i]);
             }
             out->write(unit.data(), (std::streamsize)unit.size());
           } else if (p.output == PACKAGED) {
-            out->write(reinterpret_cast<const char*>(w.payload[i].data()), (std::streamsize)w.len[i]);
+            out->write(reinterpret_cast<const char*>(r.payload[g][i].data()), (std::streamsize)r.len[g][i]);
           } else if (taps) {
             // the slots still hold this batch: read the requested intermediate back (EncodeStream -o Transform / Quantised / Indices)
             const size_t ny = (size_t)cp.geom.slices_y * cp.geom.slices_x;
@@ -355,8 +485,8 @@ int main(int argc, char** argv) {
         if (p.output == PSNR) {   // EncodeStream.cpp:676-767
           std::vector<const uint8_t*> pay(count[g]);
           std::vector<void*> pics(count[g]);
-          for (int i = 0; i < count[g]; ++i) { pay[i] = w.payload[i].data(); pics[i] = recon[i].data(); }
-          w.codec->decode(count[g], pay.data(), w.len.data(), pics.data());
+          for (int i = 0; i < count[g]; ++i) { pay[i] = r.payload[g][i].data(); pics[i] = recon[i].data(); }
+          w.codec->decode(count[g], pay.data(), r.len[g].data(), pics.data());
           const size_t ns = (size_t)cp.geom.slices_y * cp.geom.slices_x;
           std::vector<int32_t> q(ns);
           const size_t nY = (size_t)format.lumaHeight() * format.lumaWidth(), nC = (size_t)format.chromaHeight() * format.chromaWidth();
@@ -406,8 +536,8 @@ int main(int argc, char** argv) {
         if (p.output == DECODED) {   // local decode of the batch just written (EncodeStream.cpp:649-690)
           std::vector<const uint8_t*> pay(count[g]);
           std::vector<void*> pics(count[g]);
-          for (int i = 0; i < count[g]; ++i) { pay[i] = w.payload[i].data(); pics[i] = recon[i].data(); }
-          w.codec->decode(count[g], pay.data(), w.len.data(), pics.data());
+          for (int i = 0; i < count[g]; ++i) { pay[i] = r.payload[g][i].data(); pics[i] = recon[i].data(); }
+          w.codec->decode(count[g], pay.data(), r.len[g].data(), pics.data());
           for (int i = 0; i < count[g]; i += framePics) {
             if (p.interlaced) {
               merge_fields(frameBuf.data(), recon[i].data(), recon[i + 1].data(), format, p.bytes, p.topFieldFirst);
@@ -417,9 +547,14 @@ int main(int argc, char** argv) {
             }
           }
         }
-        if (!*out) { std::cerr << "Failed to write output file \"" << p.outFile << "\"" << endl; return EXIT_FAILURE; }
+        if (!*out) { failure = "Failed to write output file \"" + p.outFile + "\""; break; }
       }
+      if (!failure.empty()) break;
+      if (!done) freeQ.push(ri);   // the round's buffers go back to the reader
     }
+    } catch (...) { shutdown(); throw; }
+    shutdown();
+    if (!failure.empty()) { std::cerr << failure << endl; return EXIT_FAILURE; }
     if (p.verbose) clog << "\rEnd of input reached after " << frame << " frames" << endl;
     if (p.output == STREAM) {
       unit.clear();

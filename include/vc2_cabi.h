@@ -101,6 +101,14 @@ const char* vc2_last_error(vc2_ctx* ctx);           /* reference exception text 
 const char* vc2_status_message(int status);         /* same text, by status code                */
 int vc2_device_count(void);
 int vc2_kernel_launches(vc2_ctx* ctx, int reset);   /* kernels launched through this context    */
+/* page-locked (pinned, portable across devices) host memory for the buffers of the *_host entry points; NULL when it
+ * cannot be had (the caller may then use ordinary memory: same results, slower copies) */
+void* vc2_host_alloc(size_t bytes);
+/* pin the calling thread (and threads it starts afterwards) to the CPUs local to a GPU (sysfs local_cpulist of its PCI
+ * device): host buffers allocated and filled afterwards sit on the GPU's NUMA node.  VC2_ERR_ARG when the topology is
+ * not readable; nothing is changed then */
+int vc2_bind_thread_to_device(int device);
+void vc2_host_free(void* p);
 
 /* per-kernel timing for the roofline report: CUDA events recorded on the launch stream around every
  * kernel launched through this context (no reference counterpart; measurement only) */

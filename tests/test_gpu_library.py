@@ -254,7 +254,7 @@ def test_ld_quantise_and_pack_vs_reference(ctx, ref, depth, kernel, cf):
         same(a, b, "quantise_transform " + n)
     same(ctx.inverse_quantise_transform(want_q[0], qidx, qm), ref.dequantise_ld(want_q[0], qidx, qm), "inverse")
     n = g.slices_y * g.slices_x
-    sb = vc2.slice_bytes(g.slices_y, g.slices_x, 260 * n + 7, 1)
+    sb = vc2.slice_bytes(g.slices_y, g.slices_x, 2 * sum(p.size for p in planes) + 7, 1)   # ample: two bytes per coefficient
     want = ref.pack_slices(want_q[0], want_q[1], want_q[2], depth, qidx, 2, 0, 1, sb)
     got = ctx.ld_pack(want_q[0], want_q[1], want_q[2], g, qidx, sb)
     assert got == want

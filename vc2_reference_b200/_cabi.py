@@ -68,6 +68,9 @@ def _load():
         "vc2_quantise_ld": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, C.c_int, C.c_int, vp]),
         "vc2_slice_bits": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
         "vc2_hq_slice_sizes": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
+        "vc2_host_alloc": (vp, [C.c_size_t]),
+        "vc2_bind_thread_to_device": (C.c_int, [C.c_int]),
+        "vc2_host_free": (None, [vp]),
         "vc2_codec_create": (vp, [vp, C.POINTER(CodecParams)]),
         "vc2_codec_destroy": (None, [vp]),
         "vc2_codec_picture_in_bytes": (C.c_size_t, [vp]),

@@ -15,6 +15,9 @@
 #include <vector>
 
 #include "dwt.cuh"
+#include <sched.h>
+#include <cctype>
+#include <cstdio>
 #include "slices.cuh"
 
 namespace vc2 {
@@ -186,6 +189,54 @@ extern "C" const char* vc2_status_message(int st) {
     case VC2_ERR_LD_TOO_MANY_BYTES: return "SliceIO, LD mode: Too many bytes for the U and V slices";
     default: return "unknown error";
   }
+}
+
+// Run the calling thread (and the threads it starts later) on the CPUs next to a GPU, so that the host buffers it then
+// allocates and fills are on the GPU's NUMA node: on a multi-socket box copies from the far node share the inter-socket
+// link with every other rank.  Linux sysfs; VC2_ERR_ARG when the topology cannot be read (nothing is changed then).
+extern "C" int vc2_bind_thread_to_device(int device) {
+  char bus[32] = {0};
+  if (cudaDeviceGetPCIBusId(bus, (int)sizeof(bus), device) != cudaSuccess) { cudaGetLastError(); return VC2_ERR_CUDA; }
+  for (char* c = bus; *c; ++c) *c = (char)tolower(*c);
+  char path[128];
+  snprintf(path, sizeof(path), "/sys/bus/pci/devices/%s/local_cpulist", bus);
+  FILE* f = fopen(path, "r");
+  if (!f) return VC2_ERR_ARG;
+  char list[4096] = {0};
+  const bool got = fgets(list, (int)sizeof(list), f) != nullptr;
+  fclose(f);
+  if (!got) return VC2_ERR_ARG;
+  cpu_set_t set;
+  CPU_ZERO(&set);
+  int n = 0;
+  for (char* tok = strtok(list, ",\n"); tok; tok = strtok(nullptr, ",\n")) {   // "0-31,64-95"
+    int a = 0, b = 0;
+    const int k = sscanf(tok, "%d-%d", &a, &b);
+    if (k < 1) continue;
+    if (k == 1) b = a;
+    for (int c = a; c <= b && c < CPU_SETSIZE; ++c) { CPU_SET(c, &set); ++n; }
+  }
+  if (n == 0) return VC2_ERR_ARG;
+  // keep to the CPUs this process is allowed on (containers, taskset)
+  cpu_set_t allowed;
+  if (sched_getaffinity(0, sizeof(allowed), &allowed) == 0) {
+    cpu_set_t both;
+    CPU_AND(&both, &set, &allowed);
+    if (CPU_COUNT(&both) == 0) return VC2_ERR_ARG;
+    set = both;
+  }
+  return sched_setaffinity(0, sizeof(set), &set) == 0 ? VC2_OK : VC2_ERR_ARG;
+}
+
+// page-locked host memory for the picture / payload buffers handed to vc2_codec_encode_host / _decode_host: copies from
+// and to such buffers run at the full PCIe rate and overlap the kernels (pageable buffers are staged by the driver)
+extern "C" void* vc2_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  return p;
+}
+extern "C" void vc2_host_free(void* p) {
+  if (p) cudaFreeHost(p);
 }
 
 extern "C" int vc2_device_count(void) {
