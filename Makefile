@@ -16,14 +16,19 @@ HOSTLIB   := $(PKG)/libvc2host.so
 BIN       := $(PKG)/bin
 CXXFLAGS  := -O2 -std=c++14 -fPIC -Wall -Wno-comment -Iinclude -Ihost
 
-all: $(LIB) $(ORACLE) $(HOSTLIB) $(BIN)/EncodeStream $(BIN)/DecodeStream $(BIN)/DecodeFrame
+all: $(LIB) $(ORACLE) $(HOSTLIB) $(BIN)/EncodeStream $(BIN)/DecodeStream $(BIN)/DecodeFrame $(BIN)/test_library_mirror
 
 # C++ host layer: the Library mirror (include/vc2/*.h) and the drop-in command lines, over the C-ABI
 $(HOSTLIB): host/vc2_library.cpp host/vc2_stream.cpp include/vc2/*.h include/vc2_cabi.h include/vc2_host.h $(LIB)
 	$(CXX) $(CXXFLAGS) -shared host/vc2_library.cpp host/vc2_stream.cpp -o $@ -L$(PKG) -lvc2b200 -Wl,-rpath,'$$ORIGIN'
-$(BIN)/%: host/%.cpp host/cmdline.h include/vc2/*.h include/vc2_cabi.h $(HOSTLIB)
+$(BIN)/%: host/%.cpp host/cmdline.h host/pipeline.h include/vc2/*.h include/vc2_cabi.h $(HOSTLIB)
 	mkdir -p $(BIN)
 	$(CXX) $(CXXFLAGS) $< -o $@ -L$(PKG) -lvc2host -lvc2b200 -lpthread -Wl,-rpath,'$$ORIGIN/..'
+
+# C++ parity test of the Library mirror against the compiled reference (tests/test_gpu_library.py runs it on the GPU box)
+$(BIN)/test_library_mirror: tests/cpp/test_library_mirror.cpp include/vc2/*.h $(HOSTLIB)
+	mkdir -p $(BIN)
+	$(CXX) $(CXXFLAGS) $< -o $@ -L$(PKG) -lvc2host -lvc2b200 -ldl -Wl,-rpath,'$$ORIGIN/..'
 
 $(ORACLE): oracle/vc2_oracle.c
 	mkdir -p oracle/_build

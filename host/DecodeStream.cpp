@@ -112,6 +112,7 @@ class Decoder {
       const int first = g * B_, cnt = std::min(B_, n - first);
       if (cnt <= 0) break;
       th.emplace_back([&, g, first, cnt]() {
+        if (G_ > 1) vc2_bind_thread_to_device(g);
         try {
           std::vector<const uint8_t*> pay(cnt);
           std::vector<size_t> len(cnt);

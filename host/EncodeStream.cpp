@@ -48,6 +48,7 @@ struct Params {
   std::string inFile, outFile;
   bool verbose = false;
   int height = 0, width = 0, bytes = 2, lumaDepth = 0, chromaDepth = 0;
+  int cbytes = 2;   // bytes per sample the codec is fed with: -n 3 / 4 words are narrowed to their two leading bytes by the reader
   ColourFormat cf = CF_UNSET;
   bool interlaced = false, topFieldFirst = true;
   WaveletKernel kernel = NullKernel;
@@ -135,7 +136,10 @@ Params parse(int argc, char** argv) {
   if (p.mode == HQ_ConstQ && (p.qIndex < 0 || p.qIndex > 119)) throw std::invalid_argument("quantisation index must be in the range 0 to 119");
   if (p.frameRate < 0 || p.frameRate > 16) throw std::invalid_argument("Invalid Frame Rate: ");
   // scope of this build
-  if (p.bytes > 2) throw std::invalid_argument("this build reads 1 or 2 bytes per sample");
+  // -n 3 / 4 (Arrays.cpp:333-379 reads 1..4 byte words): the samples are MSB justified, so for depths up to 16 bits the two
+  // leading bytes of a word carry the whole sample and the codec reads those
+  if (p.bytes > 2 && std::max(p.lumaDepth, p.chromaDepth) > 16) throw std::invalid_argument("this build codes at most 16 bits per sample");
+  p.cbytes = std::min(p.bytes, 2);
   if (p.gpus < 1) p.gpus = 1;
   if (p.batch < 1) p.batch = 1;
   return p;
@@ -294,7 +298,7 @@ int main(int argc, char** argv) {
     if (vc2_make_geom(format.lumaHeight(), p.width, (int)p.cf, (int)p.kernel, p.depth, p.ySize, p.xSize, ld ? 0 : p.prefix, ld ? 1 : p.scalar,
                       &cp.geom) != VC2_OK)
       throw std::logic_error("The given waveletDepth, hSlice, and vSlice parameters cannot encode this input. See above for suggested parameters.");
-    cp.fmt.bytes_per_sample = p.bytes; cp.fmt.luma_depth = p.lumaDepth; cp.fmt.chroma_depth = p.chromaDepth;
+    cp.fmt.bytes_per_sample = p.cbytes; cp.fmt.luma_depth = p.lumaDepth; cp.fmt.chroma_depth = p.chromaDepth;
     cp.mode = ld ? VC2_LD : p.mode == HQ_CBR ? VC2_HQ_CBR : VC2_HQ_VBR;
     cp.qindex = p.qIndex; cp.picture_bytes = pictureBytes;
     const bool taps = p.output == TRANSFORM || p.output == QUANTISED || p.output == INDICES;
@@ -333,15 +337,34 @@ int main(int argc, char** argv) {
     const bool pipelined = p.output == STREAM || p.output == PACKAGED;
     const int NR = pipelined ? 3 : 1;
     std::vector<Round> rounds(NR);
-    for (Round& r : rounds) {
-      r.frames.resize(G); r.payload.resize(G); r.len.assign(G, std::vector<size_t>(B, 0)); r.count.assign(G, 0);
+    for (Round& r : rounds) { r.frames.resize(G); r.payload.resize(G); r.len.assign(G, std::vector<size_t>(B, 0)); r.count.assign(G, 0); }
+    {
+      // the buffers of GPU g are allocated by a thread that runs next to it (first touch decides the NUMA node)
+      std::vector<std::thread> th;
       for (int g = 0; g < G; ++g)
-        for (int i = 0; i < B; ++i) { r.frames[g].emplace_back(picBytes); r.payload[g].emplace_back(cap); }
+        th.emplace_back([&, g]() {
+          if (G > 1) vc2_bind_thread_to_device(g);
+          for (Round& r : rounds)
+            for (int i = 0; i < B; ++i) { r.frames[g].emplace_back(picBytes); r.payload[g].emplace_back(cap); }
+        });
+      for (auto& t : th) t.join();
     }
     std::vector<std::vector<uint8_t>> recon;
     if (p.output == DECODED || p.output == PSNR) recon.assign(B, std::vector<uint8_t>(picBytes));
-    std::vector<uint8_t> frameBuf(p.interlaced ? 2 * picBytes : 0);
-    FrameSource source(p.inFile, picBytes * framePics);
+    std::vector<uint8_t> frameBuf(p.interlaced ? 2 * picBytes : 0), wideOut;
+    // file words of 3 / 4 bytes: a frame is read whole and narrowed to the codec's 2-byte words
+    const int wide = p.bytes > 2 ? p.bytes : 0;
+    const size_t fileFrameBytes = wide ? picBytes / 2 * (size_t)wide * framePics : picBytes * framePics;
+    auto narrow = [wide](const uint8_t* src, uint8_t* dst, size_t samples) {
+      for (size_t i = 0; i < samples; ++i) { dst[2 * i] = src[(size_t)wide * i]; dst[2 * i + 1] = src[(size_t)wide * i + 1]; }
+    };
+    auto widen = [wide](const uint8_t* src, uint8_t* dst, size_t samples) {   // -o Decoded: back to the file's word width
+      for (size_t i = 0; i < samples; ++i) {
+        dst[(size_t)wide * i] = src[2 * i]; dst[(size_t)wide * i + 1] = src[2 * i + 1];
+        for (int k = 2; k < wide; ++k) dst[(size_t)wide * i + k] = 0;
+      }
+    };
+    FrameSource source(p.inFile, fileFrameBytes);
     vc2cli::Channel<int> freeQ, readQ, codedQ;
     for (int r = 0; r < NR; ++r) freeQ.push(r);
     std::atomic<bool> stop(false);
@@ -349,7 +372,7 @@ int main(int argc, char** argv) {
     // stage 1: read
     std::thread reader([&]() {
       bool eof = false, first = true;
-      std::vector<uint8_t> fieldsIn(p.interlaced ? 2 * picBytes : 0);
+      std::vector<uint8_t> fieldsIn(p.interlaced ? 2 * picBytes : 0), fileIn(wide ? fileFrameBytes : 0);
       while (!eof) {
         const int ri = freeQ.pop();
         Round& r = rounds[ri];
@@ -367,12 +390,13 @@ int main(int argc, char** argv) {
           std::vector<char> bad(T > 0 ? T : 1, 0);
           for (int t = 0; t < T; ++t)
             th.emplace_back([&, t]() {
-              std::vector<uint8_t> both(p.interlaced ? 2 * picBytes : 0);
+              std::vector<uint8_t> both(p.interlaced ? 2 * picBytes : 0), file(wide ? fileFrameBytes : 0);
               for (long long f = t; f < have; f += T) {
                 const int g = (int)(f / framesPerBatch), i = (int)(f % framesPerBatch) * framePics;
                 uint8_t* dst = p.interlaced ? both.data() : r.frames[g][i].data();
-                if (!source.readAt(f0 + f, dst)) { bad[t] = 1; return; }
-                if (p.interlaced) split_fields(both.data(), r.frames[g][i].data(), r.frames[g][i + 1].data(), format, p.bytes, p.topFieldFirst);
+                if (!source.readAt(f0 + f, wide ? file.data() : dst)) { bad[t] = 1; return; }
+                if (wide) narrow(file.data(), dst, picBytes / 2 * framePics);
+                if (p.interlaced) split_fields(both.data(), r.frames[g][i].data(), r.frames[g][i + 1].data(), format, p.cbytes, p.topFieldFirst);
               }
             });
           for (auto& t : th) t.join();
@@ -383,12 +407,14 @@ int main(int argc, char** argv) {
           for (int g = 0; g < G && !eof; ++g)
             for (int i = 0; i < B; i += framePics) {
               uint8_t* dst = p.interlaced ? fieldsIn.data() : r.frames[g][i].data();
-              if (!source.readNext(dst)) {
+              const bool got = source.readNext(wide ? fileIn.data() : dst);
+              if (got && wide) narrow(fileIn.data(), dst, picBytes / 2 * framePics);
+              if (!got) {
                 if (first && g == 0 && i == 0) r.noFrame0 = true;
                 eof = true;
                 break;
               }
-              if (p.interlaced) split_fields(fieldsIn.data(), r.frames[g][i].data(), r.frames[g][i + 1].data(), format, p.bytes, p.topFieldFirst);
+              if (p.interlaced) split_fields(fieldsIn.data(), r.frames[g][i].data(), r.frames[g][i + 1].data(), format, p.cbytes, p.topFieldFirst);
               r.count[g] += framePics;
             }
         }
@@ -408,6 +434,7 @@ int main(int argc, char** argv) {
           if (!r.count[g] || r.noFrame0) continue;
           th.emplace_back([&, g]() {
             Worker& w = workers[g];
+            if (G > 1) vc2_bind_thread_to_device(g);
             try {
               std::vector<const void*> pics(r.count[g]);
               std::vector<uint8_t*> pay(r.count[g]);
@@ -502,10 +529,10 @@ int main(int argc, char** argv) {
               size_t off = 0;
               for (int c = 0; c < 3; ++c) {
                 const size_t n = c == 0 ? nY : nC;
-                const int shift = 8 * p.bytes - (c == 0 ? p.lumaDepth : p.chromaDepth);
-                for (size_t j = 0; j < n; ++j, off += p.bytes) {
-                  const int va = p.bytes == 2 ? ((a[off] << 8 | a[off + 1]) >> shift) : (a[off] >> shift);
-                  const int vb = p.bytes == 2 ? ((b[off] << 8 | b[off + 1]) >> shift) : (b[off] >> shift);
+                const int shift = 8 * p.cbytes - (c == 0 ? p.lumaDepth : p.chromaDepth);
+                for (size_t j = 0; j < n; ++j, off += p.cbytes) {
+                  const int va = p.cbytes == 2 ? ((a[off] << 8 | a[off + 1]) >> shift) : (a[off] >> shift);
+                  const int vb = p.cbytes == 2 ? ((b[off] << 8 | b[off + 1]) >> shift) : (b[off] >> shift);
                   const int d = va - vb;
                   ss[c] += d * d;
                 }
@@ -539,12 +566,18 @@ int main(int argc, char** argv) {
           for (int i = 0; i < count[g]; ++i) { pay[i] = r.payload[g][i].data(); pics[i] = recon[i].data(); }
           w.codec->decode(count[g], pay.data(), r.len[g].data(), pics.data());
           for (int i = 0; i < count[g]; i += framePics) {
+            const uint8_t* pic = recon[i].data();
+            size_t n = picBytes;
             if (p.interlaced) {
-              merge_fields(frameBuf.data(), recon[i].data(), recon[i + 1].data(), format, p.bytes, p.topFieldFirst);
-              out->write(reinterpret_cast<const char*>(frameBuf.data()), (std::streamsize)frameBuf.size());
-            } else {
-              out->write(reinterpret_cast<const char*>(recon[i].data()), (std::streamsize)picBytes);
+              merge_fields(frameBuf.data(), recon[i].data(), recon[i + 1].data(), format, p.cbytes, p.topFieldFirst);
+              pic = frameBuf.data(); n = frameBuf.size();
             }
+            if (wide) {
+              wideOut.resize(n / 2 * (size_t)wide);
+              widen(pic, wideOut.data(), n / 2);
+              pic = wideOut.data(); n = wideOut.size();
+            }
+            out->write(reinterpret_cast<const char*>(pic), (std::streamsize)n);
           }
         }
         if (!*out) { failure = "Failed to write output file \"" + p.outFile + "\""; break; }

@@ -10,7 +10,7 @@
 set -euo pipefail
 HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
 REF="${VC2_REFERENCE_ROOT:-/root/reference}"
-OUT="$HERE/_ref"
+OUT="${VC2_REF_OUT:-$HERE/_ref}"
 OPT="${VC2_REF_OPT:--O2}"
 if [ ! -d "$REF/src/Library" ]; then
   echo "build_ref.sh: $REF not present (GPU box?) - keeping prebuilt oracle/_ref" >&2

@@ -101,6 +101,21 @@ CASES += [
     case("D5_Haar0_d5_422_pad", 640, 330, "422", 8, 2, "HQ_ConstQ", "Haar0", 5, 1, 2, q=5, S=16, seed=602),
 ]
 
+# sample words of 3 and 4 bytes in the input file (-n, Arrays.cpp:333-379): same pictures, wider words
+CASES += [
+    case("N4_LeGall_d2_422", 176, 96, "422", 10, 2, "HQ_ConstQ", "LeGall", 2, 1, 2, q=7, seed=700, nbytes=4),
+    case("N3_Haar1_d2_444_12b", 128, 64, "444", 12, 2, "HQ_CBR", "Haar1", 2, 2, 2, s=9000, seed=701, nbytes=3),
+]
+
+
+def widen(raw, nbytes):
+    """16-bit big-endian MSB-justified words -> nbytes-wide ones (the sample stays MSB justified)"""
+    import numpy as np
+    a = np.frombuffer(raw, np.uint8).reshape(-1, 2)
+    out = np.zeros((a.shape[0], nbytes), np.uint8)
+    out[:, :2] = a
+    return out.tobytes()
+
 
 def md5_file(path):
     h = hashlib.md5()
@@ -124,6 +139,8 @@ def enc_args(c):
         a += ["-s", str(c["s"])]
     if c["mode"] != "LD":
         a += ["-S", str(c["S"]), "-P", str(c["P"])]
+    if c.get("nbytes"):
+        a += ["-n", str(c["nbytes"])]
     return a + list(c.get("extra", []))
 
 
@@ -133,7 +150,8 @@ def run_case(c):
         src = os.path.join(td, "in.yuv")
         with open(src, "wb") as fo:
             for f in range(c["frames"]):
-                fo.write(gen.frame_bytes(c["seed"], f, c["w"], c["h"], c["fmt"], c["bits"], c["smooth"]))
+                raw = gen.frame_bytes(c["seed"], f, c["w"], c["h"], c["fmt"], c["bits"], c["smooth"])
+                fo.write(widen(raw, c["nbytes"]) if c.get("nbytes") else raw)
         out["taps"]["input"] = md5_file(src)
         taps = ["Transform", "Quantised", "Packaged", "Stream"]
         if c["mode"] != "HQ_ConstQ":

@@ -25,6 +25,8 @@ def enc_args(c):
     a += ["-q", str(c["q"])] if c["mode"] == "HQ_ConstQ" else ["-s", str(c["s"])]
     if c["mode"] != "LD":
         a += ["-S", str(c["S"]), "-P", str(c["P"])]
+    if c.get("nbytes"):
+        a += ["-n", str(c["nbytes"])]
     return a + list(c.get("extra", []))
 
 
@@ -32,10 +34,20 @@ def md5(path):
     return hashlib.md5(open(path, "rb").read()).hexdigest()
 
 
+def widen(raw, nbytes):
+    """16-bit big-endian MSB-justified words -> nbytes-wide ones (-n 3 / 4 input files)"""
+    import numpy as np
+    a = np.frombuffer(raw, np.uint8).reshape(-1, 2)
+    out = np.zeros((a.shape[0], nbytes), np.uint8)
+    out[:, :2] = a
+    return out.tobytes()
+
+
 def write_input(c, path):
     with open(path, "wb") as f:
         for i in range(c["frames"]):
-            f.write(gen.frame_bytes(c["seed"], i, c["w"], c["h"], c["fmt"], c["bits"], c["smooth"]))
+            raw = gen.frame_bytes(c["seed"], i, c["w"], c["h"], c["fmt"], c["bits"], c["smooth"])
+            f.write(widen(raw, c["nbytes"]) if c.get("nbytes") else raw)
 
 
 def run(cmd):
@@ -48,6 +60,8 @@ def run(cmd):
                                   "B00_DD97_d2_420", "B06_Daub97_d3_444", "C1", "C2",
                                   # wavelet depths 5 and 6 (quantMatrix is computed for any depth, WaveletTransform.cpp:345-423)
                                   "D5_DD97_d5_422", "D6_LeGall_d6_444",
+                                  # input words of 4 and 3 bytes (-n, Arrays.cpp:333-379)
+                                  "N4_LeGall_d2_422", "N3_Haar1_d2_444_12b",
                                   # interlaced coding (two field pictures per frame) and fragmented pictures
                                   "I00_LeGall_d3_422_tff", "I01_DD137_d2_420_bff", "I02_Haar1_d3_444_tff",
                                   "F00_DD97_d3_422", "F01_LeGall_d2_420_small", "F02_Fidelity_d2_422_il",
@@ -60,7 +74,7 @@ def test_command_lines_vs_golden(tmp_path, name):
     src = str(tmp_path / "in.yuv")
     write_input(c, src)
     # a batch smaller than the clip and (when there are several GPUs) two devices: chunking and reassembly
-    extra = ["-B", "1", "-G", "2"] if name[0] in "SID" else ["-B", "3"] if name[0] in "FL" else []
+    extra = ["-B", "1", "-G", "2"] if name[0] in "SIDN" else ["-B", "3"] if name[0] in "FL" else []
     small = not name.startswith("C")       # the 1080p configs: stream and pictures only (each run pays a CUDA start-up)
     for tap in ["Stream"] + (["Packaged", "Transform", "Quantised"] if small else []) + (["Indices"] if c["mode"] != "HQ_ConstQ" else []):
         dst = str(tmp_path / ("enc_" + tap))
@@ -83,7 +97,10 @@ def test_command_lines_vs_golden(tmp_path, name):
         return
     dst = str(tmp_path / "enc_Decoded")
     run([os.path.join(BIN, "EncodeStream")] + enc_args(c) + ["-o", "Decoded", src, dst])
-    if c["bits"] != 8:     # the stand-alone decoder writes 8-bit streams as one byte per sample, the encoder keeps -n
+    if c.get("nbytes"):    # the encoder's local decode keeps the input's word width: the decoder's 2-byte words, widened
+        dec = open(str(tmp_path / "dec_Decoded"), "rb").read()
+        assert open(dst, "rb").read() == widen(dec, c["nbytes"])
+    elif c["bits"] != 8:   # the stand-alone decoder writes 8-bit streams as one byte per sample, the encoder keeps -n
         assert md5(dst) == taps["dec_Decoded"]["md5"]
 
 

@@ -241,7 +241,7 @@ def test_component_slice_bytes_scalar_too_small(ctx, ref):
 @pytest.mark.parametrize("depth,kernel,cf", [(3, "LeGall", "422"), (2, "DD97", "420"), (4, "Haar1", "444")])
 def test_ld_quantise_and_pack_vs_reference(ctx, ref, depth, kernel, cf):
     """vc2_quantise_ld (quantise_transform with DC prediction) and vc2_ld_pack (the LD slice writer) against the reference"""
-    g = vc2.make_geom(96, 192, cf, kernel, depth, 1, 2 if cf != "444" else 1)
+    g = vc2.make_geom(96, 192, cf, kernel, depth, 2 if cf == "420" else 1, 2 if cf != "444" else 1)
     (ph, pw), (ch, cw) = vc2.api.padded_dims(g)
     qm = vc2.quant_matrix(kernel, depth)
     planes = [rnd((ph, pw), -300, 300, 21), rnd((ch, cw), -300, 300, 22), rnd((ch, cw), -300, 300, 23)]
@@ -265,3 +265,16 @@ def test_ld_quantise_and_pack_vs_reference(ctx, ref, depth, kernel, cf):
     with pytest.raises(vc2.Vc2Error) as e:
         ctx.ld_pack(want_q[0], want_q[1], want_q[2], g, qidx, tight)
     assert "Too many bytes" in str(e_ref.value) and "Too many bytes" in str(e.value)
+
+
+def test_cpp_library_mirror_vs_reference(ref):
+    """every function of the C++ Library mirror (include/vc2/*.h) against the compiled reference, for all seven kernels:
+    the test program is C++ (tests/cpp/test_library_mirror.cpp), its output lists each comparison"""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "vc2_reference_b200", "bin", "test_library_mirror")
+    r = subprocess.run([exe, ref.PATH], stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+    out = r.stdout.decode()
+    assert r.returncode == 0, out[-3000:]
+    assert out.count(" same") >= 7 * 18 and "DIFFERENT" not in out

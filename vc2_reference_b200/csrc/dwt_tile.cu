@@ -145,6 +145,20 @@ __device__ __forceinline__ int scale1_smag(unsigned t, const uint2 fo) {
 __device__ __forceinline__ int4 scale4_smag(const uint2 w, const uint2 fo) {
   return make_int4(scale1_smag(w.x & 0xFFFFu, fo), scale1_smag(w.x >> 16, fo), scale1_smag(w.y & 0xFFFFu, fo), scale1_smag(w.y >> 16, fo));
 }
+// The same through a table in shared memory, for pictures with one index (HQ_ConstQ streams): lut[t] = scale1_smag(t, fo) for
+// the VC2_SCALE_LUT smallest sign-magnitude words of a band - two ALU instructions and a shared-memory load per coefficient
+// instead of ten ALU instructions.  MEASURED SLOWER and therefore off (VC2_SCALE_LUT = 0): level 0 inverse 1.079 ms per 32 C3
+// pictures without, 1.336 with 128 entries, 1.419 with 512 (bit exact all three; profiles/r2_v4_scale_lut_ab.txt) - the
+// data-dependent shared-memory loads and the branch around the fallback cost more than the arithmetic they replace.
+#ifndef VC2_SCALE_LUT
+#define VC2_SCALE_LUT 0
+#endif
+__device__ __forceinline__ int4 scale4_lut(const uint2 w, const int* __restrict__ lut, const uint2 fo) {
+  if (VC2_SCALE_LUT == 0) return scale4_smag(w, fo);
+  if (((w.x | w.y) & ~(unsigned)(((VC2_SCALE_LUT - 1) << 16) | (VC2_SCALE_LUT - 1))) == 0u)
+    return make_int4(lut[w.x & 0xFFFFu], lut[w.x >> 16], lut[w.y & 0xFFFFu], lut[w.y >> 16]);
+  return scale4_smag(w, fo);
+}
 __device__ __forceinline__ uint2 scale_params(const DwtParams& p, const DwtComp& C, int pic, int slice, int b) {
   const int q = min(max(__ldg(p.qidx + (long long)pic * p.nslices + slice) - C.qmat[b], 0), 127);
   return __ldg(p.scale_tab + q);
@@ -469,6 +483,18 @@ __global__ void __launch_bounds__(32 * T::NW, T::MINB) dwt_tile_inv_kernel(const
   const int bxmax = C.lat_w / 2 - 1;
   const BandAddr ba = {C.bh, C.bw, C.lgbh, C.lgbw, C.nx, C.NC >> 2};
   int32_t* coef = C.coef + (long long)S.pic * C.coef_pic_stride;
+  // narrow block of a picture with one index: the scale() of the small words of the four bands as a table behind the tile
+  int* const slut = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(mid) + T::SMEM);
+  bool use_lut = false;
+  if (p.narrow) {
+    const BandScale* bs = p.band_scale + S.pic;
+    use_lut = VC2_SCALE_LUT > 0 && __ldg(&bs->diff) == 0u;
+    if (use_lut) {
+      for (int i = threadIdx.x; i < 4 * VC2_SCALE_LUT; i += 32 * T::NW)
+        slut[i] = scale1_smag((unsigned)(i % (VC2_SCALE_LUT > 0 ? VC2_SCALE_LUT : 1)), __ldg(&bs->fo[C.band[i / (VC2_SCALE_LUT > 0 ? VC2_SCALE_LUT : 1)]]));
+      __syncthreads();
+    }
+  }
 
 #pragma unroll 1
   for (int tx = S.tx; tx < S.tx_end; ++tx) {
@@ -524,12 +550,14 @@ __global__ void __launch_bounds__(32 * T::NW, T::MINB) dwt_tile_inv_kernel(const
             for (int i = 0; i < NB; ++i) {
               const int m = g + (i0 + i) * T::NG, y = S.ys + 2 * m;
               if (!fast || y < 0 || y >= C.lat_h) continue;
-              uint2 f0 = fu[0], f1 = fu[1], f2 = fu[2], f3 = fu[3];
-              if (!uni) {
-                const int sl = F.slice(y >> 1);
-                f0 = scale_params(p, C, S.pic, sl, 0); f1 = scale_params(p, C, S.pic, sl, 1);
-                f2 = scale_params(p, C, S.pic, sl, 2); f3 = scale_params(p, C, S.pic, sl, 3);
+              if (uni) {
+                put(m, F.plane_ll ? l4[i] : scale4_lut(w[i][0], slut, fu[0]), scale4_lut(w[i][1], slut + VC2_SCALE_LUT, fu[1]),
+                    scale4_lut(w[i][2], slut + 2 * VC2_SCALE_LUT, fu[2]), scale4_lut(w[i][3], slut + 3 * VC2_SCALE_LUT, fu[3]));
+                continue;
               }
+              const int sl = F.slice(y >> 1);
+              const uint2 f0 = scale_params(p, C, S.pic, sl, 0), f1 = scale_params(p, C, S.pic, sl, 1);
+              const uint2 f2 = scale_params(p, C, S.pic, sl, 2), f3 = scale_params(p, C, S.pic, sl, 3);
               put(m, F.plane_ll ? l4[i] : scale4_smag(w[i][0], f0), scale4_smag(w[i][1], f1), scale4_smag(w[i][2], f2), scale4_smag(w[i][3], f3));
             }
           }
@@ -658,19 +686,27 @@ cudaError_t launch_tile(cudaStream_t s, const DwtParams& p, int npictures) {
 #else
   auto kern = dwt_tile_inv_kernel<K, KIND, T>;
 #endif
+#if VC2_DWT_PART == 1
+  const int smem_bytes = T::SMEM;
+#else
+  const int smem_bytes = T::SMEM + 4 * VC2_SCALE_LUT * (int)sizeof(int);   // + the scale() table of the narrow path
+#endif
   static bool configured[16] = {};   // per device
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 0 || dev >= 16 || !configured[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     if (e != cudaSuccess) return e;
+#ifdef VC2_TILE_CARVEOUT
+    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, VC2_TILE_CARVEOUT);
+#endif
     if (dev >= 0 && dev < 16) configured[dev] = true;
   }
   if (gy > 65535 || (long long)npictures * p.ncomp > 65535) return cudaErrorInvalidValue;
 #if VC2_DWT_PART == 1
-  kern<<<dim3((unsigned)gx, (unsigned)gy, (unsigned)(npictures * p.ncomp)), 32 * T::NW, T::SMEM, s>>>(p, tl, maps, use_tma);
+  kern<<<dim3((unsigned)gx, (unsigned)gy, (unsigned)(npictures * p.ncomp)), 32 * T::NW, smem_bytes, s>>>(p, tl, maps, use_tma);
 #else
-  kern<<<dim3((unsigned)gx, (unsigned)gy, (unsigned)(npictures * p.ncomp)), 32 * T::NW, T::SMEM, s>>>(p, tl);
+  kern<<<dim3((unsigned)gx, (unsigned)gy, (unsigned)(npictures * p.ncomp)), 32 * T::NW, smem_bytes, s>>>(p, tl);
 #endif
   return cudaGetLastError();
 }
