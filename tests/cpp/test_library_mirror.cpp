@@ -63,7 +63,7 @@ int main(int argc, char** argv) {
   const i4_f ref_valid = sym<i4_f>("ref_slice_size_is_valid");
   const i2_f ref_padded = sym<i2_f>("ref_padded_size");
 
-  const int H = 70, W = 150, depth = 3, prefix = 1, scalar = 2;   // needs padding: 72 x 152
+  const int H = 70, W = 300, depth = 3, prefix = 1, scalar = 2;   // needs padding: 72 x 304 (chroma 72 x 152)
   const WaveletKernel kernels[] = {DD97, LeGall, DD137, Haar0, Haar1, Fidelity, Daub97};
   try {
     const PictureFormat f(H, W, CF422);
@@ -148,8 +148,8 @@ int main(int argc, char** argv) {
       ref_qld(ry.data(), ph, pw, qc.data(), ny, nx, rqm.data(), (int)rqm.size(), ly.data());
       ref_qld(ru.data(), ch, cw, qc.data(), ny, nx, rqm.data(), (int)rqm.size(), lu.data());
       ref_qld(rv.data(), ch, cw, qc.data(), ny, nx, rqm.data(), (int)rqm.size(), lv.data());
-      const Array2D ldsb = slice_bytes(ny, nx, 2 * (ph * pw + 2 * ch * cw), 1);
-      ref_sb(ny, nx, 2 * (ph * pw + 2 * ch * cw), 1, lsb.data());
+      const Array2D ldsb = slice_bytes(ny, nx, 5 * (ph * pw + 2 * ch * cw), 1);   // ample: five bytes per coefficient
+      ref_sb(ny, nx, 5 * (ph * pw + 2 * ch * cw), 1, lsb.data());
       if (ref_pack(ly.data(), lu.data(), lv.data(), ph, pw, ch, cw, depth, qc.data(), ny, nx, 2, 0, 1, lsb.data(), rbuf.data(), (long)rbuf.size(), &rlen) == 0) {
         const Slices ld = readSlicesLD(rbuf.data(), (size_t)rlen, tf, k, depth, ny, nx, ldsb);
         ref_unpack(rbuf.data(), rlen, ph, pw, ch, cw, depth, ny, nx, 2, 0, 1, lsb.data(), by.data(), bu.data(), bv.data(), bq.data());

@@ -297,18 +297,10 @@ struct CountOp {      // component_slice_bytes' bit count of quantise(v) (rate-c
   const uint32_t* lut;
   int bits, last;
   unsigned bigor;
-  __device__ __forceinline__ void operator()(int v, const BandP& bp) {
-    const uint32_t mag = quant_mag(v, bp);
-    if (mag < (uint32_t)ENC_LUT_MAG) bits += (int)(lut[2u * mag] & 31u);
-    else {
-      const uint32_t m = mag + 1u;
-      bigor |= m;
-      bits += 2 * (31 - __clz(min(m, 65535u))) + 2;
-    }
-    if (mag) last = bits;
-  }
+  const uint8_t* blut;   // SignedVLC(v).numOfBits() for |v| < ENC_LUT_MAG as bytes (shared memory): the probes only need the length
+  __device__ __forceinline__ void operator()(int v, const BandP& bp) { count(quant_mag(v, bp)); }
   __device__ __forceinline__ void count(uint32_t mag) {
-    if (mag < (uint32_t)ENC_LUT_MAG) bits += (int)(lut[2u * mag] & 31u);
+    if (mag < (uint32_t)ENC_LUT_MAG) bits += (int)blut[mag];
     else {
       const uint32_t m = mag + 1u;
       bigor |= m;
@@ -316,13 +308,22 @@ struct CountOp {      // component_slice_bytes' bit count of quantise(v) (rate-c
     }
     if (mag) last = bits;
   }
-  // the probes of the rate control quantise every coefficient seven times: small coefficients (nearly all of them) take
-  // the full-rate multiply instead of the multiply-high
+  // The probes of the rate control quantise every coefficient seven times.  Nearly all pairs take the first branch: both
+  // coefficients small enough for the full-rate multiply (instead of the multiply-high) and both codes in the table - one test
+  // for the pair, then straight-line code: multiply, shift, byte look-up, add, and the move that remembers the last non-zero.
   __device__ __forceinline__ void pair(int v0, int v1, const BandP& bp) {
     const uint32_t a0 = (uint32_t)abs(v0), a1 = (uint32_t)abs(v1);
     if (bp.mul16 != 0u && (a0 | a1) < (uint32_t)VC2_NARROW_FAST_MAX) {
-      count((a0 * bp.mul16) >> bp.sh16);
-      count((a1 * bp.mul16) >> bp.sh16);
+      const uint32_t m0 = (a0 * bp.mul16) >> bp.sh16, m1 = (a1 * bp.mul16) >> bp.sh16;
+      if ((m0 | m1) < (uint32_t)ENC_LUT_MAG) {
+        bits += (int)blut[m0];
+        last = m0 ? bits : last;
+        bits += (int)blut[m1];
+        last = m1 ? bits : last;
+      } else {
+        count(m0);
+        count(m1);
+      }
     } else {
       (*this)(v0, bp);
       (*this)(v1, bp);
@@ -384,7 +385,9 @@ __device__ __forceinline__ int scaled_bytes(int count, int scalar, bool& too_big
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) hq_pack_kernel(const PackParams p) {
   __shared__ uint32_t s_enc[2 * ENC_LUT_MAG];
+  __shared__ uint8_t s_bits[ENC_LUT_MAG];   // code lengths alone, for the rate-control probes
   stage_table(s_enc, d_enc_lut, 2 * ENC_LUT_MAG);
+  for (int i = threadIdx.x; i < ENC_LUT_MAG; i += blockDim.x) s_bits[i] = (uint8_t)(d_enc_lut[2 * i] & 31u);
   __syncthreads();
   const SliceGeom& g = p.g;
   const int nslices = g.slices_x * g.slices_y;
@@ -409,7 +412,7 @@ __global__ void __launch_bounds__(128) hq_pack_kernel(const PackParams p) {
       int need = 0;
       bool too_big = false, badq = false;
       for (int c = 0; c < 3; ++c) {
-        CountOp op = {s_enc, 0, 0, 0u};
+        CountOp op = {s_enc, 0, 0, 0u, s_bits};
         walk_component(base, src + (size_t)(g.comp_start[c] >> 2) * 32, g, c, trialQ, badq, op);
         need += scaled_bytes(op.last, g.scalar, too_big);
       }
