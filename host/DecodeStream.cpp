@@ -21,6 +21,7 @@
 #include <thread>
 #include <vector>
 
+#include <chrono>
 #include <fcntl.h>
 #include <sys/stat.h>
 #include <unistd.h>
@@ -47,6 +48,9 @@ static int ld_picture_bytes(const PicturePreamble& pre) {
   if (pre.slices_y < 1 || pre.slices_x < 1) throw std::logic_error("Stream Error: slice counts must be positive");
   return (int)((long long)pre.slice_bytes.numerator * pre.slices_y * pre.slices_x / pre.slice_bytes.denominator);
 }
+
+// VC2_CLI_TIMING=1: where the wall-clock time of a run goes (standard error; measurement only)
+static double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 struct PictureUnit {
   const uint8_t* data;
@@ -106,6 +110,7 @@ class Decoder {
     if (pending_.empty()) return;
     if (output_ != DECODED) { taps(); pending_.clear(); owned_.clear(); return; }
     const int n = (int)pending_.size();
+    const double t0 = now_s();
     std::vector<std::string> errors(G_);
     std::vector<std::thread> th;
     for (int g = 0; g < G_; ++g) {
@@ -123,6 +128,7 @@ class Decoder {
       });
     }
     for (auto& t : th) t.join();
+    t_decode_ += now_s() - t0;
     for (int g = 0; g < G_; ++g) if (!errors[g].empty()) throw std::logic_error(errors[g]);
     // the pictures of this batch are written by a second thread while the next batch is parsed and decoded into the other
     // set of buffers (the reference decodes and writes one picture at a time, DecodeStream.cpp:512-605)
@@ -145,9 +151,12 @@ class Decoder {
   ~Decoder() { if (writer_.joinable()) writer_.join(); }
 
   long frames() { finishWrite(); return frames_; }
+  double decodeSeconds() const { return t_decode_; }
+  double writeSeconds() const { return t_write_; }
 
  private:
   void writeSet(int set, int n, const Config& cfg) {
+    const double t0 = now_s();
     const size_t bytes = recon_[set][0].size();
     for (int i = 0; i < n; ++i) {
       const uint8_t* pic = recon_[set][i].data();
@@ -164,6 +173,7 @@ class Decoder {
       ++frames_;
     }
     if (!out_) throw std::runtime_error("Failed to write output file");
+    t_write_ += now_s() - t0;
   }
 
   // two field pictures -> the rows of one frame (Frame::firstField / secondField, Frame.cpp:40-110)
@@ -212,11 +222,24 @@ class Decoder {
     if (output_ == DECODED) {
       const int G = std::min(G_, std::max(1, vc2_device_count()));
       G_ = G;
-      for (int g = 0; g < G; ++g) codecs_.emplace_back(new Codec(g, cp));
-      for (int set = 0; set < 2; ++set) {
-        recon_[set].clear();
-        for (int i = 0; i < G * B_; ++i) recon_[set].emplace_back(codecs_[0]->pictureBytes());
-      }
+      // one thread per GPU: a CUDA context, the codec's device buffers and the pinned pictures of its batches (allocated next
+      // to the GPU, vc2_bind_thread_to_device) take most of a second per device
+      codecs_.resize(G);
+      for (int set = 0; set < 2; ++set) { recon_[set].clear(); recon_[set].resize((size_t)G * B_); }
+      std::vector<std::thread> th;
+      std::vector<std::string> err(G);
+      for (int g = 0; g < G; ++g)
+        th.emplace_back([&, g]() {
+          try {
+            if (G > 1) vc2_bind_thread_to_device(g);
+            codecs_[g].reset(new Codec(g, cp));
+            for (int set = 0; set < 2; ++set)
+              for (int i = 0; i < B_; ++i) recon_[set][(size_t)g * B_ + i].resize(codecs_[g]->pictureBytes());
+          } catch (const std::exception& e) { err[g] = e.what(); }
+        });
+      for (auto& t : th) t.join();
+      for (int g = 0; g < G; ++g)
+        if (!err[g].empty()) throw std::invalid_argument(err[g]);
     }
   }
 
@@ -257,6 +280,7 @@ class Decoder {
   std::vector<std::unique_ptr<Codec>> codecs_;
   std::vector<vc2cli::HostBuf> recon_[2];   // two sets of decoded pictures: one is written out while the other is decoded into
   int cur_ = 0;
+  double t_decode_ = 0, t_write_ = 0;
   std::thread writer_;
   std::string writeError_;
   std::vector<PictureUnit> pending_;
@@ -303,6 +327,8 @@ int main(int argc, char** argv) {
       std::cerr << "Error: " << e.what() << endl;
       return EXIT_FAILURE;
     }
+    const bool timing = getenv("VC2_CLI_TIMING") != nullptr;
+    const double t_start = now_s();
     // the whole stream in memory, read in large pieces
     std::vector<uint8_t> stream;
     {
@@ -322,6 +348,7 @@ int main(int argc, char** argv) {
       }
       if (fd > 0) ::close(fd);
     }
+    const double t_loaded = now_s();
     stream.resize(stream.size() + 64, 0);   // slack behind the last payload for the parser's word reads
     const size_t streamLen = stream.size() - 64;
     std::ofstream outF;
@@ -436,6 +463,9 @@ int main(int argc, char** argv) {
     dec.flush();
     dec.finishWrite();
     out->flush();
+    if (timing)
+      std::cerr << "timing: stream read " << t_loaded - t_start << " s, parse + decode + write " << now_s() - t_loaded << " s for " << dec.frames()
+                << " frames (busy: decode calls " << dec.decodeSeconds() << ", writer " << dec.writeSeconds() << ")" << std::endl;
     clog << "End of data stream reached successfully, exiting." << endl;
   } catch (const std::exception& ex) {   // DecodeStream.cpp:985-988
     std::cout << "Error: " << ex.what() << endl;

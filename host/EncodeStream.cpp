@@ -9,6 +9,7 @@
 // and the PSNR of the local decode, with the reference's float arithmetic.
 // LD mode (-m LD; quantIndicesLD EncodeStream.cpp:139-245, LD slice and data unit syntax) runs on the same codec.
 #include <atomic>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cmath>
@@ -178,6 +179,9 @@ void merge_fields(uint8_t* frame, const uint8_t* first, const uint8_t* second, c
     }
 }
 
+// VC2_CLI_TIMING=1: where the wall-clock time of a run goes (standard error; measurement only)
+double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
 struct Worker {
   std::unique_ptr<Codec> codec;
   std::string error;
@@ -305,8 +309,23 @@ int main(int argc, char** argv) {
     const int G = taps ? 1 : std::min(p.gpus, std::max(1, vc2_device_count()));
     const int B = p.interlaced ? (p.batch + 1) / 2 * 2 : p.batch;   // both fields of a frame in one batch
     cp.max_pictures = B;
+    const bool timing = getenv("VC2_CLI_TIMING") != nullptr;
+    const double t_start = now_s();
+    double t_read = 0, t_code = 0, t_write = 0;   // busy seconds of the three stages
     std::vector<Worker> workers(G);
-    for (int g = 0; g < G; ++g) workers[g].codec.reset(new Codec(g, cp));
+    {
+      // one thread per GPU: creating a CUDA context and the codec's device buffers takes most of a second each
+      std::vector<std::thread> th;
+      std::vector<std::string> err(G);
+      for (int g = 0; g < G; ++g)
+        th.emplace_back([&, g]() {
+          try { workers[g].codec.reset(new Codec(g, cp)); } catch (const std::exception& e) { err[g] = e.what(); }
+        });
+      for (auto& t : th) t.join();
+      for (int g = 0; g < G; ++g)
+        if (!err[g].empty()) throw std::invalid_argument(err[g]);
+    }
+    const double t_codecs = now_s();
     const size_t picBytes = workers[0].codec->pictureBytes();
     const size_t cap = workers[0].codec->payloadCapacity();
 
@@ -364,6 +383,7 @@ int main(int argc, char** argv) {
         for (int k = 2; k < wide; ++k) dst[(size_t)wide * i + k] = 0;
       }
     };
+    const double t_buffers = now_s();
     FrameSource source(p.inFile, fileFrameBytes);
     vc2cli::Channel<int> freeQ, readQ, codedQ;
     for (int r = 0; r < NR; ++r) freeQ.push(r);
@@ -379,6 +399,7 @@ int main(int argc, char** argv) {
         std::fill(r.count.begin(), r.count.end(), 0);
         r.last = false; r.noFrame0 = false;
         if (stop) { r.last = true; readQ.push(ri); return; }
+        const double t0 = now_s();
         const int framesPerBatch = B / framePics;
         if (source.seekable()) {
           // frame f of this round goes to batch f / framesPerBatch; the reads are independent: several threads
@@ -420,6 +441,7 @@ int main(int argc, char** argv) {
         }
         first = false;
         r.last = eof;
+        t_read += now_s() - t0;
         readQ.push(ri);
       }
     });
@@ -429,6 +451,7 @@ int main(int argc, char** argv) {
       for (;;) {
         const int ri = readQ.pop();
         Round& r = rounds[ri];
+        const double t0 = now_s();
         std::vector<std::thread> th;
         for (int g = 0; g < G; ++g) {
           if (!r.count[g] || r.noFrame0) continue;
@@ -444,6 +467,7 @@ int main(int argc, char** argv) {
           });
         }
         for (auto& t : th) t.join();
+        t_code += now_s() - t0;
         const bool last = r.last;
         codedQ.push(ri);
         if (last) break;
@@ -464,6 +488,7 @@ int main(int argc, char** argv) {
     for (bool done = false; !done;) {
       const int ri = codedQ.pop();
       Round& r = rounds[ri];
+      const double t0 = now_s();
       done = r.last;
       if (r.noFrame0) { failure = "\rFailed to read input frame number 0"; break; }
       std::vector<int>& count = r.count;
@@ -583,6 +608,7 @@ int main(int argc, char** argv) {
         if (!*out) { failure = "Failed to write output file \"" + p.outFile + "\""; break; }
       }
       if (!failure.empty()) break;
+      t_write += now_s() - t0;
       if (!done) freeQ.push(ri);   // the round's buffers go back to the reader
     }
     } catch (...) { shutdown(); throw; }
@@ -595,6 +621,9 @@ int main(int argc, char** argv) {
       out->write(unit.data(), (std::streamsize)unit.size());
     }
     out->flush();
+    if (timing)
+      std::cerr << "timing: codecs " << t_codecs - t_start << " s, host buffers " << t_buffers - t_codecs << " s, pipeline " << now_s() - t_buffers
+                << " s for " << frame << " pictures (busy: read " << t_read << ", code " << t_code << ", write " << t_write << ")" << endl;
   } catch (const std::exception& ex) {   // EncodeStream.cpp:782-785: message on standard OUTPUT, failure status
     std::cout << "Error: " << ex.what() << endl;
     return EXIT_FAILURE;
