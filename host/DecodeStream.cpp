@@ -23,6 +23,7 @@
 
 #include <chrono>
 #include <fcntl.h>
+#include <sys/mman.h>
 #include <sys/stat.h>
 #include <unistd.h>
 
@@ -90,8 +91,9 @@ size_t hq_payload_length(const uint8_t* p, size_t avail, int nslices, int prefix
 
 class Decoder {
  public:
-  Decoder(std::ostream& out, Output output, int gpus, int batch, bool verbose)
-      : out_(out), output_(output), G_(gpus), B_(batch), verbose_(verbose), frames_(0) {}
+  // decoded pictures go through the positional writer `pw` (large pieces, several threads), the tap outputs through `out`
+  Decoder(std::ostream& out, vc2cli::PositionalWriter* pw, Output output, int gpus, int batch, bool verbose)
+      : out_(out), pw_(pw), output_(output), G_(gpus), B_(batch), verbose_(verbose), frames_(0) {}
 
   // a payload this object keeps alive until it has been decoded (reassembled fragments)
   const uint8_t* keep(std::vector<uint8_t>&& bytes) {
@@ -158,6 +160,7 @@ class Decoder {
   void writeSet(int set, int n, const Config& cfg) {
     const double t0 = now_s();
     const size_t bytes = recon_[set][0].size();
+    std::vector<vc2cli::PositionalWriter::Piece> pieces;
     for (int i = 0; i < n; ++i) {
       const uint8_t* pic = recon_[set][i].data();
       if (cfg.interlace) {
@@ -165,14 +168,15 @@ class Decoder {
         if (field_.empty()) { field_.assign(pic, pic + bytes); continue; }
         weave(cfg, field_.data(), pic, bytes);
         field_.clear();
-        out_.write(reinterpret_cast<const char*>(frame_.data()), (std::streamsize)frame_.size());
+        pw_->append({{frame_.data(), frame_.size()}});
       } else {
-        out_.write(reinterpret_cast<const char*>(pic), (std::streamsize)bytes);
+        pieces.push_back({pic, bytes});
       }
       if (verbose_) clog << "Decoded frame number " << frames_ << endl;
       ++frames_;
     }
-    if (!out_) throw std::runtime_error("Failed to write output file");
+    if (!pieces.empty()) pw_->append(pieces);
+    if (!pw_->ok()) throw std::runtime_error("Failed to write output file");
     t_write_ += now_s() - t0;
   }
 
@@ -271,6 +275,7 @@ class Decoder {
   }
 
   std::ostream& out_;
+  vc2cli::PositionalWriter* pw_;
   Output output_;
   int G_, B_;
   bool verbose_;
@@ -329,38 +334,57 @@ int main(int argc, char** argv) {
     }
     const bool timing = getenv("VC2_CLI_TIMING") != nullptr;
     const double t_start = now_s();
-    // the whole stream in memory, read in large pieces
-    std::vector<uint8_t> stream;
+    // The whole stream in memory.  A regular file is mapped (no copy; the mapping is laid over an anonymous one that is 64
+    // bytes longer, so the word reads of the parsers behind the last payload stay inside mapped memory); standard input and
+    // pipes are read in large pieces.
+    std::vector<uint8_t> streamBuf;
+    const uint8_t* streamData = nullptr;
+    size_t streamLen = 0;
     {
       int fd = 0;
+      bool mapped = false;
       if (inName != "-") {
         fd = ::open(inName.c_str(), O_RDONLY);
         if (fd < 0) { perror(("Failed to open input file \"" + inName + "\"").c_str()); return EXIT_FAILURE; }
         struct stat st;
-        if (fstat(fd, &st) == 0 && S_ISREG(st.st_mode)) stream.reserve((size_t)st.st_size + 64);
+        if (fstat(fd, &st) == 0 && S_ISREG(st.st_mode) && st.st_size > 0) {
+          const size_t n = (size_t)st.st_size;
+          void* base = mmap(nullptr, n + 4096 + 64, PROT_READ, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+          if (base != MAP_FAILED && mmap(base, n, PROT_READ, MAP_PRIVATE | MAP_FIXED, fd, 0) == base) {
+            streamData = static_cast<const uint8_t*>(base);
+            streamLen = n;
+            mapped = true;
+          } else if (base != MAP_FAILED) {
+            munmap(base, n + 4096 + 64);
+          }
+        }
       }
-      const size_t piece = 16u << 20;
-      for (size_t have = 0;;) {
-        if (stream.size() < have + piece) stream.resize(have + piece);
-        const ssize_t r = ::read(fd, stream.data() + have, piece);
-        if (r <= 0) { stream.resize(have); break; }
-        have += (size_t)r;
+      if (!mapped) {
+        const size_t piece = 16u << 20;
+        for (size_t have = 0;;) {
+          if (streamBuf.size() < have + piece) streamBuf.resize(have + piece);
+          const ssize_t r = ::read(fd, streamBuf.data() + have, piece);
+          if (r <= 0) { streamBuf.resize(have + 64, 0); streamLen = have; break; }   // + slack behind the last payload
+          have += (size_t)r;
+        }
+        streamData = streamBuf.data();
       }
       if (fd > 0) ::close(fd);
     }
     const double t_loaded = now_s();
-    stream.resize(stream.size() + 64, 0);   // slack behind the last payload for the parser's word reads
-    const size_t streamLen = stream.size() - 64;
     std::ofstream outF;
     std::ostream* out = &std::cout;
-    if (outName != "-") {
+    vc2cli::PositionalWriter pw;
+    if (output == DECODED) {
+      if (!pw.open(outName.c_str())) { perror(("Failed to open output file \"" + outName + "\"").c_str()); return EXIT_FAILURE; }
+    } else if (outName != "-") {
       outF.open(outName.c_str(), std::ios::out | std::ios::binary);
       if (!outF) { perror(("Failed to open output file \"" + outName + "\"").c_str()); return EXIT_FAILURE; }
       out = &outF;
     }
 
-    Decoder dec(*out, output, gpus, batch, verbose);
-    StreamReader rd(stream.data(), streamLen);
+    Decoder dec(*out, &pw, output, gpus, batch, verbose);
+    StreamReader rd(streamData, streamLen);
     rd.synchronise();   // DecodeStream.cpp:177-178
     bool haveSeq = false;
     SequenceHeader seq;
@@ -397,7 +421,7 @@ int main(int argc, char** argv) {
           cfg.ld = ld; cfg.height = seq.interlace ? seq.height / 2 : seq.height; cfg.width = seq.width; cfg.bits = seq.bitdepth;
           cfg.cf = seq.chromaFormat; cfg.pre = pre; cfg.interlace = seq.interlace; cfg.tff = seq.topFieldFirst;
           PictureUnit u;
-          u.data = stream.data() + rd.pos();
+          u.data = streamData + rd.pos();
           if (ld) {
             // DecodeStream.cpp:312: bytes of the whole picture from the slice-bytes ratio
             cfg.compressedBytes = ld_picture_bytes(pre);
@@ -437,7 +461,7 @@ int main(int argc, char** argv) {
             FragmentedPicture& fp = it->second;
             if (verbose) clog << "Picture " << fh.picture_number << ": Reading " << fh.n_slices << " slices, starting from (" << fh.slice_offset_x
                               << ", " << fh.slice_offset_y << ")" << endl;
-            fp.parts[fh.slice_offset_y * fp.cfg.pre.slices_x + fh.slice_offset_x] = std::make_pair(stream.data() + rd.pos(), (size_t)fh.fragment_length);
+            fp.parts[fh.slice_offset_y * fp.cfg.pre.slices_x + fh.slice_offset_x] = std::make_pair(streamData + rd.pos(), (size_t)fh.fragment_length);
             fp.have += fh.n_slices;
             if (fp.have >= fp.needed) {
               std::vector<uint8_t> payload;
@@ -467,6 +491,14 @@ int main(int argc, char** argv) {
       std::cerr << "timing: stream read " << t_loaded - t_start << " s, parse + decode + write " << now_s() - t_loaded << " s for " << dec.frames()
                 << " frames (busy: decode calls " << dec.decodeSeconds() << ", writer " << dec.writeSeconds() << ")" << std::endl;
     clog << "End of data stream reached successfully, exiting." << endl;
+    if (output == DECODED) {
+      // everything is written: leave without unpinning the host buffers and tearing the CUDA contexts down one by one
+      if (!pw.ok()) { std::cerr << "Failed to write output file" << endl; return EXIT_FAILURE; }
+      pw.close();
+      std::cout.flush(); std::clog.flush(); std::cerr.flush();
+      fflush(nullptr);
+      _exit(EXIT_SUCCESS);
+    }
   } catch (const std::exception& ex) {   // DecodeStream.cpp:985-988
     std::cout << "Error: " << ex.what() << endl;
     return EXIT_FAILURE;

@@ -100,7 +100,10 @@ Params parse(int argc, char** argv) {
   p.scalar = c.integer("S", 1); p.prefix = c.integer("P", 0); p.fragment = c.integer("F", 0);
   p.compressedBytes = c.integer("s", 0); p.qIndex = c.integer("q", 0);
   p.gpus = c.integer("G", getenv("VC2_GPUS") ? atoi(getenv("VC2_GPUS")) : 1);
-  p.batch = c.integer("B", getenv("VC2_BATCH") ? atoi(getenv("VC2_BATCH")) : 8);
+  // default batch: 4 pictures per GPU and round for the pipelined outputs (three rounds of pinned buffers are in flight, and
+  // pinning memory is the largest fixed cost of a run), 8 for the others
+  const bool streamOut = c.str("o", "Stream") == "Stream" || c.str("o", "Stream") == "Packaged";
+  p.batch = c.integer("B", getenv("VC2_BATCH") ? atoi(getenv("VC2_BATCH")) : (streamOut ? 4 : 8));
 
   if (c.isSet("z") && (c.isSet("l") || c.isSet("c")))
     throw std::invalid_argument("bitDepth is incompatible with luma depth (and/or chroma depth): use one or the other");
@@ -260,9 +263,15 @@ int main(int argc, char** argv) {
       if (probe < 0) { perror(("Failed to open input file \"" + p.inFile + "\"").c_str()); return EXIT_FAILURE; }
       ::close(probe);
     }
+    // -o Stream / Packaged (the pipelined outputs) go through a positional writer: large pieces, several threads; the other
+    // outputs through an ostream
+    const bool pipelined = p.output == STREAM || p.output == PACKAGED;
     std::ofstream outF;
     std::ostream* out = &std::cout;
-    if (p.outFile != "-") {
+    vc2cli::PositionalWriter pw;
+    if (pipelined) {
+      if (!pw.open(p.outFile.c_str())) { perror(("Failed to open output file \"" + p.outFile + "\"").c_str()); return EXIT_FAILURE; }
+    } else if (p.outFile != "-") {
       outF.open(p.outFile.c_str(), std::ios::out | std::ios::binary);
       if (!outF) { perror(("Failed to open output file \"" + p.outFile + "\"").c_str()); return EXIT_FAILURE; }
       out = &outF;
@@ -336,7 +345,7 @@ int main(int argc, char** argv) {
       // fragmentedPictures raises the stream to major version 3 (DataUnit.cpp:1062-1067, 1412-1421)
       writer.startSequence(unit, SequenceHeader(ld ? PROFILE_LD : PROFILE_HQ, frameFormat.lumaHeight(), frameFormat.lumaWidth(), frameFormat.chromaFormat(),
                                                 p.interlaced, (FrameRate)p.frameRate, p.topFieldFirst, p.lumaDepth, p.fragment > 0));
-      out->write(unit.data(), (std::streamsize)unit.size());
+      pw.append({{unit.data(), unit.size()}});
     }
     PicturePreamble pre;
     pre.wavelet_kernel = p.kernel; pre.depth = p.depth; pre.slices_x = xSlices; pre.slices_y = ySlices;
@@ -353,10 +362,12 @@ int main(int argc, char** argv) {
     // one round = up to G batches of B pictures; frames[g][i] is picture number frame0 + g*B + i.
     // -o Stream / Packaged: three rounds in flight - the reader fills one while the GPUs code the second and this thread
     // writes the third.  The other outputs read codec slots back after the encode, so they keep to one round.
-    const bool pipelined = p.output == STREAM || p.output == PACKAGED;
     const int NR = pipelined ? 3 : 1;
     std::vector<Round> rounds(NR);
     for (Round& r : rounds) { r.frames.resize(G); r.payload.resize(G); r.len.assign(G, std::vector<size_t>(B, 0)); r.count.assign(G, 0); }
+    // payload buffers start at the size of a raw picture (pinning memory costs about half a second per gigabyte, and the
+    // worst case - every coefficient a 32-bit code - is 1.5 x raw for C3); a batch that does not fit is redone with full-size ones
+    const size_t paycap = std::min(cap, std::max(picBytes, (size_t)1 << 20));
     {
       // the buffers of GPU g are allocated by a thread that runs next to it (first touch decides the NUMA node)
       std::vector<std::thread> th;
@@ -364,7 +375,7 @@ int main(int argc, char** argv) {
         th.emplace_back([&, g]() {
           if (G > 1) vc2_bind_thread_to_device(g);
           for (Round& r : rounds)
-            for (int i = 0; i < B; ++i) { r.frames[g].emplace_back(picBytes); r.payload[g].emplace_back(cap); }
+            for (int i = 0; i < B; ++i) { r.frames[g].emplace_back(picBytes); r.payload[g].emplace_back(paycap); }
         });
       for (auto& t : th) t.join();
     }
@@ -462,7 +473,15 @@ int main(int argc, char** argv) {
               std::vector<const void*> pics(r.count[g]);
               std::vector<uint8_t*> pay(r.count[g]);
               for (int i = 0; i < r.count[g]; ++i) { pics[i] = r.frames[g][i].data(); pay[i] = r.payload[g][i].data(); }
-              w.codec->encode(r.count[g], pics.data(), pay.data(), cap, r.len[g].data());
+              const int st = vc2_codec_encode_host(w.codec->handle(), r.count[g], pics.data(), pay.data(), r.payload[g][0].size(), r.len[g].data());
+              if (st == VC2_ERR_CAPACITY && r.payload[g][0].size() < cap) {
+                vc2_synchronize(w.codec->context());   // whatever of the failed call is still in flight
+                for (int i = 0; i < B; ++i) r.payload[g][i].resize(cap);
+                for (int i = 0; i < r.count[g]; ++i) pay[i] = r.payload[g][i].data();
+                w.codec->encode(r.count[g], pics.data(), pay.data(), cap, r.len[g].data());
+              } else {
+                w.codec->check(st);
+              }
             } catch (const std::exception& e) { w.error = e.what(); }
           });
         }
@@ -493,7 +512,15 @@ int main(int argc, char** argv) {
       if (r.noFrame0) { failure = "\rFailed to read input frame number 0"; break; }
       std::vector<int>& count = r.count;
       std::vector<std::vector<vc2cli::HostBuf>>& frames = r.frames;
-      // ordered reassembly
+      // ordered reassembly.  Pipelined outputs: the data unit headers of the round as small strings, the slice bytes straight
+      // from the pinned payload buffers, all handed to the positional writer as one ordered list of pieces
+      std::vector<std::string> heads;
+      std::vector<vc2cli::PositionalWriter::Piece> pieces;
+      if (pipelined) {
+        size_t total = 0;
+        for (int g = 0; g < G; ++g) total += (size_t)count[g];
+        heads.reserve(total);   // the pieces point into the strings: no reallocation
+      }
       for (int g = 0; g < G; ++g) {
         Worker& w = workers[g];
         if (!count[g]) continue;
@@ -501,20 +528,23 @@ int main(int argc, char** argv) {
         for (int i = 0; i < count[g]; ++i, ++frame) {
           if (p.verbose) clog << "Encoded frame number " << frame << " (" << r.len[g][i] << " bytes)" << endl;
           if (p.output == STREAM) {
-            unit.clear();
+            heads.emplace_back();
+            std::string& head = heads.back();
             // picture number = field + frame * fields per frame, wrapping at 2^32 (Utils.cpp:52-63)
-            if (p.fragment > 0) {
+            const unsigned long number = (unsigned long)(frame & 0xFFFFFFFFull);
+            if (p.fragment > 0) {   // fragments re-chunk the slices: the whole data units are built in the string
               if (r.len[g][i] != sliceOff.back()) throw std::logic_error("fragment writer: payload length does not match the slice table");
-              if (ld) writer.ldFragmentedPicture(unit, (unsigned long)(frame & 0xFFFFFFFFull), pre, r.payload[g][i].data(), sliceOff.data(), p.fragment);
-              else writer.hqFragmentedPicture(unit, (unsigned long)(frame & 0xFFFFFFFFull), pre, r.payload[g][i].data(), sliceOff.data(), p.fragment);
-            } else if (ld) {
-              writer.ldPicture(unit, (unsigned long)(frame & 0xFFFFFFFFull), pre, r.payload[g][i].data(), r.len[g][i]);
+              if (ld) writer.ldFragmentedPicture(head, number, pre, r.payload[g][i].data(), sliceOff.data(), p.fragment);
+              else writer.hqFragmentedPicture(head, number, pre, r.payload[g][i].data(), sliceOff.data(), p.fragment);
+              pieces.push_back({head.data(), head.size()});
             } else {
-              writer.hqPicture(unit, (unsigned long)(frame & 0xFFFFFFFFull), pre, r.payload[g][i].data(), r.len[g][i]);
+              if (ld) writer.ldPicture(head, number, pre, nullptr, r.len[g][i]);
+              else writer.hqPicture(head, number, pre, nullptr, r.len[g][i]);
+              pieces.push_back({head.data(), head.size()});
+              pieces.push_back({r.payload[g][i].data(), r.len[g][i]});
             }
-            out->write(unit.data(), (std::streamsize)unit.size());
           } else if (p.output == PACKAGED) {
-            out->write(reinterpret_cast<const char*>(r.payload[g][i].data()), (std::streamsize)r.len[g][i]);
+            pieces.push_back({r.payload[g][i].data(), r.len[g][i]});
           } else if (taps) {
             // the slots still hold this batch: read the requested intermediate back (EncodeStream -o Transform / Quantised / Indices)
             const size_t ny = (size_t)cp.geom.slices_y * cp.geom.slices_x;
@@ -607,6 +637,10 @@ int main(int argc, char** argv) {
         }
         if (!*out) { failure = "Failed to write output file \"" + p.outFile + "\""; break; }
       }
+      if (pipelined) {
+        pw.append(pieces);
+        if (!pw.ok()) failure = "Failed to write output file \"" + p.outFile + "\"";
+      }
       if (!failure.empty()) break;
       t_write += now_s() - t0;
       if (!done) freeQ.push(ri);   // the round's buffers go back to the reader
@@ -618,12 +652,21 @@ int main(int argc, char** argv) {
     if (p.output == STREAM) {
       unit.clear();
       writer.endSequence(unit);
-      out->write(unit.data(), (std::streamsize)unit.size());
+      pw.append({{unit.data(), unit.size()}});
+      if (!pw.ok()) { std::cerr << "Failed to write output file \"" << p.outFile << "\"" << endl; return EXIT_FAILURE; }
     }
+    pw.close();
     out->flush();
     if (timing)
       std::cerr << "timing: codecs " << t_codecs - t_start << " s, host buffers " << t_buffers - t_codecs << " s, pipeline " << now_s() - t_buffers
                 << " s for " << frame << " pictures (busy: read " << t_read << ", code " << t_code << ", write " << t_write << ")" << endl;
+    if (pipelined) {
+      // everything is written and closed: leave without unpinning gigabytes of host buffers and tearing the CUDA contexts down
+      // one by one (about a second for a job that takes a few)
+      std::cout.flush(); std::clog.flush(); std::cerr.flush();
+      fflush(nullptr);
+      _exit(EXIT_SUCCESS);
+    }
   } catch (const std::exception& ex) {   // EncodeStream.cpp:782-785: message on standard OUTPUT, failure status
     std::cout << "Error: " << ex.what() << endl;
     return EXIT_FAILURE;

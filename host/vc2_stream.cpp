@@ -241,7 +241,7 @@ void StreamWriter::hqPicture(std::string& out, unsigned long pictureNumber, cons
   transformParameters(hdr, p, false, major_ >= 3);   // :249-252
   parseInfo(out, 0xE8, (unsigned)(hdr.size() + len) + 13);
   out += hdr;
-  out.append(reinterpret_cast<const char*>(slices), len);
+  if (slices) out.append(reinterpret_cast<const char*>(slices), len);   // NULL: headers only, the caller writes the slice bytes itself
 }
 
 void StreamWriter::ldPicture(std::string& out, unsigned long pictureNumber, const PicturePreamble& p, const uint8_t* slices, size_t len) {
@@ -250,7 +250,7 @@ void StreamWriter::ldPicture(std::string& out, unsigned long pictureNumber, cons
   transformParameters(hdr, p, true, major_ >= 3);    // :138-141
   parseInfo(out, 0xC8, (unsigned)(hdr.size() + len) + 13);
   out += hdr;
-  out.append(reinterpret_cast<const char*>(slices), len);
+  if (slices) out.append(reinterpret_cast<const char*>(slices), len);
 }
 
 void StreamWriter::fragmented(std::string& out, unsigned char code, bool ld, unsigned long pictureNumber, const PicturePreamble& p,
