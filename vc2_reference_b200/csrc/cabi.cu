@@ -1182,6 +1182,8 @@ struct vc2_codec {
   // picture for about a millisecond) on a per-slot stream, between the payload upload and the parse kernel, so
   // the walks of all pictures in flight overlap each other and the other stages
   std::vector<cudaStream_t> index_stream;
+  std::vector<cudaEvent_t> ev_idx_fork;   // [slot] device-resident decode: the sub-batch stream has reached its index walk
+  bool index_prio = true;                 // run the device-resident index walks on the priority streams too
   std::vector<cudaEvent_t> ev_idx;
   uint32_t* host_flags = nullptr;     // pinned: per-slot error flags [B][nslices]
   uint32_t* host_len = nullptr;       // pinned: per-slot payload length [B]
@@ -1203,6 +1205,7 @@ static void codec_free(vc2_codec* k) {
   for (auto e : k->ev_out) cudaEventDestroy(e);
   for (auto e : k->ev_idx) cudaEventDestroy(e);
   for (auto st : k->index_stream) cudaStreamDestroy(st);
+  for (auto e : k->ev_idx_fork) cudaEventDestroy(e);
   if (k->copy_in) cudaStreamDestroy(k->copy_in);
   if (k->copy_out) cudaStreamDestroy(k->copy_out);
   for (int i = 0; i < vc2_codec::MAX_SUB; ++i) {
@@ -1299,10 +1302,19 @@ extern "C" vc2_codec* vc2_codec_create(vc2_ctx* ctx, const vc2_codec_params* prm
     cudaEvent_t e;
     if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) ok = false; else k->ev_idx.push_back(e);
   }
+  // the slice index walks run on streams of the highest priority: a walk is 1.4 ms of latency on one SM per picture, its CTAs
+  // should take the first SM that has room instead of queueing behind the thousands of CTAs of the lifting kernels
+  int prio_lo = 0, prio_hi = 0;
+  cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
   for (int i = 0; ok && i < std::min(B, 8); ++i) {
     cudaStream_t st;
-    if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) ok = false; else k->index_stream.push_back(st);
+    if (cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, prio_hi) != cudaSuccess) ok = false; else k->index_stream.push_back(st);
   }
+  for (int i = 0; ok && i < B; ++i) {
+    cudaEvent_t e;
+    if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) ok = false; else k->ev_idx_fork.push_back(e);
+  }
+  k->index_prio = getenv("VC2_INDEX_PRIO") ? atoi(getenv("VC2_INDEX_PRIO")) != 0 : true;
   if (ok && cudaStreamCreateWithFlags(&k->copy_in, cudaStreamNonBlocking) != cudaSuccess) ok = false;
   if (ok && cudaStreamCreateWithFlags(&k->copy_out, cudaStreamNonBlocking) != cudaSuccess) ok = false;
   if (const char* e = getenv("VC2_CODEC_SUBBATCH")) k->nsub = std::min(std::max(atoi(e), 1), (int)vc2_codec::MAX_SUB);
@@ -1545,8 +1557,19 @@ static int codec_decode_range(vc2_codec* k, int first, int n, bool index_here, b
     ip.len_dev = k->dev_len.as<uint32_t>() + first;
     ip.slice_off = k->slice_off.as<uint32_t>() + (size_t)first * (k->nslices + 1);
     ip.nslices = k->nslices; ip.prefix = g.prefix; ip.scalar = g.scalar;
-    ProfScope ps(ctx, VC2_STAGE_INDEX);
-    CU(index_launch(ctx->stream, ip, n));
+    if (k->index_prio && !ctx->profiling && !k->index_stream.empty()) {
+      // on a priority stream, between two events of the sub-batch's own stream
+      const int B = k->prm.max_pictures;
+      cudaStream_t is = k->index_stream[(size_t)((long long)first * (long long)k->index_stream.size() / B) % k->index_stream.size()];
+      CU(cudaEventRecord(k->ev_idx_fork[first], ctx->stream));
+      CU(cudaStreamWaitEvent(is, k->ev_idx_fork[first], 0));
+      CU(index_launch(is, ip, n));
+      CU(cudaEventRecord(k->ev_idx[first], is));
+      CU(cudaStreamWaitEvent(ctx->stream, k->ev_idx[first], 0));
+    } else {
+      ProfScope ps(ctx, VC2_STAGE_INDEX);
+      CU(index_launch(ctx->stream, ip, n));
+    }
     ctx->launches++;
   }
   {

@@ -1353,7 +1353,10 @@ __global__ void narrow_scale_kernel(const UnpackParams p, const uint2* __restric
 // shared-memory loads per slice instead of three DRAM round trips).
 // A payload that runs off its end leaves the remaining slices empty; the parser flags those.
 // ------------------------------------------------------------------------------------------
-constexpr int INDEX_SEG = 16 * 1024;                 // bytes per ring segment
+#ifndef VC2_INDEX_SEG_KB
+#define VC2_INDEX_SEG_KB 16
+#endif
+constexpr int INDEX_SEG = VC2_INDEX_SEG_KB * 1024;    // bytes per ring segment (a slice longer than a segment takes the plain walk in global memory)
 constexpr int INDEX_RING = 4 * INDEX_SEG;             // four segments: two being walked, one being filled, one spare
 constexpr unsigned INDEX_MASK = INDEX_RING - 1;
 
