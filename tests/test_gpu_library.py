@@ -278,3 +278,15 @@ def test_cpp_library_mirror_vs_reference(ref):
     out = r.stdout.decode()
     assert r.returncode == 0, [l for l in out.splitlines() if not l.endswith(" same")]
     assert out.count(" same") >= 7 * 18 and "DIFFERENT" not in out
+
+
+def test_cbr_rate_control_from_shared_memory_is_bit_exact():
+    """the optional rate-control kernel that keeps its slices in shared memory (VC2_SEARCH_SMEM=1, read once per process):
+    the CBR parity tests again in a process that has it switched on"""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_library.py"), "-q", "-m", "gpu", "-k", "cbr_rate_control_and_pack"],
+                       env=dict(os.environ, VC2_SEARCH_SMEM="1"), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, cwd=root)
+    assert r.returncode == 0, r.stdout.decode()[-2000:]

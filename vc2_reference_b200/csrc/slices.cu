@@ -311,8 +311,10 @@ struct CountOp {      // component_slice_bytes' bit count of quantise(v) (rate-c
   // The probes of the rate control quantise every coefficient seven times.  Nearly all pairs take the first branch: both
   // coefficients small enough for the full-rate multiply (instead of the multiply-high) and both codes in the table - one test
   // for the pair, then straight-line code: multiply, shift, byte look-up, add, and the move that remembers the last non-zero.
-  __device__ __forceinline__ void pair(int v0, int v1, const BandP& bp) {
-    const uint32_t a0 = (uint32_t)abs(v0), a1 = (uint32_t)abs(v1);
+  __device__ __forceinline__ void pair(int v0, int v1, const BandP& bp) { mags((uint32_t)abs(v0), (uint32_t)abs(v1), bp); }
+  // the same on magnitudes (the bit count does not depend on the sign)
+  __device__ __forceinline__ void mag1(uint32_t a, const BandP& bp) { count(__umulhi(bp.qm, a << 2) >> bp.ql); }
+  __device__ __forceinline__ void mags(uint32_t a0, uint32_t a1, const BandP& bp) {
     if (bp.mul16 != 0u && (a0 | a1) < (uint32_t)VC2_NARROW_FAST_MAX) {
       const uint32_t m0 = (a0 * bp.mul16) >> bp.sh16, m1 = (a1 * bp.mul16) >> bp.sh16;
       if ((m0 | m1) < (uint32_t)ENC_LUT_MAG) {
@@ -325,8 +327,8 @@ struct CountOp {      // component_slice_bytes' bit count of quantise(v) (rate-c
         count(m1);
       }
     } else {
-      (*this)(v0, bp);
-      (*this)(v1, bp);
+      mag1(a0, bp);
+      mag1(a1, bp);
     }
   }
 };
@@ -337,6 +339,14 @@ struct SseOp {        // yss_for_slice (Quantisation.cpp:627-642): product in in
     acc += (long long)(int)((unsigned)d * (unsigned)d);
   }
   __device__ __forceinline__ void pair(int v0, int v1, const BandP& bp) { (*this)(v0, bp); (*this)(v1, bp); }
+  // on magnitudes: v - scale(quant(v)) only changes sign with v, its square does not
+  __device__ __forceinline__ void mag1(uint32_t a, const BandP& bp) {
+    const uint32_t m = __umulhi(bp.qm, a << 2) >> bp.ql;
+    const uint32_t r = (m * bp.qf + (m ? bp.qo : 0u)) >> 2;
+    const unsigned d = a - r;
+    acc += (long long)(int)(d * d);
+  }
+  __device__ __forceinline__ void mags(uint32_t a0, uint32_t a1, const BandP& bp) { mag1(a0, bp); mag1(a1, bp); }
 };
 template <bool QUANT, class Writer>
 struct EmitOp {
@@ -376,6 +386,140 @@ __device__ __forceinline__ int scaled_bytes(int count, int scalar, bool& too_big
   return units * scalar;
 }
 
+// ---- rate control of one slice: literal replay of quantIndicesCBR (EncodeStream.cpp:85-122).  walk(c, q, badq, op) feeds the
+// coefficients of component c, in coding order, to op.  Returns the index (0 when the search died; flags say why).
+template <class Walk>
+__device__ __forceinline__ int search_slice(const PackParams& p, const SliceGeom& g, int s, const uint32_t* s_enc, const uint8_t* s_bits,
+                                            unsigned& flags, Walk& walk) {
+  const int avail = p.slice_bytes[s] - 4;
+  int trialQ = 63, q = 127, delta = 64;
+  bool dead = false;
+  while (delta > 0) {
+    delta >>= 1;
+    int need = 0;
+    bool too_big = false, badq = false;
+    for (int c = 0; c < 3; ++c) {
+      CountOp op = {s_enc, 0, 0, 0u, s_bits};
+      walk(c, trialQ, badq, op);
+      need += scaled_bytes(op.last, g.scalar, too_big);
+    }
+    if (badq) { flags |= VC2_FLAG_QUANT_INDEX | VC2_FLAG_SEARCH_PHASE; dead = true; break; }
+    if (too_big) { flags |= VC2_FLAG_SCALAR_TOO_SMALL | VC2_FLAG_SEARCH_PHASE; dead = true; break; }
+    if (need <= avail) { if (trialQ < q) q = trialQ; trialQ -= delta; }
+    else trialQ += delta;
+  }
+  if (!dead) {
+    // "try a few higher quantisers": keep going while the luma squared error strictly drops
+    trialQ = q;
+    bool badq = false;
+    SseOp prev = {0};
+    walk(0, trialQ, badq, prev);
+    while (!badq) {
+      ++trialQ;
+      SseOp cur = {0};
+      walk(0, trialQ, badq, cur);
+      if (badq) break;
+      const long long d = cur.acc - prev.acc;
+      prev = cur;
+      if (!(d < 0)) break;
+    }
+    if (badq) { flags |= VC2_FLAG_QUANT_INDEX | VC2_FLAG_SEARCH_PHASE; dead = true; }
+    q = trialQ - 1;
+  }
+  return dead ? 0 : q;
+}
+
+// The coefficient list of a slice component as 16-bit MAGNITUDES in shared memory (hq_search_kernel): piece i of this lane at
+// sm[i * stride], four magnitudes per piece.  Same band bookkeeping as walk_component; the ops take magnitudes.
+template <class Op>
+__device__ __forceinline__ void walk_component_mag(const uint2* sm, int stride, const SliceGeom& g, int c, int q, bool& badq, Op& op) {
+  const int np = g.band_start[c][g.nbands] >> 2;
+  int k = 0, b = 0, bend = g.band_start[c][1];
+  BandP bp = band_params(q, g.qmatrix[0], badq);
+  int piece = 0;
+  while (piece < np) {
+    while (k == bend) {
+      ++b;
+      bend = g.band_start[c][b + 1];
+      bp = band_params(q, g.qmatrix[b], badq);
+    }
+    const int run = min((bend - k) >> 2, np - piece);
+    if (run > 0) {
+      k += 4 * run;
+      const uint2* q2 = sm + (size_t)piece * stride;
+      piece += run;
+#pragma unroll 2
+      for (int i = 0; i < run; ++i) {
+        const uint2 w = *q2;
+        q2 += stride;
+        op.mags(w.x & 0xFFFFu, w.x >> 16, bp);
+        op.mags(w.y & 0xFFFFu, w.y >> 16, bp);
+      }
+    } else {
+      const uint2 w = sm[(size_t)piece * stride];
+      ++piece;
+      const uint32_t a[4] = {w.x & 0xFFFFu, w.x >> 16, w.y & 0xFFFFu, w.y >> 16};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        while (k == bend) {
+          ++b;
+          bend = g.band_start[c][b + 1];
+          bp = band_params(q, g.qmatrix[b], badq);
+        }
+        op.mag1(a[e], bp);
+        ++k;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// HQ_CBR rate control with the slice in shared memory (optional, see search_in_smem()).  The seven probes and the squared-error walk of a slice read its
+// coefficients ten times; hq_pack_kernel streams them from DRAM every time (7.2 x the block, and the load latency is the first
+// stall reason, ncu).  Here a CTA first copies the magnitudes of its slices - neither the bit count nor the squared error
+// depends on the sign - as 16-bit words into shared memory, [piece][lane] so that the lanes of a warp read consecutive 8-byte
+// words, and every walk runs from there.  A slice with a magnitude beyond 16 bits keeps the walks in global memory.
+// blockDim.x slices per CTA, dynamic shared memory = blockDim.x * NC * 2 bytes.
+// ------------------------------------------------------------------------------------------
+__global__ void hq_search_kernel(const PackParams p) {
+  extern __shared__ uint2 s_mag[];
+  __shared__ uint8_t s_bits[ENC_LUT_MAG];
+  for (int i = threadIdx.x; i < ENC_LUT_MAG; i += blockDim.x) s_bits[i] = (uint8_t)(d_enc_lut[2 * i] & 31u);
+  const SliceGeom& g = p.g;
+  const int nslices = g.slices_x * g.slices_y;
+  const int pic = blockIdx.y, spc = blockDim.x;
+  const int s = blockIdx.x * spc + threadIdx.x;
+  const int nc4 = g.comp_start[3] >> 2;
+  const int4* base = reinterpret_cast<const int4*>(p.coef + (long long)pic * g.coef_pic_stride);
+  const size_t src = (size_t)(s >> 5) * nc4 * 32 + (s & 31);
+  bool wide = false;
+  if (s < nslices) {
+    uint2* dst = s_mag + threadIdx.x;
+    const int4* q4 = base + src;
+#pragma unroll 4
+    for (int i = 0; i < nc4; ++i) {
+      const int4 v = __ldg(q4 + (size_t)i * 32);
+      const uint32_t a0 = (uint32_t)abs(v.x), a1 = (uint32_t)abs(v.y), a2 = (uint32_t)abs(v.z), a3 = (uint32_t)abs(v.w);
+      wide |= ((a0 | a1 | a2 | a3) >> 16) != 0u;
+      dst[(size_t)i * spc] = make_uint2(a0 | (a1 << 16), a2 | (a3 << 16));
+    }
+  }
+  __syncthreads();
+  if (s >= nslices) return;
+  const long long sidx = (long long)pic * nslices + s;
+  unsigned flags = 0;
+  int qi;
+  if (!wide) {
+    auto walk = [&](int c, int q, bool& badq, auto& op) { walk_component_mag(s_mag + (size_t)(g.comp_start[c] >> 2) * spc + threadIdx.x, spc, g, c, q, badq, op); };
+    qi = search_slice(p, g, s, nullptr, s_bits, flags, walk);
+  } else {
+    auto walk = [&](int c, int q, bool& badq, auto& op) { walk_component(base, src + (size_t)(g.comp_start[c] >> 2) * 32, g, c, q, badq, op); };
+    qi = search_slice(p, g, s, nullptr, s_bits, flags, walk);
+  }
+  p.qidx[sidx] = qi;
+  p.err_flags[sidx] = flags;
+}
+
 // ------------------------------------------------------------------------------------------
 // HQ slice encoder: ONE THREAD PER SLICE, a warp = one group of 32 consecutive slices.
 //   stream the slice's coefficient list (coalesced through the group-interleaved layout) ->
@@ -403,43 +547,8 @@ __global__ void __launch_bounds__(128) hq_pack_kernel(const PackParams p) {
   int qi = 0;
 
   if (p.search) {
-    // ---- rate control: literal replay of quantIndicesCBR (EncodeStream.cpp:85-122)
-    const int avail = p.slice_bytes[s] - 4;
-    int trialQ = 63, q = 127, delta = 64;
-    bool dead = false;
-    while (delta > 0) {
-      delta >>= 1;
-      int need = 0;
-      bool too_big = false, badq = false;
-      for (int c = 0; c < 3; ++c) {
-        CountOp op = {s_enc, 0, 0, 0u, s_bits};
-        walk_component(base, src + (size_t)(g.comp_start[c] >> 2) * 32, g, c, trialQ, badq, op);
-        need += scaled_bytes(op.last, g.scalar, too_big);
-      }
-      if (badq) { flags |= VC2_FLAG_QUANT_INDEX | VC2_FLAG_SEARCH_PHASE; dead = true; break; }
-      if (too_big) { flags |= VC2_FLAG_SCALAR_TOO_SMALL | VC2_FLAG_SEARCH_PHASE; dead = true; break; }
-      if (need <= avail) { if (trialQ < q) q = trialQ; trialQ -= delta; }
-      else trialQ += delta;
-    }
-    if (!dead) {
-      // "try a few higher quantisers": keep going while the luma squared error strictly drops
-      trialQ = q;
-      bool badq = false;
-      SseOp prev = {0};
-      walk_component(base, src, g, 0, trialQ, badq, prev);
-      while (!badq) {
-        ++trialQ;
-        SseOp cur = {0};
-        walk_component(base, src, g, 0, trialQ, badq, cur);
-        if (badq) break;
-        const long long d = cur.acc - prev.acc;
-        prev = cur;
-        if (!(d < 0)) break;
-      }
-      if (badq) { flags |= VC2_FLAG_QUANT_INDEX | VC2_FLAG_SEARCH_PHASE; dead = true; }
-      q = trialQ - 1;
-    }
-    qi = dead ? 0 : q;
+    auto walk = [&](int c, int q, bool& badq, auto& op) { walk_component(base, src + (size_t)(g.comp_start[c] >> 2) * 32, g, c, q, badq, op); };
+    qi = search_slice(p, g, s, s_enc, s_bits, flags, walk);
     p.qidx[sidx] = qi;
   } else if (p.const_q >= 0) {
     qi = p.const_q;
@@ -1613,6 +1722,14 @@ __global__ void __launch_bounds__(1024) ld_dc_batch_kernel(const LdDcBatch b) {
 
 }  // namespace
 
+// VC2_SEARCH_SMEM=1: rate control with the slices in shared memory (hq_search_kernel).  Bit exact, MEASURED SLOWER and therefore
+// off: 11.5 against 7.95 ms per 256 C2 pictures (profiles/r2_v6_search_smem_ab.txt) - 64 KB per 128 slices leaves 12 warps per
+// SM where the streaming kernel has 32, and the probe arithmetic is a dependent chain per coefficient that needs the warps.
+static bool search_in_smem() {
+  static const bool on = getenv("VC2_SEARCH_SMEM") && atoi(getenv("VC2_SEARCH_SMEM")) != 0;
+  return on;
+}
+
 cudaError_t pack_launch(cudaStream_t s, const PackParams& p, int npictures) {
   const int nslices = p.g.slices_x * p.g.slices_y;
   if (p.narrow) {
@@ -1620,6 +1737,20 @@ cudaError_t pack_launch(cudaStream_t s, const PackParams& p, int npictures) {
     if (p.fuse && p.tiles != (nslices + 127) / 128) return cudaErrorInvalidValue;
     hq_pack_narrow_kernel<<<dim3((nslices + 127) / 128, npictures), 128, 0, s>>>(p);
     return cudaGetLastError();
+  }
+  if (p.search && !p.emit && search_in_smem()) {
+    // rate control alone: the slices of a CTA in shared memory when they fit (16-bit magnitudes; 128, 64 or 32 slices per CTA)
+    const size_t per_slice = (size_t)p.g.comp_start[3] * 2;
+    int spc = 0;
+    for (int t = 128; t >= 32 && !spc; t >>= 1)
+      if (per_slice * t <= (size_t)(t == 32 ? 160 : 72) * 1024) spc = t;
+    if (spc) {
+      const size_t smem = per_slice * spc;
+      cudaError_t e = cudaFuncSetAttribute(hq_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+      hq_search_kernel<<<dim3((nslices + spc - 1) / spc, npictures), spc, smem, s>>>(p);
+      return cudaGetLastError();
+    }
   }
   hq_pack_kernel<<<dim3((nslices + 127) / 128, npictures), 128, 0, s>>>(p);
   return cudaGetLastError();
