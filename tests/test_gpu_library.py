@@ -280,13 +280,14 @@ def test_cpp_library_mirror_vs_reference(ref):
     assert out.count(" same") >= 7 * 18 and "DIFFERENT" not in out
 
 
-def test_cbr_rate_control_from_shared_memory_is_bit_exact():
-    """the optional rate-control kernel that keeps its slices in shared memory (VC2_SEARCH_SMEM=1, read once per process):
-    the CBR parity tests again in a process that has it switched on"""
+@pytest.mark.parametrize("switch", ["VC2_SEARCH_SMEM", "VC2_SEARCH_WARP"])
+def test_optional_rate_control_kernels_are_bit_exact(switch):
+    """the two optional rate-control kernels (slices in shared memory / a warp per slice with the slice in registers; both measured
+    slower and off by default, the switch is read once per process): the CBR parity tests again in a process that has one switched on"""
     import os
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_library.py"), "-q", "-m", "gpu", "-k", "cbr_rate_control_and_pack"],
-                       env=dict(os.environ, VC2_SEARCH_SMEM="1"), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, cwd=root)
+                       env=dict(os.environ, **{switch: "1"}), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, cwd=root)
     assert r.returncode == 0, r.stdout.decode()[-2000:]

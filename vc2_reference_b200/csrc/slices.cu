@@ -521,6 +521,208 @@ __global__ void hq_search_kernel(const PackParams p) {
 }
 
 // ------------------------------------------------------------------------------------------
+// HQ_CBR rate control, ONE WARP PER SLICE, the slice in registers (quantIndicesCBR, EncodeStream.cpp:73-125); optional, see
+// search_in_registers().
+// The seven probes and the squared-error walk read a slice ten times; with a thread per slice that is ten passes over
+// memory (hq_pack_kernel).  Here lane l of the warp loads pieces l, l + 32, ... of the slice's coefficient list ONCE - R
+// pieces of four magnitudes per lane; neither the bit count nor the squared error depends on the sign - and every probe is
+// arithmetic on those registers plus two warp reductions per component:
+//   bits of a component up to its last non-zero coefficient = (sum of all its code lengths) - (coefficients behind the last
+//   non-zero one), since a zero costs exactly one bit; the sum is a REDUX add, the position of the last non-zero a REDUX max.
+// The quantiser parameters of the bands for the probed index sit in a small per-warp table in shared memory (one lane per
+// band fills it), the band of every coefficient is worked out once.  The search itself is warp uniform.
+// Eight slices per CTA: the eight warps read the same 128-byte lines of the group-interleaved block.
+// ------------------------------------------------------------------------------------------
+struct WarpBand {                 // per warp: the parameters of every band for the index being probed, as three 8-byte tables
+  uint2 fast[VC2_MAX_BANDS];      // (qmul16, qsh16): |q| = (|v| * mul) >> sh for small |v|
+  uint2 slow[VC2_MAX_BANDS];      // (qm31, ql31):    |q| = mulhi(4 |v|, m) >> l
+  uint2 back[VC2_MAX_BANDS];      // (quant_factor, quant_offset + 2)
+};
+
+template <int R>
+__global__ void __launch_bounds__(256) hq_search_warp_kernel(const PackParams p) {
+  __shared__ uint8_t s_bits[ENC_LUT_MAG];
+  __shared__ WarpBand s_band[8];
+  // the quantiser tables by index, out of the constant bank: the lanes of set_index() look up different indices, which the
+  // constant cache serves one distinct address at a time
+  __shared__ uint2 s_qfast[128], s_qslow[128], s_qback[128];
+  for (int i = threadIdx.x; i < ENC_LUT_MAG; i += blockDim.x) s_bits[i] = (uint8_t)(d_enc_lut[2 * i] & 31u);
+  for (int i = threadIdx.x; i < 128; i += blockDim.x) {
+    s_qfast[i] = make_uint2(c_qt.qmul16[i], c_qt.qsh16[i]);
+    s_qslow[i] = make_uint2(c_qt.qm31[i], c_qt.ql31[i]);
+    s_qback[i] = make_uint2(c_qt.qf[i], c_qt.qo[i] + 2u);
+  }
+  __syncthreads();
+  const SliceGeom& g = p.g;
+  const int nslices = g.slices_x * g.slices_y;
+  const int pic = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int s = blockIdx.x * 8 + warp;
+  if (s >= nslices) return;   // whole warps leave
+  const int nc4 = g.comp_start[3] >> 2;
+  const int4* base = reinterpret_cast<const int4*>(p.coef + (long long)pic * g.coef_pic_stride) + (size_t)(s >> 5) * nc4 * 32 + (s & 31);
+  // ---- the slice: magnitudes, component, position inside the component and band of every coefficient this lane holds
+  uint32_t a[R][4];
+  int comp[R], kc0[R];      // component of the piece (-1: no such piece), index of its first coefficient inside the component
+  uint32_t bands[R];        // the bands of its four coefficients, 8 bits each
+  bool fastmag = true;      // every magnitude is below VC2_NARROW_FAST_MAX (then the full-rate multiply is exact)
+#pragma unroll
+  for (int j = 0; j < R; ++j) {
+    const int piece = j * 32 + lane;
+    comp[j] = -1; kc0[j] = 0; bands[j] = 0;
+    a[j][0] = a[j][1] = a[j][2] = a[j][3] = 0u;
+    if (piece < nc4) {
+      const int4 v = __ldg(base + (size_t)piece * 32);
+      a[j][0] = (uint32_t)abs(v.x); a[j][1] = (uint32_t)abs(v.y); a[j][2] = (uint32_t)abs(v.z); a[j][3] = (uint32_t)abs(v.w);
+      fastmag = fastmag && (a[j][0] | a[j][1] | a[j][2] | a[j][3]) < (uint32_t)VC2_NARROW_FAST_MAX;
+      const int k = 4 * piece;
+      const int c = k >= g.comp_start[2] ? 2 : (k >= g.comp_start[1] ? 1 : 0);
+      comp[j] = c;
+      kc0[j] = k - g.comp_start[c];
+      int b = 0;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        while (kc0[j] + e >= g.band_start[c][b + 1]) ++b;   // bands are in coding order: b only grows
+        bands[j] |= (uint32_t)b << (8 * e);
+      }
+    }
+  }
+  fastmag = __all_sync(FULL, fastmag);
+  // which lanes hold component c in slot j (warp uniform; zero: nobody)
+  unsigned cmask[R][3];
+#pragma unroll
+  for (int j = 0; j < R; ++j)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) cmask[j][c] = __ballot_sync(FULL, comp[j] == c);
+  WarpBand& tab = s_band[warp];
+  int my_qmat = 0;                       // lane b: the quantisation matrix entry of band b
+  if (lane < g.nbands) my_qmat = g.qmatrix[lane];
+  // the quantiser parameters of every band for index q; false when the reference would throw (Quantisation.cpp:60-63)
+  auto set_index = [&](int q, bool& allfast) -> bool {
+    bool bad = false, fast = true;
+    __syncwarp();
+    if (lane < g.nbands) {
+      const int aq = max(q - my_qmat, 0);
+      bad = aq > 119;
+      const int i = min(aq, 127);
+      const uint2 f = s_qfast[i];
+      fast = f.x != 0u;
+      tab.fast[lane] = f; tab.slow[lane] = s_qslow[i]; tab.back[lane] = s_qback[i];
+    }
+    __syncwarp();
+    allfast = fastmag && __all_sync(FULL, fast);
+    return !__any_sync(FULL, bad);
+  };
+  // bytes the three components need at the index in the table (component_slice_bytes, Slices.cpp:97-119)
+  auto need_bytes = [&](bool allfast, bool& too_big) -> int {
+    int need = 0;
+    int total[3] = {0, 0, 0}, lastpos[3] = {-1, -1, -1};
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+      if (__all_sync(FULL, comp[j] < 0)) continue;
+      uint32_t m[4];
+      if (allfast) {   // warp uniform
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const uint2 w = tab.fast[(bands[j] >> (8 * e)) & 0xFFu];
+          m[e] = (a[j][e] * w.x) >> w.y;
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const uint2 w = tab.slow[(bands[j] >> (8 * e)) & 0xFFu];
+          m[e] = __umulhi(w.x, a[j][e] << 2) >> w.y;
+        }
+      }
+      int bits = 0, last = -1;
+      if (!__any_sync(FULL, (m[0] | m[1] | m[2] | m[3]) >= (uint32_t)ENC_LUT_MAG)) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { bits += (int)s_bits[m[e]]; last = m[e] ? kc0[j] + e : last; }
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          bits += m[e] < (uint32_t)ENC_LUT_MAG ? (int)s_bits[m[e]] : 2 * (31 - __clz(min(m[e] + 1u, 65535u))) + 2;
+          last = m[e] ? kc0[j] + e : last;
+        }
+      }
+      if (comp[j] < 0) { bits = 0; last = -1; }
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        if (cmask[j][c] == 0u) continue;          // warp uniform
+        int t = 0, l = -1;
+        if (comp[j] == c) { t = __reduce_add_sync(cmask[j][c], bits); l = __reduce_max_sync(cmask[j][c], last); }
+        const int src = __ffs(cmask[j][c]) - 1;
+        total[c] += __shfl_sync(FULL, t, src);
+        lastpos[c] = max(lastpos[c], __shfl_sync(FULL, l, src));
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const int n = g.band_start[c][g.nbands];
+      const int count = lastpos[c] < 0 ? 0 : total[c] - (n - 1 - lastpos[c]);
+      need += scaled_bytes(count, g.scalar, too_big);
+    }
+    return need;
+  };
+  // yss_for_slice (Quantisation.cpp:627-642) at the index in the table: luma only
+  auto luma_sse = [&]() -> long long {
+    long long acc = 0;
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+      if (comp[j] != 0) continue;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const unsigned b = (bands[j] >> (8 * e)) & 0xFFu;
+        const uint2 ws = tab.slow[b], wb = tab.back[b];
+        const uint32_t m = __umulhi(ws.x, a[j][e] << 2) >> ws.y;
+        const uint32_t r = (m * wb.x + (m ? wb.y : 0u)) >> 2;
+        const unsigned d = a[j][e] - r;
+        acc += (long long)(int)(d * d);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(FULL, acc, o);
+    return acc;
+  };
+
+  // ---- the search, warp uniform: literal replay of EncodeStream.cpp:85-122
+  const int avail = p.slice_bytes[s] - 4;
+  unsigned flags = 0;
+  int trialQ = 63, q = 127, delta = 64;
+  bool dead = false;
+  while (delta > 0) {
+    delta >>= 1;
+    bool too_big = false, allfast = false;
+    if (!set_index(trialQ, allfast)) { flags |= VC2_FLAG_QUANT_INDEX | VC2_FLAG_SEARCH_PHASE; dead = true; break; }
+    const int need = need_bytes(allfast, too_big);
+    if (too_big) { flags |= VC2_FLAG_SCALAR_TOO_SMALL | VC2_FLAG_SEARCH_PHASE; dead = true; break; }
+    if (need <= avail) { if (trialQ < q) q = trialQ; trialQ -= delta; }
+    else trialQ += delta;
+  }
+  if (!dead) {
+    trialQ = q;
+    bool allfast = false;
+    bool ok = set_index(trialQ, allfast);
+    long long prev = ok ? luma_sse() : 0;
+    while (ok) {
+      ++trialQ;
+      ok = set_index(trialQ, allfast);
+      if (!ok) break;
+      const long long cur = luma_sse();
+      const long long d = cur - prev;
+      prev = cur;
+      if (!(d < 0)) break;
+    }
+    if (!ok) { flags |= VC2_FLAG_QUANT_INDEX | VC2_FLAG_SEARCH_PHASE; dead = true; }
+    q = trialQ - 1;
+  }
+  if (lane == 0) {
+    const long long sidx = (long long)pic * nslices + s;
+    p.qidx[sidx] = dead ? 0 : q;
+    p.err_flags[sidx] = flags;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // HQ slice encoder: ONE THREAD PER SLICE, a warp = one group of 32 consecutive slices.
 //   stream the slice's coefficient list (coalesced through the group-interleaved layout) ->
 //   [quantIndicesCBR, literal replay] -> quantise -> SignedVLC -> MSB-first words of the slice image
@@ -1725,6 +1927,15 @@ __global__ void __launch_bounds__(1024) ld_dc_batch_kernel(const LdDcBatch b) {
 // VC2_SEARCH_SMEM=1: rate control with the slices in shared memory (hq_search_kernel).  Bit exact, MEASURED SLOWER and therefore
 // off: 11.5 against 7.95 ms per 256 C2 pictures (profiles/r2_v6_search_smem_ab.txt) - 64 KB per 128 slices leaves 12 warps per
 // SM where the streaming kernel has 32, and the probe arithmetic is a dependent chain per coefficient that needs the warps.
+// VC2_SEARCH_WARP=1: rate control with a warp per slice and the slice in registers (hq_search_warp_kernel).  Bit exact, MEASURED
+// SLOWER and therefore off: 18.2 against 7.95 ms per 256 C2 pictures (profiles/r2_v6_search_smem_ab.txt).  With 256 coefficients a
+// lane holds eight, and everything that is per slice rather than per coefficient - the band table, the reductions, the byte
+// rounding with its division - costs a whole warp instruction for ONE slice instead of 32: 6400 warp instructions per slice
+// against 3100 (ncu, gpurun_out/r2_g36_search.ncu-rep), 15 % of them the arithmetic the kernel exists for.
+static bool search_in_registers() {
+  static const bool on = getenv("VC2_SEARCH_WARP") && atoi(getenv("VC2_SEARCH_WARP")) != 0;
+  return on;
+}
 static bool search_in_smem() {
   static const bool on = getenv("VC2_SEARCH_SMEM") && atoi(getenv("VC2_SEARCH_SMEM")) != 0;
   return on;
@@ -1737,6 +1948,17 @@ cudaError_t pack_launch(cudaStream_t s, const PackParams& p, int npictures) {
     if (p.fuse && p.tiles != (nslices + 127) / 128) return cudaErrorInvalidValue;
     hq_pack_narrow_kernel<<<dim3((nslices + 127) / 128, npictures), 128, 0, s>>>(p);
     return cudaGetLastError();
+  }
+  if (p.search && !p.emit && search_in_registers()) {
+    // rate control alone, a warp per slice with the slice in registers: R pieces per lane
+    const int pieces = (p.g.comp_start[3] >> 2);
+    const int r = (pieces + 31) / 32;
+    const dim3 grid((nslices + 7) / 8, npictures);
+    if (r <= 1) { hq_search_warp_kernel<1><<<grid, 256, 0, s>>>(p); return cudaGetLastError(); }
+    if (r <= 2) { hq_search_warp_kernel<2><<<grid, 256, 0, s>>>(p); return cudaGetLastError(); }
+    if (r <= 4) { hq_search_warp_kernel<4><<<grid, 256, 0, s>>>(p); return cudaGetLastError(); }
+    if (r <= 8) { hq_search_warp_kernel<8><<<grid, 256, 0, s>>>(p); return cudaGetLastError(); }
+    // larger slices: the thread-per-slice kernel below
   }
   if (p.search && !p.emit && search_in_smem()) {
     // rate control alone: the slices of a CTA in shared memory when they fit (16-bit magnitudes; 128, 64 or 32 slices per CTA)
