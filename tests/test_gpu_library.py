@@ -280,9 +280,9 @@ def test_cpp_library_mirror_vs_reference(ref):
     assert out.count(" same") >= 7 * 18 and "DIFFERENT" not in out
 
 
-@pytest.mark.parametrize("switch", ["VC2_SEARCH_SMEM", "VC2_SEARCH_WARP"])
+@pytest.mark.parametrize("switch", ["VC2_SEARCH_SMEM", "VC2_SEARCH_WARP", "VC2_SEARCH_SUB"])
 def test_optional_rate_control_kernels_are_bit_exact(switch):
-    """the two optional rate-control kernels (slices in shared memory / a warp per slice with the slice in registers; both measured
+    """the optional rate-control kernels (slices in shared memory / a warp per slice / eight lanes per slice with the slice in registers; all measured
     slower and off by default, the switch is read once per process): the CBR parity tests again in a process that has one switched on"""
     import os
     import subprocess

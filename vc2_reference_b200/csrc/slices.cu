@@ -723,6 +723,210 @@ __global__ void __launch_bounds__(256) hq_search_warp_kernel(const PackParams p)
 }
 
 // ------------------------------------------------------------------------------------------
+// HQ_CBR rate control, EIGHT LANES PER SLICE (a warp = four slices, a CTA of eight warps = one group of 32 slices), the slice in
+// registers; optional, see search_in_subwarps().  The middle way between hq_pack_kernel (a thread per slice: ten passes over memory) and hq_search_warp_kernel (a
+// warp per slice: the per-slice work costs a whole warp instruction per slice): lane l of a slice's eight loads pieces l, l + 8,
+// ... ONCE, R pieces of four magnitudes; a probe is arithmetic on those registers, per-lane sums per component, and one
+// three-step butterfly per component.  Needs every slot (eight consecutive pieces) to lie inside one component - the host checks.
+// ------------------------------------------------------------------------------------------
+template <int R>
+__global__ void __launch_bounds__(256) hq_search_sub_kernel(const PackParams p) {
+  __shared__ uint8_t s_bits[ENC_LUT_MAG];
+  __shared__ WarpBand s_band[32];                 // one table per slice of the CTA
+  __shared__ uint2 s_qfast[128], s_qslow[128], s_qback[128];
+  for (int i = threadIdx.x; i < ENC_LUT_MAG; i += blockDim.x) s_bits[i] = (uint8_t)(d_enc_lut[2 * i] & 31u);
+  for (int i = threadIdx.x; i < 128; i += blockDim.x) {
+    s_qfast[i] = make_uint2(c_qt.qmul16[i], c_qt.qsh16[i]);
+    s_qslow[i] = make_uint2(c_qt.qm31[i], c_qt.ql31[i]);
+    s_qback[i] = make_uint2(c_qt.qf[i], c_qt.qo[i] + 2u);
+  }
+  __syncthreads();
+  const SliceGeom& g = p.g;
+  const int nslices = g.slices_x * g.slices_y;
+  const int pic = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sub = lane >> 3, l8 = lane & 7;                     // slice inside the warp, lane inside the slice
+  const int in_cta = warp * 4 + sub;
+  const int s = blockIdx.x * 32 + in_cta;
+  const bool live = s < nslices;                                // a dead slice walks along on zeros and writes nothing
+  const int nc4 = g.comp_start[3] >> 2;
+  const int4* base = reinterpret_cast<const int4*>(p.coef + (long long)pic * g.coef_pic_stride) + (size_t)blockIdx.x * nc4 * 32 + in_cta;
+  uint32_t a[R][4];
+  uint32_t bands[R];        // the bands of the four coefficients of a piece, 8 bits each
+  int kc0[R];               // index of the piece's first coefficient inside its component
+  int cslot[R];             // component of slot j (the same for every lane and slice: warp uniform), -1: no such slot
+  bool fastmag = true;
+#pragma unroll
+  for (int j = 0; j < R; ++j) {
+    const int piece = j * 8 + l8, first = 4 * (j * 8);
+    cslot[j] = j * 8 >= nc4 ? -1 : (first >= g.comp_start[2] ? 2 : (first >= g.comp_start[1] ? 1 : 0));
+    a[j][0] = a[j][1] = a[j][2] = a[j][3] = 0u;
+    bands[j] = 0; kc0[j] = 0;
+    if (piece < nc4) {
+      if (live) {
+        const int4 v = __ldg(base + (size_t)piece * 32);
+        a[j][0] = (uint32_t)abs(v.x); a[j][1] = (uint32_t)abs(v.y); a[j][2] = (uint32_t)abs(v.z); a[j][3] = (uint32_t)abs(v.w);
+      }
+      fastmag = fastmag && (a[j][0] | a[j][1] | a[j][2] | a[j][3]) < (uint32_t)VC2_NARROW_FAST_MAX;
+      const int c = cslot[j];
+      kc0[j] = 4 * piece - g.comp_start[c];
+      int b = 0;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        while (kc0[j] + e >= g.band_start[c][b + 1]) ++b;
+        bands[j] |= (uint32_t)b << (8 * e);
+      }
+    } else if (cslot[j] >= 0) {
+      kc0[j] = -1 << 20;   // a lane behind the end of the list in the last slot: zeros that are never the last non-zero
+    }
+  }
+  fastmag = __all_sync(FULL, fastmag);
+  WarpBand& tab = s_band[in_cta];
+  const int ncomp[3] = {g.band_start[0][g.nbands], g.band_start[1][g.nbands], g.band_start[2][g.nbands]};
+  // the band parameters of this slice for its index q (the four slices of a warp probe different indices)
+  auto set_index = [&](int q, bool& bad) -> bool {   // returns: every band of every slice of the warp has the full-rate form
+    bool fast = true;
+    bad = false;
+    __syncwarp();
+    for (int b = l8; b < g.nbands; b += 8) {
+      const int aq = max(q - g.qmatrix[b], 0);
+      bad = bad || aq > 119;
+      const int i = min(aq, 127);
+      const uint2 f = s_qfast[i];
+      fast = fast && f.x != 0u;
+      tab.fast[b] = f; tab.slow[b] = s_qslow[i]; tab.back[b] = s_qback[i];
+    }
+    __syncwarp();
+    // bad is per slice: any of its eight lanes
+    bad = (__ballot_sync(FULL, bad) >> (8 * sub) & 0xFFu) != 0u;
+    return fastmag && __all_sync(FULL, fast);
+  };
+  auto need_bytes = [&](bool allfast, bool& too_big) -> int {
+    int total[3] = {0, 0, 0}, lastpos[3] = {-1, -1, -1};
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+      if (cslot[j] < 0) continue;   // warp uniform
+      uint32_t m[4];
+      if (allfast) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const uint2 w = tab.fast[(bands[j] >> (8 * e)) & 0xFFu];
+          m[e] = (a[j][e] * w.x) >> w.y;
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const uint2 w = tab.slow[(bands[j] >> (8 * e)) & 0xFFu];
+          m[e] = __umulhi(w.x, a[j][e] << 2) >> w.y;
+        }
+      }
+      int bits = 0, last = -1;
+      if (!__any_sync(FULL, (m[0] | m[1] | m[2] | m[3]) >= (uint32_t)ENC_LUT_MAG)) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { bits += (int)s_bits[m[e]]; last = m[e] ? kc0[j] + e : last; }
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          bits += m[e] < (uint32_t)ENC_LUT_MAG ? (int)s_bits[m[e]] : 2 * (31 - __clz(min(m[e] + 1u, 65535u))) + 2;
+          last = m[e] ? kc0[j] + e : last;
+        }
+      }
+      if (kc0[j] < 0) bits = 0;     // no piece here (the tail of the last slot)
+      // the slot's component is warp uniform: these are plain branches
+      if (cslot[j] == 0) { total[0] += bits; lastpos[0] = max(lastpos[0], last); }
+      else if (cslot[j] == 1) { total[1] += bits; lastpos[1] = max(lastpos[1], last); }
+      else { total[2] += bits; lastpos[2] = max(lastpos[2], last); }
+    }
+    int need = 0;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+#pragma unroll
+      for (int o = 4; o > 0; o >>= 1) {   // butterfly over the eight lanes of the slice
+        total[c] += __shfl_xor_sync(FULL, total[c], o);
+        lastpos[c] = max(lastpos[c], __shfl_xor_sync(FULL, lastpos[c], o));
+      }
+      const int count = lastpos[c] < 0 ? 0 : total[c] - (ncomp[c] - 1 - lastpos[c]);
+      if (g.scalar == 1) {
+        const int units = (count + 7) >> 3;
+        if (units > 0xFF) too_big = true;
+        need += units;
+      } else {
+        need += scaled_bytes(count, g.scalar, too_big);
+      }
+    }
+    return need;
+  };
+  auto luma_sse = [&]() -> long long {
+    long long acc = 0;
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+      if (cslot[j] != 0) continue;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const unsigned b = (bands[j] >> (8 * e)) & 0xFFu;
+        const uint2 ws = tab.slow[b], wb = tab.back[b];
+        const uint32_t m = __umulhi(ws.x, a[j][e] << 2) >> ws.y;
+        const uint32_t r = (m * wb.x + (m ? wb.y : 0u)) >> 2;
+        const unsigned d = a[j][e] - r;
+        acc += (long long)(int)(d * d);
+      }
+    }
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) acc += __shfl_xor_sync(FULL, acc, o);
+    return acc;
+  };
+
+  // ---- the search of EncodeStream.cpp:85-122, four slices in lockstep: the seven probes are seven iterations for every slice,
+  // a slice that has died (or finished its squared-error walk) idles through the rest
+  const int avail = live ? p.slice_bytes[s] - 4 : 0;
+  unsigned flags = 0;
+  int trialQ = 63, q = 127, delta = 64;
+  bool dead = false;
+  while (delta > 0) {
+    delta >>= 1;
+    bool too_big = false, bad = false;
+    const bool allfast = set_index(trialQ, bad);
+    const int need = need_bytes(allfast, too_big);
+    if (!dead) {
+      if (bad) { flags |= VC2_FLAG_QUANT_INDEX | VC2_FLAG_SEARCH_PHASE; dead = true; }
+      else if (too_big) { flags |= VC2_FLAG_SCALAR_TOO_SMALL | VC2_FLAG_SEARCH_PHASE; dead = true; }
+      else if (need <= avail) { if (trialQ < q) q = trialQ; trialQ -= delta; }
+      else trialQ += delta;
+    }
+  }
+  // "try a few higher quantisers": every slice walks until its squared error stops dropping; the warp until all four have stopped
+  bool walking = !dead;
+  trialQ = q;
+  long long prev = 0;
+  {
+    bool bad = false;
+    set_index(trialQ, bad);
+    const long long first = luma_sse();
+    if (walking && bad) { flags |= VC2_FLAG_QUANT_INDEX | VC2_FLAG_SEARCH_PHASE; dead = true; walking = false; }
+    prev = first;
+  }
+  while (__any_sync(FULL, walking)) {
+    const int tq = walking ? trialQ + 1 : trialQ;
+    bool bad = false;
+    set_index(tq, bad);
+    const long long cur = luma_sse();
+    if (walking) {
+      trialQ = tq;
+      if (bad) { flags |= VC2_FLAG_QUANT_INDEX | VC2_FLAG_SEARCH_PHASE; dead = true; walking = false; }
+      else {
+        const long long d = cur - prev;
+        prev = cur;
+        if (!(d < 0)) walking = false;
+      }
+    }
+  }
+  if (live && l8 == 0) {
+    const long long sidx = (long long)pic * nslices + s;
+    p.qidx[sidx] = dead ? 0 : trialQ - 1;
+    p.err_flags[sidx] = flags;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // HQ slice encoder: ONE THREAD PER SLICE, a warp = one group of 32 consecutive slices.
 //   stream the slice's coefficient list (coalesced through the group-interleaved layout) ->
 //   [quantIndicesCBR, literal replay] -> quantise -> SignedVLC -> MSB-first words of the slice image
@@ -1932,6 +2136,13 @@ __global__ void __launch_bounds__(1024) ld_dc_batch_kernel(const LdDcBatch b) {
 // lane holds eight, and everything that is per slice rather than per coefficient - the band table, the reductions, the byte
 // rounding with its division - costs a whole warp instruction for ONE slice instead of 32: 6400 warp instructions per slice
 // against 3100 (ncu, gpurun_out/r2_g36_search.ncu-rep), 15 % of them the arithmetic the kernel exists for.
+// VC2_SEARCH_SUB=1: rate control with eight lanes per slice and the slice in registers (hq_search_sub_kernel).  Bit exact, MEASURED
+// SLOWER and therefore off: 11.25 against 7.95 ms per 256 C2 pictures.  Same instruction count as the thread-per-slice kernel (1.54 G
+// against 1.64 G warp instructions per 64 pictures, ncu) at 128 registers and 16 warps per SM: IPC 1.9 against 2.75.
+static bool search_in_subwarps() {
+  static const bool on = getenv("VC2_SEARCH_SUB") && atoi(getenv("VC2_SEARCH_SUB")) != 0;
+  return on;
+}
 static bool search_in_registers() {
   static const bool on = getenv("VC2_SEARCH_WARP") && atoi(getenv("VC2_SEARCH_WARP")) != 0;
   return on;
@@ -1948,6 +2159,20 @@ cudaError_t pack_launch(cudaStream_t s, const PackParams& p, int npictures) {
     if (p.fuse && p.tiles != (nslices + 127) / 128) return cudaErrorInvalidValue;
     hq_pack_narrow_kernel<<<dim3((nslices + 127) / 128, npictures), 128, 0, s>>>(p);
     return cudaGetLastError();
+  }
+  if (p.search && !p.emit && search_in_subwarps()) {
+    // rate control alone, eight lanes per slice with the slice in registers: up to eight pieces per lane, and every slot of eight
+    // consecutive pieces inside one component
+    const int pieces = p.g.comp_start[3] >> 2;
+    const bool whole = (p.g.comp_start[1] >> 2) % 8 == 0 && (p.g.comp_start[2] >> 2) % 8 == 0;
+    if (whole && pieces <= 64) {
+      const dim3 grid((nslices + 31) / 32, npictures);
+      const int r = (pieces + 7) / 8;
+      if (r <= 2) hq_search_sub_kernel<2><<<grid, 256, 0, s>>>(p);
+      else if (r <= 4) hq_search_sub_kernel<4><<<grid, 256, 0, s>>>(p);
+      else hq_search_sub_kernel<8><<<grid, 256, 0, s>>>(p);
+      return cudaGetLastError();
+    }
   }
   if (p.search && !p.emit && search_in_registers()) {
     // rate control alone, a warp per slice with the slice in registers: R pieces per lane
