@@ -117,3 +117,42 @@ def test_no_cpu_fallback_without_gpu():
         pytest.skip("a GPU is present")
     with pytest.raises(vc2.Vc2Error):
         vc2.Context(0)
+
+
+def test_command_line_pipeline_pieces(tmp_path):
+    """host/pipeline.h without a GPU: the positional writer (multi-threaded pwrite, awkward piece sizes), the host buffer's
+    fallback to ordinary memory, the round queue (tests/cpp/test_pipeline_host.cpp)"""
+    import subprocess
+    exe = os.path.join(ROOT, "vc2_reference_b200", "bin", "test_pipeline_host")
+    r = subprocess.run([exe, str(tmp_path / "out.bin")], stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+    assert r.returncode == 0, r.stdout.decode()
+
+
+@pytest.mark.parametrize("args", [
+    ["-x", "100", "-y", "60", "-f", "4:2:2", "-d", "3", "-u", "1", "-a", "1"],      # depth impossible: suggests depth and slice sizes
+    ["-x", "1920", "-y", "1080", "-f", "4:2:2", "-d", "3", "-u", "5", "-a", "7"],   # slice sizes that do not divide: suggests others
+    ["-x", "176", "-y", "144", "-f", "4:2:0", "-d", "2", "-u", "1", "-a", "1"],     # 4:2:0 needs even slice sizes
+    ["-x", "64", "-y", "34", "-f", "4:4:4", "-d", "4", "-u", "3", "-a", "3"],
+])
+def test_parameter_advice_matches_reference(tmp_path, args):
+    """bad wavelet depth / slice sizes: the advice on standard error (suggestWaveletDepth, suggestSliceSize,
+    waveletTransformIsPossible, EncodeStream.cpp:379-405) and the error text are the reference's, for the drop-in command line and for
+    the reference's own main over the drop-in Library bodies (no GPU is needed: nothing is transformed)"""
+    import subprocess
+    ref = os.path.join(ROOT, "oracle", "_ref", "EncodeStream")
+    if not os.path.exists(ref):
+        pytest.skip("oracle/_ref not built")
+    src = str(tmp_path / "in.yuv")
+    open(src, "wb").write(b"\\0" * 200000)
+    full = ["-m", "HQ_ConstQ", "-z", "10", "-k", "LeGall", "-q", "5"] + args + [src, str(tmp_path / "out")]
+
+    def advice(exe):
+        r = subprocess.run([exe] + full, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+        lines = [l for l in r.stderr.decode().splitlines() if l.startswith("Consider") or l.startswith("It is not possible")]
+        return r.returncode != 0, lines, r.stdout.decode().strip()
+    want = advice(ref)
+    assert want[0] and want[1], "the reference accepts these parameters"
+    assert advice(os.path.join(ROOT, "vc2_reference_b200", "bin", "EncodeStream")) == want
+    dropin = os.path.join(ROOT, "tests", "dropin", "_build", "EncodeStream")
+    if os.path.exists(dropin):
+        assert advice(dropin) == want
