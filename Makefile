@@ -16,7 +16,7 @@ HOSTLIB   := $(PKG)/libvc2host.so
 BIN       := $(PKG)/bin
 CXXFLAGS  := -O2 -std=c++14 -fPIC -Wall -Wno-comment -Iinclude -Ihost
 
-all: $(LIB) $(ORACLE) $(HOSTLIB) $(BIN)/EncodeStream $(BIN)/DecodeStream $(BIN)/DecodeFrame $(BIN)/test_library_mirror $(BIN)/test_pipeline_host
+all: $(LIB) $(ORACLE) $(HOSTLIB) $(BIN)/EncodeStream $(BIN)/DecodeStream $(BIN)/DecodeFrame $(BIN)/test_library_mirror $(BIN)/test_pipeline_host $(BIN)/test_vlc_host
 
 # C++ host layer: the Library mirror (include/vc2/*.h) and the drop-in command lines, over the C-ABI
 $(HOSTLIB): host/vc2_library.cpp host/vc2_stream.cpp include/vc2/*.h include/vc2_cabi.h include/vc2_host.h $(LIB)
@@ -29,6 +29,11 @@ $(BIN)/%: host/%.cpp host/cmdline.h host/pipeline.h include/vc2/*.h include/vc2_
 $(BIN)/test_library_mirror: tests/cpp/test_library_mirror.cpp include/vc2/*.h $(HOSTLIB)
 	mkdir -p $(BIN)
 	$(CXX) $(CXXFLAGS) $< -o $@ -L$(PKG) -lvc2host -lvc2b200 -ldl -Wl,-rpath,'$$ORIGIN/..'
+
+# include/vc2/VLC.h against the compiled reference (host only)
+$(BIN)/test_vlc_host: tests/cpp/test_vlc_host.cpp include/vc2/VLC.h
+	mkdir -p $(BIN)
+	$(CXX) $(CXXFLAGS) $< -o $@ -ldl
 
 # host-only check of host/pipeline.h (tests/test_host_helpers.py runs it without a GPU)
 $(BIN)/test_pipeline_host: tests/cpp/test_pipeline_host.cpp host/pipeline.h $(LIB)

@@ -156,3 +156,14 @@ def test_parameter_advice_matches_reference(tmp_path, args):
     dropin = os.path.join(ROOT, "tests", "dropin", "_build", "EncodeStream")
     if os.path.exists(dropin):
         assert advice(dropin) == want
+
+
+def test_vlc_value_classes_vs_reference():
+    """include/vc2/VLC.h (UnsignedVLC / SignedVLC value classes, VLC.h:17-46) against SignedVLC of the compiled reference for 7000 values,
+    and round trips through the MSB-first bit buffer (tests/cpp/test_vlc_host.cpp)"""
+    import subprocess
+    ref = os.path.join(ROOT, "oracle", "_ref", "libvc2ref.so")
+    if not os.path.exists(ref):
+        pytest.skip("oracle/_ref not built")
+    r = subprocess.run([os.path.join(ROOT, "vc2_reference_b200", "bin", "test_vlc_host"), ref], stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+    assert r.returncode == 0, r.stdout.decode()
