@@ -30,6 +30,8 @@ def plane(seed, c, f, H, W, depth, smooth=False):
         k = (np.uint32(seed) ^ (np.uint32(c) * np.uint32(0x9E3779B1)) ^ (np.uint32(f) * np.uint32(0x85EBCA77))
              ^ (y * np.uint32(0xC2B2AE3D)) ^ (x * np.uint32(0x27D4EB2F)))
         h = fmix32(k)
+    if isinstance(smooth, str) and smooth == "noise":   # full-range white noise: incompressible pictures
+        return (h >> np.uint32(32 - depth)).astype(np.uint16)
     noise = (h >> np.uint32(26)).astype(np.int32) - 32
     if smooth:
         noise = noise >> 3

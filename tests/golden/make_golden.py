@@ -107,6 +107,12 @@ CASES += [
     case("N3_Haar1_d2_444_12b", 128, 64, "444", 12, 2, "HQ_CBR", "Haar1", 2, 2, 2, s=9000, seed=701, nbytes=3),
 ]
 
+# an incompressible picture: full-range noise at index 0 codes to more bytes than the raw picture has (the command line's payload
+# buffers start at the raw size and must grow)
+CASES += [
+    case("R00_noise_q0_444", 1024, 512, "444", 10, 2, "HQ_ConstQ", "LeGall", 2, 2, 4, q=0, S=8, seed=800, smooth="noise"),
+]
+
 
 def widen(raw, nbytes):
     """16-bit big-endian MSB-justified words -> nbytes-wide ones (the sample stays MSB justified)"""

@@ -62,6 +62,9 @@ def run(cmd):
                                   "D5_DD97_d5_422", "D6_LeGall_d6_444",
                                   # input words of 4 and 3 bytes (-n, Arrays.cpp:333-379)
                                   "N4_LeGall_d2_422", "N3_Haar1_d2_444_12b",
+                                  # full-range noise at index 0: the payload is larger than the raw picture, the command line's
+                                  # payload buffers (raw size to begin with) have to grow and the batch is encoded again
+                                  "R00_noise_q0_444",
                                   # interlaced coding (two field pictures per frame) and fragmented pictures
                                   "I00_LeGall_d3_422_tff", "I01_DD137_d2_420_bff", "I02_Haar1_d3_444_tff",
                                   "F00_DD97_d3_422", "F01_LeGall_d2_420_small", "F02_Fidelity_d2_422_il",

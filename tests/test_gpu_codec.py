@@ -82,7 +82,7 @@ def load_ld_payloads(name, g, c):
     return [z["p%d" % i].tobytes() for i in range(c["frames"])]
 
 
-SMALL = sorted(k for k in GOLD if k[0] in "SBLWD" and not GOLD[k]["params"].get("extra"))
+SMALL = sorted(k for k in GOLD if k[0] in "SBLWDR" and not GOLD[k]["params"].get("extra"))
 
 
 @pytest.mark.parametrize("name", SMALL)
