@@ -15,12 +15,15 @@ constexpr int ENC_LUT_MAG = 256;
 constexpr int DEC_LUT_BITS = 12;
 __device__ uint32_t d_enc_lut[2 * ENC_LUT_MAG];
 __device__ int16_t d_dec_lut[1 << DEC_LUT_BITS];
+// the same for the narrow parser: (t << 4) | bits with t = 2 * |value| + (value < 0), the word the narrow block stores
+__device__ uint16_t d_dec_lut_sm[1 << DEC_LUT_BITS];
 
 cudaError_t upload_quant_tables(const QuantTables& t) {
   cudaError_t e = cudaMemcpyToSymbol(c_qt, &t, sizeof(t));
   if (e != cudaSuccess) return e;
   static uint32_t enc[2 * ENC_LUT_MAG];
   static int16_t dec[1 << DEC_LUT_BITS];
+  static uint16_t dec_sm[1 << DEC_LUT_BITS];
   for (int mag = 0; mag < ENC_LUT_MAG; ++mag)
     for (int neg = 0; neg < 2; ++neg) {
       uint32_t code = 1, nb = 1;
@@ -55,8 +58,12 @@ cudaError_t upload_quant_tables(const QuantTables& t) {
       --pos;
     }
     dec[i] = (int16_t)entry;
+    const int val = entry >> 4, len = entry & 15;   // arithmetic shift: the value is signed
+    dec_sm[i] = entry ? (uint16_t)(((2 * (val < 0 ? -val : val) + (val < 0 ? 1 : 0)) << 4) | len) : (uint16_t)0;
   }
   e = cudaMemcpyToSymbol(d_enc_lut, enc, sizeof(enc));
+  if (e != cudaSuccess) return e;
+  e = cudaMemcpyToSymbol(d_dec_lut_sm, dec_sm, sizeof(dec_sm));
   if (e != cudaSuccess) return e;
   return cudaMemcpyToSymbol(d_dec_lut, dec, sizeof(dec));
 }
@@ -1639,6 +1646,28 @@ struct BitReader {
     else { ensure(); v1 = long_vlc(range_err); }
     ensure();
   }
+  // the same as sign-magnitude words t = 2 * |v| + (v < 0) for the narrow block, straight from the table; `big` collects the
+  // magnitudes of the long codes (only those can overflow the narrow word)
+  __device__ __forceinline__ static unsigned lookup_sm(const uint16_t* lut, uint32_t window) {
+    unsigned e;
+    const unsigned addr = (unsigned)__cvta_generic_to_shared(lut) + ((window >> (31 - DEC_LUT_BITS)) & ((2u << DEC_LUT_BITS) - 2u));
+    asm("ld.shared.u16 %0, [%1];" : "=r"(e) : "r"(addr));
+    return e;
+  }
+  __device__ __forceinline__ static unsigned smag_of(int v, unsigned& big) {
+    const unsigned a = (unsigned)abs(v);
+    big |= a;
+    return 2u * min(a, (unsigned)VC2_NARROW_MAX_MAG) + ((unsigned)v >> 31);
+  }
+  __device__ __forceinline__ void get_smag2(const uint16_t* lut, bool& range_err, unsigned& big, unsigned& t0, unsigned& t1) {
+    const unsigned e0 = lookup_sm(lut, hi);
+    if (e0 != 0u) { consume((int)(e0 & 15u)); t0 = e0 >> 4; }
+    else { const int v = long_vlc(range_err); ensure(); t0 = smag_of(v, big); }
+    const unsigned e1 = lookup_sm(lut, hi);
+    if (e1 != 0u) { consume((int)(e1 & 15u)); t1 = e1 >> 4; }
+    else { ensure(); const int v = long_vlc(range_err); t1 = smag_of(v, big); }
+    ensure();
+  }
   __device__ __forceinline__ uint32_t get_bits(int n) {   // n in 1..32
     const uint32_t w = n == 32 ? hi : (hi >> (32 - n));
     skip(n);
@@ -1790,8 +1819,8 @@ __global__ void __launch_bounds__(128) slice_unpack_kernel(const UnpackParams p)
 // raises narrow_ovf[picture]: the caller decodes that picture again through the 32-bit path.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) slice_unpack_narrow_kernel(const UnpackParams p) {
-  __shared__ int16_t s_dec[1 << DEC_LUT_BITS];
-  stage_table(reinterpret_cast<uint32_t*>(s_dec), reinterpret_cast<const uint32_t*>(d_dec_lut), (1 << DEC_LUT_BITS) / 2);
+  __shared__ uint16_t s_dec[1 << DEC_LUT_BITS];
+  stage_table(reinterpret_cast<uint32_t*>(s_dec), reinterpret_cast<const uint32_t*>(d_dec_lut_sm), (1 << DEC_LUT_BITS) / 2);
   __syncthreads();
   const SliceGeom& g = p.g;
   const int nslices = g.slices_x * g.slices_y;
@@ -1823,16 +1852,9 @@ __global__ void __launch_bounds__(128) slice_unpack_narrow_kernel(const UnpackPa
     uint2* cdst = dst + (size_t)(g.comp_start[c] >> 2) * 32;
     const int np = g.band_start[c][g.nbands] >> 2;
     for (int i = 0; i < np; ++i) {
-      int v[4];
-      br.get_vlc2(s_dec, range_err, v[0], v[1]);
-      br.get_vlc2(s_dec, range_err, v[2], v[3]);
-      unsigned t[4];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const unsigned a = (unsigned)abs(v[e]);
-        big |= a;
-        t[e] = 2u * min(a, (unsigned)VC2_NARROW_MAX_MAG) + ((unsigned)v[e] >> 31);
-      }
+      unsigned t[4];   // the table holds the narrow words themselves: no sign / magnitude conversion for the codes it covers
+      br.get_smag2(s_dec, range_err, big, t[0], t[1]);
+      br.get_smag2(s_dec, range_err, big, t[2], t[3]);
       *cdst = make_uint2(t[0] | (t[1] << 16), t[2] | (t[3] << 16));
       cdst += 32;
     }
